@@ -1,0 +1,119 @@
+/* vmsm.h -- C ABI of the B200-native MSM / generator-fold engine (libvmsm.so).
+ *
+ * The reference (toonsegers/verifiable_mpc) is pure Python and has NO FFI layer for this path: the seam is Python
+ * name binding.  Each entry point below therefore cites the reference *call site* whose group
+ * arithmetic it replaces.  The Python host layer (verifiable_mpc_b200/) binds exactly these symbols with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = VMSM_OK, negative = error; vmsm_last_error() gives the
+ *     thread-local message of the last failure.  No exception crosses the boundary.
+ *   - host buffers are owned by the caller; device objects are opaque uint64 handles owned by a context and
+ *     freed explicitly (or with the context).
+ *   - a context is bound to ONE CUDA device and ONE stream; calls on one context must be serialised by the
+ *     caller; different contexts may be driven from different threads/processes (ctypes releases the GIL).
+ *   - wire formats (little-endian):   scalar = 32 B, already reduced below the group order;
+ *       Ed25519 point = 64 B canonical affine x || y (identity = (0, 1));
+ *       extended point (multi-GPU partials) = 128 B X || Y || Z || T, any representative.
+ *   - there is no CPU fallback: without a CUDA device vmsm_ctx_create fails with VMSM_ERR_CUDA.
+ */
+#ifndef VMSM_H
+#define VMSM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMSM_OK 0
+#define VMSM_ERR_INVALID (-1)  /* bad argument / handle / range */
+#define VMSM_ERR_CUDA (-2)     /* CUDA runtime error, no device */
+#define VMSM_ERR_POINT (-3)    /* uploaded point not canonical or not on the curve */
+#define VMSM_ERR_NOMEM (-4)
+#define VMSM_ERR_UNSUPPORTED (-5)
+#define VMSM_ERR_TIMEOUT (-6)  /* a multi-GPU partial did not arrive */
+
+/* curves (mpyc.fingroups.EllipticCurve names used by the reference: demos/demo_zkp_ac20.py:46,
+ * demos/demo_zkp_pynocchio.py:27-29) */
+#define VMSM_CURVE_ED25519 0
+#define VMSM_CURVE_BN256_G1 1
+#define VMSM_CURVE_BN256_G2 2
+
+/* vmsm_ctx_set_option keys */
+#define VMSM_OPT_WINDOW_BITS 1  /* 0 = auto (default), else force the Pippenger window c in [2, 18] */
+#define VMSM_OPT_PHASE_TIMING 2 /* 1 = bracket every MSM phase with CUDA events (see vmsm_phase_times) */
+#define VMSM_OPT_SORT_BUCKETS 3 /* 1 = process buckets in order of decreasing population (default 1) */
+#define VMSM_OPT_CHECK_POINTS 4 /* 1 = validate uploaded points (default 1) */
+#define VMSM_OPT_REDUCE_RADIX 5 /* log2 of the bucket-tree radix (default 3) */
+
+/* phases reported by vmsm_phase_times */
+#define VMSM_PHASE_DIGITS 0
+#define VMSM_PHASE_SCAN 1
+#define VMSM_PHASE_SCATTER 2
+#define VMSM_PHASE_ORDER 3
+#define VMSM_PHASE_ACCUMULATE 4
+#define VMSM_PHASE_REDUCE 5
+#define VMSM_PHASE_FINAL 6
+#define VMSM_PHASE_COUNT 7
+
+int32_t vmsm_version(void);
+const char *vmsm_last_error(void);
+int32_t vmsm_device_count(int32_t *count);
+
+/* ---- contexts ------------------------------------------------------------------------------------------- */
+int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx);
+int32_t vmsm_ctx_destroy(uint64_t ctx);
+int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value);
+int32_t vmsm_sync(uint64_t ctx);
+/* CUDA-event timer on the context's stream (the stream every kernel of this context is launched on). */
+int32_t vmsm_timer_start(uint64_t ctx);
+int32_t vmsm_timer_stop(uint64_t ctx, float *ms); /* synchronises */
+/* cumulative per-phase device time (ms) and number of MSM calls since the last query; resets the sums. */
+int32_t vmsm_phase_times(uint64_t ctx, double *ms_out /* [VMSM_PHASE_COUNT] */, uint64_t *calls);
+/* number of kernels this context has launched so far (bench.py's gpu_launches). */
+int32_t vmsm_launch_count(uint64_t ctx, uint64_t *launches);
+
+/* ---- device-resident point vectors (the generator lists g, g_hat of pivot.py:139 / compressed_pivot.py:29) */
+int32_t vmsm_points_upload(uint64_t ctx, int32_t curve, const uint8_t *affine, uint64_t n, uint64_t *pts);
+/* g_i = r_i * B, r_i given (32 B LE each, < order) or, when scalars == NULL, r_i = synth(seed, i) -- the batch
+ * form of create_generators (verifiable_mpc/ac20/circuit_sat_r1cs.py:59-74: g.append(h ** r)). */
+int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scalars, uint64_t seed, uint64_t n,
+                               uint64_t *pts);
+int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *affine_out);
+int32_t vmsm_points_count(uint64_t ctx, uint64_t pts, uint64_t *n);
+int32_t vmsm_points_free(uint64_t ctx, uint64_t pts);
+
+/* ---- device-resident scalar vectors ----------------------------------------------------------------------- */
+int32_t vmsm_scalars_upload(uint64_t ctx, const uint8_t *le32, uint64_t n, uint64_t *sc);
+int32_t vmsm_scalars_synth(uint64_t ctx, int32_t curve, uint64_t seed, uint64_t n, uint64_t *sc);
+int32_t vmsm_scalars_download(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t n, uint8_t *le32_out);
+int32_t vmsm_scalars_free(uint64_t ctx, uint64_t sc);
+
+/* ---- multi-scalar multiplication -------------------------------------------------------------------------
+ * out = sum_{i<n} s_i * P[off + i].  Replaces pivot.vector_commitment / list_mul
+ * (verifiable_mpc/ac20/pivot.py:139-145, :26-28; call sites compressed_pivot.py:41-42,110,193,
+ * circuit_sat_cb.py:103) and the per-key sums of pynocchio.compute_proof (trinocchio/pynocchio.py:229-246). */
+/* end to end: host scalars in, host canonical-affine point out (H2D + kernels + D2H, synchronous) */
+int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
+                 uint8_t *out_affine);
+/* device resident, asynchronous on the context's stream: result goes to result slot `slot` (0..63) */
+int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
+                     uint32_t slot);
+int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine);      /* synchronises */
+int32_t vmsm_result_extended(uint64_t ctx, uint32_t slot, uint8_t *out_extended);  /* synchronises */
+
+/* ---- generator fold ----------------------------------------------------------------------------------------
+ * In place: P[j] = c * P[j] + P[half + j] for j < half, then the vector length becomes `half`.
+ * Replaces the comprehension g_prime = [(g_hat_l[i] ** c) * g_hat_r[i] ...]
+ * (verifiable_mpc/ac20/compressed_pivot.py:64 prover, :178 verifier; mpc_ac20.py:176). */
+int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le32);
+
+/* ---- small group helper: out = sum_i s_i * P_i for a handful of host points (Q' = A * Q^c * B^(c^2),
+ * compressed_pivot.py:66; Q = A * P^c0 * k^(...), :140).  n <= 64. */
+int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const uint8_t *scalars_le32, uint64_t n,
+                     uint8_t *out_affine);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMSM_H */

@@ -1,0 +1,132 @@
+// Host emulation of the kernel bodies (TESTS ONLY -- never loaded by verifiable_mpc_b200/).
+// Compiles csrc/kernels.cuh + csrc/pipeline.cuh with g++ (portable 64-bit arithmetic path of fe25519.cuh) and runs
+// each functor in a plain loop, so the pipeline's indexing, digit recoding, bucket tree, Horner step, fold and
+// fixed-base logic can be checked against oracle/ in the GPU-less build container.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "../../verifiable_mpc_b200/csrc/pipeline.cuh"
+
+using namespace vmsm;
+
+struct HostBE {
+    void *alloc(size_t bytes) { return aligned_alloc(64, (bytes + 63) / 64 * 64 + 64); }
+    void free(void *p) { ::free(p); }
+    void zero(void *p, size_t bytes) { memset(p, 0, bytes); }
+    template <class F>
+    void launch(const F &f, uint32_t n) {
+        for (uint32_t t = 0; t < n; t++) f(t);
+    }
+    void scan_offsets(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g) {
+        for (uint32_t w = 0; w < g.W; w++) {
+            uint32_t run = w * g.n;
+            for (uint32_t b = 0; b < g.NB; b++) {
+                offsets[(size_t)w * g.NB + b] = cursor[(size_t)w * g.NB + b] = run;
+                run += counts[(size_t)w * g.NB + b];
+            }
+        }
+    }
+    bool order_buckets(const uint32_t *counts, uint32_t *order, uint32_t nb, uint32_t n) {
+        if (n == 0) return false;
+        std::iota(order, order + nb, 0u);
+        std::stable_sort(order, order + nb, [&](uint32_t a, uint32_t b) { return counts[a] > counts[b]; });
+        return true;
+    }
+    void phase_begin() {}
+    void phase_mark(int) {}
+    void phase_end() {}
+};
+
+extern "C" {
+
+void hostemu_fe_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out) {
+    fe x, y, r;
+    memcpy(x.v, a, 32);
+    memcpy(y.v, b, 32);
+    switch (op) {
+        case 0: r = fe_add(x, y); break;
+        case 1: r = fe_sub(x, y); break;
+        case 2: r = fe_mul(x, y); break;
+        case 3: r = fe_inv(x); break;
+        case 4: r = fe_canon(x); break;
+        case 5: r = fe_sqr(x); break;
+        case 6: r = fe_mul_small(x, b[0]); break;
+        default: r = fe_zero();
+    }
+    memcpy(out, r.v, 32);
+}
+
+// returns the error word of the upload validation (0 = ok)
+uint32_t hostemu_msm(const uint8_t *affine, const uint8_t *scalars, uint32_t n, uint32_t window_bits, int sort,
+                     uint32_t log2r, uint8_t *out_affine, uint8_t *out_ext) {
+    HostBE be;
+    std::vector<ge_niels> niels(n ? n : 1);
+    uint32_t err = 0;
+    std::vector<ge_aff> aff(n ? n : 1);
+    memcpy(aff.data(), affine, (size_t)n * 64);
+    KAffToNiels k = {aff.data(), niels.data(), &err, 1u};
+    be.launch(k, n);
+    std::vector<uint32_t> sc((size_t)(n ? n : 1) * 8 + 8);
+    memcpy(sc.data(), scalars, (size_t)n * 32);
+    Workspace ws;
+    MsmOptions opt;
+    opt.window_bits = window_bits;
+    opt.sort_buckets = sort != 0;
+    opt.reduce_log2r = log2r;
+    ge_ext oe;
+    ge_aff oa;
+    msm_run(be, ws, opt, 253, niels.data(), sc.data(), n, &oe, &oa);
+    ws_release(be, ws);
+    memcpy(out_affine, &oa, 64);
+    if (out_ext) memcpy(out_ext, &oe, 128);
+    return err;
+}
+
+void hostemu_fold(const uint8_t *affine, uint32_t n, const uint8_t *c_le32, uint8_t *out_affine) {
+    HostBE be;
+    uint32_t half = n / 2, err = 0;
+    std::vector<ge_aff> aff(n);
+    std::vector<ge_niels> niels(n);
+    std::vector<ge_ext> tmp(half);
+    memcpy(aff.data(), affine, (size_t)n * 64);
+    KAffToNiels k = {aff.data(), niels.data(), &err, 0u};
+    be.launch(k, n);
+    uint32_t cs[8];
+    memcpy(cs, c_le32, 32);
+    fold_run(be, aff.data(), niels.data(), tmp.data(), half, cs);
+    memcpy(out_affine, aff.data(), (size_t)half * 64);
+}
+
+void hostemu_fixed_base(const uint8_t *scalars, uint64_t seed, uint32_t n, uint8_t *out_affine) {
+    HostBE be;
+    std::vector<ge_niels> tbl(512);
+    build_fixed_base_table(tbl.data());
+    std::vector<uint32_t> sc;
+    if (scalars) {
+        sc.resize((size_t)n * 8 + 8);
+        memcpy(sc.data(), scalars, (size_t)n * 32);
+    }
+    std::vector<ge_ext> tmp(n);
+    std::vector<ge_aff> aff(n);
+    std::vector<ge_niels> niels(n);
+    KFixedBase k = {tbl.data(), scalars ? sc.data() : nullptr, seed, tmp.data()};
+    be.launch(k, n);
+    KNormalize kn = {tmp.data(), aff.data(), niels.data()};
+    be.launch(kn, n);
+    memcpy(out_affine, aff.data(), (size_t)n * 64);
+}
+
+void hostemu_synth_scalars(uint64_t seed, uint32_t n, uint8_t *out) {
+    HostBE be;
+    std::vector<uint32_t> sc((size_t)n * 8 + 8);
+    KSynthScalars k = {sc.data(), seed};
+    be.launch(k, n);
+    memcpy(out, sc.data(), (size_t)n * 32);
+}
+
+uint32_t hostemu_choose_window(uint64_t n) { return choose_window(n, 253); }
+}

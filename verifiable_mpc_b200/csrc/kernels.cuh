@@ -1,0 +1,393 @@
+// Kernel bodies of the Ed25519 MSM / fold engine, written as per-thread functors.
+//
+// Every kernel without intra-block cooperation is a struct with `void operator()(uint32_t tid) const`; the CUDA
+// backend (vmsm.cu) launches it through vmsm_kernel<F><<<...>>>, the host-emulation backend (tests/hostemu, tests
+// only, never shipped) runs the very same body in a loop so that all indexing and arithmetic can be checked
+// against the oracle in a container without a GPU.
+//
+// Pipeline (signed-window Pippenger; replaces pivot.py:139-145 vector_commitment's n independent
+// double-and-add scalar multiplications):
+//   KDigitsHist  scalar -> W signed c-bit digits, histogram of |digit| per (window, bucket)
+//   scan         exclusive prefix sums per window -> CSR offsets              (cooperative, backend specific)
+//   KScatter     second pass over the scalars: counting-sort (index|sign) into the CSR lists
+//   KAccumulate  one thread per bucket: sum of its (signed) bases with 7M mixed additions, bases gathered from L2
+//   KReduce      radix-R tree over buckets carrying (S, T) = (sum B_k, sum (k - lo) B_k) per node
+//   KFinal       Horner over windows, one inversion, canonical affine out
+#pragma once
+#include "ed25519.cuh"
+
+namespace vmsm {
+
+#if defined(__CUDA_ARCH__)
+#define VMSM_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define VMSM_ATOMIC_OR(p, v) atomicOr((p), (v))
+#else
+static inline uint32_t vmsm_host_atomic_add(uint32_t *p, uint32_t v) {
+    uint32_t o = *p;
+    *p = o + v;
+    return o;
+}
+static inline uint32_t vmsm_host_atomic_or(uint32_t *p, uint32_t v) {
+    uint32_t o = *p;
+    *p = o | v;
+    return o;
+}
+#define VMSM_ATOMIC_ADD(p, v) vmsm_host_atomic_add((p), (v))
+#define VMSM_ATOMIC_OR(p, v) vmsm_host_atomic_or((p), (v))
+#endif
+
+// ---------------------------------------------------------------------------------------------- vector loads
+struct alignas(16) u32x4 {
+    uint32_t x, y, z, w;
+};
+
+VMSM_HD u32x4 ld128(const void *p) {
+#if defined(__CUDA_ARCH__)
+    uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+    u32x4 r = {t.x, t.y, t.z, t.w};
+    return r;
+#else
+    return *reinterpret_cast<const u32x4 *>(p);
+#endif
+}
+VMSM_HD void st128(void *p, const u32x4 &v) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4 *>(p) = make_uint4(v.x, v.y, v.z, v.w);
+#else
+    *reinterpret_cast<u32x4 *>(p) = v;
+#endif
+}
+
+VMSM_HD fe ld_fe(const fe *p) {
+    u32x4 a = ld128(p), b = ld128(reinterpret_cast<const uint8_t *>(p) + 16);
+    fe r = {{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+    return r;
+}
+VMSM_HD void st_fe(fe *p, const fe &v) {
+    u32x4 a = {v.v[0], v.v[1], v.v[2], v.v[3]}, b = {v.v[4], v.v[5], v.v[6], v.v[7]};
+    st128(p, a);
+    st128(reinterpret_cast<uint8_t *>(p) + 16, b);
+}
+VMSM_HD ge_niels ld_niels(const ge_niels *p) {
+    ge_niels r;
+    r.ypx = ld_fe(&p->ypx);
+    r.ymx = ld_fe(&p->ymx);
+    r.t2d = ld_fe(&p->t2d);
+    return r;
+}
+VMSM_HD void st_niels(ge_niels *p, const ge_niels &v) {
+    st_fe(&p->ypx, v.ypx);
+    st_fe(&p->ymx, v.ymx);
+    st_fe(&p->t2d, v.t2d);
+}
+VMSM_HD ge_ext ld_ext(const ge_ext *p) {
+    ge_ext r;
+    r.X = ld_fe(&p->X);
+    r.Y = ld_fe(&p->Y);
+    r.Z = ld_fe(&p->Z);
+    r.T = ld_fe(&p->T);
+    return r;
+}
+VMSM_HD void st_ext(ge_ext *p, const ge_ext &v) {
+    st_fe(&p->X, v.X);
+    st_fe(&p->Y, v.Y);
+    st_fe(&p->Z, v.Z);
+    st_fe(&p->T, v.T);
+}
+VMSM_HD ge_aff ld_aff(const ge_aff *p) {
+    ge_aff r;
+    r.x = ld_fe(&p->x);
+    r.y = ld_fe(&p->y);
+    return r;
+}
+VMSM_HD void st_aff(ge_aff *p, const ge_aff &v) {
+    st_fe(&p->x, v.x);
+    st_fe(&p->y, v.y);
+}
+
+// ---------------------------------------------------------------------------------------------- scalars
+struct MsmGeom {
+    uint32_t n;   // terms
+    uint32_t c;   // window bits
+    uint32_t W;   // windows, c*W >= scalar_bits + 1
+    uint32_t NB;  // buckets per window = 2^(c-1), bucket b holds |digit| = b+1
+};
+
+struct sc256 {
+    uint32_t v[9];  // v[8] = 0 sentinel so window extraction can read one limb past the top
+};
+
+VMSM_HD sc256 ld_scalar(const uint32_t *base, uint32_t i) {
+    u32x4 a = ld128(base + 8ull * i), b = ld128(base + 8ull * i + 4);
+    sc256 s = {{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0u}};
+    return s;
+}
+
+// raw c-bit window at bit offset `bit` (bit + c may run past 256: zero extended)
+VMSM_HD uint32_t sc_bits(const sc256 &s, uint32_t bit, uint32_t c) {
+    uint32_t limb = bit >> 5, sh = bit & 31;
+    if (limb >= 8) return 0;
+    uint64_t two = (uint64_t)s.v[limb] | ((uint64_t)s.v[limb + 1] << 32);
+    return (uint32_t)(two >> sh) & ((1u << c) - 1u);
+}
+
+// signed digit of window w given the carry from window w-1; digits lie in [-(2^(c-1) - 1), 2^(c-1)]
+VMSM_HD int32_t sc_digit(const sc256 &s, uint32_t w, uint32_t c, uint32_t &carry) {
+    uint32_t raw = sc_bits(s, w * c, c) + carry;
+    uint32_t half = 1u << (c - 1);
+    if (raw > half) {
+        carry = 1;
+        return (int32_t)raw - (int32_t)(1u << c);
+    }
+    carry = 0;
+    return (int32_t)raw;
+}
+
+// ---------------------------------------------------------------------------------------------- synthetic inputs
+// Counter-based generator; the spec lives in oracle/prng.py (independent Python restatement) and DESIGN.md.
+VMSM_HD uint64_t splitmix64_mix(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// uniform-ish scalar below the Ed25519 group order l: 253 low bits, minus l if >= l
+VMSM_HD sc256 synth_scalar_ed(uint64_t seed, uint64_t i) {
+    sc256 s;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint64_t wv = splitmix64_mix(seed + 0x9E3779B97F4A7C15ull * (4 * i + j + 1));
+        s.v[2 * j] = (uint32_t)wv;
+        s.v[2 * j + 1] = (uint32_t)(wv >> 32);
+    }
+    s.v[7] &= 0x1fffffffu;
+    s.v[8] = 0;
+    const uint32_t L[8] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
+    uint32_t d[8];
+    int64_t bw = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        bw += (int64_t)s.v[k] - (int64_t)L[k];
+        d[k] = (uint32_t)bw;
+        bw >>= 32;
+    }
+    if (bw == 0) {  // no borrow: s >= l
+#pragma unroll
+        for (int k = 0; k < 8; k++) s.v[k] = d[k];
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------- MSM kernels
+struct KDigitsHist {
+    enum { kBlock = 256 };
+    const uint32_t *scalars;  // n x 8 limbs, each < group order
+    uint32_t *counts;         // W x NB
+    MsmGeom g;
+    VMSM_HD void operator()(uint32_t tid) const {
+        sc256 s = ld_scalar(scalars, tid);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < g.W; w++) {
+            int32_t d = sc_digit(s, w, g.c, carry);
+            if (d != 0) {
+                uint32_t a = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                VMSM_ATOMIC_ADD(&counts[w * g.NB + (a - 1)], 1u);
+            }
+        }
+    }
+};
+
+struct KScatter {
+    enum { kBlock = 256 };
+    const uint32_t *scalars;
+    uint32_t *cursor;  // W x NB, initialised to the CSR offsets; ends at offsets + counts
+    uint32_t *idx;     // W x n entries: base index | sign << 31
+    MsmGeom g;
+    VMSM_HD void operator()(uint32_t tid) const {
+        sc256 s = ld_scalar(scalars, tid);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < g.W; w++) {
+            int32_t d = sc_digit(s, w, g.c, carry);
+            if (d != 0) {
+                uint32_t a = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                uint32_t pos = VMSM_ATOMIC_ADD(&cursor[w * g.NB + (a - 1)], 1u);
+                idx[pos] = tid | (d < 0 ? 0x80000000u : 0u);
+            }
+        }
+    }
+};
+
+// One thread per bucket.  `order` (optional) lists bucket ids by decreasing population so the lanes of a warp
+// run the same trip count.
+struct KAccumulate {
+    enum { kBlock = 128 };
+    const ge_niels *bases;
+    const uint32_t *offsets;  // W x NB exclusive prefix (absolute position in idx)
+    const uint32_t *counts;   // W x NB
+    const uint32_t *idx;
+    const uint32_t *order;    // may be null
+    ge_ext *buckets;          // W x NB
+    uint32_t nbuckets;
+    VMSM_HD void operator()(uint32_t tid) const {
+        uint32_t b = order ? order[tid] : tid;
+        uint32_t pos = offsets[b], cnt = counts[b];
+        ge_ext acc = ge_identity();
+        if (cnt) {
+            uint32_t e = idx[pos];
+            for (uint32_t k = 0; k < cnt; k++) {
+                uint32_t en = (k + 1 < cnt) ? idx[pos + k + 1] : 0u;  // index prefetch: one load ahead of the gather
+                ge_niels q = ld_niels(bases + (e & 0x7fffffffu));
+                acc = ge_madd(acc, q, (e >> 31) != 0);
+                e = en;
+            }
+        }
+        st_ext(buckets + b, acc);
+    }
+};
+
+// Radix-R merge of bucket-tree nodes.  A node covering buckets [lo, lo + s) carries
+//   S = sum B_k            T = sum (k - lo) B_k
+// Leaves are the buckets themselves (s = 1, T = 0, inT == null).  Merging children i = 0..m-1 of size s:
+//   S' = sum S_i           T' = sum T_i + s * sum i S_i
+struct KReduce {
+    enum { kBlock = 128 };
+    const ge_ext *inS;
+    const ge_ext *inT;  // null at the leaf level
+    ge_ext *outS;
+    ge_ext *outT;
+    uint32_t cnt_in;   // nodes per window on input
+    uint32_t cnt_out;  // nodes per window on output = ceil(cnt_in / R)
+    uint32_t R;        // radix (power of two)
+    uint32_t log2s;    // log2 of the bucket span of one input node
+    VMSM_HD void operator()(uint32_t tid) const {
+        uint32_t w = tid / cnt_out, j = tid - w * cnt_out;
+        uint32_t first = j * R;
+        uint32_t m = cnt_in - first < R ? cnt_in - first : R;
+        const ge_ext *s = inS + (size_t)w * cnt_in + first;
+        ge_ext acc = ge_identity(), run = ge_identity();
+        for (uint32_t i = m - 1; i >= 1; i--) {
+            acc = ge_add(acc, ld_ext(s + i));
+            run = ge_add(run, acc);
+        }
+        acc = ge_add(acc, ld_ext(s));
+        for (uint32_t k = 0; k < log2s; k++) run = ge_dbl(run);
+        if (inT) {
+            const ge_ext *t = inT + (size_t)w * cnt_in + first;
+            for (uint32_t i = 0; i < m; i++) run = ge_add(run, ld_ext(t + i));
+        }
+        st_ext(outS + (size_t)w * cnt_out + j, acc);
+        st_ext(outT + (size_t)w * cnt_out + j, run);
+    }
+};
+
+// Single thread: window w total = T_w + S_w (bucket b weighs b+1), Horner over windows, normalise.
+struct KFinal {
+    enum { kBlock = 32 };
+    const ge_ext *S;  // W root nodes
+    const ge_ext *T;
+    ge_ext *out_ext;
+    ge_aff *out_aff;
+    uint32_t W, c;
+    VMSM_HD void operator()(uint32_t) const {
+        ge_ext acc = ge_identity();
+        for (int32_t w = (int32_t)W - 1; w >= 0; w--) {
+            if (w != (int32_t)W - 1)
+                for (uint32_t k = 0; k < c; k++) acc = ge_dbl(acc);
+            acc = ge_add(acc, ge_add(ld_ext(S + w), ld_ext(T + w)));
+        }
+        st_ext(out_ext, acc);
+        st_aff(out_aff, ge_ext_to_aff(acc));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- point-set kernels
+// Upload path: canonical affine -> niels, with validation (coordinates < p, on the curve).
+struct KAffToNiels {
+    enum { kBlock = 128 };
+    const ge_aff *aff;
+    ge_niels *niels;
+    uint32_t *err;  // bit 0: non-canonical coordinate, bit 1: not on curve
+    uint32_t check;
+    VMSM_HD void operator()(uint32_t tid) const {
+        ge_aff a = ld_aff(aff + tid);
+        if (check) {
+            uint32_t e = 0;
+            if (!fe_is_canonical(a.x) || !fe_is_canonical(a.y)) e |= 1u;
+            if (!ge_aff_on_curve(a)) e |= 2u;
+            if (e) VMSM_ATOMIC_OR(err, e);
+        }
+        st_niels(niels + tid, ge_aff_to_niels(a));
+    }
+};
+
+// extended -> canonical affine + niels (one inversion per thread)
+struct KNormalize {
+    enum { kBlock = 128 };
+    const ge_ext *in;
+    ge_aff *aff;
+    ge_niels *niels;
+    VMSM_HD void operator()(uint32_t tid) const {
+        ge_aff a = ge_ext_to_aff(ld_ext(in + tid));
+        st_aff(aff + tid, a);
+        st_niels(niels + tid, ge_aff_to_niels(a));
+    }
+};
+
+// Generator fold (compressed_pivot.py:64 / :178):  out[j] = c * P[j] + P[half + j]  with ONE shared scalar c,
+// given in non-adjacent form as two 256-bit masks (nz: digit != 0, ng: digit < 0).  Uniform control flow across
+// the grid; ~253 doublings + ~85 mixed additions per element.
+struct KFold {
+    enum { kBlock = 128 };
+    const ge_niels *niels;  // 2*half inputs
+    ge_ext *out;            // half outputs
+    uint32_t half;
+    int32_t top;  // index of the highest non-zero NAF digit, -1 when c == 0
+    uint32_t nz[9];
+    uint32_t ng[9];
+    VMSM_HD void operator()(uint32_t tid) const {
+        ge_niels p = ld_niels(niels + tid);
+        ge_ext acc = ge_identity();
+        for (int32_t i = top; i >= 0; i--) {
+            acc = ge_dbl(acc);
+            if ((nz[i >> 5] >> (i & 31)) & 1u) acc = ge_madd(acc, p, ((ng[i >> 5] >> (i & 31)) & 1u) != 0);
+        }
+        acc = ge_madd(acc, ld_niels(niels + half + tid), false);
+        st_ext(out + tid, acc);
+    }
+};
+
+// Fixed-base batch  out[i] = r_i * B  with r_i = synth_scalar_ed(seed, i) or explicit scalars; signed 4-bit windows
+// over a host-built table tbl[64][8] (j * 16^w * B in niels form): 64 mixed additions, no doublings.
+// This is the shape of create_generators (circuit_sat_r1cs.py:59-74: g_i = h ** r_i with h = group.generator).
+struct KFixedBase {
+    enum { kBlock = 128 };
+    const ge_niels *tbl;      // 64 x 8
+    const uint32_t *scalars;  // null -> synthetic from seed
+    uint64_t seed;
+    ge_ext *out;
+    VMSM_HD void operator()(uint32_t tid) const {
+        sc256 s = scalars ? ld_scalar(scalars, tid) : synth_scalar_ed(seed, tid);
+        ge_ext acc = ge_identity();
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < 64; w++) {
+            int32_t d = sc_digit(s, w, 4, carry);
+            uint32_t a = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            ge_niels q = a ? ld_niels(tbl + w * 8 + (a - 1)) : ge_niels_identity();
+            acc = ge_madd(acc, q, d < 0);
+        }
+        st_ext(out + tid, acc);
+    }
+};
+
+struct KSynthScalars {
+    enum { kBlock = 256 };
+    uint32_t *out;
+    uint64_t seed;
+    VMSM_HD void operator()(uint32_t tid) const {
+        sc256 s = synth_scalar_ed(seed, tid);
+        u32x4 a = {s.v[0], s.v[1], s.v[2], s.v[3]}, b = {s.v[4], s.v[5], s.v[6], s.v[7]};
+        st128(out + 8ull * tid, a);
+        st128(out + 8ull * tid + 4, b);
+    }
+};
+
+}  // namespace vmsm

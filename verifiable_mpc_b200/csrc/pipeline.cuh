@@ -1,0 +1,223 @@
+// Backend-independent launch sequence of the MSM / fold pipeline.  `BE` is either the CUDA backend (vmsm.cu) or the
+// host-emulation backend used by the CPU tests (tests/hostemu/hostemu.cpp); both run the kernel bodies of kernels.cuh.
+#pragma once
+#include <stddef.h>
+#include "kernels.cuh"
+
+namespace vmsm {
+
+enum Phase {
+    PH_DIGITS = 0,
+    PH_SCAN = 1,
+    PH_SCATTER = 2,
+    PH_ORDER = 3,
+    PH_ACCUMULATE = 4,
+    PH_REDUCE = 5,
+    PH_FINAL = 6,
+    PH_COUNT = 7
+};
+
+struct MsmOptions {
+    uint32_t window_bits = 0;  // 0 = auto
+    uint32_t reduce_log2r = 3;
+    bool sort_buckets = true;
+};
+
+struct Workspace {
+    uint32_t *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *order = nullptr;  // W*NB each
+    uint32_t *idx = nullptr;                                                              // W*n
+    ge_ext *buckets = nullptr;                                                            // W*NB
+    ge_ext *nodeS[2] = {nullptr, nullptr}, *nodeT[2] = {nullptr, nullptr};                // ping-pong tree levels
+    size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0;
+};
+
+// Work model of SURVEY.md App. E (limb products), with the tree reduction's ~30 % overhead over a serial running sum.
+inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits) {
+    if (n == 0) return 4;
+    double best = 0;
+    uint32_t best_c = 4;
+    for (uint32_t c = 3; c <= 17; c++) {
+        double W = (double)((scalar_bits + 1 + c - 1) / c);
+        double NB = (double)(1u << (c - 1));
+        double cost = (double)n * W * 504.0 + W * NB * 2.0 * 648.0 * 1.3 + (W - 1) * c * 464.0;
+        if (c == 3 || cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
+}
+
+inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits) {
+    MsmGeom g;
+    g.n = n;
+    g.c = c;
+    g.W = (scalar_bits + 1 + c - 1) / c;
+    g.NB = 1u << (c - 1);
+    return g;
+}
+
+template <class BE>
+int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R) {
+    size_t nb = (size_t)g.W * g.NB, ni = (size_t)g.W * g.n, nn = (size_t)g.W * ((g.NB + R - 1) / R);
+    if (nn < g.W) nn = g.W;
+    if (nb > ws.cap_buckets) {
+        be.free(ws.counts), be.free(ws.offsets), be.free(ws.cursor), be.free(ws.order), be.free(ws.buckets);
+        ws.cap_buckets = 0;
+        ws.counts = (uint32_t *)be.alloc(nb * 4);
+        ws.offsets = (uint32_t *)be.alloc(nb * 4);
+        ws.cursor = (uint32_t *)be.alloc(nb * 4);
+        ws.order = (uint32_t *)be.alloc(nb * 4);
+        ws.buckets = (ge_ext *)be.alloc(nb * sizeof(ge_ext));
+        if (!ws.counts || !ws.offsets || !ws.cursor || !ws.order || !ws.buckets) return -1;
+        ws.cap_buckets = nb;
+    }
+    if (ni > ws.cap_idx) {
+        be.free(ws.idx);
+        ws.cap_idx = 0;
+        ws.idx = (uint32_t *)be.alloc((ni ? ni : 1) * 4);
+        if (!ws.idx) return -1;
+        ws.cap_idx = ni;
+    }
+    if (nn > ws.cap_nodes) {
+        for (int k = 0; k < 2; k++) {
+            be.free(ws.nodeS[k]), be.free(ws.nodeT[k]);
+            ws.nodeS[k] = (ge_ext *)be.alloc(nn * sizeof(ge_ext));
+            ws.nodeT[k] = (ge_ext *)be.alloc(nn * sizeof(ge_ext));
+            if (!ws.nodeS[k] || !ws.nodeT[k]) {
+                ws.cap_nodes = 0;
+                return -1;
+            }
+        }
+        ws.cap_nodes = nn;
+    }
+    return 0;
+}
+
+template <class BE>
+void ws_release(BE &be, Workspace &ws) {
+    be.free(ws.counts), be.free(ws.offsets), be.free(ws.cursor), be.free(ws.order), be.free(ws.buckets);
+    be.free(ws.idx);
+    for (int k = 0; k < 2; k++) be.free(ws.nodeS[k]), be.free(ws.nodeT[k]);
+    ws = Workspace();
+}
+
+// out = sum_i scalars[i] * bases[i].  All pointers are backend ("device") memory.  Returns 0 or -1 (allocation).
+template <class BE>
+int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, const ge_niels *bases,
+            const uint32_t *scalars, uint32_t n, ge_ext *out_ext, ge_aff *out_aff) {
+    uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits);
+    MsmGeom g = make_geom(n, c, scalar_bits);
+    uint32_t R = 1u << opt.reduce_log2r;
+    if (ws_ensure(be, ws, g, R)) return -1;
+    uint32_t nbuckets = g.W * g.NB;
+
+    be.phase_begin();
+    be.zero(ws.counts, (size_t)nbuckets * 4);
+    if (n) {
+        KDigitsHist k1 = {scalars, ws.counts, g};
+        be.launch(k1, n);
+    }
+    be.phase_mark(PH_DIGITS);
+    be.scan_offsets(ws.counts, ws.offsets, ws.cursor, g);
+    be.phase_mark(PH_SCAN);
+    if (n) {
+        KScatter k3 = {scalars, ws.cursor, ws.idx, g};
+        be.launch(k3, n);
+    }
+    be.phase_mark(PH_SCATTER);
+    const uint32_t *order = nullptr;
+    if (opt.sort_buckets && be.order_buckets(ws.counts, ws.order, nbuckets, n)) order = ws.order;
+    be.phase_mark(PH_ORDER);
+    {
+        KAccumulate k5 = {bases, ws.offsets, ws.counts, ws.idx, order, ws.buckets, nbuckets};
+        be.launch(k5, nbuckets);
+    }
+    be.phase_mark(PH_ACCUMULATE);
+    // bucket tree
+    const ge_ext *inS = ws.buckets, *inT = nullptr;
+    uint32_t cnt = g.NB, log2s = 0;
+    int pp = 0;
+    do {
+        uint32_t cnt_out = (cnt + R - 1) / R;
+        KReduce k6 = {inS, inT, ws.nodeS[pp], ws.nodeT[pp], cnt, cnt_out, R, log2s};
+        be.launch(k6, g.W * cnt_out);
+        inS = ws.nodeS[pp];
+        inT = ws.nodeT[pp];
+        pp ^= 1;
+        cnt = cnt_out;
+        log2s += opt.reduce_log2r;
+    } while (cnt > 1);
+    be.phase_mark(PH_REDUCE);
+    {
+        KFinal k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
+        be.launch(k7, 1);
+    }
+    be.phase_mark(PH_FINAL);
+    be.phase_end();
+    return 0;
+}
+
+// Non-adjacent form of a 256-bit little-endian scalar as two bit masks; returns the top non-zero digit index or -1.
+inline int32_t naf_masks(const uint32_t s_in[8], uint32_t nz[9], uint32_t ng[9]) {
+    uint32_t s[10];
+    for (int i = 0; i < 8; i++) s[i] = s_in[i];
+    s[8] = s[9] = 0;
+    for (int i = 0; i < 9; i++) nz[i] = ng[i] = 0;
+    int32_t top = -1;
+    for (int i = 0; i < 288; i++) {
+        bool any = false;
+        for (int k = 0; k < 10; k++) any |= s[k] != 0;
+        if (!any) break;
+        if (s[0] & 1u) {
+            if ((s[0] & 3u) == 3u) {  // digit -1: s += 1
+                ng[i >> 5] |= 1u << (i & 31);
+                uint64_t cy = 1;
+                for (int k = 0; k < 10 && cy; k++) {
+                    cy += s[k];
+                    s[k] = (uint32_t)cy;
+                    cy >>= 32;
+                }
+            } else {  // digit +1: s -= 1
+                s[0] &= ~1u;
+            }
+            nz[i >> 5] |= 1u << (i & 31);
+            top = i;
+        }
+        for (int k = 0; k < 9; k++) s[k] = (s[k] >> 1) | (s[k + 1] << 31);
+        s[9] >>= 1;
+    }
+    return top;
+}
+
+// In place fold of a point vector held as (aff, niels): P[j] = c*P[j] + P[half+j].  `tmp` holds `half` extended points.
+template <class BE>
+void fold_run(BE &be, ge_aff *aff, ge_niels *niels, ge_ext *tmp, uint32_t half, const uint32_t c[8]) {
+    KFold kf;
+    kf.niels = niels;
+    kf.out = tmp;
+    kf.half = half;
+    kf.top = naf_masks(c, kf.nz, kf.ng);
+    be.launch(kf, half);
+    KNormalize kn = {tmp, aff, niels};
+    be.launch(kn, half);
+}
+
+// Host-side construction of the fixed-base table tbl[w][j-1] = j * 16^w * B (niels), w < 64, j = 1..8.
+inline void build_fixed_base_table(ge_niels *tbl /* 512 entries, host memory */) {
+    ge_aff B;
+    const uint32_t bx[8] = {0x8f25d51au, 0xc9562d60u, 0x9525a7b2u, 0x692cc760u, 0xfdd6dc5cu, 0xc0a4e231u, 0xcd6e53feu, 0x216936d3u};
+    const uint32_t by[8] = {0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u};
+    for (int i = 0; i < 8; i++) B.x.v[i] = bx[i], B.y.v[i] = by[i];
+    ge_ext base = ge_aff_to_ext(B);
+    for (int w = 0; w < 64; w++) {
+        ge_ext m = base;
+        for (int j = 1; j <= 8; j++) {
+            tbl[w * 8 + (j - 1)] = ge_aff_to_niels(ge_ext_to_aff(m));
+            if (j < 8) m = ge_add(m, base);
+        }
+        for (int k = 0; k < 4; k++) base = ge_dbl(base);
+    }
+}
+
+}  // namespace vmsm

@@ -1,0 +1,732 @@
+// libvmsm.so -- CUDA backend and C ABI (include/vmsm.h) of the MSM / generator-fold engine.  sm_100a only.
+// No PyTorch, no NCCL, no CPU fallback: every entry point needs a live CUDA context.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/vmsm.h"
+#include "pipeline.cuh"
+
+using namespace vmsm;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int32_t fail(int32_t code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(VMSM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ kernels
+template <class F>
+__global__ void __launch_bounds__(F::kBlock) vmsm_kernel(const F f, uint32_t n) {
+    uint32_t tid = blockIdx.x * (uint32_t)F::kBlock + threadIdx.x;
+    if (tid < n) f(tid);
+}
+
+// Exclusive scan of the bucket populations of one window per block; offsets are absolute positions in idx.
+__global__ void __launch_bounds__(1024) vmsm_scan_offsets(const uint32_t *__restrict__ counts,
+                                                          uint32_t *__restrict__ offsets,
+                                                          uint32_t *__restrict__ cursor, MsmGeom g) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t w = blockIdx.x, t = threadIdx.x;
+    const uint32_t *cw = counts + (size_t)w * g.NB;
+    uint32_t ipt = (g.NB + 1023u) / 1024u;
+    uint32_t lo = t * ipt, hi = lo + ipt;
+    if (lo > g.NB) lo = g.NB;
+    if (hi > g.NB) hi = g.NB;
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += cw[i];
+    // block-wide exclusive scan of `sum`
+    uint32_t incl = sum;
+    const uint32_t lane = t & 31, wid = t >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (uint32_t)d) wi += v;
+        }
+        warp_sums[lane] = wi - ws;
+    }
+    __syncthreads();
+    uint32_t run = w * g.n + warp_sums[wid] + (incl - sum);
+    for (uint32_t i = lo; i < hi; i++) {
+        uint32_t cnt = cw[i];
+        offsets[(size_t)w * g.NB + i] = run;
+        cursor[(size_t)w * g.NB + i] = run;
+        run += cnt;
+    }
+}
+
+// Counting sort of bucket ids by population, largest first (keys clamped to ORDER_BINS-1).
+#define ORDER_BINS 1024
+#define ORDER_TILE 2048  // buckets per block (256 threads x 8)
+__global__ void __launch_bounds__(256) vmsm_order_hist(const uint32_t *__restrict__ counts, uint32_t nb,
+                                                       uint32_t *__restrict__ bins) {
+    __shared__ uint32_t h[ORDER_BINS];
+    for (uint32_t i = threadIdx.x; i < ORDER_BINS; i += 256) h[i] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * ORDER_TILE;
+    for (uint32_t k = threadIdx.x; k < ORDER_TILE; k += 256) {
+        uint32_t b = base + k;
+        if (b < nb) {
+            uint32_t c = counts[b];
+            atomicAdd(&h[c < ORDER_BINS ? c : ORDER_BINS - 1], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ORDER_BINS; i += 256)
+        if (h[i]) atomicAdd(&bins[i], h[i]);
+}
+// bins[k] <- number of buckets with key > k (start of key k in descending order)
+__global__ void __launch_bounds__(ORDER_BINS) vmsm_order_scan(uint32_t *bins) {
+    __shared__ uint32_t s[ORDER_BINS];
+    uint32_t t = threadIdx.x;
+    uint32_t r = ORDER_BINS - 1 - t;  // reversed index: position t in descending order holds key r
+    uint32_t v = bins[r];
+    s[t] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < ORDER_BINS; d <<= 1) {
+        uint32_t add = t >= d ? s[t - d] : 0;
+        __syncthreads();
+        s[t] += add;
+        __syncthreads();
+    }
+    bins[r] = s[t] - v;
+}
+__global__ void __launch_bounds__(256) vmsm_order_scatter(const uint32_t *__restrict__ counts, uint32_t nb,
+                                                          uint32_t *__restrict__ bins, uint32_t *__restrict__ order) {
+    __shared__ uint32_t h[ORDER_BINS];
+    __shared__ uint32_t start[ORDER_BINS];
+    for (uint32_t i = threadIdx.x; i < ORDER_BINS; i += 256) h[i] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * ORDER_TILE;
+    uint32_t key[ORDER_TILE / 256], rank[ORDER_TILE / 256];
+#pragma unroll
+    for (uint32_t j = 0; j < ORDER_TILE / 256; j++) {
+        uint32_t b = base + j * 256 + threadIdx.x;
+        key[j] = 0xffffffffu;
+        if (b < nb) {
+            uint32_t c = counts[b];
+            key[j] = c < ORDER_BINS ? c : ORDER_BINS - 1;
+            rank[j] = atomicAdd(&h[key[j]], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ORDER_BINS; i += 256)
+        if (h[i]) start[i] = atomicAdd(&bins[i], h[i]);
+    __syncthreads();
+#pragma unroll
+    for (uint32_t j = 0; j < ORDER_TILE / 256; j++) {
+        uint32_t b = base + j * 256 + threadIdx.x;
+        if (key[j] != 0xffffffffu) order[start[key[j]] + rank[j]] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ context
+namespace {
+
+struct PointSet {
+    int32_t curve;
+    uint64_t n;
+    ge_aff *aff;
+    ge_niels *niels;
+};
+struct ScalarSet {
+    uint64_t n;
+    uint32_t *data;
+};
+struct EventSet {
+    cudaEvent_t ev[PH_COUNT + 1];
+};
+
+constexpr uint32_t kSlots = 64;
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    MsmOptions opt;
+    bool phase_timing = false;
+    bool check_points = true;
+    Workspace ws;
+    uint32_t *order_bins = nullptr;
+    uint32_t *err_word = nullptr;   // device
+    ge_niels *fb_table = nullptr;   // device 64 x 8
+    ge_ext *res_ext = nullptr;      // kSlots
+    ge_aff *res_aff = nullptr;      // kSlots
+    uint32_t *stage_scalars = nullptr;  // device staging for vmsm_msm / vmsm_lincomb
+    size_t stage_cap = 0;
+    ge_ext *tmp_ext = nullptr;  // fold / fixed-base scratch
+    size_t tmp_cap = 0;
+    ge_aff *small_aff = nullptr;  // lincomb scratch (64 points)
+    ge_niels *small_niels = nullptr;
+    uint8_t *pin = nullptr;  // pinned host bounce buffer (results, error word)
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    std::map<uint64_t, PointSet> points;
+    std::map<uint64_t, ScalarSet> scalars;
+    uint64_t next_id = 1;
+    uint64_t launches = 0;
+    // phase timing
+    std::vector<EventSet> ev_pool;
+    size_t ev_used = 0;
+    int ev_cur = -1;
+    double phase_ms[PH_COUNT] = {0};
+    uint64_t phase_calls = 0;
+};
+
+std::mutex g_mu;
+std::set<Ctx *> g_ctxs;
+
+Ctx *get_ctx(uint64_t h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    return g_ctxs.count(c) ? c : nullptr;
+}
+
+struct CudaBE {
+    Ctx *c;
+    cudaError_t err = cudaSuccess;
+    void note(cudaError_t e) {
+        if (err == cudaSuccess && e != cudaSuccess) err = e;
+    }
+    void *alloc(size_t bytes) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e != cudaSuccess) {
+            note(e);
+            return nullptr;
+        }
+        return p;
+    }
+    void free(void *p) {
+        if (p) cudaFree(p);
+    }
+    void zero(void *p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, c->stream)); }
+    template <class F>
+    void launch(const F &f, uint32_t n) {
+        if (!n) return;
+        uint32_t grid = (n + F::kBlock - 1) / F::kBlock;
+        vmsm_kernel<F><<<grid, F::kBlock, 0, c->stream>>>(f, n);
+        c->launches++;
+        note(cudaGetLastError());
+    }
+    void scan_offsets(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g) {
+        vmsm_scan_offsets<<<g.W, 1024, 0, c->stream>>>(counts, offsets, cursor, g);
+        c->launches++;
+        note(cudaGetLastError());
+    }
+    bool order_buckets(const uint32_t *counts, uint32_t *order, uint32_t nb, uint32_t n) {
+        if (nb < 8192 || n == 0) return false;  // too few buckets for ordering to matter
+        note(cudaMemsetAsync(c->order_bins, 0, ORDER_BINS * 4, c->stream));
+        uint32_t grid = (nb + ORDER_TILE - 1) / ORDER_TILE;
+        vmsm_order_hist<<<grid, 256, 0, c->stream>>>(counts, nb, c->order_bins);
+        vmsm_order_scan<<<1, ORDER_BINS, 0, c->stream>>>(c->order_bins);
+        vmsm_order_scatter<<<grid, 256, 0, c->stream>>>(counts, nb, c->order_bins, order);
+        c->launches += 3;
+        note(cudaGetLastError());
+        return true;
+    }
+    // phase timing
+    void phase_begin() {
+        c->ev_cur = -1;
+        if (!c->phase_timing) return;
+        if (c->ev_used == c->ev_pool.size()) {
+            EventSet es;
+            for (auto &e : es.ev) note(cudaEventCreate(&e));
+            c->ev_pool.push_back(es);
+        }
+        c->ev_cur = (int)c->ev_used++;
+        note(cudaEventRecord(c->ev_pool[c->ev_cur].ev[0], c->stream));
+    }
+    void phase_mark(int ph) {
+        if (c->ev_cur >= 0) note(cudaEventRecord(c->ev_pool[c->ev_cur].ev[ph + 1], c->stream));
+    }
+    void phase_end() {}
+};
+
+int32_t harvest_phases(Ctx *c) {
+    if (!c->ev_used) return VMSM_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < c->ev_used; k++) {
+        for (int p = 0; p < PH_COUNT; p++) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, c->ev_pool[k].ev[p], c->ev_pool[k].ev[p + 1]));
+            c->phase_ms[p] += ms;
+        }
+        c->phase_calls++;
+    }
+    c->ev_used = 0;
+    return VMSM_OK;
+}
+
+int32_t ensure_stage(Ctx *c, size_t n_scalars) {
+    if (n_scalars <= c->stage_cap) return VMSM_OK;
+    if (c->stage_scalars) cudaFree(c->stage_scalars);
+    c->stage_scalars = nullptr;
+    c->stage_cap = 0;
+    CU(cudaMalloc(&c->stage_scalars, n_scalars * 32));
+    c->stage_cap = n_scalars;
+    return VMSM_OK;
+}
+int32_t ensure_tmp(Ctx *c, size_t n_pts) {
+    if (n_pts <= c->tmp_cap) return VMSM_OK;
+    if (c->tmp_ext) cudaFree(c->tmp_ext);
+    c->tmp_ext = nullptr;
+    c->tmp_cap = 0;
+    CU(cudaMalloc(&c->tmp_ext, n_pts * sizeof(ge_ext)));
+    c->tmp_cap = n_pts;
+    return VMSM_OK;
+}
+
+int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t n, uint32_t slot) {
+    if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "n = %llu exceeds 2^26 terms per MSM call", (unsigned long long)n);
+    CudaBE be{c};
+    int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff + slot);
+    if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
+    return VMSM_OK;
+}
+
+}  // namespace
+
+#define GET_CTX(h)                                                        \
+    Ctx *c = get_ctx(h);                                                  \
+    if (!c) return fail(VMSM_ERR_INVALID, "invalid context handle");      \
+    CU(cudaSetDevice(c->device))
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int32_t vmsm_version(void) { return 100; }
+const char *vmsm_last_error(void) { return g_err; }
+
+int32_t vmsm_device_count(int32_t *count) {
+    if (!count) return fail(VMSM_ERR_INVALID, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(VMSM_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return VMSM_OK;
+}
+
+int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
+    if (!ctx) return fail(VMSM_ERR_INVALID, "null argument");
+    *ctx = 0;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(VMSM_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(VMSM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    Ctx *c = new Ctx();
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->order_bins, ORDER_BINS * 4));
+    CU(cudaMalloc(&c->err_word, 16));
+    CU(cudaMalloc(&c->fb_table, 512 * sizeof(ge_niels)));
+    CU(cudaMalloc(&c->res_ext, kSlots * sizeof(ge_ext)));
+    CU(cudaMalloc(&c->res_aff, kSlots * sizeof(ge_aff)));
+    CU(cudaMalloc(&c->small_aff, 64 * sizeof(ge_aff)));
+    CU(cudaMalloc(&c->small_niels, 64 * sizeof(ge_niels)));
+    CU(cudaHostAlloc(&c->pin, 4096, cudaHostAllocDefault));
+    CU(cudaEventCreate(&c->t0));
+    CU(cudaEventCreate(&c->t1));
+    {
+        std::vector<ge_niels> tbl(512);
+        build_fixed_base_table(tbl.data());
+        CU(cudaMemcpy(c->fb_table, tbl.data(), 512 * sizeof(ge_niels), cudaMemcpyHostToDevice));
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_ctxs.insert(c);
+    }
+    *ctx = reinterpret_cast<uint64_t>(c);
+    return VMSM_OK;
+}
+
+int32_t vmsm_ctx_destroy(uint64_t ctx) {
+    GET_CTX(ctx);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->points) cudaFree(kv.second.aff), cudaFree(kv.second.niels);
+    for (auto &kv : c->scalars) cudaFree(kv.second.data);
+    CudaBE be{c};
+    ws_release(be, c->ws);
+    cudaFree(c->order_bins), cudaFree(c->err_word), cudaFree(c->fb_table), cudaFree(c->res_ext), cudaFree(c->res_aff);
+    cudaFree(c->stage_scalars), cudaFree(c->tmp_ext), cudaFree(c->small_aff), cudaFree(c->small_niels);
+    cudaFreeHost(c->pin);
+    for (auto &es : c->ev_pool)
+        for (auto &e : es.ev) cudaEventDestroy(e);
+    cudaEventDestroy(c->t0), cudaEventDestroy(c->t1);
+    cudaStreamDestroy(c->stream);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_ctxs.erase(c);
+    }
+    delete c;
+    return VMSM_OK;
+}
+
+int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
+    GET_CTX(ctx);
+    switch (key) {
+        case VMSM_OPT_WINDOW_BITS:
+            if (value != 0 && (value < 2 || value > 18)) return fail(VMSM_ERR_INVALID, "window bits must be 0 or in [2, 18]");
+            c->opt.window_bits = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_PHASE_TIMING:
+            c->phase_timing = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_SORT_BUCKETS:
+            c->opt.sort_buckets = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_CHECK_POINTS:
+            c->check_points = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_REDUCE_RADIX:
+            if (value < 1 || value > 6) return fail(VMSM_ERR_INVALID, "reduce radix log2 must be in [1, 6]");
+            c->opt.reduce_log2r = (uint32_t)value;
+            return VMSM_OK;
+    }
+    return fail(VMSM_ERR_INVALID, "unknown option %d", key);
+}
+
+int32_t vmsm_sync(uint64_t ctx) {
+    GET_CTX(ctx);
+    CU(cudaStreamSynchronize(c->stream));
+    return VMSM_OK;
+}
+
+int32_t vmsm_timer_start(uint64_t ctx) {
+    GET_CTX(ctx);
+    CU(cudaEventRecord(c->t0, c->stream));
+    return VMSM_OK;
+}
+int32_t vmsm_timer_stop(uint64_t ctx, float *ms) {
+    GET_CTX(ctx);
+    if (!ms) return fail(VMSM_ERR_INVALID, "null argument");
+    CU(cudaEventRecord(c->t1, c->stream));
+    CU(cudaEventSynchronize(c->t1));
+    CU(cudaEventElapsedTime(ms, c->t0, c->t1));
+    return VMSM_OK;
+}
+
+int32_t vmsm_phase_times(uint64_t ctx, double *ms_out, uint64_t *calls) {
+    GET_CTX(ctx);
+    if (!ms_out || !calls) return fail(VMSM_ERR_INVALID, "null argument");
+    int32_t rc = harvest_phases(c);
+    if (rc) return rc;
+    for (int p = 0; p < PH_COUNT; p++) ms_out[p] = c->phase_ms[p], c->phase_ms[p] = 0;
+    *calls = c->phase_calls;
+    c->phase_calls = 0;
+    return VMSM_OK;
+}
+
+int32_t vmsm_launch_count(uint64_t ctx, uint64_t *launches) {
+    GET_CTX(ctx);
+    if (!launches) return fail(VMSM_ERR_INVALID, "null argument");
+    *launches = c->launches;
+    return VMSM_OK;
+}
+
+// ---- points
+static int32_t new_pointset(Ctx *c, int32_t curve, uint64_t n, PointSet *ps) {
+    ps->curve = curve;
+    ps->n = n;
+    ps->aff = nullptr;
+    ps->niels = nullptr;
+    CU(cudaMalloc(&ps->aff, (n ? n : 1) * sizeof(ge_aff)));
+    cudaError_t e = cudaMalloc(&ps->niels, (n ? n : 1) * sizeof(ge_niels));
+    if (e != cudaSuccess) {
+        cudaFree(ps->aff);
+        return fail(VMSM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    return VMSM_OK;
+}
+
+int32_t vmsm_points_upload(uint64_t ctx, int32_t curve, const uint8_t *affine, uint64_t n, uint64_t *pts) {
+    GET_CTX(ctx);
+    if (!pts || (n && !affine)) return fail(VMSM_ERR_INVALID, "null argument");
+    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "curve %d not supported yet", curve);
+    if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many points");
+    PointSet ps;
+    int32_t rc = new_pointset(c, curve, n, &ps);
+    if (rc) return rc;
+    CudaBE be{c};
+    if (n) {
+        be.note(cudaMemcpyAsync(ps.aff, affine, n * sizeof(ge_aff), cudaMemcpyHostToDevice, c->stream));
+        be.zero(c->err_word, 4);
+        KAffToNiels k = {ps.aff, ps.niels, c->err_word, c->check_points ? 1u : 0u};
+        be.launch(k, (uint32_t)n);
+        be.note(cudaMemcpyAsync(c->pin, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
+        be.note(cudaStreamSynchronize(c->stream));
+        uint32_t ew = *reinterpret_cast<uint32_t *>(c->pin);
+        if (be.err != cudaSuccess || ew) {
+            cudaFree(ps.aff), cudaFree(ps.niels);
+            if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "upload: %s", cudaGetErrorString(be.err));
+            return fail(VMSM_ERR_POINT, "invalid point in upload (%s%s)", (ew & 1) ? "non-canonical coordinate " : "",
+                        (ew & 2) ? "not on curve" : "");
+        }
+    }
+    uint64_t id = c->next_id++;
+    c->points[id] = ps;
+    *pts = id;
+    return VMSM_OK;
+}
+
+int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scalars, uint64_t seed, uint64_t n,
+                               uint64_t *pts) {
+    GET_CTX(ctx);
+    if (!pts) return fail(VMSM_ERR_INVALID, "null argument");
+    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "curve %d not supported yet", curve);
+    if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many points");
+    PointSet ps;
+    int32_t rc = new_pointset(c, curve, n, &ps);
+    if (rc) return rc;
+    if (n) {
+        const uint32_t *dsc = nullptr;
+        if (scalars) {
+            rc = ensure_stage(c, n);
+            if (!rc) {
+                cudaError_t e = cudaMemcpyAsync(c->stage_scalars, scalars, n * 32, cudaMemcpyHostToDevice, c->stream);
+                if (e != cudaSuccess) rc = fail(VMSM_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
+            }
+            dsc = c->stage_scalars;
+        }
+        if (!rc) rc = ensure_tmp(c, n);
+        if (rc) {
+            cudaFree(ps.aff), cudaFree(ps.niels);
+            return rc;
+        }
+        CudaBE be{c};
+        KFixedBase k = {c->fb_table, dsc, seed, c->tmp_ext};
+        be.launch(k, (uint32_t)n);
+        KNormalize kn = {c->tmp_ext, ps.aff, ps.niels};
+        be.launch(kn, (uint32_t)n);
+        be.note(cudaStreamSynchronize(c->stream));
+        if (be.err != cudaSuccess) {
+            cudaFree(ps.aff), cudaFree(ps.niels);
+            return fail(VMSM_ERR_CUDA, "fixed_base: %s", cudaGetErrorString(be.err));
+        }
+    }
+    uint64_t id = c->next_id++;
+    c->points[id] = ps;
+    *pts = id;
+    return VMSM_OK;
+}
+
+int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *affine_out) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "range out of bounds");
+    if (n && !affine_out) return fail(VMSM_ERR_INVALID, "null argument");
+    if (n) CU(cudaMemcpyAsync(affine_out, it->second.aff + off, n * sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VMSM_OK;
+}
+
+int32_t vmsm_points_count(uint64_t ctx, uint64_t pts, uint64_t *n) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end() || !n) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    *n = it->second.n;
+    return VMSM_OK;
+}
+
+int32_t vmsm_points_free(uint64_t ctx, uint64_t pts) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(it->second.aff), cudaFree(it->second.niels);
+    c->points.erase(it);
+    return VMSM_OK;
+}
+
+// ---- scalars
+int32_t vmsm_scalars_upload(uint64_t ctx, const uint8_t *le32, uint64_t n, uint64_t *sc) {
+    GET_CTX(ctx);
+    if (!sc || (n && !le32)) return fail(VMSM_ERR_INVALID, "null argument");
+    ScalarSet ss{n, nullptr};
+    CU(cudaMalloc(&ss.data, (n ? n : 1) * 32));
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(ss.data, le32, n * 32, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            cudaFree(ss.data);
+            return fail(VMSM_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
+        }
+    }
+    uint64_t id = c->next_id++;
+    c->scalars[id] = ss;
+    *sc = id;
+    return VMSM_OK;
+}
+
+int32_t vmsm_scalars_synth(uint64_t ctx, int32_t curve, uint64_t seed, uint64_t n, uint64_t *sc) {
+    GET_CTX(ctx);
+    if (!sc) return fail(VMSM_ERR_INVALID, "null argument");
+    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "curve %d not supported yet", curve);
+    if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
+    ScalarSet ss{n, nullptr};
+    CU(cudaMalloc(&ss.data, (n ? n : 1) * 32));
+    CudaBE be{c};
+    KSynthScalars k = {ss.data, seed};
+    be.launch(k, (uint32_t)n);
+    be.note(cudaStreamSynchronize(c->stream));
+    if (be.err != cudaSuccess) {
+        cudaFree(ss.data);
+        return fail(VMSM_ERR_CUDA, "synth: %s", cudaGetErrorString(be.err));
+    }
+    uint64_t id = c->next_id++;
+    c->scalars[id] = ss;
+    *sc = id;
+    return VMSM_OK;
+}
+
+int32_t vmsm_scalars_download(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t n, uint8_t *le32_out) {
+    GET_CTX(ctx);
+    auto it = c->scalars.find(sc);
+    if (it == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "range out of bounds");
+    if (n && !le32_out) return fail(VMSM_ERR_INVALID, "null argument");
+    if (n) CU(cudaMemcpyAsync(le32_out, it->second.data + off * 8, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VMSM_OK;
+}
+
+int32_t vmsm_scalars_free(uint64_t ctx, uint64_t sc) {
+    GET_CTX(ctx);
+    auto it = c->scalars.find(sc);
+    if (it == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(it->second.data);
+    c->scalars.erase(it);
+    return VMSM_OK;
+}
+
+// ---- MSM
+int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
+                 uint8_t *out_affine) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "Not enough generators.");
+    if (!out_affine || (n && !scalars_le32)) return fail(VMSM_ERR_INVALID, "null argument");
+    int32_t rc = ensure_stage(c, n ? n : 1);
+    if (rc) return rc;
+    if (n) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = run_msm(c, it->second.niels + off, c->stage_scalars, n, kSlots - 1);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->pin, c->res_aff + (kSlots - 1), sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(out_affine, c->pin, sizeof(ge_aff));
+    return VMSM_OK;
+}
+
+int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
+                     uint32_t slot) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    auto is = c->scalars.find(sc);
+    if (is == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (poff > it->second.n || n > it->second.n - poff) return fail(VMSM_ERR_INVALID, "Not enough generators.");
+    if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+    if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    return run_msm(c, it->second.niels + poff, is->second.data + soff * 8, n, slot);
+}
+
+int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine) {
+    GET_CTX(ctx);
+    if (slot >= kSlots || !out_affine) return fail(VMSM_ERR_INVALID, "bad slot / null argument");
+    CU(cudaMemcpyAsync(c->pin, c->res_aff + slot, sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(out_affine, c->pin, sizeof(ge_aff));
+    return VMSM_OK;
+}
+
+int32_t vmsm_result_extended(uint64_t ctx, uint32_t slot, uint8_t *out_extended) {
+    GET_CTX(ctx);
+    if (slot >= kSlots || !out_extended) return fail(VMSM_ERR_INVALID, "bad slot / null argument");
+    CU(cudaMemcpyAsync(c->pin, c->res_ext + slot, sizeof(ge_ext), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(out_extended, c->pin, sizeof(ge_ext));
+    return VMSM_OK;
+}
+
+// ---- fold
+int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le32) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (!c_le32) return fail(VMSM_ERR_INVALID, "null argument");
+    if (half == 0 || 2 * half > it->second.n) return fail(VMSM_ERR_INVALID, "fold: need 2*half <= length");
+    int32_t rc = ensure_tmp(c, half);
+    if (rc) return rc;
+    uint32_t cs[8];
+    memcpy(cs, c_le32, 32);
+    CudaBE be{c};
+    fold_run(be, it->second.aff, it->second.niels, c->tmp_ext, (uint32_t)half, cs);
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "fold: %s", cudaGetErrorString(be.err));
+    it->second.n = half;
+    return VMSM_OK;
+}
+
+// ---- small linear combination of host points
+int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const uint8_t *scalars_le32, uint64_t n,
+                     uint8_t *out_affine) {
+    GET_CTX(ctx);
+    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "curve %d not supported yet", curve);
+    if (n > 64) return fail(VMSM_ERR_INVALID, "lincomb takes at most 64 terms");
+    if (!out_affine || (n && (!affine || !scalars_le32))) return fail(VMSM_ERR_INVALID, "null argument");
+    int32_t rc = ensure_stage(c, 64);
+    if (rc) return rc;
+    CudaBE be{c};
+    if (n) {
+        be.note(cudaMemcpyAsync(c->small_aff, affine, n * sizeof(ge_aff), cudaMemcpyHostToDevice, c->stream));
+        be.note(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
+        be.zero(c->err_word, 4);
+        KAffToNiels k = {c->small_aff, c->small_niels, c->err_word, c->check_points ? 1u : 0u};
+        be.launch(k, (uint32_t)n);
+    }
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "lincomb: %s", cudaGetErrorString(be.err));
+    rc = run_msm(c, c->small_niels, c->stage_scalars, n, kSlots - 1);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->pin, c->res_aff + (kSlots - 1), sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->pin + 64, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n && *reinterpret_cast<uint32_t *>(c->pin + 64)) return fail(VMSM_ERR_POINT, "invalid point in lincomb input");
+    memcpy(out_affine, c->pin, sizeof(ge_aff));
+    return VMSM_OK;
+}
+
+}  // extern "C"
