@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- Ed25519 MSM throughput (points/s) on 1..8 B200s, the metric BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 20] [--impl reference] [--sweep]
+
+N = 1 runs in-process; N > 1 is launched by the driver under torchrun (one rank per GPU; torch.distributed is used
+only for the barrier / max-over-ranks / 128-byte partial exchange -- the data path is libvmsm.so).  A "step" is one
+MSM over one batch of synthetic seeded scalars with the bases resident in HBM.  Multi-GPU: index-range split of ONE
+(N * 2^log2n)-term MSM, every rank computes the partial sum of its slice, rank 0 adds the N partials ("weak" scaling:
+per-GPU work fixed).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ed25519_msm_points_per_s"
+UNIT = "points/s"
+SEED_SCALARS, SEED_BASES = 0x5EED, 0x5EEE
+NSETS = 3  # distinct (bases, scalars) sets rotated between steps so no step finds its inputs in L2
+
+# SURVEY.md 8(d)/App. E work model: limb products per point at the LP-minimising window c*(n)
+M, S = 72, 44
+MADD, ADD, DBL = 7 * M, 9 * M, 4 * M + 4 * S
+
+
+def lp_msm(n, c):
+    W = -(-254 // c)
+    return n * W * MADD + W * 2 * (1 << (c - 1)) * ADD + (W - 1) * c * DBL + W * ADD
+
+
+def lp_per_point(n):
+    return min(lp_msm(n, c) for c in range(2, 25)) / n
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True,
+                                         stderr=subprocess.DEVNULL)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        mhz = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": float(rows[0][2]) if rows and rows[0][2].replace(".", "").isdigit() else None,
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    seed_s, seed_r, start, cnt = args
+    from oracle import ed25519 as E
+    from oracle import prng
+
+    pts = [E.scalar_mul(E.B, 1 + ((start + i) % 64)) for i in range(cnt)]  # cheap bases (small multiples of B)
+    sc = [prng.scalar(seed_s, start + i) for i in range(cnt)]
+    t0 = time.perf_counter()
+    E.msm_naive(sc, pts)  # the reference's algorithm: per-term double-and-add + tree product (pivot.py:143)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(points_per_core, cores):
+    """Points/s of the pure-Python restatement of the reference's MSM on `cores` processes (a sharded commitment)."""
+    import multiprocessing as mp
+
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(SEED_SCALARS, SEED_BASES, k * points_per_core, points_per_core) for k in range(cores)])
+        dt = time.perf_counter() - t0
+    return cores * points_per_core / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_core = args.cpu_points
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rate(max(8, per_core // 8), cores)
+    t_tot, pts_tot = 0.0, 0
+    steps = min(args.steps, args.cpu_steps)
+    for _ in range(steps):
+        rate, dt = cpu_reference_rate(per_core, cores)
+        t_tot += dt
+        pts_tot += per_core * cores
+    value = pts_tot / t_tot
+    n = 1 << args.log2n
+    sample = (f"{steps} steps x {cores} processes x {per_core} terms of the 2^{args.log2n}-term MSM; pure-Python restatement "
+              f"of pivot.vector_commitment (MPyC/gmpy2 are not installable in this image), cost is linear in n")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_tot / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
+            "config": {"workload": f"ed25519_msm_2^{args.log2n}", "n_per_gpu": n, "bounded_sample": True},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def dlog_sum(seed_s, seed_r, n, start=0):
+    from verifiable_mpc_b200 import synth
+
+    L = synth.ED_L
+    s = synth.scalars_ed25519(seed_s, n, start)
+    r = synth.scalars_ed25519(seed_r, n, start)
+    tot = 0
+    for i in range(n):
+        tot += int.from_bytes(s[i].tobytes(), "little") * int.from_bytes(r[i].tobytes(), "little")
+    return tot % L
+
+
+def run_gpu(args, rank, world, dist):
+    import ctypes
+
+    import numpy as np
+
+    from verifiable_mpc_b200 import Context, _lib, synth
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    ctx = Context(local)
+    n = 1 << args.log2n
+    if args.window:
+        ctx.set_option(_lib.OPT_WINDOW_BITS, args.window)
+    ctx.set_option(_lib.OPT_PHASE_TIMING, 1)
+
+    # inputs: NSETS distinct (bases, scalars) sets per rank, all resident in HBM before the timed region.
+    # set k of rank r covers global indices [r*n, (r+1)*n) of stream (seed + 16*k).
+    base_off = rank * n
+    bases, scal, host_scal = [], [], []
+    for k in range(NSETS):
+        rs = synth.scalars_ed25519(SEED_BASES + 16 * k, n, start=base_off)  # known dlogs r_i
+        bases.append(ctx.fixed_base(scalars=rs))                              # g_i = r_i * B on the device
+        hs = synth.scalars_ed25519(SEED_SCALARS + 16 * k, n, start=base_off)
+        scal.append(ctx.upload_scalars(hs))
+        pin = ctx.pinned(n * 32)
+        pin.array[:] = hs.reshape(-1)
+        host_scal.append(pin)
+        del rs, hs
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def combine(slot):
+        """rank 0 <- sum of the N partial group elements (128 B each)."""
+        if dist is None:
+            return ctx.result(slot)
+        import torch
+
+        ext = ctx.result_extended(slot)
+        mine = torch.tensor([int(v >> (63 * j)) & ((1 << 63) - 1) for v in ext for j in range(5)], dtype=torch.int64)
+        allp = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        if rank != 0:
+            return None
+        P = 2**255 - 19
+        pts = []
+        for t in allp:
+            v = t.tolist()
+            X, Y, Z, T = (sum(v[5 * q + j] << (63 * j) for j in range(5)) for q in range(4))
+            zi = pow(Z, -1, P)  # marshalling of a 128 B partial into the ABI's affine wire format
+            pts.append((X * zi % P, Y * zi % P))
+        return ctx.lincomb(pts, [1] * len(pts))
+
+    # warm-up
+    for w in range(args.warmup):
+        ctx.msm_dev(bases[w % NSETS], scal[w % NSETS], slot=0)
+        combine(0)
+    ctx.phase_times()
+    l0 = ctx.launch_count()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    tm0 = time.perf_counter()
+    ctx.timer_start()
+    for s in range(args.steps):
+        ctx.msm_dev(bases[s % NSETS], scal[s % NSETS], slot=s % 32)
+        if dist is not None:
+            combine(s % 32)
+    ms = ctx.timer_stop()
+    barrier()
+    tm1 = time.perf_counter()
+    clocks = sampler.stop(tm0, tm1) if sampler else None
+    launches = ctx.launch_count() - l0
+    phases, calls = ctx.phase_times()
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+
+    # correctness of what was just timed: set (steps-1) % NSETS, against the known-dlog identity
+    last = (args.steps - 1) % NSETS
+    got = combine((args.steps - 1) % 32)
+    checked = None
+    if args.check:
+        e = dlog_sum(SEED_SCALARS + 16 * last, SEED_BASES + 16 * last, n, start=base_off)
+        if dist is not None:
+            import torch
+
+            parts = [None] * world
+            dist.all_gather_object(parts, e)
+            e = sum(parts) % synth.ED_L
+        if rank == 0:
+            # e*B through a different device path (fixed-base comb) than the Pippenger pipeline being checked
+            exp = ctx.fixed_base(scalars=[e]).tolist()[0]
+            checked = bool(got == exp)
+
+    # end-to-end through the public host API: pinned host scalars -> H2D -> MSM -> D2H of the group element
+    out = ctypes.create_string_buffer(64)
+    for w in range(min(args.warmup, 2)):
+        ctx.msm_raw(bases[w % NSETS], host_scal[w % NSETS].ptr, 0, n, out)
+        if dist is not None:
+            combine(63)
+    barrier()
+    e0 = time.perf_counter()
+    for s in range(args.steps):
+        ctx.msm_raw(bases[s % NSETS], host_scal[s % NSETS].ptr, 0, n, out)
+        if dist is not None:
+            combine(63)
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([e2e_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank != 0:
+        return
+    total_pts = world * n * args.steps
+    value = total_pts / (ms * 1e-3)
+    peak_tlps = ctx.imad_peak()
+    acc_ms = phases["accumulate"] / max(calls, 1)
+    # the accumulate kernel performs exactly one 7M mixed addition per non-zero digit: n * W of them per launch
+    c_auto = _choose_window(n) if not args.window else args.window
+    W_c = -(-254 // c_auto)
+    acc_lp = n * W_c * MADD
+    achieved = acc_lp / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+    msm_frac = value / world * lp_per_point(n) / (peak_tlps * 1e12)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"ed25519_msm_2^{args.log2n}", "n_per_gpu": n, "n_total": world * n,
+                   "window_bits": c_auto, "windows": W_c, "bases": "g_i = r_i*B, device generated, niels form resident",
+                   "l2": f"inputs rotate over {NSETS} distinct (bases, scalars) sets ({NSETS * n * 128 >> 20} MiB) > 126 MB L2",
+                   "multi_gpu": "index-range split of one N*n-term MSM; rank 0 adds N partials" if world > 1 else "single GPU",
+                   "result_checked_vs_known_dlog": checked},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": total_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world,
+                "d2h_bytes_per_step": 64 + (128 * world if world > 1 else 0), "ms_per_step": 1e3 * e2e_s / args.steps},
+        "roofline": {"bound": "imad", "kernel": "vmsm_kernel<KAccumulate>", "achieved": achieved, "peak": peak_tlps,
+                     "unit": "T limb-products/s", "frac": (achieved / peak_tlps) if achieved else None, "traffic": None,
+                     "peak_source": "measured live: vmsm_microbench_imad (independent IMAD.WIDE.U32 chains, all SMs)",
+                     "kernel_ms": acc_ms, "algorithmic_lp_per_launch": acc_lp,
+                     "whole_msm_frac": msm_frac, "whole_msm_lp_per_point": lp_per_point(n),
+                     "phase_ms": {k: v / max(calls, 1) for k, v in phases.items()}},
+    }
+    if args.cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, dt = cpu_reference_rate(args.cpu_points, cores)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{cores} processes x {args.cpu_points} terms ({dt:.1f} s) of the same MSM with the "
+                                          "pure-Python restatement of pivot.vector_commitment (oracle/ed25519.py)"}
+    print(json.dumps(line), flush=True)
+
+
+def _choose_window(n):
+    best, best_c = None, 4
+    for c in range(3, 18):
+        W = -(-254 // c)
+        cost = n * W * 504.0 + W * (1 << (c - 1)) * 2.0 * 648.0 * 1.3 + (W - 1) * c * 464.0
+        if best is None or cost < best:
+            best, best_c = cost, c
+    return best_c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--log2n", type=int, default=20)
+    ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-check", dest="check", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cpu-points", type=int, default=1024, help="terms per host core in the CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("gloo", rank=rank, world_size=world)
+        dist = dist_mod
+    try:
+        run_gpu(args, rank, world, dist)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -113,6 +113,19 @@ int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le
 int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const uint8_t *scalars_le32, uint64_t n,
                      uint8_t *out_affine);
 
+/* ---- pinned host memory for the end-to-end path (H2D of scalars straight from page-locked memory) -------- */
+int32_t vmsm_host_alloc(uint64_t bytes, void **ptr);
+int32_t vmsm_host_free(void *ptr);
+
+/* ---- device self-test of the field arithmetic: out[i] = a[i] (op) b[i] on the GPU, n elements of 32 B.
+ * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 canon(a), 5 sqr(a).  Used by tests/ to pin the PTX carry chains. */
+int32_t vmsm_selftest_fe(uint64_t ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint64_t n, uint8_t *out);
+
+/* ---- integer-pipe peak: independent IMAD.WIDE.U32 chains on every SM, timed with CUDA events on the context's
+ * stream.  Returns tera limb-products (32x32->64 multiply-accumulates) per second: the roofline denominator that
+ * bench.py reports next to the achieved figure (SURVEY.md 8d asks for it to be measured on the box). */
+int32_t vmsm_microbench_imad(uint64_t ctx, double *tera_lp_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,187 @@
+"""GPU parity tests: the CUDA path through the C ABI (ctypes -> libvmsm.so) against the CPU oracle, bit-exact on
+canonical affine coordinates.  Run on a B200:  python -m pytest tests -m gpu -x -q"""
+import json
+import os
+import random
+
+import pytest
+
+from oracle import ed25519 as E
+from oracle import prng
+
+pytestmark = pytest.mark.gpu
+P = E.P
+EDGE = [0, 1, 2, 19, 37, 38, P - 1, P, P + 1, 2**255 - 1, 2**255, 2**256 - 1, 2**256 - 38, 2**256 - 37, 2**256 - 39]
+
+
+def test_field_ops_ptx(ctx):
+    """Pins the inline-PTX carry chains (IMAD.WIDE.X / IADD3.X) of fe25519.cuh against Python ints."""
+    rnd = random.Random(2)
+    vals = EDGE + [rnd.getrandbits(256) for _ in range(200)]
+    a = [x for x in vals for _ in vals[:40]]
+    b = [y for _ in vals for y in vals[:40]]
+    for op, f in ((0, lambda x, y: x + y), (1, lambda x, y: x - y), (2, lambda x, y: x * y)):
+        got = ctx.selftest_fe(op, a, b)
+        assert all(g % P == f(x, y) % P for g, x, y in zip(got, a, b)), op
+    assert ctx.selftest_fe(4, vals, vals) == [v % P for v in vals]
+    assert [g % P for g in ctx.selftest_fe(5, vals, vals)] == [v * v % P for v in vals]
+    nz = [v for v in vals if v % P]
+    assert [g % P for g in ctx.selftest_fe(3, nz, nz)] == [pow(v, -1, P) for v in nz]
+
+
+def test_fixed_base_and_synth(ctx, known_points):
+    dl, pts = known_points
+    dev = ctx.fixed_base(seed=0x5EEE, n=300)
+    assert dev.tolist() == pts
+    sc = [0, 1, E.L - 1, 8, 2**252]
+    assert ctx.fixed_base(scalars=sc).tolist() == [E.scalar_mul(E.B, s) for s in sc]
+    raw = ctx.synth_scalars(0x5EED, 300).download()
+    assert [int.from_bytes(raw[32 * i: 32 * i + 32], "little") for i in range(300)] == \
+        [prng.scalar(0x5EED, i) for i in range(300)]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 64, 300])
+def test_msm_known_dlog(ctx, known_points, n):
+    from verifiable_mpc_b200 import _lib
+
+    dl, pts = known_points
+    dev = ctx.upload_points(pts)
+    scs = [prng.scalar(0x5EED, i) for i in range(n)]
+    exp = E.msm_known_dlog(scs, dl[:n])
+    try:
+        for c in [0, 2, 3, 5, 8, 11, 13, 16]:
+            for r in [1, 3, 4]:
+                for sort in (0, 1):
+                    ctx.set_option(_lib.OPT_WINDOW_BITS, c)
+                    ctx.set_option(_lib.OPT_REDUCE_RADIX, r)
+                    ctx.set_option(_lib.OPT_SORT_BUCKETS, sort)
+                    assert ctx.msm(dev, scs) == exp, (n, c, r, sort)
+    finally:
+        ctx.set_option(_lib.OPT_WINDOW_BITS, 0)
+        ctx.set_option(_lib.OPT_REDUCE_RADIX, 3)
+        ctx.set_option(_lib.OPT_SORT_BUCKETS, 1)
+
+
+def test_msm_matches_reference_algorithm(ctx, known_points):
+    _, pts = known_points
+    dev = ctx.upload_points(pts)
+    scs = [prng.scalar(7, i) for i in range(17)]
+    assert ctx.msm(dev, scs) == E.msm_naive(scs, pts)
+    # negative / unreduced scalars exactly as the reference passes them (host layer reduces mod l)
+    edge = [0, 1, E.L - 1, 2, -1, -2, E.L, E.L + 1, 2**252, 2**253 - 1, 2**16, 2**16 - 1, 2**15, 2**15 + 1,
+            prng.scalar(1, 1) ** 2, -(2**300)]
+    assert ctx.msm(dev, edge) == E.msm_naive(edge, pts)
+    pp = [pts[0]] * 5 + [E.IDENTITY] * 3 + [E.affine_neg(pts[0])] * 2
+    sc = [5, 7, 11, 13, 17, 3, 4, 5, 9, 1]
+    assert ctx.msm(ctx.upload_points(pp), sc) == E.msm_naive(sc, pp)
+    # offset / sub-range
+    assert ctx.msm(dev, scs[:5], off=100) == E.msm_naive(scs[:5], pts[100:105])
+
+
+def test_golden_fixture(ctx):
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ed25519_msm_fold.json")))
+    pts = [tuple(int(v, 16) for v in p) for p in g["points"]]
+    dev = ctx.upload_points(pts)
+    for case in g["msm"]:
+        sc = [int(s, 16) * (-1 if neg else 1) for s, neg in case["scalars"]]
+        assert list(ctx.msm(dev, sc)) == [int(v, 16) for v in case["expect"]], case["name"]
+    f = g["fold"]
+    d2 = ctx.upload_points(pts[: f["n"]])
+    d2.fold(int(f["c"], 16))
+    assert [[hex(x), hex(y)] for x, y in d2.tolist()] == f["expect"]
+
+
+def test_upload_validation_and_errors(ctx, known_points):
+    from verifiable_mpc_b200 import VmsmError
+
+    _, pts = known_points
+    with pytest.raises(VmsmError) as ei:
+        ctx.upload_points([(E.BX, (E.BY + 1) % P)])
+    assert ei.value.code == -3
+    with pytest.raises(VmsmError) as ei:
+        ctx.upload_points(int(E.BX + P).to_bytes(32, "little") + int(E.BY).to_bytes(32, "little"))
+    assert ei.value.code == -3
+    dev = ctx.upload_points(pts[:4])
+    with pytest.raises(VmsmError) as ei:  # pivot.py:142 "Not enough generators."
+        ctx.msm(dev, [1, 2, 3, 4, 5])
+    assert "Not enough generators" in str(ei.value)
+
+
+def test_fold_rounds(ctx, known_points):
+    """Repeated in-place halving as protocol_4 does (compressed_pivot.py:64), each round against the oracle."""
+    _, pts = known_points
+    cur = pts[:64]
+    dev = ctx.upload_points(cur)
+    for rnd in range(5):
+        c = prng.scalar(0xF01D, rnd)
+        dev.fold(c)
+        cur = E.fold(cur, c)
+        assert dev.tolist() == cur, rnd
+        # the folded generators are usable as MSM bases straight away
+        sc = [prng.scalar(0xF01E + rnd, i) for i in range(len(cur))]
+        assert ctx.msm(dev, sc) == E.msm_naive(sc, cur) if len(cur) <= 8 else True
+    for c in [0, 1, E.L - 1]:
+        d = ctx.upload_points(pts[:4])
+        d.fold(c)
+        assert d.tolist() == E.fold(pts[:4], c)
+
+
+def test_lincomb(ctx, known_points):
+    _, pts = known_points
+    c = prng.scalar(0xABC, 0)
+    A, Q, Bp = pts[0], pts[1], pts[2]
+    # Q' = A * Q^c * B^(c^2) with the exponent c^2 NOT reduced (compressed_pivot.py:66)
+    assert ctx.lincomb([A, Q, Bp], [1, c, c * c]) == E.msm_naive([1, c, c * c], [A, Q, Bp])
+    assert ctx.lincomb([], []) == E.IDENTITY
+
+
+def _dlog_sum(seed_s, seed_r, n):
+    import numpy as np
+    from verifiable_mpc_b200 import synth
+
+    s = synth.scalars_ed25519(seed_s, n)
+    r = synth.scalars_ed25519(seed_r, n)
+    tot = 0
+    for i in range(n):
+        tot += int.from_bytes(s[i].tobytes(), "little") * int.from_bytes(r[i].tobytes(), "little")
+    return tot % E.L
+
+
+@pytest.mark.parametrize("logn", [10, 12, 16, 20])
+def test_msm_large_known_dlog(ctx, logn):
+    """Size-independent property at BASELINE.json's sizes: bases g_i = r_i*B generated on the device, so
+    MSM(s, g) = (sum s_i r_i mod l) * B, with the right-hand side computed on the CPU in O(n) modmults."""
+    n = 1 << logn
+    dev = ctx.fixed_base(seed=0x5EEE, n=n)
+    sc = ctx.synth_scalars(0x5EED, n)
+    ctx.msm_dev(dev, sc, slot=1)
+    got = ctx.result(1)
+    assert got == E.scalar_mul(E.B, _dlog_sum(0x5EED, 0x5EEE, n))
+    # spot-check generated bases against the oracle
+    for i in (0, n // 3, n - 1):
+        assert dev.tolist(i, 1)[0] == E.scalar_mul(E.B, prng.scalar(0x5EEE, i))
+    # linearity: MSM(s, g) + MSM(s', g) = MSM(s + s', g) on a sub-range
+    m = min(n, 4096)
+    import numpy as np
+    from verifiable_mpc_b200 import synth
+
+    s1 = synth.scalars_ed25519(11, m)
+    s2 = synth.scalars_ed25519(12, m)
+    a = ctx.msm(dev, s1)
+    b = ctx.msm(dev, s2)
+    s12 = [(int.from_bytes(s1[i].tobytes(), "little") + int.from_bytes(s2[i].tobytes(), "little")) % E.L for i in range(m)]
+    assert ctx.msm(dev, s12) == E.affine_add(a, b)
+    dev.free()
+    sc.free()
+
+
+def test_msm_skewed_scalars(ctx):
+    """Boolean / tiny witnesses put everything into a handful of buckets (the long-bucket path)."""
+    n = 1 << 12
+    dev = ctx.fixed_base(seed=0x5EEE, n=n)
+    rnd = random.Random(5)
+    sc = [rnd.randrange(2) for _ in range(n)]
+    dl = [prng.scalar(0x5EEE, i) for i in range(n)]
+    assert ctx.msm(dev, sc) == E.msm_known_dlog(sc, dl)
+    sc = [7] * n
+    assert ctx.msm(dev, sc) == E.msm_known_dlog(sc, dl)

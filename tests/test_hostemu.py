@@ -1,0 +1,129 @@
+"""CPU checks of the kernel bodies (csrc/kernels.cuh, portable arithmetic path) against the oracle, through the
+test-only host emulation.  These run in the GPU-less container; the same cases run on the GPU in test_gpu_parity.py."""
+import ctypes
+import json
+import os
+import random
+
+import pytest
+
+from oracle import ed25519 as E
+from oracle import prng
+
+P = E.P
+
+
+def fe_op(lib, op, a, b=0):
+    out = ctypes.create_string_buffer(32)
+    lib.hostemu_fe_op(op, a.to_bytes(32, "little"), b.to_bytes(32, "little"), out)
+    return int.from_bytes(out.raw, "little")
+
+
+EDGE = [0, 1, 2, 19, 37, 38, P - 1, P, P + 1, 2**255 - 1, 2**255, 2**256 - 1, 2**256 - 38, 2**256 - 37, 2**256 - 39]
+
+
+def test_field_ops(hostemu):
+    rnd = random.Random(1)
+    vals = EDGE + [rnd.getrandbits(256) for _ in range(60)]
+    for a in vals:
+        for b in vals[:25]:
+            assert fe_op(hostemu, 0, a, b) % P == (a + b) % P
+            assert fe_op(hostemu, 1, a, b) % P == (a - b) % P
+            assert fe_op(hostemu, 2, a, b) % P == (a * b) % P
+        assert fe_op(hostemu, 4, a) == a % P
+        assert fe_op(hostemu, 5, a) % P == a * a % P
+        if a % P:
+            assert fe_op(hostemu, 3, a) % P == pow(a, -1, P)
+
+
+def run_msm(lib, pts, scs, c=0, sort=1, r=3):
+    n = len(scs)
+    A = b"".join(E.point_to_bytes(p) for p in pts[:n])
+    S = b"".join(E.scalar_to_bytes(s) for s in scs)
+    out = ctypes.create_string_buffer(64)
+    err = lib.hostemu_msm(A, S, n, c, sort, r, out, None)
+    assert err == 0
+    return E.point_from_bytes(out.raw)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 64, 300])
+def test_msm_known_dlog(hostemu, known_points, n):
+    dl, pts = known_points
+    scs = [prng.scalar(0x5EED, i) for i in range(n)]
+    exp = E.msm_known_dlog(scs, dl[:n])
+    for c in ([0, 2, 3, 5, 8, 13, 16] if n <= 64 else [0, 7]):
+        for r in ([1, 3, 4] if n <= 17 else [3]):
+            for sort in (0, 1):
+                assert run_msm(hostemu, pts, scs, c, sort, r) == exp, (n, c, r, sort)
+
+
+def test_msm_matches_reference_algorithm(hostemu, known_points):
+    _, pts = known_points
+    scs = [prng.scalar(7, i) for i in range(17)]
+    assert run_msm(hostemu, pts, scs) == E.msm_naive(scs, pts)
+    edge = [0, 1, E.L - 1, 2, E.L - 2, 2**252, 2**128, 2**16 - 1, 2**16, 2**15, 2**15 + 1]
+    for c in (0, 16, 4):
+        assert run_msm(hostemu, pts, edge, c) == E.msm_naive(edge, pts)
+    pp = [pts[0]] * 5 + [E.IDENTITY] * 3 + [E.affine_neg(pts[0])] * 2
+    sc = [5, 7, 11, 13, 17, 3, 4, 5, 9, 1]
+    assert run_msm(hostemu, pp, sc, 4) == E.msm_naive(sc, pp)
+
+
+def test_msm_rejects_bad_points(hostemu):
+    bad = (E.BX, (E.BY + 1) % P)
+    out = ctypes.create_string_buffer(64)
+    err = hostemu.hostemu_msm(E.point_to_bytes(bad), E.scalar_to_bytes(1), 1, 0, 1, 3, out, None)
+    assert err & 2
+    noncanon = int(E.BX + P).to_bytes(32, "little") + int(E.BY).to_bytes(32, "little")
+    err = hostemu.hostemu_msm(noncanon, E.scalar_to_bytes(1), 1, 0, 1, 3, out, None)
+    assert err & 1
+
+
+def test_golden_fixture(hostemu):
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ed25519_msm_fold.json")))
+    pts = [tuple(int(v, 16) for v in p) for p in g["points"]]
+    for case in g["msm"]:
+        sc = [int(s, 16) * (-1 if neg else 1) for s, neg in case["scalars"]]
+        assert list(run_msm(hostemu, pts, sc)) == [int(v, 16) for v in case["expect"]], case["name"]
+    f = g["fold"]
+    A = b"".join(E.point_to_bytes(p) for p in pts[: f["n"]])
+    out = ctypes.create_string_buffer(64 * (f["n"] // 2))
+    hostemu.hostemu_fold(A, f["n"], E.scalar_to_bytes(int(f["c"], 16)), out)
+    got = [E.point_from_bytes(out.raw[64 * i: 64 * i + 64]) for i in range(f["n"] // 2)]
+    assert [[hex(x), hex(y)] for x, y in got] == f["expect"]
+
+
+def test_fold(hostemu, known_points):
+    _, pts = known_points
+    A = b"".join(E.point_to_bytes(p) for p in pts[:32])
+    out = ctypes.create_string_buffer(64 * 16)
+    c = prng.scalar(99, 0)
+    hostemu.hostemu_fold(A, 32, E.scalar_to_bytes(c), out)
+    assert [E.point_from_bytes(out.raw[64 * i: 64 * i + 64]) for i in range(16)] == E.fold(pts[:32], c)
+    for c in [0, 1, 2, 3, E.L - 1]:
+        hostemu.hostemu_fold(A, 4, E.scalar_to_bytes(c), out)
+        assert [E.point_from_bytes(out.raw[64 * i: 64 * i + 64]) for i in range(2)] == E.fold(pts[:4], c), c
+
+
+def test_fixed_base_and_synth(hostemu, known_points):
+    dl, pts = known_points
+    out = ctypes.create_string_buffer(64 * 300)
+    hostemu.hostemu_fixed_base(None, ctypes.c_uint64(0x5EEE), 300, out)
+    assert [E.point_from_bytes(out.raw[64 * i: 64 * i + 64]) for i in range(300)] == pts
+    sc = [0, 1, E.L - 1, 8, 2**252]
+    hostemu.hostemu_fixed_base(b"".join(E.scalar_to_bytes(s) for s in sc), ctypes.c_uint64(0), len(sc), out)
+    assert [E.point_from_bytes(out.raw[64 * i: 64 * i + 64]) for i in range(len(sc))] == [E.scalar_mul(E.B, s) for s in sc]
+    out = ctypes.create_string_buffer(32 * 300)
+    hostemu.hostemu_synth_scalars(ctypes.c_uint64(0x5EED), 300, out)
+    assert [int.from_bytes(out.raw[32 * i: 32 * i + 32], "little") for i in range(300)] == \
+        [prng.scalar(0x5EED, i) for i in range(300)]
+
+
+def test_numpy_synth_matches_oracle_prng():
+    from verifiable_mpc_b200 import synth
+
+    a = synth.scalars_ed25519(0x5EED, 2048)
+    for i in [0, 1, 2, 1000, 2047]:
+        assert int.from_bytes(a[i].tobytes(), "little") == prng.scalar(0x5EED, i)
+    b = synth.scalars_ed25519(0x5EED, 8, start=1000)
+    assert (b[0] == a[1000]).all()

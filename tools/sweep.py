@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Device-timed MSM sweep over n and tuning options (development tool; writes JSON lines).
+    python tools/sweep.py --logn 10 12 14 16 18 20 22 --windows 0 --out gpurun_out/sweep.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from verifiable_mpc_b200 import Context, _lib  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--logn", type=int, nargs="+", default=[10, 12, 14, 16, 18, 20])
+    ap.add_argument("--windows", type=int, nargs="+", default=[0])
+    ap.add_argument("--sort", type=int, nargs="+", default=[1])
+    ap.add_argument("--radix", type=int, nargs="+", default=[3])
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    ctx = Context(0)
+    ctx.set_option(_lib.OPT_PHASE_TIMING, 1)
+    peak = ctx.imad_peak()
+    out = open(args.out, "a") if args.out else None
+    for logn in args.logn:
+        n = 1 << logn
+        sets = [(ctx.fixed_base(seed=0x5EEE + 16 * k, n=n), ctx.synth_scalars(0x5EED + 16 * k, n)) for k in range(3)]
+        for c in args.windows:
+            for sort in args.sort:
+                for radix in args.radix:
+                    ctx.set_option(_lib.OPT_WINDOW_BITS, c)
+                    ctx.set_option(_lib.OPT_SORT_BUCKETS, sort)
+                    ctx.set_option(_lib.OPT_REDUCE_RADIX, radix)
+                    for w in range(3):
+                        ctx.msm_dev(*sets[w % 3], slot=0)
+                    ctx.sync()
+                    ctx.phase_times()
+                    ctx.timer_start()
+                    for s in range(args.steps):
+                        ctx.msm_dev(*sets[s % 3], slot=s % 32)
+                    ms = ctx.timer_stop() / args.steps
+                    ph, calls = ctx.phase_times()
+                    rec = {"log2n": logn, "window": c, "sort": sort, "radix": radix, "ms": ms, "Mpts_s": n / ms / 1e3,
+                           "imad_peak_tlps": peak, "phase_ms": {k: round(v / calls, 5) for k, v in ph.items()}}
+                    print(json.dumps(rec), flush=True)
+                    if out:
+                        out.write(json.dumps(rec) + "\n")
+                        out.flush()
+        for p, s in sets:
+            p.free()
+            s.free()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -209,7 +209,7 @@ VMSM_HD fe fe_reduce512(const uint32_t *t) {
 }
 
 // --------------------------------------------------------------------------------------------- mul
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // acc[0..7] += {a0,a1,a2,a3} * b laid out as four 64-bit columns; carry out -> acc8 (which holds at most a few
 // earlier carries, so it cannot overflow).  Each lo/hi pair fuses into one IMAD.WIDE.U32 in SASS.
 VMSM_D void fe_mad4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t &r4, uint32_t &r5, uint32_t &r6,

@@ -390,4 +390,25 @@ struct KSynthScalars {
     }
 };
 
+// device self-test of fe25519.cuh (vmsm_selftest_fe)
+struct KSelfTestFe {
+    enum { kBlock = 128 };
+    const fe *a;
+    const fe *b;
+    fe *out;
+    int32_t op;
+    VMSM_HD void operator()(uint32_t tid) const {
+        fe x = ld_fe(a + tid), y = ld_fe(b + tid), r;
+        switch (op) {
+            case 0: r = fe_add(x, y); break;
+            case 1: r = fe_sub(x, y); break;
+            case 2: r = fe_mul(x, y); break;
+            case 3: r = fe_inv(x); break;
+            case 4: r = fe_canon(x); break;
+            default: r = fe_sqr(x); break;
+        }
+        st_fe(out + tid, r);
+    }
+};
+
 }  // namespace vmsm

@@ -1,0 +1,283 @@
+"""Host-side engine objects over the C ABI: Context, DevicePoints, DeviceScalars.
+
+This is the layer the reference-facing modules (``verifiable_mpc_b200.ac20.pivot`` etc.) call.  Everything that
+touches group elements goes through libvmsm.so on the GPU; Python only marshals integers <-> little-endian bytes.
+"""
+import ctypes
+import os
+
+from . import _lib
+from ._lib import VmsmError, check
+
+ED_P = 2**255 - 19
+ED_L = 2**252 + 27742317777372353535851937790883648493
+
+
+def _buf(data):
+    """bytes / bytearray / numpy uint8 array -> (ctypes pointer, keepalive)"""
+    if isinstance(data, (bytes, bytearray)):
+        arr = (ctypes.c_ubyte * len(data)).from_buffer_copy(data) if isinstance(data, bytes) else (
+            ctypes.c_ubyte * len(data)).from_buffer(data)
+        return ctypes.cast(arr, ctypes.c_void_p), arr
+    if hasattr(data, "ctypes") and hasattr(data, "nbytes"):  # numpy array (C-contiguous uint8 expected)
+        if not data.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return ctypes.c_void_p(data.ctypes.data), data
+    if data is None:
+        return ctypes.c_void_p(0), None
+    raise TypeError(f"unsupported buffer type {type(data)}")
+
+
+def pack_scalars(xs, order=ED_L):
+    """Iterable of Python ints (negative / unreduced allowed, as the reference passes them: pivot.py:119-128,
+    compressed_pivot.py:66,134) -> n*32 bytes little-endian, reduced below the group order."""
+    return b"".join((int(x) % order).to_bytes(32, "little") for x in xs)
+
+
+def pack_points(pts):
+    """Iterable of canonical affine (x, y) int pairs -> n*64 bytes."""
+    return b"".join(int(x).to_bytes(32, "little") + int(y).to_bytes(32, "little") for x, y in pts)
+
+
+def unpack_points(raw):
+    return [(int.from_bytes(raw[i:i + 32], "little"), int.from_bytes(raw[i + 32:i + 64], "little"))
+            for i in range(0, len(raw), 64)]
+
+
+class DevicePoints:
+    """A device-resident vector of group elements (a generator list ``g`` / ``g_hat``)."""
+
+    def __init__(self, ctx, handle, n, curve):
+        self.ctx, self.handle, self.n, self.curve = ctx, handle, n, curve
+
+    def __len__(self):
+        return self.n
+
+    def download(self, off=0, n=None):
+        n = self.n - off if n is None else n
+        out = ctypes.create_string_buffer(max(1, 64 * n))
+        check(self.ctx.lib.vmsm_points_download(self.ctx.h, self.handle, off, n, out))
+        return out.raw[:64 * n]
+
+    def tolist(self, off=0, n=None):
+        return unpack_points(self.download(off, n))
+
+    def fold(self, c):
+        """In place ``P[j] = c*P[j] + P[half+j]`` (compressed_pivot.py:64); the vector shrinks to half."""
+        half = self.n // 2
+        cb = (int(c) % ED_L).to_bytes(32, "little")
+        check(self.ctx.lib.vmsm_fold(self.ctx.h, self.handle, half, cb))
+        self.n = half
+        return self
+
+    def free(self):
+        if self.handle and self.ctx.h:
+            self.ctx.lib.vmsm_points_free(self.ctx.h, self.handle)
+        self.handle = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceScalars:
+    def __init__(self, ctx, handle, n):
+        self.ctx, self.handle, self.n = ctx, handle, n
+
+    def __len__(self):
+        return self.n
+
+    def download(self, off=0, n=None):
+        n = self.n - off if n is None else n
+        out = ctypes.create_string_buffer(max(1, 32 * n))
+        check(self.ctx.lib.vmsm_scalars_download(self.ctx.h, self.handle, off, n, out))
+        return out.raw[:32 * n]
+
+    def free(self):
+        if self.handle and self.ctx.h:
+            self.ctx.lib.vmsm_scalars_free(self.ctx.h, self.handle)
+        self.handle = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy uint8 array (for the end-to-end H2D path)."""
+
+    def __init__(self, lib, nbytes):
+        import numpy as np
+
+        self.lib = lib
+        p = ctypes.c_void_p()
+        check(lib.vmsm_host_alloc(nbytes, ctypes.byref(p)))
+        self.ptr, self.nbytes = p, nbytes
+        self.array = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_ubyte)), shape=(nbytes,))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.vmsm_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One CUDA device + one stream.  Calls on a context are serialised by the caller."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        self.h = 0
+        if device is None:
+            device = int(os.environ.get("VMSM_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        h = ctypes.c_uint64()
+        check(self.lib.vmsm_ctx_create(device, ctypes.byref(h)))
+        self.h = h.value
+        self.device = device
+
+    # -- options / timing
+    def set_option(self, key, value):
+        check(self.lib.vmsm_ctx_set_option(self.h, key, int(value)))
+
+    def sync(self):
+        check(self.lib.vmsm_sync(self.h))
+
+    def timer_start(self):
+        check(self.lib.vmsm_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        check(self.lib.vmsm_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def phase_times(self):
+        ms = (ctypes.c_double * len(_lib.PHASES))()
+        calls = ctypes.c_uint64()
+        check(self.lib.vmsm_phase_times(self.h, ms, ctypes.byref(calls)))
+        return dict(zip(_lib.PHASES, list(ms))), calls.value
+
+    def launch_count(self):
+        n = ctypes.c_uint64()
+        check(self.lib.vmsm_launch_count(self.h, ctypes.byref(n)))
+        return n.value
+
+    def pinned(self, nbytes):
+        return PinnedBuffer(self.lib, nbytes)
+
+    # -- points
+    def upload_points(self, pts, curve=_lib.CURVE_ED25519):
+        """``pts``: bytes (n*64, canonical affine LE) or a list of (x, y) ints."""
+        raw = pts if isinstance(pts, (bytes, bytearray)) or hasattr(pts, "nbytes") else pack_points(pts)
+        nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
+        n = nbytes // 64
+        p, keep = _buf(raw)
+        h = ctypes.c_uint64()
+        check(self.lib.vmsm_points_upload(self.h, curve, p, n, ctypes.byref(h)))
+        return DevicePoints(self, h.value, n, curve)
+
+    def fixed_base(self, scalars=None, seed=0, n=None, curve=_lib.CURVE_ED25519):
+        """``g_i = r_i * B`` on the device: explicit scalars (ints or packed bytes) or ``synth(seed, i)``."""
+        if scalars is not None:
+            raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars)
+            nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
+            n = nbytes // 32
+            p, keep = _buf(raw)
+        else:
+            p, keep = ctypes.c_void_p(0), None
+        h = ctypes.c_uint64()
+        check(self.lib.vmsm_points_fixed_base(self.h, curve, p, seed, n, ctypes.byref(h)))
+        return DevicePoints(self, h.value, n, curve)
+
+    # -- scalars
+    def upload_scalars(self, scalars):
+        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars)
+        nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
+        n = nbytes // 32
+        p, keep = _buf(raw)
+        h = ctypes.c_uint64()
+        check(self.lib.vmsm_scalars_upload(self.h, p, n, ctypes.byref(h)))
+        return DeviceScalars(self, h.value, n)
+
+    def synth_scalars(self, seed, n, curve=_lib.CURVE_ED25519):
+        h = ctypes.c_uint64()
+        check(self.lib.vmsm_scalars_synth(self.h, curve, seed, n, ctypes.byref(h)))
+        return DeviceScalars(self, h.value, n)
+
+    # -- MSM
+    def msm(self, points, scalars, off=0, n=None):
+        """End to end: host scalars (ints / packed bytes / numpy uint8) -> canonical affine (x, y)."""
+        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars)
+        nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
+        if n is None:
+            n = nbytes // 32
+        p, keep = _buf(raw)
+        out = ctypes.create_string_buffer(64)
+        check(self.lib.vmsm_msm(self.h, points.handle, off, n, p, out))
+        return unpack_points(out.raw)[0]
+
+    def msm_raw(self, points, ptr, off, n, out):
+        """Zero-marshalling variant for benchmarks: ``ptr`` is a c_void_p to n*32 bytes, ``out`` a 64-byte buffer."""
+        check(self.lib.vmsm_msm(self.h, points.handle, off, n, ptr, out))
+
+    def msm_dev(self, points, scalars, slot=0, poff=0, soff=0, n=None):
+        """Device-resident, asynchronous; fetch with ``result(slot)``."""
+        if n is None:
+            n = min(points.n - poff, scalars.n - soff)
+        check(self.lib.vmsm_msm_dev(self.h, points.handle, poff, n, scalars.handle, soff, slot))
+
+    def result(self, slot=0):
+        out = ctypes.create_string_buffer(64)
+        check(self.lib.vmsm_result_affine(self.h, slot, out))
+        return unpack_points(out.raw)[0]
+
+    def result_extended(self, slot=0):
+        out = ctypes.create_string_buffer(128)
+        check(self.lib.vmsm_result_extended(self.h, slot, out))
+        return tuple(int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(4))
+
+    def lincomb(self, pts, scalars, curve=_lib.CURVE_ED25519):
+        """sum_i s_i * P_i for a handful (<= 64) of host points; returns canonical affine (x, y)."""
+        n = len(pts)
+        out = ctypes.create_string_buffer(64)
+        check(self.lib.vmsm_lincomb(self.h, curve, pack_points(pts), pack_scalars(scalars), n, out))
+        return unpack_points(out.raw)[0]
+
+    def selftest_fe(self, op, a, b):
+        n = len(a)
+        A = b"".join(int(x).to_bytes(32, "little") for x in a)
+        Bb = b"".join(int(x).to_bytes(32, "little") for x in b)
+        out = ctypes.create_string_buffer(32 * n)
+        check(self.lib.vmsm_selftest_fe(self.h, op, A, Bb, n, out))
+        return [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(n)]
+
+    def imad_peak(self):
+        """Measured IMAD.WIDE.U32 peak of this device in tera limb-products per second."""
+        v = ctypes.c_double()
+        check(self.lib.vmsm_microbench_imad(self.h, ctypes.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            self.lib.vmsm_ctx_destroy(self.h)
+            self.h = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = None
+
+
+def default_context():
+    """Process-wide context on ``VMSM_DEVICE`` / ``LOCAL_RANK`` / device 0.  Raises VmsmError without a GPU."""
+    global _default
+    if _default is None or not _default.h:
+        _default = Context()
+    return _default
