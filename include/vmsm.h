@@ -118,12 +118,13 @@ int32_t vmsm_host_alloc(uint64_t bytes, void **ptr);
 int32_t vmsm_host_free(void *ptr);
 
 /* ---- device self-test of the field arithmetic: out[i] = a[i] (op) b[i] on the GPU, n elements of 32 B.
- * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 canon(a), 5 sqr(a).  Used by tests/ to pin the PTX carry chains. */
+ * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 canon(a), 5 sqr(a), 6 (a+b)(a+2b), 7 (a-b)*2(a+b), 8 (a+b)^2, 9 (2a+b)-3b,
+ * 10 -a; results are canonical.  Used by tests/ to pin the device field arithmetic (PTX carry chains). */
 int32_t vmsm_selftest_fe(uint64_t ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint64_t n, uint8_t *out);
 
-/* ---- integer-pipe peak: independent IMAD.WIDE.U32 chains on every SM, timed with CUDA events on the context's
- * stream.  Returns tera limb-products (32x32->64 multiply-accumulates) per second: the roofline denominator that
- * bench.py reports next to the achieved figure (SURVEY.md 8d asks for it to be measured on the box). */
+/* ---- integer-pipe peak: independent IMAD.WIDE.U32 multiply-accumulate chains (64-bit register addend) on every SM,
+ * timed with CUDA events on the context's stream.  Returns tera limb-products (32x32+64->64) per second: the
+ * roofline denominator bench.py reports next to the achieved figure ("measure on the box"). */
 int32_t vmsm_microbench_imad(uint64_t ctx, double *tera_lp_per_s);
 
 #ifdef __cplusplus

@@ -16,7 +16,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 2 --warmup 3 --no-check --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 tail -3 gpurun_out/launches.csv
 echo "== ncu full accumulate"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:KAccumulate -s 2 -c 2 -o gpurun_out/prof_acc -f \
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:KAccumulate -s 2 -c 2 -o gpurun_out/prof_acc -f \
     python bench.py --steps 2 --warmup 3 --no-check --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out

@@ -10,16 +10,17 @@ using namespace vmsm;
 
 #define ITERS 4096
 
-// 1) independent IMAD.WIDE.U32 chains (no carry): 8 accumulators per thread
-__global__ void k_imad_wide(uint64_t *out, uint32_t a, uint32_t b, long long *cycles) {
+// 1) IMAD.WIDE.U32 Rd = Ra * Rb + RZ (multiply only): 8 chains per thread, the multiplicand is the low word of the
+//    chain's previous product so nothing is loop invariant.
+__global__ void k_imad_wide_rz(uint64_t *out, uint32_t a, uint32_t b, long long *cycles) {
     uint64_t acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
-    uint32_t x = a + threadIdx.x, y = b;
+    for (int i = 0; i < 8; i++) acc[i] = a + threadIdx.x + i;
+    uint32_t y = b | 1u;
     long long t0 = clock64();
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(x), "r"(y));
+        for (int i = 0; i < 8; i++) acc[i] = (uint64_t)((uint32_t)acc[i] + (uint32_t)(acc[i] >> 32)) * y;
     }
     long long t1 = clock64();
     uint64_t s = 0;
@@ -29,16 +30,35 @@ __global__ void k_imad_wide(uint64_t *out, uint32_t a, uint32_t b, long long *cy
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
-// 2) 32-bit IMAD (mad.lo): 8 accumulators
-__global__ void k_imad_lo(uint32_t *out, uint32_t a, uint32_t b, long long *cycles) {
-    uint32_t acc[8];
+// 2) IMAD.WIDE.U32 Rd = Ra * Rb + Rc64 (multiply-accumulate with a 64-bit register addend, no carry out)
+__global__ void k_imad_wide_acc(uint64_t *out, uint32_t a, uint32_t b, long long *cycles) {
+    uint64_t acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
-    uint32_t x = a + threadIdx.x, y = b;
+    for (int i = 0; i < 8; i++) acc[i] = a + threadIdx.x + i;
+    uint32_t y = b | 1u;
     long long t0 = clock64();
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x), "r"(y));
+        for (int i = 0; i < 8; i++) acc[i] = (uint64_t)((uint32_t)acc[(i + 1) & 7]) * y + acc[i];
+    }
+    long long t1 = clock64();
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// 3) 32-bit IMAD Rd = Ra * Rb + Rc
+__global__ void k_imad_lo(uint32_t *out, uint32_t a, uint32_t b, long long *cycles) {
+    uint32_t acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = a + threadIdx.x + i;
+    uint32_t y = b | 1u;
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = acc[(i + 1) & 7] * y + acc[i];
     }
     long long t1 = clock64();
     uint32_t s = 0;
@@ -48,19 +68,18 @@ __global__ void k_imad_lo(uint32_t *out, uint32_t a, uint32_t b, long long *cycl
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
-// 3) mad.hi.u32
-__global__ void k_imad_hi(uint32_t *out, uint32_t a, uint32_t b, long long *cycles) {
-    uint32_t acc[8];
+// 3b) 64-bit add pairs (IADD3 + IADD3.X) on the ALU pipe
+__global__ void k_iadd64(uint64_t *out, uint32_t a, uint32_t b, long long *cycles) {
+    uint64_t acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
-    uint32_t x = a + threadIdx.x, y = b;
+    for (int i = 0; i < 8; i++) acc[i] = a + threadIdx.x + i;
     long long t0 = clock64();
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x), "r"(y));
+        for (int i = 0; i < 8; i++) acc[i] += acc[(i + 1) & 7] ^ b;
     }
     long long t1 = clock64();
-    uint32_t s = 0;
+    uint64_t s = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) s ^= acc[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
@@ -101,6 +120,21 @@ __global__ void k_fe_mul(fe *out, const fe *in, int iters, long long *cycles) {
     for (int it = 0; it < iters; it++) {
         c = fe_mul(c, a);
         d = fe_mul(d, b);
+    }
+    long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = fe_add(c, d);
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// 5b) dependent squarings
+__global__ void k_fe_sqr(fe *out, const fe *in, int iters, long long *cycles) {
+    fe c = in[0], d = in[1];
+    c.v[0] += threadIdx.x;
+    d.v[1] += blockIdx.x;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        c = fe_sqr(c);
+        d = fe_sqr(d);
     }
     long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = fe_add(c, d);
@@ -191,16 +225,18 @@ int main() {
 
     for (int bps = 1; bps <= 2; bps++) {
         int blocks = 148 * bps, threads = 512;
-        run("imad_wide_u32", blocks, threads, 8.0 * ITERS, 1.0, cyc, [&] { k_imad_wide<<<blocks, threads>>>((uint64_t *)out, 12345, 6789, cyc); });
+        run("imad_wide_rz_multiply_only", blocks, threads, 8.0 * ITERS, 1.0, cyc, [&] { k_imad_wide_rz<<<blocks, threads>>>((uint64_t *)out, 12345, 6789, cyc); });
+        run("imad_wide_acc64_fused", blocks, threads, 8.0 * ITERS, 1.0, cyc, [&] { k_imad_wide_acc<<<blocks, threads>>>((uint64_t *)out, 12345, 6789, cyc); });
         run("imad_lo_u32", blocks, threads, 8.0 * ITERS, 0.5, cyc, [&] { k_imad_lo<<<blocks, threads>>>((uint32_t *)out, 12345, 6789, cyc); });
-        run("imad_hi_u32", blocks, threads, 8.0 * ITERS, 0.5, cyc, [&] { k_imad_hi<<<blocks, threads>>>((uint32_t *)out, 12345, 6789, cyc); });
+        run("iadd64_pairs", blocks, threads, 8.0 * ITERS, 0.0, cyc, [&] { k_iadd64<<<blocks, threads>>>((uint64_t *)out, 12345, 6789, cyc); });
         run("imad_wide_carry_chain", blocks, threads, 8.0 * ITERS, 1.0, cyc, [&] { k_imad_wide_cc<<<blocks, threads>>>((uint32_t *)out, 12345, 6789, cyc); });
     }
     const int it = 512;
     for (int threads = 128; threads <= 512; threads *= 2) {
         int blocks = 148 * (512 / threads) ;
         run("fe_mul", blocks, threads, 2.0 * it, 72.0, cyc, [&] { k_fe_mul<<<blocks, threads>>>((fe *)out, din, it, cyc); });
-        run("ge_madd", blocks, threads, 1.0 * it, 504.0, cyc, [&] { k_madd<<<blocks, threads>>>((ge_ext *)out, din, it, cyc); });
+        run("fe_sqr", blocks, threads, 2.0 * it, 44.0, cyc, [&] { k_fe_sqr<<<blocks, threads>>>((fe *)out, din, it, cyc); });
+        if (threads <= 256) run("ge_madd", blocks, threads, 1.0 * it, 504.0, cyc, [&] { k_madd<<<blocks, threads>>>((ge_ext *)out, din, it, cyc); });
         run("ge_dbl", blocks, threads, 1.0 * it, 464.0, cyc, [&] { k_dbl<<<blocks, threads>>>((ge_ext *)out, din, it, cyc); });
     }
     {

@@ -390,7 +390,7 @@ struct KSynthScalars {
     }
 };
 
-// device self-test of fe25519.cuh (vmsm_selftest_fe)
+// device self-test of fe25519.cuh (vmsm_selftest_fe): results are canonicalised
 struct KSelfTestFe {
     enum { kBlock = 128 };
     const fe *a;
@@ -404,10 +404,15 @@ struct KSelfTestFe {
             case 1: r = fe_sub(x, y); break;
             case 2: r = fe_mul(x, y); break;
             case 3: r = fe_inv(x); break;
-            case 4: r = fe_canon(x); break;
-            default: r = fe_sqr(x); break;
+            case 4: r = x; break;  // canon(a)
+            case 5: r = fe_sqr(x); break;
+            case 6: r = fe_mul(fe_add(x, y), fe_add(fe_add(x, y), y)); break;
+            case 7: r = fe_mul(fe_sub(x, y), fe_dbl(fe_add(x, y))); break;
+            case 8: r = fe_sqr(fe_add(x, y)); break;
+            case 9: r = fe_sub(fe_add(fe_add(x, y), x), fe_add(fe_add(y, y), y)); break;
+            default: r = fe_neg(x); break;
         }
-        st_fe(out + tid, r);
+        st_fe(out + tid, fe_canon(r));
     }
 };
 

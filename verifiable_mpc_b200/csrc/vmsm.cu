@@ -38,26 +38,17 @@ __global__ void __launch_bounds__(F::kBlock) vmsm_kernel(const F f, uint32_t n) 
     if (tid < n) f(tid);
 }
 
-// Exclusive scan of the bucket populations of one window per block; offsets are absolute positions in idx.
-__global__ void __launch_bounds__(1024) vmsm_scan_offsets(const uint32_t *__restrict__ counts,
-                                                          uint32_t *__restrict__ offsets,
-                                                          uint32_t *__restrict__ cursor, MsmGeom g) {
-    __shared__ uint32_t warp_sums[32];
-    const uint32_t w = blockIdx.x, t = threadIdx.x;
-    const uint32_t *cw = counts + (size_t)w * g.NB;
-    uint32_t ipt = (g.NB + 1023u) / 1024u;
-    uint32_t lo = t * ipt, hi = lo + ipt;
-    if (lo > g.NB) lo = g.NB;
-    if (hi > g.NB) hi = g.NB;
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += cw[i];
-    // block-wide exclusive scan of `sum`
-    uint32_t incl = sum;
-    const uint32_t lane = t & 31, wid = t >> 5;
+// Exclusive scan of the bucket populations, one block per (window, tile of 1024 buckets).  Each block first sums
+// the tiles before it in the same window (coalesced re-read of at most NB counters from L2), then scans its own
+// tile: one launch, W * NB / 1024 blocks, no inter-block dependency.  Offsets are absolute positions in idx.
+#define SCAN_TILE 1024
+__device__ __forceinline__ uint32_t block_scan_1024(uint32_t v, uint32_t *warp_sums, uint32_t *total) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += v;
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
     }
     if (lane == 31) warp_sums[wid] = incl;
     __syncthreads();
@@ -65,18 +56,36 @@ __global__ void __launch_bounds__(1024) vmsm_scan_offsets(const uint32_t *__rest
         uint32_t ws = warp_sums[lane], wi = ws;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= (uint32_t)d) wi += v;
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (uint32_t)d) wi += t;
         }
         warp_sums[lane] = wi - ws;
+        if (lane == 31) *total = wi;
     }
     __syncthreads();
-    uint32_t run = w * g.n + warp_sums[wid] + (incl - sum);
-    for (uint32_t i = lo; i < hi; i++) {
-        uint32_t cnt = cw[i];
-        offsets[(size_t)w * g.NB + i] = run;
-        cursor[(size_t)w * g.NB + i] = run;
-        run += cnt;
+    return warp_sums[wid] + incl - v;  // exclusive prefix of v within the block
+}
+
+__global__ void __launch_bounds__(SCAN_TILE) vmsm_scan_offsets(const uint32_t *__restrict__ counts,
+                                                               uint32_t *__restrict__ offsets,
+                                                               uint32_t *__restrict__ cursor, MsmGeom g,
+                                                               uint32_t tiles_per_window) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total;
+    const uint32_t w = blockIdx.x / tiles_per_window, tile = blockIdx.x - w * tiles_per_window, t = threadIdx.x;
+    const uint32_t *cw = counts + (size_t)w * g.NB;
+    uint32_t before = 0;
+    for (uint32_t i = t; i < tile * SCAN_TILE; i += SCAN_TILE) before += cw[i];
+    block_scan_1024(before, warp_sums, &total);
+    uint32_t prefix = total;
+    __syncthreads();
+    uint32_t i = tile * SCAN_TILE + t;
+    uint32_t cnt = i < g.NB ? cw[i] : 0u;
+    uint32_t excl = block_scan_1024(cnt, warp_sums, &total);
+    if (i < g.NB) {
+        uint32_t off = w * g.n + prefix + excl;
+        offsets[(size_t)w * g.NB + i] = off;
+        cursor[(size_t)w * g.NB + i] = off;
     }
 }
 
@@ -145,16 +154,19 @@ __global__ void __launch_bounds__(256) vmsm_order_scatter(const uint32_t *__rest
     }
 }
 
-// Independent IMAD.WIDE.U32 chains (8 accumulators per thread): the integer-pipe peak the roofline is quoted against.
+// Integer-pipe peak for limb products: 8 independent 32x32+64 multiply-accumulate chains per thread, each compiled
+// to IMAD.WIDE.U32 Rd, Ra, Rb, Rc with a 64-bit register addend (the multiplicand comes from a neighbouring chain so
+// nothing is loop invariant).  This is the instruction form a multi-precision MAC needs; the multiply-only form
+// (addend RZ) issues twice as fast but cannot accumulate -- see tools/microbench.cu and profiles/.
 #define MB_ITERS 2048
 __global__ void __launch_bounds__(512) vmsm_imad_peak(uint64_t *out, uint32_t a, uint32_t b) {
     uint64_t acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
-    uint32_t x = a + threadIdx.x, y = b;
+    for (int i = 0; i < 8; i++) acc[i] = a + threadIdx.x + i;
+    uint32_t y = b | 1u;
     for (int it = 0; it < MB_ITERS; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(x), "r"(y));
+        for (int i = 0; i < 8; i++) acc[i] = (uint64_t)((uint32_t)acc[(i + 1) & 7]) * y + acc[i];
     }
     uint64_t s = 0;
 #pragma unroll
@@ -250,7 +262,8 @@ struct CudaBE {
         note(cudaGetLastError());
     }
     void scan_offsets(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g) {
-        vmsm_scan_offsets<<<g.W, 1024, 0, c->stream>>>(counts, offsets, cursor, g);
+        uint32_t tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
+        vmsm_scan_offsets<<<g.W * tiles, SCAN_TILE, 0, c->stream>>>(counts, offsets, cursor, g, tiles);
         c->launches++;
         note(cudaGetLastError());
     }
