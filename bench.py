@@ -293,7 +293,7 @@ def run_gpu(args, rank, world, dist):
                 "d2h_bytes_per_step": 64 + (128 * world if world > 1 else 0), "ms_per_step": 1e3 * e2e_s / args.steps},
         "roofline": {"bound": "imad", "kernel": "vmsm_kernel<KAccumulate>", "achieved": achieved, "peak": peak_tlps,
                      "unit": "T limb-products/s", "frac": (achieved / peak_tlps) if achieved else None, "traffic": None,
-                     "peak_source": "measured live: vmsm_microbench_imad (independent IMAD.WIDE.U32 multiply-accumulate chains with 64-bit addend, all SMs)",
+                     "peak_source": "measured live: vmsm_microbench_imad (independent carry-chained IMAD.WIDE.U32 multiply-accumulate chains, all SMs; every IMAD.WIDE form is half-rate on B200)",
                      "kernel_ms": acc_ms, "algorithmic_lp_per_launch": acc_lp,
                      "whole_msm_frac": msm_frac, "whole_msm_lp_per_point": lp_per_point(n),
                      "phase_ms": {k: v / max(calls, 1) for k, v in phases.items()}},

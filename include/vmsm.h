@@ -45,6 +45,7 @@ extern "C" {
 #define VMSM_OPT_SORT_BUCKETS 3 /* 1 = process buckets in order of decreasing population (default 1) */
 #define VMSM_OPT_CHECK_POINTS 4 /* 1 = validate uploaded points (default 1) */
 #define VMSM_OPT_REDUCE_RADIX 5 /* log2 of the bucket-tree radix (default 3) */
+#define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */
 #define VMSM_PHASE_DIGITS 0
@@ -122,7 +123,7 @@ int32_t vmsm_host_free(void *ptr);
  * 10 -a; results are canonical.  Used by tests/ to pin the device field arithmetic (PTX carry chains). */
 int32_t vmsm_selftest_fe(uint64_t ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint64_t n, uint8_t *out);
 
-/* ---- integer-pipe peak: independent IMAD.WIDE.U32 multiply-accumulate chains (64-bit register addend) on every SM,
+/* ---- integer-pipe peak: independent carry-chained IMAD.WIDE.U32 multiply-accumulate chains on every SM,
  * timed with CUDA events on the context's stream.  Returns tera limb-products (32x32+64->64) per second: the
  * roofline denominator bench.py reports next to the achieved figure ("measure on the box"). */
 int32_t vmsm_microbench_imad(uint64_t ctx, double *tera_lp_per_s);

@@ -15,6 +15,7 @@
 //   KFinal       Horner over windows, one inversion, canonical affine out
 #pragma once
 #include "ed25519.cuh"
+#include "ed25519_quad.cuh"
 
 namespace vmsm {
 
@@ -249,7 +250,7 @@ struct KAccumulate {
 // Leaves are the buckets themselves (s = 1, T = 0, inT == null).  Merging children i = 0..m-1 of size s:
 //   S' = sum S_i           T' = sum T_i + s * sum i S_i
 struct KReduce {
-    enum { kBlock = 128 };
+    enum { kBlock = 128, kMinBlocks = 4 };
     const ge_ext *inS;
     const ge_ext *inT;  // null at the leaf level
     ge_ext *outS;
@@ -296,6 +297,78 @@ struct KFinal {
         }
         st_ext(out_ext, acc);
         st_aff(out_aff, ge_ext_to_aff(acc));
+    }
+};
+
+// Quad-cooperative twin of KReduce for the upper (latency-bound) levels of the bucket tree: 4 lanes per output node
+// (ed25519_quad.cuh).  `nodes` output nodes, launched with 4 * nodes threads rounded up to a warp; the children count
+// m = min(R, cnt_in) is uniform over the launch (all sizes are powers of two), so every shuffle is warp-uniform.
+struct KReduceQ {
+    enum { kBlock = 128 };
+    const ge_ext *inS;
+    const ge_ext *inT;  // null at the leaf level
+    ge_ext *outS;
+    ge_ext *outT;
+    uint32_t cnt_in, cnt_out, R, log2s;
+    uint32_t nodes;  // W * cnt_out
+    VMSM_HD void operator()(uint32_t tid) const {
+#if defined(__CUDA_ARCH__)
+        const int q = tid & 3;
+        uint32_t node = tid >> 2;
+        const bool live = node < nodes;
+        if (!live) node = nodes - 1;
+        uint32_t w = node / cnt_out, j = node - w * cnt_out;
+        const uint32_t m = cnt_in < R ? cnt_in : R;
+        const ge_ext *s = inS + (size_t)w * cnt_in + (size_t)j * m;
+        fe acc = quad_identity(q), run = quad_identity(q);
+        for (uint32_t i = m - 1; i >= 1; i--) {
+            acc = quad_add(q, acc, quad_load(s + i, q));
+            run = quad_add(q, run, acc);
+        }
+        acc = quad_add(q, acc, quad_load(s, q));
+        for (uint32_t k = 0; k < log2s; k++) run = quad_dbl(q, run);
+        if (inT) {
+            const ge_ext *t = inT + (size_t)w * cnt_in + (size_t)j * m;
+            for (uint32_t i = 0; i < m; i++) run = quad_add(q, run, quad_load(t + i, q));
+        }
+        if (live) {
+            quad_store(outS + (size_t)w * cnt_out + j, q, acc);
+            quad_store(outT + (size_t)w * cnt_out + j, q, run);
+        }
+#else
+        if ((tid & 3) || (tid >> 2) >= nodes) return;
+        KReduce k = {inS, inT, outS, outT, cnt_in, cnt_out, R, log2s};
+        k(tid >> 2);
+#endif
+    }
+};
+
+// Quad-cooperative twin of KFinal (one warp; every quad computes the same thing, quad 0 stores).
+struct KFinalQ {
+    enum { kBlock = 32 };
+    const ge_ext *S;
+    const ge_ext *T;
+    ge_ext *out_ext;
+    ge_aff *out_aff;
+    uint32_t W, c;
+    VMSM_HD void operator()(uint32_t tid) const {
+#if defined(__CUDA_ARCH__)
+        const int q = tid & 3;
+        fe acc = quad_identity(q);
+        for (int32_t w = (int32_t)W - 1; w >= 0; w--) {
+            if (w != (int32_t)W - 1)
+                for (uint32_t k = 0; k < c; k++) acc = quad_dbl(q, acc);
+            acc = quad_add(q, acc, quad_add(q, quad_load(S + w, q), quad_load(T + w, q)));
+        }
+        fe zi = fe_inv(quad_get(acc, 2));
+        fe aff = fe_canon(fe_mul(acc, zi));  // lane 0: x, lane 1: y
+        if (tid < 4) quad_store(out_ext, q, acc);
+        if (tid < 2) st_fe(q == 0 ? &out_aff->x : &out_aff->y, aff);
+#else
+        if (tid) return;
+        KFinal k = {S, T, out_ext, out_aff, W, c};
+        k(0);
+#endif
     }
 };
 

@@ -21,6 +21,7 @@ struct MsmOptions {
     uint32_t window_bits = 0;  // 0 = auto
     uint32_t reduce_log2r = 3;
     bool sort_buckets = true;
+    uint32_t quad_threshold = 16384;  // tree levels with at most this many output nodes run quad-cooperative; 0 = never
 };
 
 struct Workspace {
@@ -140,8 +141,14 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     int pp = 0;
     do {
         uint32_t cnt_out = (cnt + R - 1) / R;
-        KReduce k6 = {inS, inT, ws.nodeS[pp], ws.nodeT[pp], cnt, cnt_out, R, log2s};
-        be.launch(k6, g.W * cnt_out);
+        uint32_t nodes = g.W * cnt_out;
+        if (nodes <= opt.quad_threshold) {
+            KReduceQ k6 = {inS, inT, ws.nodeS[pp], ws.nodeT[pp], cnt, cnt_out, R, log2s, nodes};
+            be.launch(k6, (4 * nodes + 31) & ~31u);
+        } else {
+            KReduce k6 = {inS, inT, ws.nodeS[pp], ws.nodeT[pp], cnt, cnt_out, R, log2s};
+            be.launch(k6, nodes);
+        }
         inS = ws.nodeS[pp];
         inT = ws.nodeT[pp];
         pp ^= 1;
@@ -150,8 +157,13 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
     {
-        KFinal k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
-        be.launch(k7, 1);
+        if (opt.quad_threshold) {
+            KFinalQ k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
+            be.launch(k7, 32);
+        } else {
+            KFinal k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
+            be.launch(k7, 1);
+        }
     }
     be.phase_mark(PH_FINAL);
     be.phase_end();

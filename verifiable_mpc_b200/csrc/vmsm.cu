@@ -33,7 +33,16 @@ static int32_t fail(int32_t code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------------------------------------ kernels
 template <class F>
-__global__ void __launch_bounds__(F::kBlock) vmsm_kernel(const F f, uint32_t n) {
+struct min_blocks {
+    template <class G>
+    static constexpr int get(decltype(G::kMinBlocks) *) { return G::kMinBlocks; }
+    template <class G>
+    static constexpr int get(...) { return 1; }
+    static constexpr int value = get<F>(nullptr);
+};
+
+template <class F>
+__global__ void __launch_bounds__(F::kBlock, min_blocks<F>::value) vmsm_kernel(const F f, uint32_t n) {
     uint32_t tid = blockIdx.x * (uint32_t)F::kBlock + threadIdx.x;
     if (tid < n) f(tid);
 }
@@ -154,23 +163,28 @@ __global__ void __launch_bounds__(256) vmsm_order_scatter(const uint32_t *__rest
     }
 }
 
-// Integer-pipe peak for limb products: 8 independent 32x32+64 multiply-accumulate chains per thread, each compiled
-// to IMAD.WIDE.U32 Rd, Ra, Rb, Rc with a 64-bit register addend (the multiplicand comes from a neighbouring chain so
-// nothing is loop invariant).  This is the instruction form a multi-precision MAC needs; the multiply-only form
-// (addend RZ) issues twice as fast but cannot accumulate -- see tools/microbench.cu and profiles/.
+// Integer-pipe peak for limb products: carry-chained 32x32+64 multiply-accumulates exactly as a multi-precision
+// multiplication issues them (IMAD.WIDE.U32 / IMAD.WIDE.U32.X with predicate carry), two independent chains of four
+// per thread and iteration.  Every IMAD.WIDE form measured on B200 issues at 32 lanes/clk/SM, half the 32-bit IMAD
+// rate (tools/microbench.cu, profiles/r01/s3_microbench_valid.jsonl); this form reaches that limit.
 #define MB_ITERS 2048
-__global__ void __launch_bounds__(512) vmsm_imad_peak(uint64_t *out, uint32_t a, uint32_t b) {
-    uint64_t acc[8];
+__global__ void __launch_bounds__(512) vmsm_imad_peak(uint32_t *out, uint32_t a, uint32_t b) {
+    uint32_t r[2][9];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = a + threadIdx.x + i;
-    uint32_t y = b | 1u;
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < 9; i++) r[k][i] = threadIdx.x + i + k;
+    uint32_t x0 = a + threadIdx.x, x1 = x0 * 3, x2 = x0 * 5, x3 = x0 * 7, y = b;
     for (int it = 0; it < MB_ITERS; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = (uint64_t)((uint32_t)acc[(i + 1) & 7]) * y + acc[i];
+        for (int k = 0; k < 2; k++)
+            fe_mad4(r[k][0], r[k][1], r[k][2], r[k][3], r[k][4], r[k][5], r[k][6], r[k][7], r[k][8], x0, x1, x2, x3, y);
     }
-    uint64_t s = 0;
+    uint32_t s = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) s ^= acc[i];
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < 9; i++) s ^= r[k][i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -443,6 +457,10 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
         case VMSM_OPT_REDUCE_RADIX:
             if (value < 1 || value > 6) return fail(VMSM_ERR_INVALID, "reduce radix log2 must be in [1, 6]");
             c->opt.reduce_log2r = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_QUAD_THRESHOLD:
+            if (value < 0 || value > (1 << 24)) return fail(VMSM_ERR_INVALID, "quad threshold out of range");
+            c->opt.quad_threshold = (uint32_t)value;
             return VMSM_OK;
     }
     return fail(VMSM_ERR_INVALID, "unknown option %d", key);
@@ -795,8 +813,8 @@ int32_t vmsm_microbench_imad(uint64_t ctx, double *tera_lp_per_s) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, c->device));
     int blocks = prop.multiProcessorCount * 4, threads = 512;
-    uint64_t *out = nullptr;
-    CU(cudaMalloc(&out, (size_t)blocks * threads * 8));
+    uint32_t *out = nullptr;
+    CU(cudaMalloc(&out, (size_t)blocks * threads * 4));
     float best = 1e30f;
     for (int rep = 0; rep < 6; rep++) {
         cudaEventRecord(c->t0, c->stream);
