@@ -36,6 +36,9 @@ struct HostBE {
         std::stable_sort(order, order + nb, [&](uint32_t a, uint32_t b) { return counts[a] > counts[b]; });
         return true;
     }
+    void head_wait_tail(int) {}
+    void tail_begin() {}
+    void tail_end(int) {}
     void phase_begin() {}
     void phase_mark(int) {}
     void phase_end() {}

@@ -307,7 +307,120 @@ VMSM_HD fe fe_mul(const fe &a, const fe &b) {
     return fe_reduce512(t);
 }
 
-VMSM_HD fe fe_sqr(const fe &a) { return fe_mul(a, a); }
+#if defined(__CUDACC__)
+// shorter carry chains for the off-diagonal rows of a squaring (same layout as fe_mad4)
+VMSM_D void fe_mad3(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t &r4, uint32_t &r5, uint32_t &r6,
+                    uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+}
+VMSM_D void fe_mad2(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t &r4, uint32_t a0, uint32_t a1,
+                    uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4)
+        : "r"(a0), "r"(a1), "r"(b));
+}
+VMSM_D void fe_mad1(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t a0, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2)
+        : "r"(a0), "r"(b));
+}
+#endif
+
+// Squaring: 28 off-diagonal products (even/odd column accumulators as in fe_mul), doubled with funnel shifts, plus
+// one 8-product carry chain for the diagonal: 36 + 8 + 1 wide MADs instead of 64 + 8 + 1.
+VMSM_HD fe fe_sqr(const fe &a) {
+#if defined(__CUDA_ARCH__)
+    uint32_t e[17], o[17], t[16];
+#pragma unroll
+    for (int i = 0; i < 17; i++) e[i] = o[i] = 0;
+    // multiplier a0: even a2,a4,a6 -> limbs 2..7 ; odd a1,a3,a5,a7 -> limbs 1..8 (o index 0..7)
+    fe_mad3(e[2], e[3], e[4], e[5], e[6], e[7], e[8], a.v[2], a.v[4], a.v[6], a.v[0]);
+    fe_mad4(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], a.v[1], a.v[3], a.v[5], a.v[7], a.v[0]);
+    // a1: even a3,a5,a7 -> limbs 4..9 ; odd a2,a4,a6 -> limbs 3..8 (o 2..7)
+    fe_mad3(e[4], e[5], e[6], e[7], e[8], e[9], e[10], a.v[3], a.v[5], a.v[7], a.v[1]);
+    fe_mad3(o[2], o[3], o[4], o[5], o[6], o[7], o[8], a.v[2], a.v[4], a.v[6], a.v[1]);
+    // a2: even a4,a6 -> limbs 6..9 ; odd a3,a5,a7 -> limbs 5..10 (o 4..9)
+    fe_mad2(e[6], e[7], e[8], e[9], e[10], a.v[4], a.v[6], a.v[2]);
+    fe_mad3(o[4], o[5], o[6], o[7], o[8], o[9], o[10], a.v[3], a.v[5], a.v[7], a.v[2]);
+    // a3: even a5,a7 -> limbs 8..11 ; odd a4,a6 -> limbs 7..10 (o 6..9)
+    fe_mad2(e[8], e[9], e[10], e[11], e[12], a.v[5], a.v[7], a.v[3]);
+    fe_mad2(o[6], o[7], o[8], o[9], o[10], a.v[4], a.v[6], a.v[3]);
+    // a4: even a6 -> limbs 10,11 ; odd a5,a7 -> limbs 9..12 (o 8..11)
+    fe_mad1(e[10], e[11], e[12], a.v[6], a.v[4]);
+    fe_mad2(o[8], o[9], o[10], o[11], o[12], a.v[5], a.v[7], a.v[4]);
+    // a5: even a7 -> limbs 12,13 ; odd a6 -> limbs 11,12 (o 10,11)
+    fe_mad1(e[12], e[13], e[14], a.v[7], a.v[5]);
+    fe_mad1(o[10], o[11], o[12], a.v[6], a.v[5]);
+    // a6: odd a7 -> limbs 13,14 (o 12,13)
+    fe_mad1(o[12], o[13], o[14], a.v[7], a.v[6]);
+    // u = e + (o << 32)
+    uint32_t u[16];
+    u[0] = e[0];
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;"
+        : "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]),
+          "r"(e[10]), "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+          "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]),
+          "r"(o[12]), "r"(o[13]), "r"(o[14]));
+    // t = 2u (u < 2^511, so nothing is shifted out)
+    t[0] = u[0] << 1;
+#pragma unroll
+    for (int i = 1; i < 16; i++) t[i] = __funnelshift_l(u[i - 1], u[i], 1);
+    // t += sum a_i^2 * 2^(64 i): one carry chain over all 16 limbs
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]),
+          "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+    return fe_reduce512(t);
+#else
+    return fe_mul(a, a);
+#endif
+}
+
 
 // a * small constant (< 2^32)
 VMSM_HD fe fe_mul_small(const fe &a, uint32_t k) {

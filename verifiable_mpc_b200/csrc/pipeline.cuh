@@ -28,7 +28,9 @@ struct Workspace {
     uint32_t *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *order = nullptr;  // W*NB each
     uint32_t *idx = nullptr;                                                              // W*n
     ge_ext *buckets = nullptr;                                                            // W*NB
-    ge_ext *nodeS[2] = {nullptr, nullptr}, *nodeT[2] = {nullptr, nullptr};                // ping-pong tree levels
+    // bucket-tree levels: [parity of the MSM sequence number][ping-pong].  Two parities because the latency-bound tail
+    // of one MSM (upper tree levels + Horner) runs on a side stream underneath the head of the next MSM.
+    ge_ext *nodeS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *nodeT[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0;
 };
 
@@ -81,15 +83,16 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R) {
         ws.cap_idx = ni;
     }
     if (nn > ws.cap_nodes) {
-        for (int k = 0; k < 2; k++) {
-            be.free(ws.nodeS[k]), be.free(ws.nodeT[k]);
-            ws.nodeS[k] = (ge_ext *)be.alloc(nn * sizeof(ge_ext));
-            ws.nodeT[k] = (ge_ext *)be.alloc(nn * sizeof(ge_ext));
-            if (!ws.nodeS[k] || !ws.nodeT[k]) {
-                ws.cap_nodes = 0;
-                return -1;
+        for (int par = 0; par < 2; par++)
+            for (int k = 0; k < 2; k++) {
+                be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
+                ws.nodeS[par][k] = (ge_ext *)be.alloc(nn * sizeof(ge_ext));
+                ws.nodeT[par][k] = (ge_ext *)be.alloc(nn * sizeof(ge_ext));
+                if (!ws.nodeS[par][k] || !ws.nodeT[par][k]) {
+                    ws.cap_nodes = 0;
+                    return -1;
+                }
             }
-        }
         ws.cap_nodes = nn;
     }
     return 0;
@@ -99,14 +102,15 @@ template <class BE>
 void ws_release(BE &be, Workspace &ws) {
     be.free(ws.counts), be.free(ws.offsets), be.free(ws.cursor), be.free(ws.order), be.free(ws.buckets);
     be.free(ws.idx);
-    for (int k = 0; k < 2; k++) be.free(ws.nodeS[k]), be.free(ws.nodeT[k]);
+    for (int par = 0; par < 2; par++)
+        for (int k = 0; k < 2; k++) be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
     ws = Workspace();
 }
 
 // out = sum_i scalars[i] * bases[i].  All pointers are backend ("device") memory.  Returns 0 or -1 (allocation).
 template <class BE>
 int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, const ge_niels *bases,
-            const uint32_t *scalars, uint32_t n, ge_ext *out_ext, ge_aff *out_aff) {
+            const uint32_t *scalars, uint32_t n, ge_ext *out_ext, ge_aff *out_aff, uint32_t seq = 0) {
     uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits);
     MsmGeom g = make_geom(n, c, scalar_bits);
     uint32_t R = 1u << opt.reduce_log2r;
@@ -135,22 +139,27 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         be.launch(k5, nbuckets);
     }
     be.phase_mark(PH_ACCUMULATE);
-    // bucket tree
+    // bucket tree: throughput-bound leaf level(s) on the main stream, then the latency-bound tail (quad-cooperative
+    // levels + Horner) which the CUDA backend runs on a side stream so that it overlaps the next MSM's head
+    const int par = (int)(seq & 1);
+    be.head_wait_tail(par);
     const ge_ext *inS = ws.buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;
+    bool in_tail = false;
     do {
         uint32_t cnt_out = (cnt + R - 1) / R;
         uint32_t nodes = g.W * cnt_out;
         if (nodes <= opt.quad_threshold) {
-            KReduceQ k6 = {inS, inT, ws.nodeS[pp], ws.nodeT[pp], cnt, cnt_out, R, log2s, nodes};
+            if (!in_tail) be.tail_begin(), in_tail = true;
+            KReduceQ k6 = {inS, inT, ws.nodeS[par][pp], ws.nodeT[par][pp], cnt, cnt_out, R, log2s, nodes};
             be.launch(k6, (4 * nodes + 31) & ~31u);
         } else {
-            KReduce k6 = {inS, inT, ws.nodeS[pp], ws.nodeT[pp], cnt, cnt_out, R, log2s};
+            KReduce k6 = {inS, inT, ws.nodeS[par][pp], ws.nodeT[par][pp], cnt, cnt_out, R, log2s};
             be.launch(k6, nodes);
         }
-        inS = ws.nodeS[pp];
-        inT = ws.nodeT[pp];
+        inS = ws.nodeS[par][pp];
+        inT = ws.nodeT[par][pp];
         pp ^= 1;
         cnt = cnt_out;
         log2s += opt.reduce_log2r;
@@ -158,6 +167,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_REDUCE);
     {
         if (opt.quad_threshold) {
+            if (!in_tail) be.tail_begin(), in_tail = true;
             KFinalQ k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
             be.launch(k7, 32);
         } else {
@@ -166,6 +176,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         }
     }
     be.phase_mark(PH_FINAL);
+    if (in_tail) be.tail_end(par);
     be.phase_end();
     return 0;
 }

@@ -209,7 +209,13 @@ constexpr uint32_t kSlots = 64;
 
 struct Ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;  // main stream: everything except MSM tails
+    cudaStream_t tail = nullptr;    // side stream: upper bucket-tree levels + Horner of the previous MSM(s)
+    cudaEvent_t ev_head = nullptr, ev_tail[2] = {nullptr, nullptr};
+    bool tail_pending[2] = {false, false};
+    int last_tail = -1;
+    bool async_tail = true;
+    uint32_t msm_seq = 0;
     MsmOptions opt;
     bool phase_timing = false;
     bool check_points = true;
@@ -251,6 +257,25 @@ Ctx *get_ctx(uint64_t h) {
 struct CudaBE {
     Ctx *c;
     cudaError_t err = cudaSuccess;
+    cudaStream_t cur = nullptr;  // stream the next launch goes to (main unless inside a tail)
+    explicit CudaBE(Ctx *ctx) : c(ctx), cur(ctx->stream) {}
+    // the node buffers of parity `par` may still be read by the tail of the MSM two calls ago
+    void head_wait_tail(int par) {
+        if (c->tail_pending[par]) note(cudaStreamWaitEvent(c->stream, c->ev_tail[par], 0));
+    }
+    void tail_begin() {
+        if (!c->async_tail) return;
+        note(cudaEventRecord(c->ev_head, c->stream));
+        note(cudaStreamWaitEvent(c->tail, c->ev_head, 0));
+        cur = c->tail;
+    }
+    void tail_end(int par) {
+        if (!c->async_tail) return;
+        note(cudaEventRecord(c->ev_tail[par], c->tail));
+        c->tail_pending[par] = true;
+        c->last_tail = par;
+        cur = c->stream;
+    }
     void note(cudaError_t e) {
         if (err == cudaSuccess && e != cudaSuccess) err = e;
     }
@@ -266,12 +291,12 @@ struct CudaBE {
     void free(void *p) {
         if (p) cudaFree(p);
     }
-    void zero(void *p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, c->stream)); }
+    void zero(void *p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, cur)); }
     template <class F>
     void launch(const F &f, uint32_t n) {
         if (!n) return;
         uint32_t grid = (n + F::kBlock - 1) / F::kBlock;
-        vmsm_kernel<F><<<grid, F::kBlock, 0, c->stream>>>(f, n);
+        vmsm_kernel<F><<<grid, F::kBlock, 0, cur>>>(f, n);
         c->launches++;
         note(cudaGetLastError());
     }
@@ -305,13 +330,20 @@ struct CudaBE {
         note(cudaEventRecord(c->ev_pool[c->ev_cur].ev[0], c->stream));
     }
     void phase_mark(int ph) {
-        if (c->ev_cur >= 0) note(cudaEventRecord(c->ev_pool[c->ev_cur].ev[ph + 1], c->stream));
+        if (c->ev_cur >= 0) note(cudaEventRecord(c->ev_pool[c->ev_cur].ev[ph + 1], cur));
     }
     void phase_end() {}
 };
 
+// make the main stream wait for every MSM tail issued so far (tails are ordered on the side stream)
+cudaError_t join_tail(Ctx *c) {
+    if (c->last_tail < 0) return cudaSuccess;
+    return cudaStreamWaitEvent(c->stream, c->ev_tail[c->last_tail], 0);
+}
+
 int32_t harvest_phases(Ctx *c) {
     if (!c->ev_used) return VMSM_OK;
+    CU(join_tail(c));
     CU(cudaStreamSynchronize(c->stream));
     for (size_t k = 0; k < c->ev_used; k++) {
         for (int p = 0; p < PH_COUNT; p++) {
@@ -346,8 +378,9 @@ int32_t ensure_tmp(Ctx *c, size_t n_pts) {
 
 int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t n, uint32_t slot) {
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "n = %llu exceeds 2^26 terms per MSM call", (unsigned long long)n);
-    CudaBE be{c};
-    int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff + slot);
+    CudaBE be(c);
+    int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff + slot,
+                     c->msm_seq++);
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
     return VMSM_OK;
@@ -393,6 +426,14 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     Ctx *c = new Ctx();
     c->device = device;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;  // hi = numerically smallest = greatest priority
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->tail, cudaStreamNonBlocking, hi));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_tail[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_tail[1], cudaEventDisableTiming));
     CU(cudaMalloc(&c->order_bins, ORDER_BINS * 4));
     CU(cudaMalloc(&c->err_word, 16));
     CU(cudaMalloc(&c->fb_table, 512 * sizeof(ge_niels)));
@@ -418,10 +459,11 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
 
 int32_t vmsm_ctx_destroy(uint64_t ctx) {
     GET_CTX(ctx);
+    cudaStreamSynchronize(c->tail);
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->points) cudaFree(kv.second.aff), cudaFree(kv.second.niels);
     for (auto &kv : c->scalars) cudaFree(kv.second.data);
-    CudaBE be{c};
+    CudaBE be(c);
     ws_release(be, c->ws);
     cudaFree(c->order_bins), cudaFree(c->err_word), cudaFree(c->fb_table), cudaFree(c->res_ext), cudaFree(c->res_aff);
     cudaFree(c->stage_scalars), cudaFree(c->tmp_ext), cudaFree(c->small_aff), cudaFree(c->small_niels);
@@ -429,6 +471,8 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (auto &es : c->ev_pool)
         for (auto &e : es.ev) cudaEventDestroy(e);
     cudaEventDestroy(c->t0), cudaEventDestroy(c->t1);
+    cudaEventDestroy(c->ev_head), cudaEventDestroy(c->ev_tail[0]), cudaEventDestroy(c->ev_tail[1]);
+    cudaStreamDestroy(c->tail);
     cudaStreamDestroy(c->stream);
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -458,6 +502,9 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             if (value < 1 || value > 6) return fail(VMSM_ERR_INVALID, "reduce radix log2 must be in [1, 6]");
             c->opt.reduce_log2r = (uint32_t)value;
             return VMSM_OK;
+        case VMSM_OPT_ASYNC_TAIL:
+            c->async_tail = value != 0;
+            return VMSM_OK;
         case VMSM_OPT_QUAD_THRESHOLD:
             if (value < 0 || value > (1 << 24)) return fail(VMSM_ERR_INVALID, "quad threshold out of range");
             c->opt.quad_threshold = (uint32_t)value;
@@ -468,6 +515,7 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
 
 int32_t vmsm_sync(uint64_t ctx) {
     GET_CTX(ctx);
+    CU(join_tail(c));
     CU(cudaStreamSynchronize(c->stream));
     return VMSM_OK;
 }
@@ -480,6 +528,7 @@ int32_t vmsm_timer_start(uint64_t ctx) {
 int32_t vmsm_timer_stop(uint64_t ctx, float *ms) {
     GET_CTX(ctx);
     if (!ms) return fail(VMSM_ERR_INVALID, "null argument");
+    CU(join_tail(c));
     CU(cudaEventRecord(c->t1, c->stream));
     CU(cudaEventSynchronize(c->t1));
     CU(cudaEventElapsedTime(ms, c->t0, c->t1));
@@ -527,7 +576,7 @@ int32_t vmsm_points_upload(uint64_t ctx, int32_t curve, const uint8_t *affine, u
     PointSet ps;
     int32_t rc = new_pointset(c, curve, n, &ps);
     if (rc) return rc;
-    CudaBE be{c};
+    CudaBE be(c);
     if (n) {
         be.note(cudaMemcpyAsync(ps.aff, affine, n * sizeof(ge_aff), cudaMemcpyHostToDevice, c->stream));
         be.zero(c->err_word, 4);
@@ -573,7 +622,7 @@ int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scala
             cudaFree(ps.aff), cudaFree(ps.niels);
             return rc;
         }
-        CudaBE be{c};
+        CudaBE be(c);
         KFixedBase k = {c->fb_table, dsc, seed, c->tmp_ext};
         be.launch(k, (uint32_t)n);
         KNormalize kn = {c->tmp_ext, ps.aff, ps.niels};
@@ -646,7 +695,7 @@ int32_t vmsm_scalars_synth(uint64_t ctx, int32_t curve, uint64_t seed, uint64_t 
     if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
     ScalarSet ss{n, nullptr};
     CU(cudaMalloc(&ss.data, (n ? n : 1) * 32));
-    CudaBE be{c};
+    CudaBE be(c);
     KSynthScalars k = {ss.data, seed};
     be.launch(k, (uint32_t)n);
     be.note(cudaStreamSynchronize(c->stream));
@@ -694,6 +743,7 @@ int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uin
     if (n) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
     rc = run_msm(c, it->second.niels + off, c->stage_scalars, n, kSlots - 1);
     if (rc) return rc;
+    CU(join_tail(c));
     CU(cudaMemcpyAsync(c->pin, c->res_aff + (kSlots - 1), sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     memcpy(out_affine, c->pin, sizeof(ge_aff));
@@ -716,6 +766,7 @@ int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine) {
     GET_CTX(ctx);
     if (slot >= kSlots || !out_affine) return fail(VMSM_ERR_INVALID, "bad slot / null argument");
+    CU(join_tail(c));
     CU(cudaMemcpyAsync(c->pin, c->res_aff + slot, sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     memcpy(out_affine, c->pin, sizeof(ge_aff));
@@ -725,6 +776,7 @@ int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine) {
 int32_t vmsm_result_extended(uint64_t ctx, uint32_t slot, uint8_t *out_extended) {
     GET_CTX(ctx);
     if (slot >= kSlots || !out_extended) return fail(VMSM_ERR_INVALID, "bad slot / null argument");
+    CU(join_tail(c));
     CU(cudaMemcpyAsync(c->pin, c->res_ext + slot, sizeof(ge_ext), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     memcpy(out_extended, c->pin, sizeof(ge_ext));
@@ -742,7 +794,7 @@ int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le
     if (rc) return rc;
     uint32_t cs[8];
     memcpy(cs, c_le32, 32);
-    CudaBE be{c};
+    CudaBE be(c);
     fold_run(be, it->second.aff, it->second.niels, c->tmp_ext, (uint32_t)half, cs);
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "fold: %s", cudaGetErrorString(be.err));
     it->second.n = half;
@@ -758,7 +810,7 @@ int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const u
     if (!out_affine || (n && (!affine || !scalars_le32))) return fail(VMSM_ERR_INVALID, "null argument");
     int32_t rc = ensure_stage(c, 64);
     if (rc) return rc;
-    CudaBE be{c};
+    CudaBE be(c);
     if (n) {
         be.note(cudaMemcpyAsync(c->small_aff, affine, n * sizeof(ge_aff), cudaMemcpyHostToDevice, c->stream));
         be.note(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
@@ -769,6 +821,7 @@ int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const u
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "lincomb: %s", cudaGetErrorString(be.err));
     rc = run_msm(c, c->small_niels, c->stage_scalars, n, kSlots - 1);
     if (rc) return rc;
+    CU(join_tail(c));
     CU(cudaMemcpyAsync(c->pin, c->res_aff + (kSlots - 1), sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->pin + 64, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -795,7 +848,7 @@ int32_t vmsm_selftest_fe(uint64_t ctx, int32_t op, const uint8_t *a, const uint8
     CU(cudaMalloc(&da, n * 32));
     CU(cudaMalloc(&db, n * 32));
     CU(cudaMalloc(&dout, n * 32));
-    CudaBE be{c};
+    CudaBE be(c);
     be.note(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, c->stream));
     be.note(cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, c->stream));
     KSelfTestFe k = {da, db, dout, op};
