@@ -46,6 +46,7 @@ extern "C" {
 #define VMSM_OPT_CHECK_POINTS 4 /* 1 = validate uploaded points (default 1) */
 #define VMSM_OPT_REDUCE_RADIX 5 /* log2 of the bucket-tree radix (default 3) */
 #define VMSM_OPT_ASYNC_TAIL 7 /* 1 (default) = run the latency-bound MSM tail on a side stream under the next MSM's head */
+#define VMSM_OPT_CAP_FACTOR 8 /* per-thread bucket cap = max(64, factor * average bucket population) (default 8) */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */

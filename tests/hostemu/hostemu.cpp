@@ -36,6 +36,8 @@ struct HostBE {
         std::stable_sort(order, order + nb, [&](uint32_t a, uint32_t b) { return counts[a] > counts[b]; });
         return true;
     }
+    uint32_t overflow_warps() { return 3; }
+    uint32_t combine_threads() { return 5; }
     void head_wait_tail(int) {}
     void tail_begin() {}
     void tail_end(int) {}

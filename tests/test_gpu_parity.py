@@ -187,3 +187,13 @@ def test_msm_skewed_scalars(ctx):
     assert ctx.msm(dev, sc) == E.msm_known_dlog(sc, dl)
     sc = [7] * n
     assert ctx.msm(dev, sc) == E.msm_known_dlog(sc, dl)
+    sc = [rnd.randrange(1, 4) * (1 << 240) for _ in range(n)]
+    assert ctx.msm(dev, sc) == E.msm_known_dlog(sc, dl)
+    from verifiable_mpc_b200 import _lib
+    try:
+        for c in (4, 7, 13, 14):  # windows whose top digit is almost always 0/1: one giant bucket
+            ctx.set_option(_lib.OPT_WINDOW_BITS, c)
+            sc = [prng.scalar(0x77, i) for i in range(n)]
+            assert ctx.msm(dev, sc) == E.msm_known_dlog(sc, dl), c
+    finally:
+        ctx.set_option(_lib.OPT_WINDOW_BITS, 0)

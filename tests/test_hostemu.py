@@ -73,6 +73,19 @@ def test_msm_matches_reference_algorithm(hostemu, known_points):
     assert run_msm(hostemu, pp, sc, 4) == E.msm_naive(sc, pp)
 
 
+def test_msm_skewed_scalars_long_buckets(hostemu):
+    """Boolean / constant / top-window-only scalars force buckets far above the per-thread cap: exercises the
+    overflow-task path (KOverflow / KCombine)."""
+    n = 700
+    base = [E.scalar_mul(E.B, k + 1) for k in range(40)]
+    pts = [base[i % 40] for i in range(n)]
+    dl = [(i % 40) + 1 for i in range(n)]
+    rnd = random.Random(3)
+    for scs in ([rnd.randrange(2) for _ in range(n)], [7] * n, [rnd.randrange(1, 4) * (1 << 240) for _ in range(n)]):
+        for c in (0, 4, 13):
+            assert run_msm(hostemu, pts, scs, c) == E.msm_known_dlog(scs, dl), c
+
+
 def test_msm_rejects_bad_points(hostemu):
     bad = (E.BX, (E.BY + 1) % P)
     out = ctypes.create_string_buffer(64)

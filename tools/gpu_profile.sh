@@ -1,0 +1,21 @@
+#!/bin/bash
+# Profiling session: parity tests, bench (with CPU baseline), ncu launch list, ncu --set full of the dominant kernels.
+set -u
+mkdir -p gpurun_out
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+echo "== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2
+echo "== bench"; timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
+echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>&1; cat gpurun_out/bench_ref.json
+echo "== sweep n"; timeout 600 python tools/sweep.py --logn 10 12 14 16 18 20 22 --out gpurun_out/sweep_n.jsonl 2>&1 | tail -8
+echo "== ncu launches"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-check --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+tail -2 gpurun_out/launches.csv
+echo "== ncu full"
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:KAccumulate -s 3 -c 2 -o gpurun_out/prof_acc -f \
+    python bench.py --steps 3 --warmup 3 --no-check --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'KScatter|KDigitsHist|KReduce' -s 9 -c 4 -o gpurun_out/prof_other -f \
+    python bench.py --steps 3 --warmup 3 --no-check --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1
+tail -3 gpurun_out/ncu_full2.log
+ls -la gpurun_out

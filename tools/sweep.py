@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--windows", type=int, nargs="+", default=[0])
     ap.add_argument("--sort", type=int, nargs="+", default=[1])
     ap.add_argument("--radix", type=int, nargs="+", default=[3])
+    ap.add_argument("--cap", type=int, nargs="+", default=[0])
+    ap.add_argument("--async-tail", type=int, nargs="+", default=[1])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -30,7 +32,10 @@ def main():
         sets = [(ctx.fixed_base(seed=0x5EEE + 16 * k, n=n), ctx.synth_scalars(0x5EED + 16 * k, n)) for k in range(3)]
         for c in args.windows:
             for sort in args.sort:
-                for radix in args.radix:
+                for radix, cap, at in [(r, cp, a) for r in args.radix for cp in args.cap for a in args.async_tail]:
+                    if cap:
+                        ctx.set_option(_lib.OPT_CAP_FACTOR, cap)
+                    ctx.set_option(_lib.OPT_ASYNC_TAIL, at)
                     ctx.set_option(_lib.OPT_WINDOW_BITS, c)
                     ctx.set_option(_lib.OPT_SORT_BUCKETS, sort)
                     ctx.set_option(_lib.OPT_REDUCE_RADIX, radix)
@@ -43,7 +48,7 @@ def main():
                         ctx.msm_dev(*sets[s % 3], slot=s % 32)
                     ms = ctx.timer_stop() / args.steps
                     ph, calls = ctx.phase_times()
-                    rec = {"log2n": logn, "window": c, "sort": sort, "radix": radix, "ms": ms, "Mpts_s": n / ms / 1e3,
+                    rec = {"log2n": logn, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "ms": ms, "Mpts_s": n / ms / 1e3,
                            "imad_peak_tlps": peak, "phase_ms": {k: round(v / calls, 5) for k, v in ph.items()}}
                     print(json.dumps(rec), flush=True)
                     if out:

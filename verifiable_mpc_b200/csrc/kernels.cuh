@@ -217,6 +217,21 @@ struct KScatter {
     }
 };
 
+// Long buckets.  A thread of KAccumulate sums at most `cap` entries of its bucket; what is left of a longer bucket is
+// cut into at most 64 segments ("overflow tasks", each a multiple of 32 entries, >= 256) that KOverflow sums with one
+// warp per task, and KCombine folds the task partials back into the bucket.  This bounds the serial chain of any
+// thread whatever the scalar distribution: the top window of a 253-bit scalar has only a few live bits (few, huge
+// buckets), and real witnesses are full of tiny values (bits, padding), cf. circuit_sat_cb.py:46-56.
+struct OverflowTask {
+    uint32_t bucket, first, count;  // idx[first .. first + count)
+};
+struct LongBucket {
+    uint32_t bucket, task_base, ntask;
+};
+struct OverflowCtl {
+    uint32_t ntasks, nlong;
+};
+
 // One thread per bucket.  `order` (optional) lists bucket ids by decreasing population so the lanes of a warp
 // run the same trip count.
 struct KAccumulate {
@@ -228,9 +243,29 @@ struct KAccumulate {
     const uint32_t *order;    // may be null
     ge_ext *buckets;          // W x NB
     uint32_t nbuckets;
+    uint32_t cap;             // entries summed by the bucket's own thread
+    OverflowCtl *ctl;
+    OverflowTask *tasks;
+    LongBucket *longs;
     VMSM_HD void operator()(uint32_t tid) const {
         uint32_t b = order ? order[tid] : tid;
         uint32_t pos = offsets[b], cnt = counts[b];
+        if (cnt > cap) {
+            uint32_t over = cnt - cap;
+            uint32_t seg = (over + 63) / 64;
+            if (seg < 256) seg = 256;
+            seg = (seg + 31) & ~31u;
+            uint32_t ntask = (over + seg - 1) / seg;
+            uint32_t base = VMSM_ATOMIC_ADD(&ctl->ntasks, ntask);
+            uint32_t lpos = VMSM_ATOMIC_ADD(&ctl->nlong, 1u);
+            for (uint32_t k = 0; k < ntask; k++) {
+                OverflowTask t = {b, pos + cap + k * seg, over - k * seg < seg ? over - k * seg : seg};
+                tasks[base + k] = t;
+            }
+            LongBucket lb = {b, base, ntask};
+            longs[lpos] = lb;
+            cnt = cap;
+        }
         ge_ext acc = ge_identity();
         if (cnt) {
             uint32_t e = idx[pos];
@@ -242,6 +277,75 @@ struct KAccumulate {
             }
         }
         st_ext(buckets + b, acc);
+    }
+};
+
+// One warp per overflow task (grid-stride over the device-side task count): lanes stride over the segment, then a
+// shuffle tree adds the 32 lane sums.
+struct KOverflow {
+    enum { kBlock = 128 };
+    const ge_niels *bases;
+    const uint32_t *idx;
+    const OverflowCtl *ctl;
+    const OverflowTask *tasks;
+    ge_ext *partials;
+    uint32_t nwarps;
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint32_t ntasks = ctl->ntasks;
+#if defined(__CUDA_ARCH__)
+        const uint32_t lane = tid & 31;
+        for (uint32_t t = tid >> 5; t < ntasks; t += nwarps) {
+            OverflowTask tk = tasks[t];
+            ge_ext acc = ge_identity();
+            for (uint32_t k = lane; k < tk.count; k += 32) {
+                uint32_t e = idx[tk.first + k];
+                acc = ge_madd(acc, ld_niels(bases + (e & 0x7fffffffu)), (e >> 31) != 0);
+            }
+#pragma unroll 1
+            for (int d = 16; d >= 1; d >>= 1) {
+                ge_ext o;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    o.X.v[i] = __shfl_down_sync(0xffffffffu, acc.X.v[i], d);
+                    o.Y.v[i] = __shfl_down_sync(0xffffffffu, acc.Y.v[i], d);
+                    o.Z.v[i] = __shfl_down_sync(0xffffffffu, acc.Z.v[i], d);
+                    o.T.v[i] = __shfl_down_sync(0xffffffffu, acc.T.v[i], d);
+                }
+                acc = ge_add(acc, o);
+            }
+            if (lane == 0) st_ext(partials + t, acc);
+        }
+#else
+        if (tid & 31) return;
+        for (uint32_t t = tid >> 5; t < ntasks; t += nwarps) {
+            OverflowTask tk = tasks[t];
+            ge_ext acc = ge_identity();
+            for (uint32_t k = 0; k < tk.count; k++) {
+                uint32_t e = idx[tk.first + k];
+                acc = ge_madd(acc, ld_niels(bases + (e & 0x7fffffffu)), (e >> 31) != 0);
+            }
+            st_ext(partials + t, acc);
+        }
+#endif
+    }
+};
+
+// One thread per long bucket (grid-stride): bucket += its task partials.
+struct KCombine {
+    enum { kBlock = 128 };
+    const OverflowCtl *ctl;
+    const LongBucket *longs;
+    const ge_ext *partials;
+    ge_ext *buckets;
+    uint32_t nthreads;
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint32_t nlong = ctl->nlong;
+        for (uint32_t l = tid; l < nlong; l += nthreads) {
+            LongBucket lb = longs[l];
+            ge_ext acc = ld_ext(buckets + lb.bucket);
+            for (uint32_t k = 0; k < lb.ntask; k++) acc = ge_add(acc, ld_ext(partials + lb.task_base + k));
+            st_ext(buckets + lb.bucket, acc);
+        }
     }
 };
 

@@ -21,6 +21,7 @@ struct MsmOptions {
     uint32_t window_bits = 0;  // 0 = auto
     uint32_t reduce_log2r = 3;
     bool sort_buckets = true;
+    uint32_t cap_factor = 8;   // a bucket's own thread sums at most max(64, cap_factor * n / NB) entries (kernels.cuh)
     uint32_t quad_threshold = 16384;  // tree levels with at most this many output nodes run quad-cooperative; 0 = never
 };
 
@@ -31,24 +32,35 @@ struct Workspace {
     // bucket-tree levels: [parity of the MSM sequence number][ping-pong].  Two parities because the latency-bound tail
     // of one MSM (upper tree levels + Horner) runs on a side stream underneath the head of the next MSM.
     ge_ext *nodeS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *nodeT[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0;
+    // long-bucket overflow (kernels.cuh: KOverflow / KCombine)
+    OverflowCtl *ctl = nullptr;
+    OverflowTask *tasks = nullptr;
+    LongBucket *longs = nullptr;
+    ge_ext *partials = nullptr;
+    size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0, cap_tasks = 0;
 };
 
 // Work model of SURVEY.md App. E (limb products), with the tree reduction's ~30 % overhead over a serial running sum.
+// Windows whose top digit has few live bits are skipped: scalars are reduced below a ~2^(scalar_bits-1) group order,
+// so the last window that holds bit (scalar_bits-2) sees r = (scalar_bits-1) mod c live bits and its 2^(r-1) buckets
+// are 2^(c-r) times fuller than average (r = 0: a carry-only window, one bucket with n/2 entries).  The long-bucket
+// path keeps such cases correct and bounded; the chooser simply avoids paying for them (measured: profiles/r01).
 inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits) {
     if (n == 0) return 4;
     double best = 0;
-    uint32_t best_c = 4;
+    uint32_t best_c = 0;
     for (uint32_t c = 3; c <= 17; c++) {
+        uint32_t r = (scalar_bits - 1) % c;
+        if (r == 0 || c - r > 4) continue;
         double W = (double)((scalar_bits + 1 + c - 1) / c);
         double NB = (double)(1u << (c - 1));
         double cost = (double)n * W * 504.0 + W * NB * 2.0 * 648.0 * 1.3 + (W - 1) * c * 464.0;
-        if (c == 3 || cost < best) {
+        if (!best_c || cost < best) {
             best = cost;
             best_c = c;
         }
     }
-    return best_c;
+    return best_c ? best_c : 8;
 }
 
 inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits) {
@@ -82,6 +94,17 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R) {
         if (!ws.idx) return -1;
         ws.cap_idx = ni;
     }
+    size_t nt = ni / 32 + 64;  // >= sum over long buckets of their task counts (cap >= 64, segments >= 256)
+    if (nt > ws.cap_tasks) {
+        be.free(ws.ctl), be.free(ws.tasks), be.free(ws.longs), be.free(ws.partials);
+        ws.cap_tasks = 0;
+        ws.ctl = (OverflowCtl *)be.alloc(sizeof(OverflowCtl));
+        ws.tasks = (OverflowTask *)be.alloc(nt * sizeof(OverflowTask));
+        ws.longs = (LongBucket *)be.alloc(nt * sizeof(LongBucket));
+        ws.partials = (ge_ext *)be.alloc(nt * sizeof(ge_ext));
+        if (!ws.ctl || !ws.tasks || !ws.longs || !ws.partials) return -1;
+        ws.cap_tasks = nt;
+    }
     if (nn > ws.cap_nodes) {
         for (int par = 0; par < 2; par++)
             for (int k = 0; k < 2; k++) {
@@ -102,6 +125,7 @@ template <class BE>
 void ws_release(BE &be, Workspace &ws) {
     be.free(ws.counts), be.free(ws.offsets), be.free(ws.cursor), be.free(ws.order), be.free(ws.buckets);
     be.free(ws.idx);
+    be.free(ws.ctl), be.free(ws.tasks), be.free(ws.longs), be.free(ws.partials);
     for (int par = 0; par < 2; par++)
         for (int k = 0; k < 2; k++) be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
     ws = Workspace();
@@ -135,8 +159,19 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     if (opt.sort_buckets && be.order_buckets(ws.counts, ws.order, nbuckets, n)) order = ws.order;
     be.phase_mark(PH_ORDER);
     {
-        KAccumulate k5 = {bases, ws.offsets, ws.counts, ws.idx, order, ws.buckets, nbuckets};
+        uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
+        if (cap < 64) cap = 64;
+        be.zero(ws.ctl, sizeof(OverflowCtl));
+        KAccumulate k5 = {bases, ws.offsets, ws.counts, ws.idx, order, ws.buckets, nbuckets, cap, ws.ctl, ws.tasks, ws.longs};
         be.launch(k5, nbuckets);
+        if (n > cap) {  // otherwise no bucket can be long
+            const uint32_t ow = be.overflow_warps();
+            KOverflow ko = {bases, ws.idx, ws.ctl, ws.tasks, ws.partials, ow};
+            be.launch(ko, ow * 32);
+            const uint32_t ct = be.combine_threads();
+            KCombine kc = {ws.ctl, ws.longs, ws.partials, ws.buckets, ct};
+            be.launch(kc, ct);
+        }
     }
     be.phase_mark(PH_ACCUMULATE);
     // bucket tree: throughput-bound leaf level(s) on the main stream, then the latency-bound tail (quad-cooperative

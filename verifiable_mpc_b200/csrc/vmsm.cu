@@ -259,6 +259,8 @@ struct CudaBE {
     cudaError_t err = cudaSuccess;
     cudaStream_t cur = nullptr;  // stream the next launch goes to (main unless inside a tail)
     explicit CudaBE(Ctx *ctx) : c(ctx), cur(ctx->stream) {}
+    uint32_t overflow_warps() { return 148u * 8u * 4u; }  // 8 blocks of 4 warps per SM, grid-stride over the tasks
+    uint32_t combine_threads() { return 148u * 128u; }
     // the node buffers of parity `par` may still be read by the tail of the MSM two calls ago
     void head_wait_tail(int par) {
         if (c->tail_pending[par]) note(cudaStreamWaitEvent(c->stream, c->ev_tail[par], 0));
@@ -501,6 +503,10 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
         case VMSM_OPT_REDUCE_RADIX:
             if (value < 1 || value > 6) return fail(VMSM_ERR_INVALID, "reduce radix log2 must be in [1, 6]");
             c->opt.reduce_log2r = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_CAP_FACTOR:
+            if (value < 1 || value > 65536) return fail(VMSM_ERR_INVALID, "cap factor out of range");
+            c->opt.cap_factor = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_ASYNC_TAIL:
             c->async_tail = value != 0;
