@@ -99,7 +99,12 @@ int32_t vmsm_scalars_free(uint64_t ctx, uint64_t sc);
 /* end to end: host scalars in, host canonical-affine point out (H2D + kernels + D2H, synchronous) */
 int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
                  uint8_t *out_affine);
-/* device resident, asynchronous on the context's stream: result goes to result slot `slot` (0..63) */
+/* asynchronous end to end: the H2D copy of the scalars (page-locked memory recommended, see vmsm_host_alloc) runs on
+ * a copy stream and overlaps the previous MSM; fetch with vmsm_result_affine(slot), which waits for that result only.
+ * `scalars_le32` must stay valid until the result has been fetched. */
+int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
+                       uint32_t slot);
+/* device resident, asynchronous on the context's stream: result goes to result slot `slot` (0..62) */
 int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
                      uint32_t slot);
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine);      /* synchronises */

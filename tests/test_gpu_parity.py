@@ -177,6 +177,39 @@ def test_msm_large_known_dlog(ctx, logn):
     sc.free()
 
 
+def test_msm_async_pipeline(ctx):
+    """vmsm_msm_async: H2D on the copy stream from pinned memory, results through mapped memory, 3 in flight."""
+    import numpy as np
+    from verifiable_mpc_b200 import synth
+
+    n = 1 << 12
+    dev = ctx.fixed_base(seed=0x5EEE, n=n)
+    bufs, want = [], []
+    for k in range(6):
+        sc = synth.scalars_ed25519(100 + k, n)
+        pin = ctx.pinned(n * 32)
+        pin.array[:] = sc.reshape(-1)
+        bufs.append(pin)
+        want.append(ctx.msm(dev, sc))
+    assert len(set(want)) == 6
+    for k in range(6):
+        ctx.msm_async(dev, bufs[k].ptr, 0, n, slot=k)
+        if k >= 2:
+            assert ctx.result(k - 2) == want[k - 2]
+    assert ctx.result(4) == want[4] and ctx.result(5) == want[5]
+    # sub-range + zero-length
+    ctx.msm_async(dev, bufs[0].ptr, 5, 100, slot=7)
+    sc0 = [int.from_bytes(bufs[0].array[32 * i: 32 * i + 32].tobytes(), "little") for i in range(100)]
+    pts = dev.tolist(5, 100)
+    assert ctx.result(7) == E.msm_naive(sc0[:8], pts[:8]) or True  # full check below via known dlogs
+    dl = [prng.scalar(0x5EEE, 5 + i) for i in range(100)]
+    assert ctx.result(7) == E.msm_known_dlog(sc0, dl)
+    ctx.msm_async(dev, bufs[0].ptr, 0, 0, slot=8)
+    assert ctx.result(8) == E.IDENTITY
+    for b in bufs:
+        b.free()
+
+
 def test_msm_skewed_scalars(ctx):
     """Boolean / tiny witnesses put everything into a handful of buckets (the long-bucket path)."""
     n = 1 << 12

@@ -211,6 +211,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         }
     }
     be.phase_mark(PH_FINAL);
+    be.result_ready();
     if (in_tail) be.tail_end(par);
     be.phase_end();
     return 0;

@@ -216,6 +216,17 @@ struct Ctx {
     int last_tail = -1;
     bool async_tail = true;
     uint32_t msm_seq = 0;
+    // asynchronous end-to-end path (vmsm_msm_async): H2D of the scalars on a copy stream into one of two staging
+    // buffers, overlapping the previous MSM; results land in host-mapped pinned memory, one event per result slot
+    cudaStream_t copy = nullptr;
+    uint32_t *astage[2] = {nullptr, nullptr};
+    size_t astage_cap[2] = {0, 0};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    bool astage_used[2] = {false, false};
+    uint32_t async_seq = 0;
+    cudaEvent_t ev_slot[64] = {nullptr};
+    uint32_t cur_slot = 0;
+    ge_aff *res_aff_host = nullptr;  // pinned + mapped, kSlots entries: written by the final kernel itself
     MsmOptions opt;
     bool phase_timing = false;
     bool check_points = true;
@@ -265,6 +276,7 @@ struct CudaBE {
     void head_wait_tail(int par) {
         if (c->tail_pending[par]) note(cudaStreamWaitEvent(c->stream, c->ev_tail[par], 0));
     }
+    void result_ready() { note(cudaEventRecord(c->ev_slot[c->cur_slot], cur)); }
     void tail_begin() {
         if (!c->async_tail) return;
         note(cudaEventRecord(c->ev_head, c->stream));
@@ -381,7 +393,8 @@ int32_t ensure_tmp(Ctx *c, size_t n_pts) {
 int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t n, uint32_t slot) {
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "n = %llu exceeds 2^26 terms per MSM call", (unsigned long long)n);
     CudaBE be(c);
-    int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff + slot,
+    c->cur_slot = slot;
+    int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff_host + slot,
                      c->msm_seq++);
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
@@ -444,6 +457,13 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     CU(cudaMalloc(&c->small_aff, 64 * sizeof(ge_aff)));
     CU(cudaMalloc(&c->small_niels, 64 * sizeof(ge_niels)));
     CU(cudaHostAlloc(&c->pin, 4096, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->res_aff_host, kSlots * sizeof(ge_aff), cudaHostAllocMapped));
+    CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming));
+    }
+    for (uint32_t k = 0; k < kSlots; k++) CU(cudaEventCreateWithFlags(&c->ev_slot[k], cudaEventDisableTiming));
     CU(cudaEventCreate(&c->t0));
     CU(cudaEventCreate(&c->t1));
     {
@@ -461,8 +481,13 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
 
 int32_t vmsm_ctx_destroy(uint64_t ctx) {
     GET_CTX(ctx);
+    cudaStreamSynchronize(c->copy);
     cudaStreamSynchronize(c->tail);
     cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 2; k++) cudaFree(c->astage[k]), cudaEventDestroy(c->ev_copied[k]), cudaEventDestroy(c->ev_consumed[k]);
+    for (uint32_t k = 0; k < kSlots; k++) cudaEventDestroy(c->ev_slot[k]);
+    cudaFreeHost(c->res_aff_host);
+    cudaStreamDestroy(c->copy);
     for (auto &kv : c->points) cudaFree(kv.second.aff), cudaFree(kv.second.niels);
     for (auto &kv : c->scalars) cudaFree(kv.second.data);
     CudaBE be(c);
@@ -749,10 +774,37 @@ int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uin
     if (n) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
     rc = run_msm(c, it->second.niels + off, c->stage_scalars, n, kSlots - 1);
     if (rc) return rc;
-    CU(join_tail(c));
-    CU(cudaMemcpyAsync(c->pin, c->res_aff + (kSlots - 1), sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    memcpy(out_affine, c->pin, sizeof(ge_aff));
+    CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));  // the final kernel wrote the point into mapped pinned memory
+    memcpy(out_affine, c->res_aff_host + (kSlots - 1), sizeof(ge_aff));
+    return VMSM_OK;
+}
+
+int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
+                       uint32_t slot) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "Not enough generators.");
+    if (n && !scalars_le32) return fail(VMSM_ERR_INVALID, "null argument");
+    if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    const int b = (int)(c->async_seq++ & 1);
+    if ((n ? n : 1) > c->astage_cap[b]) {
+        if (c->astage[b]) cudaFree(c->astage[b]);  // synchronises the device
+        c->astage[b] = nullptr;
+        c->astage_cap[b] = 0;
+        CU(cudaMalloc(&c->astage[b], (n ? n : 1) * 32));
+        c->astage_cap[b] = n ? n : 1;
+        c->astage_used[b] = false;
+    }
+    // the staging buffer may still be read by the MSM issued two calls ago
+    if (c->astage_used[b]) CU(cudaStreamWaitEvent(c->copy, c->ev_consumed[b], 0));
+    if (n) CU(cudaMemcpyAsync(c->astage[b], scalars_le32, n * 32, cudaMemcpyHostToDevice, c->copy));
+    CU(cudaEventRecord(c->ev_copied[b], c->copy));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    int32_t rc = run_msm(c, it->second.niels + off, c->astage[b], n, slot);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_consumed[b], c->stream));
+    c->astage_used[b] = true;
     return VMSM_OK;
 }
 
@@ -772,10 +824,8 @@ int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine) {
     GET_CTX(ctx);
     if (slot >= kSlots || !out_affine) return fail(VMSM_ERR_INVALID, "bad slot / null argument");
-    CU(join_tail(c));
-    CU(cudaMemcpyAsync(c->pin, c->res_aff + slot, sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    memcpy(out_affine, c->pin, sizeof(ge_aff));
+    CU(cudaEventSynchronize(c->ev_slot[slot]));  // waits for THIS result only, not for MSMs issued after it
+    memcpy(out_affine, c->res_aff_host + slot, sizeof(ge_aff));
     return VMSM_OK;
 }
 
@@ -827,12 +877,11 @@ int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const u
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "lincomb: %s", cudaGetErrorString(be.err));
     rc = run_msm(c, c->small_niels, c->stage_scalars, n, kSlots - 1);
     if (rc) return rc;
-    CU(join_tail(c));
-    CU(cudaMemcpyAsync(c->pin, c->res_aff + (kSlots - 1), sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->pin + 64, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));
     if (n && *reinterpret_cast<uint32_t *>(c->pin + 64)) return fail(VMSM_ERR_POINT, "invalid point in lincomb input");
-    memcpy(out_affine, c->pin, sizeof(ge_aff));
+    memcpy(out_affine, c->res_aff_host + (kSlots - 1), sizeof(ge_aff));
     return VMSM_OK;
 }
 

@@ -223,6 +223,11 @@ class Context:
         """Zero-marshalling variant for benchmarks: ``ptr`` is a c_void_p to n*32 bytes, ``out`` a 64-byte buffer."""
         check(self.lib.vmsm_msm(self.h, points.handle, off, n, ptr, out))
 
+    def msm_async(self, points, ptr, off, n, slot):
+        """Asynchronous end-to-end MSM: ``ptr`` (c_void_p, ideally into ``pinned()`` memory) holds n*32 bytes of
+        scalars and must stay valid until ``result(slot)`` returns; H2D overlaps the previous MSM."""
+        check(self.lib.vmsm_msm_async(self.h, points.handle, off, n, ptr, slot))
+
     def msm_dev(self, points, scalars, slot=0, poff=0, soff=0, n=None):
         """Device-resident, asynchronous; fetch with ``result(slot)``."""
         if n is None:
