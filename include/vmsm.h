@@ -83,6 +83,10 @@ int32_t vmsm_points_upload(uint64_t ctx, int32_t curve, const uint8_t *affine, u
 int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scalars, uint64_t seed, uint64_t n,
                                uint64_t *pts);
 int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *affine_out);
+/* new vector = a[a_off .. a_off+a_n) || b[b_off .. b_off+b_n)  (device-side copy; b_n may be 0: a clone).  The
+ * g_hat = g + [h] of compressed_pivot.py:137 and the private copy a prover folds in place. */
+int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_n, uint64_t b, uint64_t b_off,
+                           uint64_t b_n, uint64_t *out);
 int32_t vmsm_points_count(uint64_t ctx, uint64_t pts, uint64_t *n);
 int32_t vmsm_points_free(uint64_t ctx, uint64_t pts);
 
@@ -99,6 +103,11 @@ int32_t vmsm_scalars_free(uint64_t ctx, uint64_t sc);
 /* end to end: host scalars in, host canonical-affine point out (H2D + kernels + D2H, synchronous) */
 int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
                  uint8_t *out_affine);
+/* Pedersen form  out = sum_{i<n} s_i * P[off+i]  +  sum_{j<n_extra} s_{n+j} * E[extra_off+j]  in ONE pass: the
+ * `(h ** gamma) * prod` of pivot.vector_commitment (pivot.py:143-144), also A_i/B_i of compressed_pivot.py:41-42 whose
+ * blinding base k is not part of the generator vector.  `scalars_le32` holds n + n_extra scalars. */
+int32_t vmsm_msm_ext(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint64_t extra_pts, uint64_t extra_off,
+                     uint64_t n_extra, const uint8_t *scalars_le32, uint8_t *out_affine);
 /* asynchronous end to end: the H2D copy of the scalars (page-locked memory recommended, see vmsm_host_alloc) runs on
  * a copy stream and overlaps the previous MSM; fetch with vmsm_result_affine(slot), which waits for that result only.
  * `scalars_le32` must stay valid until the result has been fetched. */

@@ -1,0 +1,75 @@
+"""Test-only stand-in for verifiable_mpc_b200.engine.Context that computes with the CPU oracle.
+
+It lets the `-m "not gpu"` suite exercise the HOST logic of the prover twins (transcript layout, form algebra,
+slicing / folding bookkeeping, PRNG draw order) against the golden fixtures in a container without a GPU.  It is
+never importable from the product: the product's Context is libvmsm.so or nothing.
+"""
+from oracle import ed25519 as E
+
+
+class FakePoints:
+    def __init__(self, ctx, pts):
+        self.ctx, self.pts, self.handle, self.curve = ctx, list(pts), 1, 0
+
+    @property
+    def n(self):
+        return len(self.pts)
+
+    @n.setter
+    def n(self, v):
+        del self.pts[v:]
+
+    def __len__(self):
+        return len(self.pts)
+
+    def download(self, off=0, n=None):
+        n = len(self.pts) - off if n is None else n
+        return b"".join(E.point_to_bytes(p) for p in self.pts[off:off + n])
+
+    def tolist(self, off=0, n=None):
+        n = len(self.pts) - off if n is None else n
+        return self.pts[off:off + n]
+
+    def fold(self, c):
+        self.pts = E.fold(self.pts[: 2 * (len(self.pts) // 2)], int(c) % E.L)
+        return self
+
+
+def _unpack_scalars(raw):
+    raw = bytes(raw)
+    return [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
+
+
+class FakeContext:
+    calls = 0
+
+    def upload_points(self, pts, curve=0):
+        if isinstance(pts, (bytes, bytearray)):
+            pts = [E.point_from_bytes(pts[i:i + 64]) for i in range(0, len(pts), 64)]
+        for p in pts:
+            assert E.on_curve(p)
+        return FakePoints(self, pts)
+
+    def fixed_base(self, scalars=None, seed=0, n=None, curve=0):
+        sc = _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else [int(s) for s in scalars]
+        return FakePoints(self, [E.scalar_mul(E.B, s) for s in sc])
+
+    def msm_ext(self, points, off, n, extra, extra_off, n_extra, scalars):
+        FakeContext.calls += 1
+        sc = _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else [int(s) % E.L for s in scalars]
+        assert len(sc) == n + n_extra
+        bases = points.pts[off:off + n] + extra.pts[extra_off:extra_off + n_extra]
+        assert len(bases) == n + n_extra
+        return E.msm_naive(sc, bases)
+
+    def msm(self, points, scalars, off=0, n=None):
+        sc = _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else [int(s) % E.L for s in scalars]
+        return E.msm_naive(sc, points.pts[off:off + len(sc)])
+
+    def concat(self, a, a_off, a_n, b=None, b_off=0, b_n=0):
+        pts = a.pts[a_off:a_off + a_n] + (b.pts[b_off:b_off + b_n] if b is not None else [])
+        return FakePoints(self, pts)
+
+    def lincomb(self, pts, scalars, curve=0):
+        FakeContext.calls += 1
+        return E.msm_naive([int(s) % E.L for s in scalars], list(pts)) if pts else E.IDENTITY

@@ -85,6 +85,33 @@ uint32_t hostemu_msm(const uint8_t *affine, const uint8_t *scalars, uint32_t n, 
     return err;
 }
 
+// Pedersen form: n_main bases + n_extra extra bases (scalars contiguous), cf. vmsm_msm_ext
+uint32_t hostemu_msm_ext(const uint8_t *affine, uint32_t n_main, const uint8_t *affine_extra, uint32_t n_extra,
+                         const uint8_t *scalars, uint32_t window_bits, uint8_t *out_affine) {
+    HostBE be;
+    uint32_t err = 0;
+    std::vector<ge_aff> aff(n_main ? n_main : 1), affx(n_extra ? n_extra : 1);
+    std::vector<ge_niels> niels(n_main ? n_main : 1), nielsx(n_extra ? n_extra : 1);
+    memcpy(aff.data(), affine, (size_t)n_main * 64);
+    memcpy(affx.data(), affine_extra, (size_t)n_extra * 64);
+    KAffToNiels k = {aff.data(), niels.data(), &err, 1u};
+    be.launch(k, n_main);
+    KAffToNiels kx = {affx.data(), nielsx.data(), &err, 1u};
+    be.launch(kx, n_extra);
+    uint32_t n = n_main + n_extra;
+    std::vector<uint32_t> sc((size_t)(n ? n : 1) * 8 + 8);
+    memcpy(sc.data(), scalars, (size_t)n * 32);
+    Workspace ws;
+    MsmOptions opt;
+    opt.window_bits = window_bits;
+    ge_ext oe;
+    ge_aff oa;
+    msm_run(be, ws, opt, 253, niels.data(), sc.data(), n, &oe, &oa, 0, nielsx.data(), n_extra);
+    ws_release(be, ws);
+    memcpy(out_affine, &oa, 64);
+    return err;
+}
+
 void hostemu_fold(const uint8_t *affine, uint32_t n, const uint8_t *c_le32, uint8_t *out_affine) {
     HostBE be;
     uint32_t half = n / 2, err = 0;

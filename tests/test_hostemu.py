@@ -86,6 +86,27 @@ def test_msm_skewed_scalars_long_buckets(hostemu):
             assert run_msm(hostemu, pts, scs, c) == E.msm_known_dlog(scs, dl), c
 
 
+def test_msm_ext_pedersen_form(hostemu, known_points):
+    """vector_commitment shape: n generators from one vector + blinding base(s) from another (pivot.py:143-144)."""
+    dl, pts = known_points
+    hostemu.hostemu_msm_ext.restype = ctypes.c_uint32
+    for n, nx in ((0, 1), (5, 1), (64, 2), (130, 1)):
+        sc = [prng.scalar(0xE0, i) for i in range(n + nx)]
+        main, extra = pts[:n], pts[200:200 + nx]
+        out = ctypes.create_string_buffer(64)
+        err = hostemu.hostemu_msm_ext(b"".join(E.point_to_bytes(p) for p in main), n,
+                                      b"".join(E.point_to_bytes(p) for p in extra), nx,
+                                      b"".join(E.scalar_to_bytes(s) for s in sc), 0, out)
+        assert err == 0
+        assert E.point_from_bytes(out.raw) == E.msm_known_dlog(sc, dl[:n] + dl[200:200 + nx])
+    # equals the oracle's vector_commitment
+    x, gamma = [prng.scalar(0xE1, i) for i in range(7)], prng.scalar(0xE2, 0)
+    out = ctypes.create_string_buffer(64)
+    hostemu.hostemu_msm_ext(b"".join(E.point_to_bytes(p) for p in pts[:7]), 7, E.point_to_bytes(E.B), 1,
+                            b"".join(E.scalar_to_bytes(s) for s in x + [gamma]), 0, out)
+    assert E.point_from_bytes(out.raw) == E.vector_commitment(x, gamma, pts[:7], E.B)
+
+
 def test_msm_rejects_bad_points(hostemu):
     bad = (E.BX, (E.BY + 1) % P)
     out = ctypes.create_string_buffer(64)

@@ -51,6 +51,8 @@ SIGNATURES = {
     "vmsm_scalars_download": [_u64, _u64, _u64, _u64, _p],
     "vmsm_scalars_free": [_u64, _u64],
     "vmsm_msm": [_u64, _u64, _u64, _u64, _p, _p],
+    "vmsm_msm_ext": [_u64, _u64, _u64, _u64, _u64, _u64, _u64, _p, _p],
+    "vmsm_points_concat": [_u64, _u64, _u64, _u64, _u64, _u64, _u64, _pu64],
     "vmsm_msm_async": [_u64, _u64, _u64, _u64, _p, _u32],
     "vmsm_msm_dev": [_u64, _u64, _u64, _u64, _u64, _u64, _u32],
     "vmsm_result_affine": [_u64, _u32, _p],

@@ -1,0 +1,171 @@
+"""GPU-backed twin of ``verifiable_mpc/ac20/compressed_pivot.py`` (AC20 protocols 4 and 5, compressed pivot).
+
+Same signatures, proof-dict keys ("t", "A", "A{i}", "B{i}", "z_prime") and Fiat-Shamir pre-images as the reference
+(compressed_pivot.py:29-239), so a proof made here verifies with the reference's verifier running on
+group types that print canonical affine coordinates, and vice versa.  Per folding round the device does: two
+(half+1)-term MSMs (A_i, B_i), one 3-term combination (Q'), and ONE fold kernel over the generator vector kept in
+HBM (``g'_j = c * g_j + g_{half+j}``, compressed_pivot.py:64 / :178).  The host keeps the scalar-field algebra and
+hashing, and downloads the folded generators once per round because their decimal text is part of the next hash.
+"""
+import logging
+from random import SystemRandom
+
+from . import pivot
+from ..fingroups import DevicePointList
+
+prng = SystemRandom()
+
+logger_cp = logging.getLogger("compressed_pivot")
+logger_cp.setLevel(logging.INFO)
+logger_cp_hin = logging.getLogger("compressed_pivot_hash_inputs")
+logger_cp_hin.setLevel(logging.INFO)
+logger_cp_hout = logging.getLogger("compressed_pivot_hash_outputs")
+logger_cp_hout.setLevel(logging.INFO)
+
+_TAG = "First hash of compressed pivot"
+
+
+def _private_device_list(g_hat, group):
+    """A device vector this call may fold in place (the caller's list stays untouched, like the reference's)."""
+    dev = pivot.as_device_list(g_hat, group)
+    if getattr(dev, "_owned", False):
+        return dev
+    own = dev.clone()
+    own._owned = True
+    return own
+
+
+def _fold_challenge(A, B, g_hat, k, Q, L_tilde, order):
+    input_list = [A.normalize(), B.normalize(), g_hat, k, Q.normalize(), L_tilde]
+    logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
+    c = pivot.fiat_shamir_hash(input_list, order)
+    logger_cp_hout.debug(f"After hash, hash=\n{c}")
+    return c
+
+
+def _fold_forms(L_tilde, c, half, gf):
+    assert L_tilde.constant == 0, "Next line assumes L_tilde is a linear form, not affine form."
+    left = [coeff * gf(c) for coeff in L_tilde.coeffs[:half]]
+    return pivot.LinearForm(left) + pivot.LinearForm(L_tilde.coeffs[half:])
+
+
+def _fold_generators(g_hat, c):
+    """In place on the device: first half <- c * first half + second half; the view shrinks to `half`."""
+    half = len(g_hat) // 2
+    assert g_hat.off == 0 and g_hat.n == g_hat.dev.n
+    g_hat.dev.fold(c)
+    g_hat.n = half
+    return g_hat
+
+
+def protocol_4_prover(g_hat, k, Q, L_tilde, z_hat, gf, proof=None, round_i=0):
+    """Non-interactive protocol 4, prover (reference :29-86).  Iterative instead of recursive; same rounds."""
+    proof = {} if proof is None else proof
+    group = type(k)
+    g_hat = _private_device_list(g_hat, group)
+    order = k.order
+    while True:
+        half = len(g_hat) // 2
+        z_l, z_r = z_hat[:half], z_hat[half:]
+        logger_cp.debug("Calculate A_i, B_i.")
+        A = pivot.vector_commitment(z_l, int(L_tilde([0] * half + z_l)), g_hat[half:], k)
+        B = pivot.vector_commitment(z_r, int(L_tilde(z_r + [0] * half)), g_hat[:half], k)
+        proof["A" + str(round_i)] = A
+        proof["B" + str(round_i)] = B
+        c = _fold_challenge(A, B, g_hat, k, Q, L_tilde, order)
+        logger_cp.debug("Calculate g_prime.")
+        g_hat = _fold_generators(g_hat, c)
+        logger_cp.debug("Calculate Q_prime.")
+        Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+        L_tilde = _fold_forms(L_tilde, c, half, gf)
+        z_hat = [l + c * r for l, r in zip(z_l, z_r)]
+        if len(z_hat) <= 2:
+            proof["z_prime"] = z_hat
+            return proof
+        round_i += 1
+
+
+def _first_challenges(t, A, generators, P, L, y, order):
+    input_list = [t, A.normalize(), generators, P.normalize(), L, y]
+    logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
+    c0 = pivot.fiat_shamir_hash(input_list + [0] + [_TAG], order)
+    c1 = pivot.fiat_shamir_hash(input_list + [1] + [_TAG], order)
+    logger_cp_hout.debug(f"After hash, hash=\n{c0}, {c1}")
+    return c0, c1
+
+
+def _g_hat(g, h, group):
+    """Device copy of g + [h], owned by the caller (it is folded in place afterwards)."""
+    dev = pivot.as_device_list(g, group)
+    hd = DevicePointList(group, pivot._device_single(group, h))
+    out = dev.clone(hd)
+    out._owned = True
+    return out
+
+
+def protocol_5_prover(generators, P, L, y, x, gamma, gf):
+    """Compressed Sigma-protocol Pi_c, prover (reference :89-145)."""
+    g, h, k = generators["g"], generators["h"], generators["k"]
+    group = type(h)
+    proof = {}
+    n = len(x)
+    L, y = pivot.affine_to_linear(L, y, n)
+    assert bin(n + 1).count("1") == 1, \
+        "This implementation requires n+1 to be power of 2 (else, use padding with zeros)."
+    order = gf.order
+    r = [prng.randrange(order) for _ in range(n)]
+    rho = prng.randrange(order)
+    logger_cp.debug("Calculate t.")
+    t = L(r)
+    logger_cp.debug("Calculate A.")
+    A = pivot.vector_commitment(r, rho, g, h)
+    proof["t"] = t
+    proof["A"] = A
+    c0, c1 = _first_challenges(t, A, generators, P, L, y, order)
+    z = [c0 * x_i + r_i for x_i, r_i in zip(x, r)]
+    phi = gf(c0 * gamma + rho)
+    z_hat = z + [phi]
+    g_hat = _g_hat(g, h, group)
+    logger_cp.debug("Calculate Q.")
+    Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
+    L_tilde = pivot.LinearForm(L.coeffs + [0]) * c1
+    assert L(z) * c1 == L_tilde(z_hat)
+    return protocol_4_prover(g_hat, k, Q, L_tilde, z_hat, gf, proof)
+
+
+def protocol_4_verifier(g_hat, k, Q, L_tilde, gf, proof, round_i=0):
+    """Non-interactive protocol 4, verifier (reference :148-202): the same folds plus one final 2-term commitment."""
+    group = type(k)
+    g_hat = _private_device_list(g_hat, group)
+    order = k.order
+    while True:
+        half = len(g_hat) // 2
+        logger_cp.debug("Load from proof: A_i, B_i.")
+        A = proof["A" + str(round_i)]
+        B = proof["B" + str(round_i)]
+        c = _fold_challenge(A, B, g_hat, k, Q, L_tilde, order)
+        g_hat = _fold_generators(g_hat, c)
+        Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+        L_tilde = _fold_forms(L_tilde, c, half, gf)
+        if len(g_hat) <= 2:
+            z_prime = proof["z_prime"]
+            Q_check = pivot.vector_commitment(z_prime, int(L_tilde(z_prime)), g_hat, k)
+            logger_cp.debug(f"Q_check= {Q_check}")
+            logger_cp.debug(f"Q_prime= {Q}")
+            return Q_check == Q
+        round_i += 1
+
+
+def protocol_5_verifier(generators, P, L, y, proof, gf):
+    """Compressed Sigma-protocol Pi_c, verifier (reference :205-239)."""
+    g, h, k = generators["g"], generators["h"], generators["k"]
+    group = type(h)
+    order = gf.order
+    L, y = pivot.affine_to_linear(L, y, len(g))
+    logger_cp.debug("Load from proof: t, A.")
+    t, A = proof["t"], proof["A"]
+    c0, c1 = _first_challenges(t, A, generators, P, L, y, order)
+    g_hat = _g_hat(g, h, group)
+    Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
+    L_tilde = pivot.LinearForm(L.coeffs + [0]) * c1
+    return protocol_4_verifier(g_hat, k, Q, L_tilde, gf, proof)

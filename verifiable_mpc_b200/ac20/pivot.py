@@ -1,0 +1,197 @@
+"""GPU-backed twin of ``verifiable_mpc/ac20/pivot.py`` (AC20 protocol 2, "pivot").
+
+Same names, argument meaning, return values and error behaviour as the reference module so callers can rebind it
+(SURVEY.md 8b1):  ``vector_commitment`` (pivot.py:139-145), ``list_mul`` (:26-28), ``fiat_shamir_hash`` (:131-136),
+``AffineForm`` / ``LinearForm`` (:31-116), ``_int`` (:119-128), ``affine_to_linear`` (:148-153),
+``prove_linear_form_eval`` (:156-181), ``verify_linear_form_proof`` (:184-205).
+
+What changes: the n independent ``g[i] ** x_i`` scalar multiplications + tree product become ONE Pippenger MSM on
+the device (libvmsm.so: vmsm_msm_ext), generators may stay resident in HBM (``DevicePointList``), and every other
+group operation is a device call too.  Linear-form algebra and hashing stay on the host exactly as in the reference.
+"""
+import hashlib
+import logging
+from random import SystemRandom
+
+from .. import fingroups
+from ..engine import pack_scalars
+from ..finfields import FiniteFieldElement as _OwnFieldElement
+from ..fingroups import DevicePointList, EllipticCurvePoint as EllipticCurveElement
+
+try:  # real MPyC field / secure types are accepted when installed (the reference's own types)
+    from mpyc.finfields import FiniteFieldElement as _MpycFieldElement
+    from mpyc.sectypes import SecureObject
+    _FIELD_TYPES = (_OwnFieldElement, _MpycFieldElement)
+except Exception:  # MPyC absent: only this package's fields and plain ints
+    class SecureObject:  # placeholder so isinstance checks read like the reference's
+        pass
+    _FIELD_TYPES = (_OwnFieldElement,)
+
+prng = SystemRandom()
+
+logger_piv = logging.getLogger("pivot")
+logger_piv.setLevel(logging.INFO)
+
+
+def _is_scalar(v):
+    return isinstance(v, (int, SecureObject) + _FIELD_TYPES)
+
+
+class AffineForm:
+    """f(x) = <coeffs, x> + constant over the scalar field (host-side bookkeeping, as in the reference)."""
+
+    def __init__(self, coeffs, constant):
+        self.coeffs = coeffs
+        self.constant = constant
+
+    def _combine(self, other):
+        if isinstance(other, AffineForm):
+            assert len(self) == len(other), "Length of linear forms to add not consistent."
+            return [a + b for a, b in zip(self.coeffs, other.coeffs)], self.constant + other.constant
+        if _is_scalar(other):
+            return self.coeffs, self.constant + other
+        return None
+
+    def __add__(self, other):
+        res = self._combine(other)
+        if res is None:
+            raise NotImplementedError(f"Addition of form not defined for type: {type(other)}")
+        return type(self)(*res)
+
+    def __radd__(self, other):
+        return self if other == 0 else self.__add__(other)
+
+    def __sub__(self, other):
+        return self + (-1) * other
+
+    def __mul__(self, other):
+        if not isinstance(other, (int,) + _FIELD_TYPES):
+            raise NotImplementedError(f"Multiplication of form not defined for type: {type(other)}")
+        return type(self)([c * other for c in self.coeffs], self.constant * other)
+
+    __rmul__ = __mul__
+
+    def __len__(self):
+        return len(self.coeffs)
+
+    def __eq__(self, other):
+        return self.coeffs == other.coeffs
+
+    def __repr__(self):
+        return f"{str(self.coeffs)}, {str(self.constant)}"
+
+    def eval(self, values):
+        assert len(values) == len(self.coeffs), "Length of inputs to be equal to coefficients of linear form."
+        return sum([c * v for c, v in zip(self.coeffs, values)]) + self.constant
+
+    __call__ = eval
+
+
+class LinearForm(AffineForm):
+    """Affine form whose constant is pinned to 0; sums fall back to AffineForm like the reference's."""
+
+    def __init__(self, coeffs, constant=0):
+        super().__init__(coeffs, 0)
+
+    def __add__(self, other):
+        res = self._combine(other)
+        if res is None:
+            raise NotImplementedError
+        return AffineForm(*res)
+
+
+def _int(value):
+    """Field elements -> ints (signed representative, as MPyC's int()); ints and secure objects pass through."""
+    if isinstance(value, (int, SecureObject)):
+        return value
+    if isinstance(value, _FIELD_TYPES):
+        return int(value)
+    raise NotImplementedError
+
+
+def fiat_shamir_hash(input_list, order):
+    digest = hashlib.sha256(str(input_list).encode("utf-8")).digest()
+    return int.from_bytes(digest, "little") % order
+
+
+def list_mul(x):
+    """Product of a list of group elements: one device call per 64 elements instead of len(x)-1 host operations."""
+    rettype = type(x[0])
+    acc = rettype.identity
+    for i in range(0, len(x), 63):
+        chunk = [acc] + list(x[i:i + 63])
+        acc = rettype.lincomb(chunk, [1] * len(chunk))
+    return acc
+
+
+# ---------------------------------------------------------------------------------------------- device plumbing
+_single_cache = {}
+
+
+def _device_single(group, pt):
+    """One-element device vector for a blinding base (h or k), cached per context."""
+    ctx = group._ctx()
+    key = (id(ctx), pt.affine())
+    hit = _single_cache.get(key)
+    if hit is None or not hit.handle:
+        if len(_single_cache) > 64:
+            _single_cache.clear()
+        hit = ctx.upload_points([pt.affine()])
+        _single_cache[key] = hit
+    return hit
+
+
+def as_device_list(g, group=None):
+    """Generator list -> DevicePointList (uploads a Python list of points once; passes device lists through)."""
+    if isinstance(g, DevicePointList):
+        return g
+    group = group or type(g[0])
+    return DevicePointList.from_points(group, g)
+
+
+def vector_commitment(x, gamma, g, h):
+    """Pedersen vector commitment ``h**gamma * prod g[i]**x[i]`` (AC20 definition 1) as ONE device MSM.
+
+    ``g``: DevicePointList or list of group elements; ``x`` / ``gamma``: ints or field elements, negative and
+    unreduced values allowed exactly as the reference passes them.
+    """
+    assert len(g) >= len(x), "Not enough generators."
+    group = type(h)
+    dev = as_device_list(g, group)
+    scalars = [_int(v) for v in x] + [_int(gamma)]
+    hd = _device_single(group, h)
+    xy = dev.dev.ctx.msm_ext(dev.dev, dev.off, len(x), hd, 0, 1, pack_scalars(scalars, group.order))
+    return group._make(xy)
+
+
+def affine_to_linear(L, y, n):
+    constant = L([0] * n)
+    return L - constant, y - constant
+
+
+def prove_linear_form_eval(g, h, P, L, y, x, gamma, gf):
+    """Sigma protocol Pi_s, non-interactive (reference pivot.py:156-181)."""
+    n = len(x)
+    L, y = affine_to_linear(L, y, n)
+    r = [gf(prng.randrange(gf.order)) for _ in range(n)]
+    rho = prng.randrange(gf.order)
+    t = L(r)
+    A = vector_commitment(r, rho, g, h)
+    logger_piv.debug(f"Prover computed A={A}.")
+    c = fiat_shamir_hash([t, A.normalize(), g, h, P.normalize(), L, y], gf.order)
+    z = [c * x_i + r_i for x_i, r_i in zip(x, r)]
+    phi = (c * gamma + rho) % gf.order
+    return z, phi, c
+
+
+def verify_linear_form_proof(g, h, P, L, y, z, phi, c):
+    n = len(z)
+    L, y = affine_to_linear(L, y, n)
+    group = type(P)
+    A_check = group.lincomb([vector_commitment(z, phi, g, h), P], [1, -int(c)])
+    t_check = L(z) - c * y
+    order = type(t_check).order
+    hash_check = fiat_shamir_hash([t_check, A_check.normalize(), g, h, P.normalize(), L, y], order)
+    logger_piv.debug(f"Value of c         ={c}")
+    logger_piv.debug(f"Value of hash_check={hash_check}")
+    return c == hash_check

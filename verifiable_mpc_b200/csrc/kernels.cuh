@@ -247,6 +247,9 @@ struct KAccumulate {
     OverflowCtl *ctl;
     OverflowTask *tasks;
     LongBucket *longs;
+    const ge_niels *extra;    // bases n_main, n_main+1, ... (e.g. the h / k of a Pedersen commitment); may be null
+    uint32_t n_main;
+    VMSM_HD const ge_niels *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
     VMSM_HD void operator()(uint32_t tid) const {
         uint32_t b = order ? order[tid] : tid;
         uint32_t pos = offsets[b], cnt = counts[b];
@@ -271,7 +274,7 @@ struct KAccumulate {
             uint32_t e = idx[pos];
             for (uint32_t k = 0; k < cnt; k++) {
                 uint32_t en = (k + 1 < cnt) ? idx[pos + k + 1] : 0u;  // index prefetch: one load ahead of the gather
-                ge_niels q = ld_niels(bases + (e & 0x7fffffffu));
+                ge_niels q = ld_niels(base_ptr(e & 0x7fffffffu));
                 acc = ge_madd(acc, q, (e >> 31) != 0);
                 e = en;
             }
@@ -290,6 +293,9 @@ struct KOverflow {
     const OverflowTask *tasks;
     ge_ext *partials;
     uint32_t nwarps;
+    const ge_niels *extra;
+    uint32_t n_main;
+    VMSM_HD const ge_niels *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
     VMSM_HD void operator()(uint32_t tid) const {
         const uint32_t ntasks = ctl->ntasks;
 #if defined(__CUDA_ARCH__)
@@ -299,7 +305,7 @@ struct KOverflow {
             ge_ext acc = ge_identity();
             for (uint32_t k = lane; k < tk.count; k += 32) {
                 uint32_t e = idx[tk.first + k];
-                acc = ge_madd(acc, ld_niels(bases + (e & 0x7fffffffu)), (e >> 31) != 0);
+                acc = ge_madd(acc, ld_niels(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
             }
 #pragma unroll 1
             for (int d = 16; d >= 1; d >>= 1) {
@@ -322,7 +328,7 @@ struct KOverflow {
             ge_ext acc = ge_identity();
             for (uint32_t k = 0; k < tk.count; k++) {
                 uint32_t e = idx[tk.first + k];
-                acc = ge_madd(acc, ld_niels(bases + (e & 0x7fffffffu)), (e >> 31) != 0);
+                acc = ge_madd(acc, ld_niels(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
             }
             st_ext(partials + t, acc);
         }
@@ -493,6 +499,19 @@ struct KAffToNiels {
             if (e) VMSM_ATOMIC_OR(err, e);
         }
         st_niels(niels + tid, ge_aff_to_niels(a));
+    }
+};
+
+// device-side copy of a point range (vmsm_points_concat)
+struct KCopyPoints {
+    enum { kBlock = 128 };
+    const ge_aff *src_aff;
+    const ge_niels *src_niels;
+    ge_aff *dst_aff;
+    ge_niels *dst_niels;
+    VMSM_HD void operator()(uint32_t tid) const {
+        st_aff(dst_aff + tid, ld_aff(src_aff + tid));
+        st_niels(dst_niels + tid, ld_niels(src_niels + tid));
     }
 };
 

@@ -134,7 +134,10 @@ void ws_release(BE &be, Workspace &ws) {
 // out = sum_i scalars[i] * bases[i].  All pointers are backend ("device") memory.  Returns 0 or -1 (allocation).
 template <class BE>
 int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, const ge_niels *bases,
-            const uint32_t *scalars, uint32_t n, ge_ext *out_ext, ge_aff *out_aff, uint32_t seq = 0) {
+            const uint32_t *scalars, uint32_t n, ge_ext *out_ext, ge_aff *out_aff, uint32_t seq = 0,
+            const ge_niels *extra = nullptr, uint32_t n_extra = 0) {
+    // terms 0 .. n-n_extra-1 use `bases`, the last n_extra terms use `extra` (scalars are contiguous)
+    const uint32_t n_main = n - n_extra;
     uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits);
     MsmGeom g = make_geom(n, c, scalar_bits);
     uint32_t R = 1u << opt.reduce_log2r;
@@ -162,11 +165,12 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < 64) cap = 64;
         be.zero(ws.ctl, sizeof(OverflowCtl));
-        KAccumulate k5 = {bases, ws.offsets, ws.counts, ws.idx, order, ws.buckets, nbuckets, cap, ws.ctl, ws.tasks, ws.longs};
+        KAccumulate k5 = {bases, ws.offsets, ws.counts, ws.idx, order, ws.buckets, nbuckets, cap, ws.ctl, ws.tasks, ws.longs,
+                          extra, n_main};
         be.launch(k5, nbuckets);
         if (n > cap) {  // otherwise no bucket can be long
             const uint32_t ow = be.overflow_warps();
-            KOverflow ko = {bases, ws.idx, ws.ctl, ws.tasks, ws.partials, ow};
+            KOverflow ko = {bases, ws.idx, ws.ctl, ws.tasks, ws.partials, ow, extra, n_main};
             be.launch(ko, ow * 32);
             const uint32_t ct = be.combine_threads();
             KCombine kc = {ws.ctl, ws.longs, ws.partials, ws.buckets, ct};

@@ -390,12 +390,13 @@ int32_t ensure_tmp(Ctx *c, size_t n_pts) {
     return VMSM_OK;
 }
 
-int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t n, uint32_t slot) {
+int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t n, uint32_t slot,
+                const ge_niels *extra = nullptr, uint32_t n_extra = 0) {
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "n = %llu exceeds 2^26 terms per MSM call", (unsigned long long)n);
     CudaBE be(c);
     c->cur_slot = slot;
     int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff_host + slot,
-                     c->msm_seq++);
+                     c->msm_seq++, extra, n_extra);
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
     return VMSM_OK;
@@ -776,6 +777,64 @@ int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uin
     if (rc) return rc;
     CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));  // the final kernel wrote the point into mapped pinned memory
     memcpy(out_affine, c->res_aff_host + (kSlots - 1), sizeof(ge_aff));
+    return VMSM_OK;
+}
+
+int32_t vmsm_msm_ext(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint64_t extra_pts, uint64_t extra_off,
+                     uint64_t n_extra, const uint8_t *scalars_le32, uint8_t *out_affine) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    auto ie = c->points.find(extra_pts);
+    if (it == c->points.end() || ie == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "Not enough generators.");
+    if (extra_off > ie->second.n || n_extra > ie->second.n - extra_off)
+        return fail(VMSM_ERR_INVALID, "extra range out of bounds");
+    uint64_t tot = n + n_extra;
+    if (!out_affine || (tot && !scalars_le32)) return fail(VMSM_ERR_INVALID, "null argument");
+    int32_t rc = ensure_stage(c, tot ? tot : 1);
+    if (rc) return rc;
+    if (tot) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, tot * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = run_msm(c, it->second.niels + off, c->stage_scalars, tot, kSlots - 1, ie->second.niels + extra_off,
+                 (uint32_t)n_extra);
+    if (rc) return rc;
+    CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));
+    memcpy(out_affine, c->res_aff_host + (kSlots - 1), sizeof(ge_aff));
+    return VMSM_OK;
+}
+
+int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_n, uint64_t b, uint64_t b_off,
+                           uint64_t b_n, uint64_t *out) {
+    GET_CTX(ctx);
+    if (!out) return fail(VMSM_ERR_INVALID, "null argument");
+    auto ia = c->points.find(a);
+    if (ia == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (a_off > ia->second.n || a_n > ia->second.n - a_off) return fail(VMSM_ERR_INVALID, "range out of bounds");
+    PointSet pb{};
+    if (b_n) {
+        auto ib = c->points.find(b);
+        if (ib == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+        if (b_off > ib->second.n || b_n > ib->second.n - b_off) return fail(VMSM_ERR_INVALID, "range out of bounds");
+        pb = ib->second;
+    }
+    PointSet ps;
+    int32_t rc = new_pointset(c, ia->second.curve, a_n + b_n, &ps);
+    if (rc) return rc;
+    CudaBE be(c);
+    if (a_n) {
+        KCopyPoints k = {ia->second.aff + a_off, ia->second.niels + a_off, ps.aff, ps.niels};
+        be.launch(k, (uint32_t)a_n);
+    }
+    if (b_n) {
+        KCopyPoints k = {pb.aff + b_off, pb.niels + b_off, ps.aff + a_n, ps.niels + a_n};
+        be.launch(k, (uint32_t)b_n);
+    }
+    if (be.err != cudaSuccess) {
+        cudaFree(ps.aff), cudaFree(ps.niels);
+        return fail(VMSM_ERR_CUDA, "concat: %s", cudaGetErrorString(be.err));
+    }
+    uint64_t id = c->next_id++;
+    c->points[id] = ps;
+    *out = id;
     return VMSM_OK;
 }
 

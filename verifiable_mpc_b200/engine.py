@@ -219,6 +219,24 @@ class Context:
         check(self.lib.vmsm_msm(self.h, points.handle, off, n, p, out))
         return unpack_points(out.raw)[0]
 
+    def msm_ext(self, points, off, n, extra, extra_off, n_extra, scalars):
+        """Pedersen form in one pass: sum_{i<n} s_i P[off+i] + sum_{j<n_extra} s_{n+j} E[extra_off+j]."""
+        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars)
+        nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
+        if nbytes != 32 * (n + n_extra):
+            raise ValueError("need n + n_extra scalars")
+        p, keep = _buf(raw)
+        out = ctypes.create_string_buffer(64)
+        check(self.lib.vmsm_msm_ext(self.h, points.handle, off, n, extra.handle, extra_off, n_extra, p, out))
+        return unpack_points(out.raw)[0]
+
+    def concat(self, a, a_off, a_n, b=None, b_off=0, b_n=0):
+        """Device-side copy: a[a_off:a_off+a_n] || b[b_off:b_off+b_n] as a new DevicePoints."""
+        h = ctypes.c_uint64()
+        check(self.lib.vmsm_points_concat(self.h, a.handle, a_off, a_n, b.handle if b is not None else 0, b_off, b_n,
+                                          ctypes.byref(h)))
+        return DevicePoints(self, h.value, a_n + b_n, a.curve)
+
     def msm_raw(self, points, ptr, off, n, out):
         """Zero-marshalling variant for benchmarks: ``ptr`` is a c_void_p to n*32 bytes, ``out`` a 64-byte buffer."""
         check(self.lib.vmsm_msm(self.h, points.handle, off, n, ptr, out))
