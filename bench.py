@@ -177,31 +177,35 @@ def run_gpu(args, rank, world, dist):
         if dist is not None:
             dist.barrier()
 
-    def combine(slot):
-        """rank 0 <- sum of the N partial group elements (128 B each)."""
-        if dist is None:
-            return ctx.result(slot)
-        import torch
-
-        ext = ctx.result_extended(slot)
-        mine = torch.tensor([int(v >> (63 * j)) & ((1 << 63) - 1) for v in ext for j in range(5)], dtype=torch.int64)
-        allp = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allp, mine)
+    # multi-GPU: index-range split; partials go GPU -> GPU through the owner's mailbox (peer stores over NVLink,
+    # mapped with CUDA IPC); torch.distributed only carries the 64-byte IPC handle, the barrier and the timing max
+    seq_counter = [0]
+    if dist is not None:
+        obj = [ctx.mailbox_create(world) if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
         if rank != 0:
-            return None
-        P = 2**255 - 19
-        pts = []
-        for t in allp:
-            v = t.tolist()
-            X, Y, Z, T = (sum(v[5 * q + j] << (63 * j) for j in range(5)) for q in range(4))
-            zi = pow(Z, -1, P)  # marshalling of a 128 B partial into the ABI's affine wire format
-            pts.append((X * zi % P, Y * zi % P))
-        return ctx.lincomb(pts, [1] * len(pts))
+            ctx.mailbox_open_ipc(obj[0], rank, world)
+        dist.barrier()
+
+    def issue(kind, k, slot):
+        """One step on this rank: its shard of the (world * n)-term MSM (or the whole MSM when world == 1)."""
+        if dist is not None:
+            seq_counter[0] += 1
+            ctx.set_option(_lib.OPT_SHARD_SEQ, seq_counter[0])
+        if kind == "dev":
+            ctx.msm_dev(bases[k], scal[k], slot=slot)
+        else:
+            ctx.msm_async(bases[k], host_scal[k].ptr, 0, n, slot=slot)
+
+    def combine(slot):
+        """Owner: the sum over all ranks (gathered on the device); other ranks: their own partial."""
+        return ctx.result(slot)
 
     # warm-up
     for w in range(args.warmup):
-        ctx.msm_dev(bases[w % NSETS], scal[w % NSETS], slot=0)
+        issue("dev", w % NSETS, 0)
         combine(0)
+    barrier()
     ctx.phase_times()
     l0 = ctx.launch_count()
 
@@ -209,10 +213,9 @@ def run_gpu(args, rank, world, dist):
     barrier()
     tm0 = time.perf_counter()
     ctx.timer_start()
+    assert args.steps <= 48, "result slots / mailbox entries are reused every 48 steps"
     for s in range(args.steps):
-        ctx.msm_dev(bases[s % NSETS], scal[s % NSETS], slot=s % 32)
-        if dist is not None:
-            combine(s % 32)
+        issue("dev", s % NSETS, s % 48)
     ms = ctx.timer_stop()
     barrier()
     tm1 = time.perf_counter()
@@ -231,7 +234,7 @@ def run_gpu(args, rank, world, dist):
 
     # correctness of what was just timed: set (steps-1) % NSETS, against the known-dlog identity
     last = (args.steps - 1) % NSETS
-    got = combine((args.steps - 1) % 32)
+    got = combine((args.steps - 1) % 48)
     checked = None
     if args.check:
         e = dlog_sum(SEED_SCALARS + 16 * last, SEED_BASES + 16 * last, n, start=base_off)
@@ -253,11 +256,10 @@ def run_gpu(args, rank, world, dist):
     def e2e_loop(steps):
         last = None
         for s in range(steps):
-            ctx.msm_async(bases[s % NSETS], host_scal[s % NSETS].ptr, 0, n, slot=s % 32)
+            issue("async", s % NSETS, s % 48)
             if s:
-                last = ctx.result((s - 1) % 32) if dist is None else combine((s - 1) % 32)
-        last = ctx.result((steps - 1) % 32) if dist is None else combine((steps - 1) % 32)
-        return last
+                last = combine((s - 1) % 48)
+        return combine((steps - 1) % 48)
 
     e2e_loop(min(args.warmup, 3))
     barrier()
@@ -294,11 +296,12 @@ def run_gpu(args, rank, world, dist):
         "config": {"workload": f"ed25519_msm_2^{args.log2n}", "n_per_gpu": n, "n_total": world * n,
                    "window_bits": c_auto, "windows": W_c, "bases": "g_i = r_i*B, device generated, niels form resident",
                    "l2": f"inputs rotate over {NSETS} distinct (bases, scalars) sets ({NSETS * n * 128 >> 20} MiB) > 126 MB L2",
-                   "multi_gpu": "index-range split of one N*n-term MSM; rank 0 adds N partials" if world > 1 else "single GPU",
+                   "multi_gpu": ("index-range split of one N*n-term MSM; partials pushed into rank 0's HBM mailbox over "
+                                 "NVLink peer stores (CUDA IPC), summed by a gather kernel; no NCCL") if world > 1 else "single GPU",
                    "result_checked_vs_known_dlog": checked, "e2e_result_matches": e2e_ok},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": total_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world,
-                "d2h_bytes_per_step": 64 + (128 * world if world > 1 else 0), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "d2h_bytes_per_step": 64 * world, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "Context.msm_async(points, pinned_scalars, slot) + Context.result(slot), pipelined two deep"},
         "roofline": {"bound": "imad", "kernel": "vmsm_kernel<KAccumulate>", "achieved": achieved, "peak": peak_tlps,
                      "unit": "T limb-products/s", "frac": (achieved / peak_tlps) if achieved else None, "traffic": None,

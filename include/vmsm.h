@@ -47,6 +47,8 @@ extern "C" {
 #define VMSM_OPT_REDUCE_RADIX 5 /* log2 of the bucket-tree radix (default 3) */
 #define VMSM_OPT_ASYNC_TAIL 7 /* 1 (default) = run the latency-bound MSM tail on a side stream under the next MSM's head */
 #define VMSM_OPT_CAP_FACTOR 8 /* per-thread bucket cap = max(64, factor * average bucket population) (default 8) */
+#define VMSM_OPT_SHARD_SEQ 9 /* non-zero: the NEXT vmsm_msm_dev / vmsm_msm_async call is one shard of a multi-GPU MSM
+                               with this sequence number (see the mailbox functions); clears itself */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */
@@ -118,6 +120,20 @@ int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint
                      uint32_t slot);
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine);      /* synchronises */
 int32_t vmsm_result_extended(uint64_t ctx, uint32_t slot, uint8_t *out_extended);  /* synchronises */
+
+/* ---- multi-GPU: index-range split of ONE MSM over the GPUs of a box ---------------------------
+ * Every GPU computes the partial sum of its slice of (bases, scalars) and its final kernel pushes the 128-byte
+ * partial into a mailbox in the owner GPU's HBM (peer store over NVLink) followed by the sequence number `seq`;
+ * on the owner a gather kernel waits for all `world` sequence numbers, adds the partials and normalises.  No host
+ * hop and no NCCL.  Owner = rank 0: vmsm_mailbox_create (+ optional CUDA-IPC handle for other processes); other
+ * ranks: vmsm_mailbox_open_ipc (another process) or vmsm_mailbox_open_local (another context of the same process).
+ * vmsm_result_affine(slot) returns the combined result on the owner (VMSM_ERR_TIMEOUT if a partial never arrived)
+ * and the rank's own partial elsewhere.  `seq` must be non-zero and strictly increase from call to call. */
+int32_t vmsm_mailbox_create(uint64_t ctx, uint32_t world, uint8_t *ipc_handle_out /* 64 B or NULL */);
+int32_t vmsm_mailbox_open_ipc(uint64_t ctx, const uint8_t *ipc_handle /* 64 B */, uint32_t rank, uint32_t world);
+int32_t vmsm_mailbox_open_local(uint64_t ctx, uint64_t owner_ctx, uint32_t rank);
+int32_t vmsm_msm_dev_shard(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
+                           uint32_t slot, uint32_t seq);
 
 /* ---- generator fold ----------------------------------------------------------------------------------------
  * In place: P[j] = c * P[j] + P[half + j] for j < half, then the vector length becomes `half`.

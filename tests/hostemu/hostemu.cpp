@@ -38,6 +38,7 @@ struct HostBE {
     }
     uint32_t overflow_warps() { return 3; }
     uint32_t combine_threads() { return 5; }
+    void after_final(ge_ext *, ge_aff *) {}
     void result_ready() {}
     void head_wait_tail(int) {}
     void tail_begin() {}

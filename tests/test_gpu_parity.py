@@ -230,3 +230,44 @@ def test_msm_skewed_scalars(ctx):
             assert ctx.msm(dev, sc) == E.msm_known_dlog(sc, dl), c
     finally:
         ctx.set_option(_lib.OPT_WINDOW_BITS, 0)
+
+
+def test_multi_gpu_mailbox_shards(ctx):
+    """Index-range split over 3 contexts (all GPUs of the box if there are several, else 3 contexts on GPU 0):
+    partials are pushed into the owner's mailbox by the final kernels and summed by the owner's gather kernel."""
+    import ctypes
+
+    from verifiable_mpc_b200 import Context, VmsmError, _lib
+
+    ndev = ctypes.c_int32()
+    _lib.load().vmsm_device_count(ctypes.byref(ndev))
+    world, n = 3, 1 << 11
+    ctxs = [Context(r % ndev.value) for r in range(world)]
+    try:
+        ctxs[0].mailbox_create(world)
+        for r in range(1, world):
+            ctxs[r].mailbox_open_local(ctxs[0], r)
+        total_sc, total_dl = [], []
+        parts = []
+        for r, c in enumerate(ctxs):
+            dl = [prng.scalar(0x900 + r, i) for i in range(n)]
+            sc = [prng.scalar(0xA00 + r, i) for i in range(n)]
+            parts.append((c.fixed_base(scalars=dl), c.upload_scalars(sc)))
+            total_sc += sc
+            total_dl += dl
+        for seq in (1, 2, 3):  # several rounds through different slots
+            order = [2, 0, 1] if seq == 2 else [0, 1, 2]
+            for r in order:
+                ctxs[r].msm_dev_shard(parts[r][0], parts[r][1], slot=seq, seq=seq)
+            assert ctxs[0].result(seq) == E.msm_known_dlog(total_sc, total_dl)
+            for r in (1, 2):  # non-owners keep their own partial
+                lo, hi = r * n, (r + 1) * n
+                assert ctxs[r].result(seq) == E.msm_known_dlog(total_sc[lo:hi], total_dl[lo:hi])
+        # a missing partial is reported, not hung on
+        ctxs[0].msm_dev_shard(parts[0][0], parts[0][1], slot=9, seq=77)
+        with pytest.raises(VmsmError) as ei:
+            ctxs[0].result(9)
+        assert ei.value.code == _lib.ERR_TIMEOUT
+    finally:
+        for c in ctxs:
+            c.close()

@@ -13,7 +13,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_POINT, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TIMEOUT = -1, -2, -3, -4, -5, -6
 CURVE_ED25519, CURVE_BN256_G1, CURVE_BN256_G2 = 0, 1, 2
 OPT_WINDOW_BITS, OPT_PHASE_TIMING, OPT_SORT_BUCKETS, OPT_CHECK_POINTS, OPT_REDUCE_RADIX = 1, 2, 3, 4, 5
-OPT_QUAD_THRESHOLD, OPT_ASYNC_TAIL, OPT_CAP_FACTOR = 6, 7, 8
+OPT_QUAD_THRESHOLD, OPT_ASYNC_TAIL, OPT_CAP_FACTOR, OPT_SHARD_SEQ = 6, 7, 8, 9
 PHASES = ("digits", "scan", "scatter", "order", "accumulate", "reduce", "final")
 
 
@@ -53,6 +53,10 @@ SIGNATURES = {
     "vmsm_msm": [_u64, _u64, _u64, _u64, _p, _p],
     "vmsm_msm_ext": [_u64, _u64, _u64, _u64, _u64, _u64, _u64, _p, _p],
     "vmsm_points_concat": [_u64, _u64, _u64, _u64, _u64, _u64, _u64, _pu64],
+    "vmsm_mailbox_create": [_u64, _u32, _p],
+    "vmsm_mailbox_open_ipc": [_u64, _p, _u32, _u32],
+    "vmsm_mailbox_open_local": [_u64, _u64, _u32],
+    "vmsm_msm_dev_shard": [_u64, _u64, _u64, _u64, _u64, _u64, _u32, _u32],
     "vmsm_msm_async": [_u64, _u64, _u64, _u64, _p, _u32],
     "vmsm_msm_dev": [_u64, _u64, _u64, _u64, _u64, _u64, _u32],
     "vmsm_result_affine": [_u64, _u32, _p],

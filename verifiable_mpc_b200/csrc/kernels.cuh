@@ -89,6 +89,18 @@ VMSM_HD ge_ext ld_ext(const ge_ext *p) {
     r.T = ld_fe(&p->T);
     return r;
 }
+// same without the read-only (non-coherent) path: for memory another GPU or stream may have just written
+VMSM_HD ge_ext ld_ext_plain(const ge_ext *p) {
+    ge_ext r;
+#if defined(__CUDA_ARCH__)
+    const volatile uint32_t *w = reinterpret_cast<const volatile uint32_t *>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.X.v[i] = w[i], r.Y.v[i] = w[8 + i], r.Z.v[i] = w[16 + i], r.T.v[i] = w[24 + i];
+#else
+    r = *p;
+#endif
+    return r;
+}
 VMSM_HD void st_ext(ge_ext *p, const ge_ext &v) {
     st_fe(&p->X, v.X);
     st_fe(&p->Y, v.Y);
@@ -479,6 +491,71 @@ struct KFinalQ {
         KFinal k = {S, T, out_ext, out_aff, W, c};
         k(0);
 #endif
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- multi-GPU partials
+// Index-range split of one MSM over G GPUs: every GPU pushes the 128-byte partial result of its slice
+// straight into a mailbox in the owner GPU's HBM (peer store over NVLink, mapped through CUDA IPC or peer access),
+// then publishes a sequence number; the owner's gather kernel waits for the G sequence numbers, adds the partials and
+// normalises.  No host hop, no NCCL.  One mailbox entry per (result slot, rank).
+struct MailSlot {
+    ge_ext pt;
+    uint32_t seq;
+    uint32_t pad[31];
+};
+
+struct KPushPartial {
+    enum { kBlock = 32 };
+    const ge_ext *src;  // this GPU's partial (its own result slot)
+    MailSlot *dst;      // mailbox entry on the owner (may be a peer pointer)
+    uint32_t seq;
+    VMSM_HD void operator()(uint32_t tid) const {
+        if (tid) return;
+        st_ext(&dst->pt, ld_ext_plain(src));
+#if defined(__CUDA_ARCH__)
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t *>(&dst->seq) = seq;
+        __threadfence_system();
+#else
+        dst->seq = seq;
+#endif
+    }
+};
+
+struct KGatherPartials {
+    enum { kBlock = 32 };
+    MailSlot *box;  // `world` consecutive entries of this result slot (owner-local memory)
+    uint32_t world, seq;
+    ge_ext *out_ext;
+    ge_aff *out_aff;
+    uint32_t *status;  // host-mapped: 0 ok, 1 timeout
+    VMSM_HD void operator()(uint32_t tid) const {
+        if (tid) return;
+        ge_ext acc = ge_identity();
+        for (uint32_t r = 0; r < world; r++) {
+#if defined(__CUDA_ARCH__)
+            volatile uint32_t *flag = reinterpret_cast<volatile uint32_t *>(&box[r].seq);
+            long long t0 = clock64();
+            while (*flag != seq) {
+                if (clock64() - t0 > (1ll << 33)) {  // ~4.5 s at 1.9 GHz: a peer died
+                    *status = 1u;
+                    return;
+                }
+                __nanosleep(200);
+            }
+            __threadfence_system();
+#else
+            if (box[r].seq != seq) {
+                *status = 1u;
+                return;
+            }
+#endif
+            acc = ge_add(acc, ld_ext_plain(&box[r].pt));
+        }
+        st_ext(out_ext, acc);
+        st_aff(out_aff, ge_ext_to_aff(acc));
+        *status = 0u;
     }
 };
 

@@ -215,6 +215,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         }
     }
     be.phase_mark(PH_FINAL);
+    be.after_final(out_ext, out_aff);  // multi-GPU: push this partial to the owner's mailbox / gather on the owner
     be.result_ready();
     if (in_tail) be.tail_end(par);
     be.phase_end();

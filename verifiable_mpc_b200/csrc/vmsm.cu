@@ -227,6 +227,13 @@ struct Ctx {
     cudaEvent_t ev_slot[64] = {nullptr};
     uint32_t cur_slot = 0;
     ge_aff *res_aff_host = nullptr;  // pinned + mapped, kSlots entries: written by the final kernel itself
+    uint32_t *res_status_host = nullptr;  // pinned + mapped, kSlots words: 0 ok, 1 = a multi-GPU partial timed out
+    // multi-GPU mailbox (kernels.cuh: KPushPartial / KGatherPartials)
+    MailSlot *mailbox = nullptr;  // [kSlots][mb_world]; owner: local allocation, others: peer mapping
+    bool mb_owner = false, mb_ipc = false;
+    uint32_t mb_world = 0, mb_rank = 0;
+    uint32_t shard_seq = 0;  // != 0 while a sharded MSM is being issued
+    uint32_t shard_next = 0;  // VMSM_OPT_SHARD_SEQ: applies to the next MSM call of any flavour, then clears
     MsmOptions opt;
     bool phase_timing = false;
     bool check_points = true;
@@ -275,6 +282,16 @@ struct CudaBE {
     // the node buffers of parity `par` may still be read by the tail of the MSM two calls ago
     void head_wait_tail(int par) {
         if (c->tail_pending[par]) note(cudaStreamWaitEvent(c->stream, c->ev_tail[par], 0));
+    }
+    void after_final(ge_ext *out_ext, ge_aff *out_aff) {
+        if (!c->shard_seq || !c->mailbox) return;
+        MailSlot *box = c->mailbox + (size_t)c->cur_slot * c->mb_world;
+        KPushPartial kp = {out_ext, box + c->mb_rank, c->shard_seq};
+        launch(kp, 32);
+        if (c->mb_owner) {
+            KGatherPartials kg = {box, c->mb_world, c->shard_seq, out_ext, out_aff, c->res_status_host + c->cur_slot};
+            launch(kg, 32);
+        }
     }
     void result_ready() { note(cudaEventRecord(c->ev_slot[c->cur_slot], cur)); }
     void tail_begin() {
@@ -395,8 +412,14 @@ int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "n = %llu exceeds 2^26 terms per MSM call", (unsigned long long)n);
     CudaBE be(c);
     c->cur_slot = slot;
+    if (c->shard_next && slot != kSlots - 1) {
+        if (!c->mailbox) return fail(VMSM_ERR_INVALID, "VMSM_OPT_SHARD_SEQ set but the context has no mailbox");
+        c->shard_seq = c->shard_next;
+        c->shard_next = 0;
+    }
     int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff_host + slot,
                      c->msm_seq++, extra, n_extra);
+    c->shard_seq = 0;
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
     return VMSM_OK;
@@ -459,6 +482,8 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     CU(cudaMalloc(&c->small_niels, 64 * sizeof(ge_niels)));
     CU(cudaHostAlloc(&c->pin, 4096, cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->res_aff_host, kSlots * sizeof(ge_aff), cudaHostAllocMapped));
+    CU(cudaHostAlloc(&c->res_status_host, kSlots * sizeof(uint32_t), cudaHostAllocMapped));
+    memset(c->res_status_host, 0, kSlots * sizeof(uint32_t));
     CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     for (int k = 0; k < 2; k++) {
         CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
@@ -488,6 +513,11 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (int k = 0; k < 2; k++) cudaFree(c->astage[k]), cudaEventDestroy(c->ev_copied[k]), cudaEventDestroy(c->ev_consumed[k]);
     for (uint32_t k = 0; k < kSlots; k++) cudaEventDestroy(c->ev_slot[k]);
     cudaFreeHost(c->res_aff_host);
+    cudaFreeHost(c->res_status_host);
+    if (c->mailbox) {
+        if (c->mb_owner) cudaFree(c->mailbox);
+        else if (c->mb_ipc) cudaIpcCloseMemHandle(c->mailbox);
+    }
     cudaStreamDestroy(c->copy);
     for (auto &kv : c->points) cudaFree(kv.second.aff), cudaFree(kv.second.niels);
     for (auto &kv : c->scalars) cudaFree(kv.second.data);
@@ -529,6 +559,10 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
         case VMSM_OPT_REDUCE_RADIX:
             if (value < 1 || value > 6) return fail(VMSM_ERR_INVALID, "reduce radix log2 must be in [1, 6]");
             c->opt.reduce_log2r = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_SHARD_SEQ:
+            if (value < 0 || value > 0xffffffffll) return fail(VMSM_ERR_INVALID, "shard seq out of range");
+            c->shard_next = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_CAP_FACTOR:
             if (value < 1 || value > 65536) return fail(VMSM_ERR_INVALID, "cap factor out of range");
@@ -838,6 +872,81 @@ int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_
     return VMSM_OK;
 }
 
+// ---- multi-GPU: index-range split of one MSM, partials through a peer mailbox
+int32_t vmsm_mailbox_create(uint64_t ctx, uint32_t world, uint8_t *ipc_handle_out) {
+    GET_CTX(ctx);
+    if (world < 1 || world > 64) return fail(VMSM_ERR_INVALID, "world must be in [1, 64]");
+    if (c->mailbox) return fail(VMSM_ERR_INVALID, "context already has a mailbox");
+    size_t bytes = (size_t)kSlots * world * sizeof(MailSlot);
+    CU(cudaMalloc(&c->mailbox, bytes));
+    CU(cudaMemset(c->mailbox, 0, bytes));
+    c->mb_owner = true;
+    c->mb_world = world;
+    c->mb_rank = 0;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, c->mailbox));
+        static_assert(sizeof(h) == 64, "IPC handle size");
+        memcpy(ipc_handle_out, &h, 64);
+    }
+    return VMSM_OK;
+}
+
+int32_t vmsm_mailbox_open_ipc(uint64_t ctx, const uint8_t *ipc_handle, uint32_t rank, uint32_t world) {
+    GET_CTX(ctx);
+    if (!ipc_handle || rank == 0 || rank >= world || world > 64) return fail(VMSM_ERR_INVALID, "bad mailbox arguments");
+    if (c->mailbox) return fail(VMSM_ERR_INVALID, "context already has a mailbox");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->mailbox = (MailSlot *)p;
+    c->mb_owner = false;
+    c->mb_ipc = true;
+    c->mb_world = world;
+    c->mb_rank = rank;
+    return VMSM_OK;
+}
+
+int32_t vmsm_mailbox_open_local(uint64_t ctx, uint64_t owner_ctx, uint32_t rank) {
+    GET_CTX(ctx);
+    Ctx *o = get_ctx(owner_ctx);
+    if (!o || !o->mailbox || !o->mb_owner) return fail(VMSM_ERR_INVALID, "owner context has no mailbox");
+    if (rank == 0 || rank >= o->mb_world) return fail(VMSM_ERR_INVALID, "bad rank");
+    if (c->mailbox) return fail(VMSM_ERR_INVALID, "context already has a mailbox");
+    if (o->device != c->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, c->device, o->device));
+        if (!can) return fail(VMSM_ERR_UNSUPPORTED, "no peer access from device %d to %d", c->device, o->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(VMSM_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    c->mailbox = o->mailbox;
+    c->mb_owner = false;
+    c->mb_ipc = false;
+    c->mb_world = o->mb_world;
+    c->mb_rank = rank;
+    return VMSM_OK;
+}
+
+int32_t vmsm_msm_dev_shard(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
+                           uint32_t slot, uint32_t seq) {
+    GET_CTX(ctx);
+    if (!c->mailbox) return fail(VMSM_ERR_INVALID, "no mailbox: call vmsm_mailbox_create / _open first");
+    if (seq == 0) return fail(VMSM_ERR_INVALID, "seq must be non-zero and increase from call to call");
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    auto is = c->scalars.find(sc);
+    if (is == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (poff > it->second.n || n > it->second.n - poff) return fail(VMSM_ERR_INVALID, "Not enough generators.");
+    if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+    if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    c->shard_next = seq;
+    return run_msm(c, it->second.niels + poff, is->second.data + soff * 8, n, slot);
+}
+
 int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
                        uint32_t slot) {
     GET_CTX(ctx);
@@ -884,6 +993,10 @@ int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine) {
     GET_CTX(ctx);
     if (slot >= kSlots || !out_affine) return fail(VMSM_ERR_INVALID, "bad slot / null argument");
     CU(cudaEventSynchronize(c->ev_slot[slot]));  // waits for THIS result only, not for MSMs issued after it
+    if (c->res_status_host[slot]) {
+        c->res_status_host[slot] = 0;
+        return fail(VMSM_ERR_TIMEOUT, "a multi-GPU partial for slot %u did not arrive", slot);
+    }
     memcpy(out_affine, c->res_aff_host + slot, sizeof(ge_aff));
     return VMSM_OK;
 }

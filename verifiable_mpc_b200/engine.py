@@ -252,6 +252,25 @@ class Context:
             n = min(points.n - poff, scalars.n - soff)
         check(self.lib.vmsm_msm_dev(self.h, points.handle, poff, n, scalars.handle, soff, slot))
 
+    # -- multi-GPU shards (one context per GPU; rank 0 owns the mailbox)
+    def mailbox_create(self, world):
+        """Owner side; returns the 64-byte CUDA-IPC handle other processes pass to ``mailbox_open_ipc``."""
+        h = ctypes.create_string_buffer(64)
+        check(self.lib.vmsm_mailbox_create(self.h, world, h))
+        return h.raw
+
+    def mailbox_open_ipc(self, handle, rank, world):
+        check(self.lib.vmsm_mailbox_open_ipc(self.h, handle, rank, world))
+
+    def mailbox_open_local(self, owner, rank):
+        check(self.lib.vmsm_mailbox_open_local(self.h, owner.h, rank))
+
+    def msm_dev_shard(self, points, scalars, slot, seq, poff=0, soff=0, n=None):
+        """This GPU's slice of a sharded MSM; the owner's ``result(slot)`` is the sum over all ranks."""
+        if n is None:
+            n = min(points.n - poff, scalars.n - soff)
+        check(self.lib.vmsm_msm_dev_shard(self.h, points.handle, poff, n, scalars.handle, soff, slot, seq))
+
     def result(self, slot=0):
         out = ctypes.create_string_buffer(64)
         check(self.lib.vmsm_result_affine(self.h, slot, out))
