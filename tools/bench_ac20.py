@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""AC20 compressed-pivot prove / verify latency on the device twins (BASELINE.json config 3: N = 2^16 generators).
+
+Synthetic statement below the circuit front-end: generators g_i = r_i*B (device fixed-base kernel),
+witness x, blinding gamma and linear form L uniform, P = commitment; then protocol_5_prover / protocol_5_verifier.
+Prints one JSON line per size with a host/device breakdown.
+"""
+import argparse
+import json
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log2n", type=int, nargs="+", default=[10, 13, 16])
+    ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+
+    from verifiable_mpc_b200 import fingroups
+    from verifiable_mpc_b200.ac20 import compressed_pivot as cp
+    from verifiable_mpc_b200.ac20 import generators as gens
+    from verifiable_mpc_b200.ac20 import pivot
+    from verifiable_mpc_b200.finfields import GF
+
+    group = fingroups.EllipticCurve("Ed25519", "projective")
+    group.is_additive, group.is_multiplicative = False, True
+    gf = GF(group.order)
+    ctx = group._ctx()
+
+    # instrument: time spent hashing (str + sha256) vs in device calls
+    acc = {"hash": 0.0, "commit": 0.0, "fold": 0.0, "lincomb": 0.0}
+    orig_hash, orig_vc, orig_fold, orig_lin = pivot.fiat_shamir_hash, pivot.vector_commitment, cp._fold_generators, group.lincomb.__func__
+
+    def timed(name, fn):
+        def wrapper(*a, **k):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **k)
+            finally:
+                acc[name] += time.perf_counter() - t0
+        return wrapper
+
+    pivot.fiat_shamir_hash = timed("hash", orig_hash)
+    pivot.vector_commitment = timed("commit", orig_vc)
+    cp._fold_generators = timed("fold", orig_fold)
+    group.lincomb = classmethod(timed("lincomb", orig_lin))
+
+    out = open(args.out, "a") if args.out else None
+    for logn in args.log2n:
+        N = 1 << logn
+        n = N - 1
+        rng = random.Random(logn)
+        gens.prng = rng
+        t0 = time.perf_counter()
+        generators = gens.create_generators(n, group)
+        ctx.sync()
+        t_gen = time.perf_counter() - t0
+        x = [gf(rng.randrange(gf.order)) for _ in range(n)]
+        gamma = gf(rng.randrange(gf.order))
+        L = pivot.LinearForm([gf(rng.randrange(gf.order)) for _ in range(n)])
+        y = L(x)
+        P = pivot.vector_commitment(x, gamma, generators["g"], generators["h"])
+        best = None
+        for rep in range(args.repeat):
+            cp.prng = random.Random(1000 + rep)
+            for k in acc:
+                acc[k] = 0.0
+            t0 = time.perf_counter()
+            proof = cp.protocol_5_prover(generators, P, L, y, x, gamma, gf)
+            t_prove = time.perf_counter() - t0
+            prove_parts = dict(acc)
+            for k in acc:
+                acc[k] = 0.0
+            t0 = time.perf_counter()
+            ok = cp.protocol_5_verifier(generators, P, L, y, proof, gf)
+            t_verify = time.perf_counter() - t0
+            rec = {"N": N, "rounds": logn - 1, "prove_s": t_prove, "verify_s": t_verify, "verified": bool(ok),
+                   "create_generators_s": t_gen,
+                   "prove_breakdown_s": {k: round(v, 4) for k, v in prove_parts.items()},
+                   "prove_host_other_s": round(t_prove - sum(prove_parts.values()), 4),
+                   "verify_breakdown_s": {k: round(v, 4) for k, v in acc.items()}}
+            if best is None or rec["prove_s"] < best["prove_s"]:
+                best = rec
+        print(json.dumps(best), flush=True)
+        if out:
+            out.write(json.dumps(best) + "\n")
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,49 @@ logger_cp_hout.setLevel(logging.INFO)
 
 _TAG = "First hash of compressed pivot"
 
+# Host scalar algebra.  The reference keeps linear forms and witnesses as lists of field-element OBJECTS and pays one
+# Python method call per coefficient per round; when every entry is an element of `gf` (the normal case) the twins
+# below run the same algebra on plain ints modulo the order and only materialise objects / text where the reference's
+# outputs require it (proof["z_prime"], the decimal text inside the Fiat-Shamir pre-image).  Mixed / plain-int inputs
+# take the generic object path, which reproduces the reference's unreduced-integer behaviour exactly.
+FAST_INT_PATH = True
+
+
+def _all_in_field(values, gf):
+    return all(type(v) is gf for v in values)
+
+
+def _signed_text(ints, q):
+    """repr of a list of gf elements (signed representatives, as MPyC prints them) from their residues."""
+    half = q >> 1
+    return "[" + ", ".join([str(v - q if v > half else v) for v in ints]) + "]"
+
+
+class _Verbatim:
+    """An object whose str() is a precomputed pre-image (fiat_shamir_hash hashes str(input_list))."""
+    __slots__ = ("text",)
+
+    def __init__(self, text):
+        self.text = text
+
+    def __str__(self):
+        return self.text
+
+
+class _IntForm:
+    """Stand-in for a LinearForm over gf inside the round loop: residues + the exact repr of the real thing."""
+    __slots__ = ("ints", "q")
+
+    def __init__(self, ints, q):
+        self.ints, self.q = ints, q
+
+    def __repr__(self):
+        return f"{_signed_text(self.ints, self.q)}, 0"
+
+
+def _dot(a, b, q):
+    return sum(map(int.__mul__, a, b)) % q
+
 
 def _private_device_list(g_hat, group):
     """A device vector this call may fold in place (the caller's list stays untouched, like the reference's)."""
@@ -64,6 +107,10 @@ def protocol_4_prover(g_hat, k, Q, L_tilde, z_hat, gf, proof=None, round_i=0):
     group = type(k)
     g_hat = _private_device_list(g_hat, group)
     order = k.order
+    if (FAST_INT_PATH and isinstance(L_tilde, pivot.LinearForm) and gf.order == order
+            and _all_in_field(L_tilde.coeffs, gf) and _all_in_field(z_hat, gf)):
+        return _protocol_4_prover_ints(g_hat, k, Q, [c.value for c in L_tilde.coeffs], [z.value for z in z_hat], gf,
+                                       proof, round_i)
     while True:
         half = len(g_hat) // 2
         z_l, z_r = z_hat[:half], z_hat[half:]
@@ -85,11 +132,55 @@ def protocol_4_prover(g_hat, k, Q, L_tilde, z_hat, gf, proof=None, round_i=0):
         round_i += 1
 
 
+def _protocol_4_prover_ints(g_hat, k, Q, coeffs, z, gf, proof, round_i):
+    """The round loop of protocol_4_prover on residues modulo the group order (same values, same transcript)."""
+    group = type(k)
+    q = k.order
+    while True:
+        half = len(g_hat) // 2
+        z_l, z_r = z[:half], z[half:]
+        logger_cp.debug("Calculate A_i, B_i.")
+        A = pivot.vector_commitment(z_l, _dot(coeffs[half:], z_l, q), g_hat[half:], k)
+        B = pivot.vector_commitment(z_r, _dot(coeffs[:half], z_r, q), g_hat[:half], k)
+        proof["A" + str(round_i)] = A
+        proof["B" + str(round_i)] = B
+        c = _fold_challenge(A, B, g_hat, k, Q, _IntForm(coeffs, q), q)
+        g_hat = _fold_generators(g_hat, c)
+        Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+        coeffs = [(l * c + r) % q for l, r in zip(coeffs[:half], coeffs[half:])]
+        z = [(l + c * r) % q for l, r in zip(z_l, z_r)]
+        if len(z) <= 2:
+            proof["z_prime"] = [gf(v) for v in z]
+            return proof
+        round_i += 1
+
+
+def _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i):
+    group = type(k)
+    q = k.order
+    while True:
+        half = len(g_hat) // 2
+        A = proof["A" + str(round_i)]
+        B = proof["B" + str(round_i)]
+        c = _fold_challenge(A, B, g_hat, k, Q, _IntForm(coeffs, q), q)
+        g_hat = _fold_generators(g_hat, c)
+        Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+        coeffs = [(l * c + r) % q for l, r in zip(coeffs[:half], coeffs[half:])]
+        if len(g_hat) <= 2:
+            z_prime = proof["z_prime"]
+            gamma = int(sum([gf(cf) * zp for cf, zp in zip(coeffs, z_prime)]) + 0)
+            Q_check = pivot.vector_commitment(z_prime, gamma, g_hat, k)
+            return Q_check == Q
+        round_i += 1
+
+
 def _first_challenges(t, A, generators, P, L, y, order):
     input_list = [t, A.normalize(), generators, P.normalize(), L, y]
     logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
-    c0 = pivot.fiat_shamir_hash(input_list + [0] + [_TAG], order)
-    c1 = pivot.fiat_shamir_hash(input_list + [1] + [_TAG], order)
+    # str(input_list + [b] + [tag]) for b = 0, 1 share everything but one character: build the O(N) text once
+    body = ", ".join([repr(item) for item in input_list])
+    c0 = pivot.fiat_shamir_hash(_Verbatim(f"[{body}, 0, {_TAG!r}]"), order)
+    c1 = pivot.fiat_shamir_hash(_Verbatim(f"[{body}, 1, {_TAG!r}]"), order)
     logger_cp_hout.debug(f"After hash, hash=\n{c0}, {c1}")
     return c0, c1
 
@@ -116,18 +207,25 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     r = [prng.randrange(order) for _ in range(n)]
     rho = prng.randrange(order)
     logger_cp.debug("Calculate t.")
-    t = L(r)
+    fast = FAST_INT_PATH and _all_in_field(L.coeffs, gf) and _all_in_field(x, gf) and L.constant == 0
+    t = gf(_dot([cf.value for cf in L.coeffs], r, order)) + L.constant if fast else L(r)
     logger_cp.debug("Calculate A.")
     A = pivot.vector_commitment(r, rho, g, h)
     proof["t"] = t
     proof["A"] = A
     c0, c1 = _first_challenges(t, A, generators, P, L, y, order)
-    z = [c0 * x_i + r_i for x_i, r_i in zip(x, r)]
+    z = [gf(c0 * x_i.value + r_i) for x_i, r_i in zip(x, r)] if fast else [c0 * x_i + r_i for x_i, r_i in zip(x, r)]
     phi = gf(c0 * gamma + rho)
     z_hat = z + [phi]
     g_hat = _g_hat(g, h, group)
     logger_cp.debug("Calculate Q.")
     Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
+    if FAST_INT_PATH and _all_in_field(L.coeffs, gf) and _all_in_field(z_hat, gf):
+        # same values as the generic lines below; the appended coefficient 0 prints as "0" either way
+        coeffs = [cf.value * c1 % order for cf in L.coeffs] + [0]
+        zi = [v.value for v in z_hat]
+        assert _dot([cf.value for cf in L.coeffs], zi[:-1], order) * c1 % order == _dot(coeffs, zi, order)
+        return _protocol_4_prover_ints(g_hat, k, Q, coeffs, zi, gf, proof, 0)
     L_tilde = pivot.LinearForm(L.coeffs + [0]) * c1
     assert L(z) * c1 == L_tilde(z_hat)
     return protocol_4_prover(g_hat, k, Q, L_tilde, z_hat, gf, proof)
@@ -138,6 +236,9 @@ def protocol_4_verifier(g_hat, k, Q, L_tilde, gf, proof, round_i=0):
     group = type(k)
     g_hat = _private_device_list(g_hat, group)
     order = k.order
+    if (FAST_INT_PATH and isinstance(L_tilde, pivot.LinearForm) and gf.order == order
+            and _all_in_field(L_tilde.coeffs, gf)):
+        return _protocol_4_verifier_ints(g_hat, k, Q, [c.value for c in L_tilde.coeffs], gf, proof, round_i)
     while True:
         half = len(g_hat) // 2
         logger_cp.debug("Load from proof: A_i, B_i.")
@@ -167,5 +268,8 @@ def protocol_5_verifier(generators, P, L, y, proof, gf):
     c0, c1 = _first_challenges(t, A, generators, P, L, y, order)
     g_hat = _g_hat(g, h, group)
     Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
+    if FAST_INT_PATH and _all_in_field(L.coeffs, gf):
+        coeffs = [cf.value * c1 % order for cf in L.coeffs] + [0]
+        return _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, 0)
     L_tilde = pivot.LinearForm(L.coeffs + [0]) * c1
     return protocol_4_verifier(g_hat, k, Q, L_tilde, gf, proof)

@@ -249,7 +249,11 @@ class DevicePointList:
         return list(self)
 
     def __repr__(self):
-        return "[" + ", ".join(f"[{x}, {y}, 1]" for x, y in self.affine_list()) + "]"
+        # byte-identical to repr(list of points); straight from the downloaded 64-byte encodings
+        raw = self.dev.download(self.off, self.n)
+        fb = int.from_bytes
+        return "[" + ", ".join([f"[{fb(raw[i:i + 32], 'little')}, {fb(raw[i + 32:i + 64], 'little')}, 1]"
+                                for i in range(0, len(raw), 64)]) + "]"
 
     def __eq__(self, other):
         if isinstance(other, DevicePointList):
