@@ -149,7 +149,7 @@ def run_gpu(args, rank, world, dist):
 
     import numpy as np
 
-    from verifiable_mpc_b200 import Context, _lib, synth
+    from verifiable_mpc_b200 import Context, _lib, shard, synth
 
     local = int(os.environ.get("LOCAL_RANK", rank))
     ctx = Context(local)
@@ -181,11 +181,7 @@ def run_gpu(args, rank, world, dist):
     # mapped with CUDA IPC); torch.distributed only carries the 64-byte IPC handle, the barrier and the timing max
     seq_counter = [0]
     if dist is not None:
-        obj = [ctx.mailbox_create(world) if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        if rank != 0:
-            ctx.mailbox_open_ipc(obj[0], rank, world)
-        dist.barrier()
+        shard.setup_mailbox(ctx, dist, rank, world)
 
     def issue(kind, k, slot):
         """One step on this rank: its shard of the (world * n)-term MSM (or the whole MSM when world == 1)."""
@@ -223,14 +219,8 @@ def run_gpu(args, rank, world, dist):
     launches = ctx.launch_count() - l0
     phases, calls = ctx.phase_times()
     if dist is not None:
-        import torch
-
-        t = torch.tensor([ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
+        ms = shard.max_over_ranks(dist, ms)
+        launches = shard.sum_over_ranks(dist, launches)
 
     # correctness of what was just timed: set (steps-1) % NSETS, against the known-dlog identity
     last = (args.steps - 1) % NSETS
@@ -268,11 +258,7 @@ def run_gpu(args, rank, world, dist):
     barrier()
     e2e_s = time.perf_counter() - e0
     if dist is not None:
-        import torch
-
-        t = torch.tensor([e2e_s], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s = shard.max_over_ranks(dist, e2e_s)
     e2e_ok = None
     if rank == 0 and checked is not None and (args.steps - 1) % NSETS == last:
         e2e_ok = bool(e2e_last == got)
