@@ -4,6 +4,7 @@ It lets the `-m "not gpu"` suite exercise the HOST logic of the prover twins (tr
 slicing / folding bookkeeping, PRNG draw order) against the golden fixtures in a container without a GPU.  It is
 never importable from the product: the product's Context is libvmsm.so or nothing.
 """
+from oracle import bn256 as BN
 from oracle import ed25519 as E
 
 
@@ -40,10 +41,31 @@ def _unpack_scalars(raw):
     return [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
 
 
+class FakeBNPoints:
+    def __init__(self, ctx, pts, curve):
+        self.ctx, self.pts, self.handle, self.curve = ctx, list(pts), 1, curve
+
+    @property
+    def n(self):
+        return len(self.pts)
+
+    def tolist(self, off=0, n=None):
+        n = len(self.pts) - off if n is None else n
+        return self.pts[off:off + n]
+
+    def free(self):
+        self.handle = 0
+
+
 class FakeContext:
     calls = 0
 
     def upload_points(self, pts, curve=0):
+        if curve:
+            F = BN.FP2 if curve == 2 else BN.FP
+            for p in pts:
+                assert BN.on_curve(F, p)
+            return FakeBNPoints(self, pts, curve)
         if isinstance(pts, (bytes, bytearray)):
             pts = [E.point_from_bytes(pts[i:i + 64]) for i in range(0, len(pts), 64)]
         for p in pts:
@@ -63,6 +85,11 @@ class FakeContext:
         return E.msm_naive(sc, bases)
 
     def msm(self, points, scalars, off=0, n=None):
+        if getattr(points, "curve", 0):
+            F = BN.FP2 if points.curve == 2 else BN.FP
+            sc = _unpack_scalars(scalars)
+            FakeContext.calls += 1
+            return BN.msm_naive(F, sc, points.pts[off:off + len(sc)])
         sc = _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else [int(s) % E.L for s in scalars]
         return E.msm_naive(sc, points.pts[off:off + len(sc)])
 
@@ -72,4 +99,7 @@ class FakeContext:
 
     def lincomb(self, pts, scalars, curve=0):
         FakeContext.calls += 1
+        if curve:
+            F = BN.FP2 if curve == 2 else BN.FP
+            return BN.msm_naive(F, [int(s) % BN.N for s in scalars], list(pts))
         return E.msm_naive([int(s) % E.L for s in scalars], list(pts)) if pts else E.IDENTITY

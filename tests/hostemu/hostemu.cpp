@@ -156,4 +156,71 @@ void hostemu_synth_scalars(uint64_t seed, uint32_t n, uint8_t *out) {
 }
 
 uint32_t hostemu_choose_window(uint64_t n) { return choose_window(n, 253); }
+
+// ---- BN256: field ops (plain in, plain out), MSM and fixed-base for G1 (g2 = 0) / G2 (g2 = 1)
+void hostemu_fbn_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out) {
+    fbn x, y, r;
+    memcpy(x.v, a, 32);
+    memcpy(y.v, b, 32);
+    x = fbn_to_mont(x);
+    y = fbn_to_mont(y);
+    switch (op) {
+        case 0: r = fbn_add(x, y); break;
+        case 1: r = fbn_sub(x, y); break;
+        case 2: r = fbn_mul(x, y); break;
+        case 3: r = fbn_inv(x); break;
+        default: r = fbn_neg(x); break;
+    }
+    r = fbn_from_mont(r);
+    memcpy(out, r.v, 32);
+}
+
+}  // extern "C"
+
+template <class F>
+static uint32_t bn_msm(const uint8_t *wire, const uint8_t *scalars, uint32_t n, uint32_t window_bits, uint8_t *out_wire) {
+    HostBE be;
+    uint32_t err = 0;
+    std::vector<waff<F>> w(n ? n : 1), base(n ? n : 1);
+    memcpy(w.data(), wire, (size_t)n * sizeof(waff<F>));
+    KUploadW<F> ku = {w.data(), base.data(), &err, 1u};
+    be.launch(ku, n);
+    std::vector<uint32_t> sc((size_t)(n ? n : 1) * 8 + 8);
+    memcpy(sc.data(), scalars, (size_t)n * 32);
+    Workspace ws;
+    MsmOptions opt;
+    opt.window_bits = window_bits;
+    wjac<F> oj;
+    waff<F> ow;
+    msm_run_w<HostBE, F>(be, ws, opt, base.data(), sc.data(), n, &oj, &ow);
+    ws_release(be, ws);
+    memcpy(out_wire, &ow, sizeof(ow));
+    return err;
+}
+extern "C" uint32_t hostemu_bn_msm(int g2, const uint8_t *wire, const uint8_t *scalars, uint32_t n, uint32_t window_bits,
+                        uint8_t *out_wire) {
+    return g2 ? bn_msm<Fp2BN>(wire, scalars, n, window_bits, out_wire) : bn_msm<FpBN>(wire, scalars, n, window_bits, out_wire);
+}
+
+template <class F>
+static void bn_fixed_base(const uint8_t *scalars, uint64_t seed, uint32_t n, uint8_t *out_wire) {
+    HostBE be;
+    std::vector<waff<F>> tbl(520);
+    build_fixed_base_table_w<F>(tbl.data());
+    std::vector<uint32_t> sc;
+    if (scalars) {
+        sc.resize((size_t)n * 8 + 8);
+        memcpy(sc.data(), scalars, (size_t)n * 32);
+    }
+    std::vector<wjac<F>> tmp(n);
+    std::vector<waff<F>> wire(n), base(n);
+    KFixedBaseW<F> k = {tbl.data(), scalars ? sc.data() : nullptr, seed, tmp.data()};
+    be.launch(k, n);
+    KNormalizeW<F> kn = {tmp.data(), wire.data(), base.data()};
+    be.launch(kn, n);
+    memcpy(out_wire, wire.data(), (size_t)n * sizeof(waff<F>));
+}
+extern "C" void hostemu_bn_fixed_base(int g2, const uint8_t *scalars, uint64_t seed, uint32_t n, uint8_t *out_wire) {
+    if (g2) bn_fixed_base<Fp2BN>(scalars, seed, n, out_wire);
+    else bn_fixed_base<FpBN>(scalars, seed, n, out_wire);
 }

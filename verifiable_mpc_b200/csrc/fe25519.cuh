@@ -242,8 +242,9 @@ VMSM_D void fe_mad4_top(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, 
 }
 #endif
 
-VMSM_HD fe fe_mul(const fe &a, const fe &b) {
-    uint32_t t[16];
+// 256 x 256 -> 512-bit schoolbook product, t[0..15].  Device: even/odd column accumulators so that every
+// mad.lo.cc / madc.hi.cc pair fuses into one IMAD.WIDE.U32[.X]; shared with the BN256 Montgomery field (fbn256.cuh).
+VMSM_HD void mp_mul8(const uint32_t *a, const uint32_t *b, uint32_t *t) {
 #if defined(__CUDA_ARCH__)
     // e[k] is limb k of the sum of a_i*b_j with i+j even; o[k] is limb k+1 of the sum with i+j odd.
     uint32_t e[17], o[17];
@@ -253,20 +254,19 @@ VMSM_HD fe fe_mul(const fe &a, const fe &b) {
     for (int j = 0; j < 8; j++) {
         if ((j & 1) == 0) {
             // even part: a0,a2,a4,a6 at limbs j..j+7 ; odd part: a1,a3,a5,a7 at limbs j+1..j+8 (o index j..j+7)
-            fe_mad4(e[j], e[j + 1], e[j + 2], e[j + 3], e[j + 4], e[j + 5], e[j + 6], e[j + 7], e[j + 8], a.v[0],
-                    a.v[2], a.v[4], a.v[6], b.v[j]);
-            fe_mad4(o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7], o[j + 8], a.v[1],
-                    a.v[3], a.v[5], a.v[7], b.v[j]);
+            fe_mad4(e[j], e[j + 1], e[j + 2], e[j + 3], e[j + 4], e[j + 5], e[j + 6], e[j + 7], e[j + 8], a[0],
+                    a[2], a[4], a[6], b[j]);
+            fe_mad4(o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7], o[j + 8], a[1],
+                    a[3], a[5], a[7], b[j]);
         } else {
             // even part: a1,a3,a5,a7 at limbs j+1..j+8 ; odd part: a0,a2,a4,a6 at limbs j..j+7 (o index j-1..j+6)
             if (j == 7)
-                fe_mad4_top(e[8], e[9], e[10], e[11], e[12], e[13], e[14], e[15], a.v[1], a.v[3], a.v[5], a.v[7],
-                            b.v[j]);
+                fe_mad4_top(e[8], e[9], e[10], e[11], e[12], e[13], e[14], e[15], a[1], a[3], a[5], a[7], b[j]);
             else
                 fe_mad4(e[j + 1], e[j + 2], e[j + 3], e[j + 4], e[j + 5], e[j + 6], e[j + 7], e[j + 8], e[j + 9],
-                        a.v[1], a.v[3], a.v[5], a.v[7], b.v[j]);
-            fe_mad4(o[j - 1], o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7], a.v[0],
-                    a.v[2], a.v[4], a.v[6], b.v[j]);
+                        a[1], a[3], a[5], a[7], b[j]);
+            fe_mad4(o[j - 1], o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7], a[0],
+                    a[2], a[4], a[6], b[j]);
         }
     }
     // t = e + (o << 32); o[15] (limb 16) is provably zero.
@@ -297,13 +297,18 @@ VMSM_HD fe fe_mul(const fe &a, const fe &b) {
     for (int i = 0; i < 8; i++) {
         uint64_t c = 0;
         for (int j = 0; j < 8; j++) {
-            c += (uint64_t)t[i + j] + (uint64_t)a.v[i] * b.v[j];
+            c += (uint64_t)t[i + j] + (uint64_t)a[i] * b[j];
             t[i + j] = (uint32_t)c;
             c >>= 32;
         }
         t[i + 8] = (uint32_t)c;
     }
 #endif
+}
+
+VMSM_HD fe fe_mul(const fe &a, const fe &b) {
+    uint32_t t[16];
+    mp_mul8(a.v, b.v, t);
     return fe_reduce512(t);
 }
 

@@ -1,0 +1,300 @@
+// MSM kernels for the BN256 groups (G1 over Fp, G2 over Fp2), written once over the field policy F (fbn256.cuh) on top
+// of the Jacobian arithmetic of bn256.cuh.  Same pipeline and same curve-agnostic front half (digit recoding,
+// histogram, scan, scatter, bucket ordering) as the Ed25519 path in kernels.cuh; only the point arithmetic differs.
+// Functors are per-thread bodies, so tests/hostemu runs them on the CPU as well.
+#pragma once
+#include "bn256.cuh"
+#include "kernels.cuh"
+
+namespace vmsm {
+
+// 16-byte vector copies of whole point structs (all sizes are multiples of 32 B, arrays are 256 B aligned)
+template <class T>
+VMSM_HD T ld_obj(const T *p) {
+    T r;
+    uint32_t *w = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); k++) {
+        u32x4 t = ld128(reinterpret_cast<const uint8_t *>(p) + 16 * k);
+        w[4 * k] = t.x, w[4 * k + 1] = t.y, w[4 * k + 2] = t.z, w[4 * k + 3] = t.w;
+    }
+    return r;
+}
+template <class T>
+VMSM_HD void st_obj(T *p, const T &v) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&v);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); k++) {
+        u32x4 t = {w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]};
+        st128(reinterpret_cast<uint8_t *>(p) + 16 * k, t);
+    }
+}
+
+// BN256 scalars are reduced below the 256-bit group order n (top bit set): all 256 bits are live
+VMSM_HD sc256 synth_scalar_bn(uint64_t seed, uint64_t i) {
+    sc256 s;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint64_t wv = splitmix64_mix(seed + 0x9E3779B97F4A7C15ull * (4 * i + j + 1));
+        s.v[2 * j] = (uint32_t)wv;
+        s.v[2 * j + 1] = (uint32_t)(wv >> 32);
+    }
+    s.v[8] = 0;
+    const uint32_t N[8] = {0x57ac7261u, 0x1a2ef45bu, 0xf82b3924u, 0x2e8d8e12u, 0x6184dc21u, 0xaa6fecb8u, 0x4aa387f9u, 0x8fb501e3u};
+    uint32_t d[8];
+    int64_t bw = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        bw += (int64_t)s.v[k] - (int64_t)N[k];
+        d[k] = (uint32_t)bw;
+        bw >>= 32;
+    }
+    if (bw == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s.v[k] = d[k];
+    }
+    return s;
+}
+
+template <class F>
+struct KAccumulateW {
+    enum { kBlock = 128 };
+    const waff<F> *bases;
+    const uint32_t *offsets, *counts, *idx, *order;
+    wjac<F> *buckets;
+    uint32_t nbuckets, cap;
+    OverflowCtl *ctl;
+    OverflowTask *tasks;
+    LongBucket *longs;
+    const waff<F> *extra;
+    uint32_t n_main;
+    VMSM_HD const waff<F> *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
+    VMSM_HD void operator()(uint32_t tid) const {
+        uint32_t b = order ? order[tid] : tid;
+        uint32_t pos = offsets[b], cnt = counts[b];
+        if (cnt > cap) {
+            uint32_t over = cnt - cap;
+            uint32_t seg = (over + 63) / 64;
+            if (seg < 256) seg = 256;
+            seg = (seg + 31) & ~31u;
+            uint32_t ntask = (over + seg - 1) / seg;
+            uint32_t base = VMSM_ATOMIC_ADD(&ctl->ntasks, ntask);
+            uint32_t lpos = VMSM_ATOMIC_ADD(&ctl->nlong, 1u);
+            for (uint32_t k = 0; k < ntask; k++) {
+                OverflowTask t = {b, pos + cap + k * seg, over - k * seg < seg ? over - k * seg : seg};
+                tasks[base + k] = t;
+            }
+            LongBucket lb = {b, base, ntask};
+            longs[lpos] = lb;
+            cnt = cap;
+        }
+        wjac<F> acc = wj_identity<F>();
+        for (uint32_t k = 0; k < cnt; k++) {
+            uint32_t e = idx[pos + k];
+            acc = wj_madd(acc, ld_obj(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+        }
+        st_obj(buckets + b, acc);
+    }
+};
+
+template <class F>
+struct KOverflowW {
+    enum { kBlock = 128 };
+    const waff<F> *bases;
+    const uint32_t *idx;
+    const OverflowCtl *ctl;
+    const OverflowTask *tasks;
+    wjac<F> *partials;
+    uint32_t nwarps;
+    const waff<F> *extra;
+    uint32_t n_main;
+    VMSM_HD const waff<F> *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint32_t ntasks = ctl->ntasks;
+#if defined(__CUDA_ARCH__)
+        const uint32_t lane = tid & 31;
+        for (uint32_t t = tid >> 5; t < ntasks; t += nwarps) {
+            OverflowTask tk = tasks[t];
+            wjac<F> acc = wj_identity<F>();
+            for (uint32_t k = lane; k < tk.count; k += 32) {
+                uint32_t e = idx[tk.first + k];
+                acc = wj_madd(acc, ld_obj(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+            }
+#pragma unroll 1
+            for (int d = 16; d >= 1; d >>= 1) {
+                wjac<F> o;
+                uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+                const uint32_t *aw = reinterpret_cast<const uint32_t *>(&acc);
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(wjac<F>) / 4); i++) ow[i] = __shfl_down_sync(0xffffffffu, aw[i], d);
+                acc = wj_add(acc, o);
+            }
+            if (lane == 0) st_obj(partials + t, acc);
+        }
+#else
+        if (tid & 31) return;
+        for (uint32_t t = tid >> 5; t < ntasks; t += nwarps) {
+            OverflowTask tk = tasks[t];
+            wjac<F> acc = wj_identity<F>();
+            for (uint32_t k = 0; k < tk.count; k++) {
+                uint32_t e = idx[tk.first + k];
+                acc = wj_madd(acc, ld_obj(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+            }
+            st_obj(partials + t, acc);
+        }
+#endif
+    }
+};
+
+template <class F>
+struct KCombineW {
+    enum { kBlock = 128 };
+    const OverflowCtl *ctl;
+    const LongBucket *longs;
+    const wjac<F> *partials;
+    wjac<F> *buckets;
+    uint32_t nthreads;
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint32_t nlong = ctl->nlong;
+        for (uint32_t l = tid; l < nlong; l += nthreads) {
+            LongBucket lb = longs[l];
+            wjac<F> acc = ld_obj(buckets + lb.bucket);
+            for (uint32_t k = 0; k < lb.ntask; k++) acc = wj_add(acc, ld_obj(partials + lb.task_base + k));
+            st_obj(buckets + lb.bucket, acc);
+        }
+    }
+};
+
+// (S, T) bucket tree, see KReduce in kernels.cuh
+template <class F>
+struct KReduceW {
+    enum { kBlock = 128 };
+    const wjac<F> *inS, *inT;
+    wjac<F> *outS, *outT;
+    uint32_t cnt_in, cnt_out, R, log2s;
+    VMSM_HD void operator()(uint32_t tid) const {
+        uint32_t w = tid / cnt_out, j = tid - w * cnt_out;
+        uint32_t first = j * R;
+        uint32_t m = cnt_in - first < R ? cnt_in - first : R;
+        const wjac<F> *s = inS + (size_t)w * cnt_in + first;
+        wjac<F> acc = wj_identity<F>(), run = wj_identity<F>();
+        for (uint32_t i = m - 1; i >= 1; i--) {
+            acc = wj_add(acc, ld_obj(s + i));
+            run = wj_add(run, acc);
+        }
+        acc = wj_add(acc, ld_obj(s));
+        for (uint32_t k = 0; k < log2s; k++) run = wj_dbl(run);
+        if (inT) {
+            const wjac<F> *t = inT + (size_t)w * cnt_in + first;
+            for (uint32_t i = 0; i < m; i++) run = wj_add(run, ld_obj(t + i));
+        }
+        st_obj(outS + (size_t)w * cnt_out + j, acc);
+        st_obj(outT + (size_t)w * cnt_out + j, run);
+    }
+};
+
+// plain (non-Montgomery) canonical affine: the wire form; identity = all zero
+template <class F>
+VMSM_HD waff<F> wa_to_wire(const waff<F> &m) {
+    waff<F> r = {F::from_mont(m.x), F::from_mont(m.y)};
+    return r;
+}
+
+template <class F>
+struct KFinalW {
+    enum { kBlock = 32 };
+    const wjac<F> *S, *T;
+    wjac<F> *out_jac;
+    waff<F> *out_wire;
+    uint32_t W, c;
+    VMSM_HD void operator()(uint32_t tid) const {
+        if (tid) return;
+        wjac<F> acc = wj_identity<F>();
+        for (int32_t w = (int32_t)W - 1; w >= 0; w--) {
+            if (w != (int32_t)W - 1)
+                for (uint32_t k = 0; k < c; k++) acc = wj_dbl(acc);
+            acc = wj_add(acc, wj_add(ld_obj(S + w), ld_obj(T + w)));
+        }
+        st_obj(out_jac, acc);
+        st_obj(out_wire, wa_to_wire(wj_to_aff(acc)));
+    }
+};
+
+// upload: wire (plain canonical) -> validation -> Montgomery base
+template <class F>
+struct KUploadW {
+    enum { kBlock = 128 };
+    const waff<F> *wire;
+    waff<F> *base;
+    uint32_t *err;  // bit 0: coordinate >= p, bit 1: not on the curve
+    uint32_t check;
+    VMSM_HD void operator()(uint32_t tid) const {
+        waff<F> w = ld_obj(wire + tid);
+        uint32_t e = 0;
+        if (check && (!F::plain_ok(w.x) || !F::plain_ok(w.y))) e |= 1u;
+        waff<F> m = {F::to_mont(w.x), F::to_mont(w.y)};
+        if (check && !wa_on_curve(m)) e |= 2u;
+        if (e) VMSM_ATOMIC_OR(err, e);
+        st_obj(base + tid, m);
+    }
+};
+
+template <class F>
+struct KNormalizeW {
+    enum { kBlock = 128 };
+    const wjac<F> *in;
+    waff<F> *wire, *base;
+    VMSM_HD void operator()(uint32_t tid) const {
+        waff<F> a = wj_to_aff(ld_obj(in + tid));
+        st_obj(base + tid, a);
+        st_obj(wire + tid, wa_to_wire(a));
+    }
+};
+
+// out[i] = r_i * G with signed 4-bit windows over a host-built table tbl[65][8] (j * 16^w * G); r_i explicit or synthetic
+template <class F>
+struct KFixedBaseW {
+    enum { kBlock = 128 };
+    const waff<F> *tbl;
+    const uint32_t *scalars;
+    uint64_t seed;
+    wjac<F> *out;
+    VMSM_HD void operator()(uint32_t tid) const {
+        sc256 s = scalars ? ld_scalar(scalars, tid) : synth_scalar_bn(seed, tid);
+        wjac<F> acc = wj_identity<F>();
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < 65; w++) {  // 65th window holds the carry out of bit 255
+            int32_t d = sc_digit(s, w, 4, carry);
+            if (d != 0) {
+                uint32_t a = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                acc = wj_madd(acc, ld_obj(tbl + w * 8 + (a - 1)), d < 0);
+            }
+        }
+        st_obj(out + tid, acc);
+    }
+};
+
+template <class F>
+struct KCopyW {
+    enum { kBlock = 128 };
+    const waff<F> *src_wire, *src_base;
+    waff<F> *dst_wire, *dst_base;
+    VMSM_HD void operator()(uint32_t tid) const {
+        st_obj(dst_wire + tid, ld_obj(src_wire + tid));
+        st_obj(dst_base + tid, ld_obj(src_base + tid));
+    }
+};
+
+struct KSynthScalarsBN {
+    enum { kBlock = 256 };
+    uint32_t *out;
+    uint64_t seed;
+    VMSM_HD void operator()(uint32_t tid) const {
+        sc256 s = synth_scalar_bn(seed, tid);
+        u32x4 a = {s.v[0], s.v[1], s.v[2], s.v[3]}, b = {s.v[4], s.v[5], s.v[6], s.v[7]};
+        st128(out + 8ull * tid, a);
+        st128(out + 8ull * tid + 4, b);
+    }
+};
+
+}  // namespace vmsm

@@ -3,6 +3,7 @@
 #pragma once
 #include <stddef.h>
 #include "kernels.cuh"
+#include "kernels_w.cuh"
 
 namespace vmsm {
 
@@ -28,16 +29,17 @@ struct MsmOptions {
 struct Workspace {
     uint32_t *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *order = nullptr;  // W*NB each
     uint32_t *idx = nullptr;                                                              // W*n
-    ge_ext *buckets = nullptr;                                                            // W*NB
+    void *buckets = nullptr;  // W*NB accumulator points (ge_ext for Ed25519, wjac<F> for BN256): sized in bytes
     // bucket-tree levels: [parity of the MSM sequence number][ping-pong].  Two parities because the latency-bound tail
     // of one MSM (upper tree levels + Horner) runs on a side stream underneath the head of the next MSM.
-    ge_ext *nodeS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *nodeT[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    void *nodeS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *nodeT[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     // long-bucket overflow (kernels.cuh: KOverflow / KCombine)
     OverflowCtl *ctl = nullptr;
     OverflowTask *tasks = nullptr;
     LongBucket *longs = nullptr;
-    ge_ext *partials = nullptr;
-    size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0, cap_tasks = 0;
+    void *partials = nullptr;
+    size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0, cap_tasks = 0;  // element counts
+    size_t elem_bytes = 0;  // size of one accumulator point the point buffers were allocated for
 };
 
 // Work model of SURVEY.md App. E (limb products), with the tree reduction's ~30 % overhead over a serial running sum.
@@ -45,13 +47,13 @@ struct Workspace {
 // so the last window that holds bit (scalar_bits-2) sees r = (scalar_bits-1) mod c live bits and its 2^(r-1) buckets
 // are 2^(c-r) times fuller than average (r = 0: a carry-only window, one bucket with n/2 entries).  The long-bucket
 // path keeps such cases correct and bounded; the chooser simply avoids paying for them (measured: profiles/r01).
-inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits) {
+inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits, bool avoid_skew = true) {
     if (n == 0) return 4;
     double best = 0;
     uint32_t best_c = 0;
     for (uint32_t c = 3; c <= 17; c++) {
         uint32_t r = (scalar_bits - 1) % c;
-        if (r == 0 || c - r > 4) continue;
+        if (avoid_skew && (r == 0 || c - r > 4)) continue;
         double W = (double)((scalar_bits + 1 + c - 1) / c);
         double NB = (double)(1u << (c - 1));
         double cost = (double)n * W * 504.0 + W * NB * 2.0 * 648.0 * 1.3 + (W - 1) * c * 464.0;
@@ -73,9 +75,14 @@ inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits) {
 }
 
 template <class BE>
-int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R) {
+int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_bytes = sizeof(ge_ext)) {
     size_t nb = (size_t)g.W * g.NB, ni = (size_t)g.W * g.n, nn = (size_t)g.W * ((g.NB + R - 1) / R);
     if (nn < g.W) nn = g.W;
+    if (elem_bytes > ws.elem_bytes) {  // a wider accumulator type than before: regrow the point buffers
+        ws.cap_buckets = ws.cap_nodes = ws.cap_tasks = 0;
+        ws.elem_bytes = elem_bytes;
+    }
+    elem_bytes = ws.elem_bytes;
     if (nb > ws.cap_buckets) {
         be.free(ws.counts), be.free(ws.offsets), be.free(ws.cursor), be.free(ws.order), be.free(ws.buckets);
         ws.cap_buckets = 0;
@@ -83,7 +90,7 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R) {
         ws.offsets = (uint32_t *)be.alloc(nb * 4);
         ws.cursor = (uint32_t *)be.alloc(nb * 4);
         ws.order = (uint32_t *)be.alloc(nb * 4);
-        ws.buckets = (ge_ext *)be.alloc(nb * sizeof(ge_ext));
+        ws.buckets = be.alloc(nb * elem_bytes);
         if (!ws.counts || !ws.offsets || !ws.cursor || !ws.order || !ws.buckets) return -1;
         ws.cap_buckets = nb;
     }
@@ -101,7 +108,7 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R) {
         ws.ctl = (OverflowCtl *)be.alloc(sizeof(OverflowCtl));
         ws.tasks = (OverflowTask *)be.alloc(nt * sizeof(OverflowTask));
         ws.longs = (LongBucket *)be.alloc(nt * sizeof(LongBucket));
-        ws.partials = (ge_ext *)be.alloc(nt * sizeof(ge_ext));
+        ws.partials = be.alloc(nt * elem_bytes);
         if (!ws.ctl || !ws.tasks || !ws.longs || !ws.partials) return -1;
         ws.cap_tasks = nt;
     }
@@ -109,8 +116,8 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R) {
         for (int par = 0; par < 2; par++)
             for (int k = 0; k < 2; k++) {
                 be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
-                ws.nodeS[par][k] = (ge_ext *)be.alloc(nn * sizeof(ge_ext));
-                ws.nodeT[par][k] = (ge_ext *)be.alloc(nn * sizeof(ge_ext));
+                ws.nodeS[par][k] = be.alloc(nn * elem_bytes);
+                ws.nodeT[par][k] = be.alloc(nn * elem_bytes);
                 if (!ws.nodeS[par][k] || !ws.nodeT[par][k]) {
                     ws.cap_nodes = 0;
                     return -1;
@@ -165,15 +172,15 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < 64) cap = 64;
         be.zero(ws.ctl, sizeof(OverflowCtl));
-        KAccumulate k5 = {bases, ws.offsets, ws.counts, ws.idx, order, ws.buckets, nbuckets, cap, ws.ctl, ws.tasks, ws.longs,
-                          extra, n_main};
+        KAccumulate k5 = {bases, ws.offsets, ws.counts, ws.idx, order, (ge_ext *)ws.buckets, nbuckets, cap, ws.ctl, ws.tasks,
+                          ws.longs, extra, n_main};
         be.launch(k5, nbuckets);
         if (n > cap) {  // otherwise no bucket can be long
             const uint32_t ow = be.overflow_warps();
-            KOverflow ko = {bases, ws.idx, ws.ctl, ws.tasks, ws.partials, ow, extra, n_main};
+            KOverflow ko = {bases, ws.idx, ws.ctl, ws.tasks, (ge_ext *)ws.partials, ow, extra, n_main};
             be.launch(ko, ow * 32);
             const uint32_t ct = be.combine_threads();
-            KCombine kc = {ws.ctl, ws.longs, ws.partials, ws.buckets, ct};
+            KCombine kc = {ws.ctl, ws.longs, (const ge_ext *)ws.partials, (ge_ext *)ws.buckets, ct};
             be.launch(kc, ct);
         }
     }
@@ -182,7 +189,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     // levels + Horner) which the CUDA backend runs on a side stream so that it overlaps the next MSM's head
     const int par = (int)(seq & 1);
     be.head_wait_tail(par);
-    const ge_ext *inS = ws.buckets, *inT = nullptr;
+    const ge_ext *inS = (const ge_ext *)ws.buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;
     bool in_tail = false;
@@ -191,14 +198,14 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         uint32_t nodes = g.W * cnt_out;
         if (nodes <= opt.quad_threshold) {
             if (!in_tail) be.tail_begin(), in_tail = true;
-            KReduceQ k6 = {inS, inT, ws.nodeS[par][pp], ws.nodeT[par][pp], cnt, cnt_out, R, log2s, nodes};
+            KReduceQ k6 = {inS, inT, (ge_ext *)ws.nodeS[par][pp], (ge_ext *)ws.nodeT[par][pp], cnt, cnt_out, R, log2s, nodes};
             be.launch(k6, (4 * nodes + 31) & ~31u);
         } else {
-            KReduce k6 = {inS, inT, ws.nodeS[par][pp], ws.nodeT[par][pp], cnt, cnt_out, R, log2s};
+            KReduce k6 = {inS, inT, (ge_ext *)ws.nodeS[par][pp], (ge_ext *)ws.nodeT[par][pp], cnt, cnt_out, R, log2s};
             be.launch(k6, nodes);
         }
-        inS = ws.nodeS[par][pp];
-        inT = ws.nodeT[par][pp];
+        inS = (const ge_ext *)ws.nodeS[par][pp];
+        inT = (const ge_ext *)ws.nodeT[par][pp];
         pp ^= 1;
         cnt = cnt_out;
         log2s += opt.reduce_log2r;
@@ -220,6 +227,89 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     if (in_tail) be.tail_end(par);
     be.phase_end();
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- BN256 (G1 / G2)
+// Same sequence as msm_run for the Weierstrass groups; everything on the main stream (these MSMs are 2^14-sized).
+template <class BE, class F>
+int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases, const uint32_t *scalars, uint32_t n,
+              wjac<F> *out_jac, waff<F> *out_wire, const waff<F> *extra = nullptr, uint32_t n_extra = 0) {
+    const uint32_t scalar_bits = 256, n_main = n - n_extra;
+    uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits, false);
+    if (c > 16) c = 16;
+    MsmGeom g = make_geom(n, c, scalar_bits);
+    uint32_t R = 1u << opt.reduce_log2r;
+    if (ws_ensure(be, ws, g, R, sizeof(wjac<F>))) return -1;
+    uint32_t nbuckets = g.W * g.NB;
+    be.phase_begin();
+    be.zero(ws.counts, (size_t)nbuckets * 4);
+    if (n) {
+        KDigitsHist k1 = {scalars, ws.counts, g};
+        be.launch(k1, n);
+    }
+    be.phase_mark(PH_DIGITS);
+    be.scan_offsets(ws.counts, ws.offsets, ws.cursor, g);
+    be.phase_mark(PH_SCAN);
+    if (n) {
+        KScatter k3 = {scalars, ws.cursor, ws.idx, g};
+        be.launch(k3, n);
+    }
+    be.phase_mark(PH_SCATTER);
+    const uint32_t *order = nullptr;
+    if (opt.sort_buckets && be.order_buckets(ws.counts, ws.order, nbuckets, n)) order = ws.order;
+    be.phase_mark(PH_ORDER);
+    {
+        uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
+        if (cap < 64) cap = 64;
+        be.zero(ws.ctl, sizeof(OverflowCtl));
+        KAccumulateW<F> k5 = {bases, ws.offsets, ws.counts, ws.idx, order, (wjac<F> *)ws.buckets, nbuckets, cap, ws.ctl,
+                              ws.tasks, ws.longs, extra, n_main};
+        be.launch(k5, nbuckets);
+        if (n > cap) {
+            const uint32_t ow = be.overflow_warps();
+            KOverflowW<F> ko = {bases, ws.idx, ws.ctl, ws.tasks, (wjac<F> *)ws.partials, ow, extra, n_main};
+            be.launch(ko, ow * 32);
+            const uint32_t ct = be.combine_threads();
+            KCombineW<F> kc = {ws.ctl, ws.longs, (const wjac<F> *)ws.partials, (wjac<F> *)ws.buckets, ct};
+            be.launch(kc, ct);
+        }
+    }
+    be.phase_mark(PH_ACCUMULATE);
+    const wjac<F> *inS = (const wjac<F> *)ws.buckets, *inT = nullptr;
+    uint32_t cnt = g.NB, log2s = 0;
+    int pp = 0;
+    do {
+        uint32_t cnt_out = (cnt + R - 1) / R;
+        KReduceW<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[0][pp], (wjac<F> *)ws.nodeT[0][pp], cnt, cnt_out, R, log2s};
+        be.launch(k6, g.W * cnt_out);
+        inS = (const wjac<F> *)ws.nodeS[0][pp];
+        inT = (const wjac<F> *)ws.nodeT[0][pp];
+        pp ^= 1;
+        cnt = cnt_out;
+        log2s += opt.reduce_log2r;
+    } while (cnt > 1);
+    be.phase_mark(PH_REDUCE);
+    KFinalW<F> k7 = {inS, inT, out_jac, out_wire, g.W, g.c};
+    be.launch(k7, 32);
+    be.phase_mark(PH_FINAL);
+    be.result_ready();
+    be.phase_end();
+    return 0;
+}
+
+// Host-side construction of the BN256 fixed-base tables tbl[w][j-1] = j * 16^w * G, w < 65, j = 1..8 (Montgomery affine)
+template <class F>
+inline void build_fixed_base_table_w(waff<F> *tbl /* 520 entries, host memory */) {
+    waff<F> G = {F::gen_x(), F::gen_y()};
+    wjac<F> base = wa_to_jac(G);
+    for (int w = 0; w < 65; w++) {
+        wjac<F> m = base;
+        for (int j = 1; j <= 8; j++) {
+            tbl[w * 8 + (j - 1)] = wj_to_aff(m);
+            if (j < 8) m = wj_add(m, base);
+        }
+        for (int k = 0; k < 4; k++) base = wj_dbl(base);
+    }
 }
 
 // Non-adjacent form of a 256-bit little-endian scalar as two bit masks; returns the top non-zero digit index or -1.

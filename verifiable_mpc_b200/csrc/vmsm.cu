@@ -194,9 +194,13 @@ namespace {
 struct PointSet {
     int32_t curve;
     uint64_t n;
-    ge_aff *aff;
-    ge_niels *niels;
+    ge_aff *aff;      // Ed25519: canonical affine (wire form)
+    ge_niels *niels;  // Ed25519: (y+x, y-x, 2dxy)
+    void *w_wire;     // BN256: plain canonical affine (wire form), waff<F>[n]; identity = all zero
+    void *w_base;     // BN256: Montgomery affine, waff<F>[n]
 };
+
+inline size_t wire_bytes(int32_t curve) { return curve == VMSM_CURVE_BN256_G2 ? 128 : 64; }
 struct ScalarSet {
     uint64_t n;
     uint32_t *data;
@@ -227,6 +231,12 @@ struct Ctx {
     cudaEvent_t ev_slot[64] = {nullptr};
     uint32_t cur_slot = 0;
     ge_aff *res_aff_host = nullptr;  // pinned + mapped, kSlots entries: written by the final kernel itself
+    // BN256 results: Jacobian on the device, plain affine in mapped pinned memory; which curve a slot last held
+    uint8_t *res_w_dev = nullptr;   // kSlots x 192 B
+    uint8_t *res_w_host = nullptr;  // kSlots x 128 B, mapped
+    int32_t slot_curve[64] = {0};
+    void *fbw_table[2] = {nullptr, nullptr};  // fixed-base tables for G1 / G2 (520 entries), built on first use
+    void *small_w_wire = nullptr, *small_w_base = nullptr;  // lincomb scratch, 64 x 128 B each
     uint32_t *res_status_host = nullptr;  // pinned + mapped, kSlots words: 0 ok, 1 = a multi-GPU partial timed out
     // multi-GPU mailbox (kernels.cuh: KPushPartial / KGatherPartials)
     MailSlot *mailbox = nullptr;  // [kSlots][mb_world]; owner: local allocation, others: peer mapping
@@ -412,6 +422,7 @@ int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "n = %llu exceeds 2^26 terms per MSM call", (unsigned long long)n);
     CudaBE be(c);
     c->cur_slot = slot;
+    c->slot_curve[slot] = VMSM_CURVE_ED25519;
     if (c->shard_next && slot != kSlots - 1) {
         if (!c->mailbox) return fail(VMSM_ERR_INVALID, "VMSM_OPT_SHARD_SEQ set but the context has no mailbox");
         c->shard_seq = c->shard_next;
@@ -422,6 +433,122 @@ int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t
     c->shard_seq = 0;
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
+    return VMSM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ BN256 paths
+template <class F>
+int32_t w_new_pointset(int32_t curve, uint64_t n, PointSet *ps) {
+    ps->curve = curve;
+    ps->n = n;
+    ps->aff = nullptr;
+    ps->niels = nullptr;
+    ps->w_wire = ps->w_base = nullptr;
+    CU(cudaMalloc(&ps->w_wire, (n ? n : 1) * sizeof(waff<F>)));
+    cudaError_t e = cudaMalloc(&ps->w_base, (n ? n : 1) * sizeof(waff<F>));
+    if (e != cudaSuccess) {
+        cudaFree(ps->w_wire);
+        return fail(VMSM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    return VMSM_OK;
+}
+
+template <class F>
+int32_t w_upload(Ctx *c, int32_t curve, const uint8_t *wire, uint64_t n, PointSet *ps) {
+    int32_t rc = w_new_pointset<F>(curve, n, ps);
+    if (rc || !n) return rc;
+    CudaBE be(c);
+    be.note(cudaMemcpyAsync(ps->w_wire, wire, n * sizeof(waff<F>), cudaMemcpyHostToDevice, c->stream));
+    be.zero(c->err_word, 4);
+    KUploadW<F> k = {(const waff<F> *)ps->w_wire, (waff<F> *)ps->w_base, c->err_word, c->check_points ? 1u : 0u};
+    be.launch(k, (uint32_t)n);
+    be.note(cudaMemcpyAsync(c->pin, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
+    be.note(cudaStreamSynchronize(c->stream));
+    uint32_t ew = *reinterpret_cast<uint32_t *>(c->pin);
+    if (be.err != cudaSuccess || ew) {
+        cudaFree(ps->w_wire), cudaFree(ps->w_base);
+        if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "upload: %s", cudaGetErrorString(be.err));
+        return fail(VMSM_ERR_POINT, "invalid point in upload (%s%s)", (ew & 1) ? "non-canonical coordinate " : "",
+                    (ew & 2) ? "not on curve" : "");
+    }
+    return VMSM_OK;
+}
+
+template <class F>
+int32_t w_table(Ctx *c, int which) {
+    if (c->fbw_table[which]) return VMSM_OK;
+    std::vector<waff<F>> tbl(520);
+    build_fixed_base_table_w<F>(tbl.data());
+    CU(cudaMalloc(&c->fbw_table[which], 520 * sizeof(waff<F>)));
+    CU(cudaMemcpy(c->fbw_table[which], tbl.data(), 520 * sizeof(waff<F>), cudaMemcpyHostToDevice));
+    return VMSM_OK;
+}
+
+template <class F>
+int32_t w_fixed_base(Ctx *c, int32_t curve, const uint8_t *scalars, uint64_t seed, uint64_t n, PointSet *ps) {
+    int32_t rc = w_table<F>(c, curve == VMSM_CURVE_BN256_G2 ? 1 : 0);
+    if (rc) return rc;
+    rc = w_new_pointset<F>(curve, n, ps);
+    if (rc || !n) return rc;
+    const uint32_t *dsc = nullptr;
+    if (scalars) {
+        rc = ensure_stage(c, n);
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(c->stage_scalars, scalars, n * 32, cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) rc = fail(VMSM_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
+        }
+        dsc = c->stage_scalars;
+    }
+    if (!rc) rc = ensure_tmp(c, (n * sizeof(wjac<F>) + sizeof(ge_ext) - 1) / sizeof(ge_ext));
+    if (rc) {
+        cudaFree(ps->w_wire), cudaFree(ps->w_base);
+        return rc;
+    }
+    CudaBE be(c);
+    KFixedBaseW<F> k = {(const waff<F> *)c->fbw_table[curve == VMSM_CURVE_BN256_G2 ? 1 : 0], dsc, seed, (wjac<F> *)c->tmp_ext};
+    be.launch(k, (uint32_t)n);
+    KNormalizeW<F> kn = {(const wjac<F> *)c->tmp_ext, (waff<F> *)ps->w_wire, (waff<F> *)ps->w_base};
+    be.launch(kn, (uint32_t)n);
+    be.note(cudaStreamSynchronize(c->stream));
+    if (be.err != cudaSuccess) {
+        cudaFree(ps->w_wire), cudaFree(ps->w_base);
+        return fail(VMSM_ERR_CUDA, "fixed_base: %s", cudaGetErrorString(be.err));
+    }
+    return VMSM_OK;
+}
+
+template <class F>
+int32_t w_run_msm(Ctx *c, const PointSet &ps, uint64_t off, const uint32_t *scalars, uint64_t n_total, uint32_t slot,
+                  const PointSet *extra, uint64_t extra_off, uint32_t n_extra) {
+    if (n_total > (1ull << 24)) return fail(VMSM_ERR_UNSUPPORTED, "BN256 MSMs are limited to 2^24 terms");
+    CudaBE be(c);
+    c->cur_slot = slot;
+    c->slot_curve[slot] = ps.curve;
+    MsmOptions opt = c->opt;
+    int rc = msm_run_w<CudaBE, F>(be, c->ws, opt, (const waff<F> *)ps.w_base + off, scalars, (uint32_t)n_total,
+                                  (wjac<F> *)(c->res_w_dev + 192 * slot), (waff<F> *)(c->res_w_host + 128 * slot),
+                                  extra ? (const waff<F> *)extra->w_base + extra_off : nullptr, n_extra);
+    if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
+    return VMSM_OK;
+}
+
+int32_t w_run_msm_any(Ctx *c, const PointSet &ps, uint64_t off, const uint32_t *scalars, uint64_t n_total, uint32_t slot,
+                      const PointSet *extra = nullptr, uint64_t extra_off = 0, uint32_t n_extra = 0) {
+    if (ps.curve == VMSM_CURVE_BN256_G1) return w_run_msm<FpBN>(c, ps, off, scalars, n_total, slot, extra, extra_off, n_extra);
+    return w_run_msm<Fp2BN>(c, ps, off, scalars, n_total, slot, extra, extra_off, n_extra);
+}
+
+// fetch a finished result slot into `out` (64 B Ed25519 / BN256 G1, 128 B BN256 G2)
+int32_t fetch_slot(Ctx *c, uint32_t slot, uint8_t *out) {
+    CU(cudaEventSynchronize(c->ev_slot[slot]));
+    if (c->res_status_host[slot]) {
+        c->res_status_host[slot] = 0;
+        return fail(VMSM_ERR_TIMEOUT, "a multi-GPU partial for slot %u did not arrive", slot);
+    }
+    if (c->slot_curve[slot] == VMSM_CURVE_ED25519) memcpy(out, c->res_aff_host + slot, sizeof(ge_aff));
+    else memcpy(out, c->res_w_host + 128 * slot, wire_bytes(c->slot_curve[slot]));
     return VMSM_OK;
 }
 
@@ -483,6 +610,10 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     CU(cudaHostAlloc(&c->pin, 4096, cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->res_aff_host, kSlots * sizeof(ge_aff), cudaHostAllocMapped));
     CU(cudaHostAlloc(&c->res_status_host, kSlots * sizeof(uint32_t), cudaHostAllocMapped));
+    CU(cudaMalloc(&c->res_w_dev, kSlots * 192));
+    CU(cudaHostAlloc(&c->res_w_host, kSlots * 128, cudaHostAllocMapped));
+    CU(cudaMalloc(&c->small_w_wire, 64 * 128));
+    CU(cudaMalloc(&c->small_w_base, 64 * 128));
     memset(c->res_status_host, 0, kSlots * sizeof(uint32_t));
     CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     for (int k = 0; k < 2; k++) {
@@ -514,12 +645,15 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (uint32_t k = 0; k < kSlots; k++) cudaEventDestroy(c->ev_slot[k]);
     cudaFreeHost(c->res_aff_host);
     cudaFreeHost(c->res_status_host);
+    cudaFree(c->res_w_dev), cudaFreeHost(c->res_w_host), cudaFree(c->fbw_table[0]), cudaFree(c->fbw_table[1]);
+    cudaFree(c->small_w_wire), cudaFree(c->small_w_base);
     if (c->mailbox) {
         if (c->mb_owner) cudaFree(c->mailbox);
         else if (c->mb_ipc) cudaIpcCloseMemHandle(c->mailbox);
     }
     cudaStreamDestroy(c->copy);
-    for (auto &kv : c->points) cudaFree(kv.second.aff), cudaFree(kv.second.niels);
+    for (auto &kv : c->points)
+        cudaFree(kv.second.aff), cudaFree(kv.second.niels), cudaFree(kv.second.w_wire), cudaFree(kv.second.w_base);
     for (auto &kv : c->scalars) cudaFree(kv.second.data);
     CudaBE be(c);
     ws_release(be, c->ws);
@@ -625,6 +759,7 @@ static int32_t new_pointset(Ctx *c, int32_t curve, uint64_t n, PointSet *ps) {
     ps->n = n;
     ps->aff = nullptr;
     ps->niels = nullptr;
+    ps->w_wire = ps->w_base = nullptr;
     CU(cudaMalloc(&ps->aff, (n ? n : 1) * sizeof(ge_aff)));
     cudaError_t e = cudaMalloc(&ps->niels, (n ? n : 1) * sizeof(ge_niels));
     if (e != cudaSuccess) {
@@ -637,9 +772,18 @@ static int32_t new_pointset(Ctx *c, int32_t curve, uint64_t n, PointSet *ps) {
 int32_t vmsm_points_upload(uint64_t ctx, int32_t curve, const uint8_t *affine, uint64_t n, uint64_t *pts) {
     GET_CTX(ctx);
     if (!pts || (n && !affine)) return fail(VMSM_ERR_INVALID, "null argument");
-    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "curve %d not supported yet", curve);
+    if (curve < VMSM_CURVE_ED25519 || curve > VMSM_CURVE_BN256_G2) return fail(VMSM_ERR_UNSUPPORTED, "unknown curve %d", curve);
     if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many points");
     PointSet ps;
+    if (curve != VMSM_CURVE_ED25519) {
+        int32_t rcw = curve == VMSM_CURVE_BN256_G1 ? w_upload<FpBN>(c, curve, affine, n, &ps)
+                                                   : w_upload<Fp2BN>(c, curve, affine, n, &ps);
+        if (rcw) return rcw;
+        uint64_t idw = c->next_id++;
+        c->points[idw] = ps;
+        *pts = idw;
+        return VMSM_OK;
+    }
     int32_t rc = new_pointset(c, curve, n, &ps);
     if (rc) return rc;
     CudaBE be(c);
@@ -668,9 +812,18 @@ int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scala
                                uint64_t *pts) {
     GET_CTX(ctx);
     if (!pts) return fail(VMSM_ERR_INVALID, "null argument");
-    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "curve %d not supported yet", curve);
+    if (curve < VMSM_CURVE_ED25519 || curve > VMSM_CURVE_BN256_G2) return fail(VMSM_ERR_UNSUPPORTED, "unknown curve %d", curve);
     if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many points");
     PointSet ps;
+    if (curve != VMSM_CURVE_ED25519) {
+        int32_t rcw = curve == VMSM_CURVE_BN256_G1 ? w_fixed_base<FpBN>(c, curve, scalars, seed, n, &ps)
+                                                   : w_fixed_base<Fp2BN>(c, curve, scalars, seed, n, &ps);
+        if (rcw) return rcw;
+        uint64_t idw = c->next_id++;
+        c->points[idw] = ps;
+        *pts = idw;
+        return VMSM_OK;
+    }
     int32_t rc = new_pointset(c, curve, n, &ps);
     if (rc) return rc;
     if (n) {
@@ -711,7 +864,12 @@ int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t 
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
     if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "range out of bounds");
     if (n && !affine_out) return fail(VMSM_ERR_INVALID, "null argument");
-    if (n) CU(cudaMemcpyAsync(affine_out, it->second.aff + off, n * sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
+    if (n && it->second.curve == VMSM_CURVE_ED25519)
+        CU(cudaMemcpyAsync(affine_out, it->second.aff + off, n * sizeof(ge_aff), cudaMemcpyDeviceToHost, c->stream));
+    else if (n) {
+        size_t wb = wire_bytes(it->second.curve);
+        CU(cudaMemcpyAsync(affine_out, (const uint8_t *)it->second.w_wire + off * wb, n * wb, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
     return VMSM_OK;
 }
@@ -729,7 +887,7 @@ int32_t vmsm_points_free(uint64_t ctx, uint64_t pts) {
     auto it = c->points.find(pts);
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(it->second.aff), cudaFree(it->second.niels);
+    cudaFree(it->second.aff), cudaFree(it->second.niels), cudaFree(it->second.w_wire), cudaFree(it->second.w_base);
     c->points.erase(it);
     return VMSM_OK;
 }
@@ -757,13 +915,18 @@ int32_t vmsm_scalars_upload(uint64_t ctx, const uint8_t *le32, uint64_t n, uint6
 int32_t vmsm_scalars_synth(uint64_t ctx, int32_t curve, uint64_t seed, uint64_t n, uint64_t *sc) {
     GET_CTX(ctx);
     if (!sc) return fail(VMSM_ERR_INVALID, "null argument");
-    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "curve %d not supported yet", curve);
+    if (curve < VMSM_CURVE_ED25519 || curve > VMSM_CURVE_BN256_G2) return fail(VMSM_ERR_UNSUPPORTED, "unknown curve %d", curve);
     if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
     ScalarSet ss{n, nullptr};
     CU(cudaMalloc(&ss.data, (n ? n : 1) * 32));
     CudaBE be(c);
-    KSynthScalars k = {ss.data, seed};
-    be.launch(k, (uint32_t)n);
+    if (curve == VMSM_CURVE_ED25519) {
+        KSynthScalars k = {ss.data, seed};
+        be.launch(k, (uint32_t)n);
+    } else {
+        KSynthScalarsBN k = {ss.data, seed};
+        be.launch(k, (uint32_t)n);
+    }
     be.note(cudaStreamSynchronize(c->stream));
     if (be.err != cudaSuccess) {
         cudaFree(ss.data);
@@ -807,11 +970,10 @@ int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uin
     int32_t rc = ensure_stage(c, n ? n : 1);
     if (rc) return rc;
     if (n) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
-    rc = run_msm(c, it->second.niels + off, c->stage_scalars, n, kSlots - 1);
+    if (it->second.curve == VMSM_CURVE_ED25519) rc = run_msm(c, it->second.niels + off, c->stage_scalars, n, kSlots - 1);
+    else rc = w_run_msm_any(c, it->second, off, c->stage_scalars, n, kSlots - 1);
     if (rc) return rc;
-    CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));  // the final kernel wrote the point into mapped pinned memory
-    memcpy(out_affine, c->res_aff_host + (kSlots - 1), sizeof(ge_aff));
-    return VMSM_OK;
+    return fetch_slot(c, kSlots - 1, out_affine);  // the final kernel wrote the point into mapped pinned memory
 }
 
 int32_t vmsm_msm_ext(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint64_t extra_pts, uint64_t extra_off,
@@ -828,12 +990,14 @@ int32_t vmsm_msm_ext(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint6
     int32_t rc = ensure_stage(c, tot ? tot : 1);
     if (rc) return rc;
     if (tot) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, tot * 32, cudaMemcpyHostToDevice, c->stream));
-    rc = run_msm(c, it->second.niels + off, c->stage_scalars, tot, kSlots - 1, ie->second.niels + extra_off,
-                 (uint32_t)n_extra);
+    if (it->second.curve != ie->second.curve) return fail(VMSM_ERR_INVALID, "point vectors are on different curves");
+    if (it->second.curve == VMSM_CURVE_ED25519)
+        rc = run_msm(c, it->second.niels + off, c->stage_scalars, tot, kSlots - 1, ie->second.niels + extra_off,
+                     (uint32_t)n_extra);
+    else
+        rc = w_run_msm_any(c, it->second, off, c->stage_scalars, tot, kSlots - 1, &ie->second, extra_off, (uint32_t)n_extra);
     if (rc) return rc;
-    CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));
-    memcpy(out_affine, c->res_aff_host + (kSlots - 1), sizeof(ge_aff));
-    return VMSM_OK;
+    return fetch_slot(c, kSlots - 1, out_affine);
 }
 
 int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_n, uint64_t b, uint64_t b_off,
@@ -851,6 +1015,30 @@ int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_
         pb = ib->second;
     }
     PointSet ps;
+    if (b_n && pb.curve != ia->second.curve) return fail(VMSM_ERR_INVALID, "point vectors are on different curves");
+    if (ia->second.curve != VMSM_CURVE_ED25519) {
+        const bool g2 = ia->second.curve == VMSM_CURVE_BN256_G2;
+        int32_t rcw = g2 ? w_new_pointset<Fp2BN>(ia->second.curve, a_n + b_n, &ps) : w_new_pointset<FpBN>(ia->second.curve, a_n + b_n, &ps);
+        if (rcw) return rcw;
+        size_t wb = wire_bytes(ia->second.curve);
+        cudaError_t e = cudaSuccess;
+        if (a_n) {
+            e = cudaMemcpyAsync(ps.w_wire, (const uint8_t *)ia->second.w_wire + a_off * wb, a_n * wb, cudaMemcpyDeviceToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ps.w_base, (const uint8_t *)ia->second.w_base + a_off * wb, a_n * wb, cudaMemcpyDeviceToDevice, c->stream);
+        }
+        if (b_n && e == cudaSuccess) {
+            e = cudaMemcpyAsync((uint8_t *)ps.w_wire + a_n * wb, (const uint8_t *)pb.w_wire + b_off * wb, b_n * wb, cudaMemcpyDeviceToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t *)ps.w_base + a_n * wb, (const uint8_t *)pb.w_base + b_off * wb, b_n * wb, cudaMemcpyDeviceToDevice, c->stream);
+        }
+        if (e != cudaSuccess) {
+            cudaFree(ps.w_wire), cudaFree(ps.w_base);
+            return fail(VMSM_ERR_CUDA, "concat: %s", cudaGetErrorString(e));
+        }
+        uint64_t idw = c->next_id++;
+        c->points[idw] = ps;
+        *out = idw;
+        return VMSM_OK;
+    }
     int32_t rc = new_pointset(c, ia->second.curve, a_n + b_n, &ps);
     if (rc) return rc;
     CudaBE be(c);
@@ -943,6 +1131,7 @@ int32_t vmsm_msm_dev_shard(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n
     if (poff > it->second.n || n > it->second.n - poff) return fail(VMSM_ERR_INVALID, "Not enough generators.");
     if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
     if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    if (it->second.curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "sharded MSM: Ed25519 only");
     c->shard_next = seq;
     return run_msm(c, it->second.niels + poff, is->second.data + soff * 8, n, slot);
 }
@@ -955,6 +1144,7 @@ int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, con
     if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "Not enough generators.");
     if (n && !scalars_le32) return fail(VMSM_ERR_INVALID, "null argument");
     if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    if (it->second.curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "vmsm_msm_async: Ed25519 only");
     const int b = (int)(c->async_seq++ & 1);
     if ((n ? n : 1) > c->astage_cap[b]) {
         if (c->astage[b]) cudaFree(c->astage[b]);  // synchronises the device
@@ -986,24 +1176,20 @@ int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint
     if (poff > it->second.n || n > it->second.n - poff) return fail(VMSM_ERR_INVALID, "Not enough generators.");
     if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
     if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    if (it->second.curve != VMSM_CURVE_ED25519) return w_run_msm_any(c, it->second, poff, is->second.data + soff * 8, n, slot);
     return run_msm(c, it->second.niels + poff, is->second.data + soff * 8, n, slot);
 }
 
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine) {
     GET_CTX(ctx);
     if (slot >= kSlots || !out_affine) return fail(VMSM_ERR_INVALID, "bad slot / null argument");
-    CU(cudaEventSynchronize(c->ev_slot[slot]));  // waits for THIS result only, not for MSMs issued after it
-    if (c->res_status_host[slot]) {
-        c->res_status_host[slot] = 0;
-        return fail(VMSM_ERR_TIMEOUT, "a multi-GPU partial for slot %u did not arrive", slot);
-    }
-    memcpy(out_affine, c->res_aff_host + slot, sizeof(ge_aff));
-    return VMSM_OK;
+    return fetch_slot(c, slot, out_affine);  // waits for THIS result only, not for MSMs issued after it
 }
 
 int32_t vmsm_result_extended(uint64_t ctx, uint32_t slot, uint8_t *out_extended) {
     GET_CTX(ctx);
     if (slot >= kSlots || !out_extended) return fail(VMSM_ERR_INVALID, "bad slot / null argument");
+    if (c->slot_curve[slot] != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "extended results: Ed25519 only");
     CU(join_tail(c));
     CU(cudaMemcpyAsync(c->pin, c->res_ext + slot, sizeof(ge_ext), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1017,6 +1203,7 @@ int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le
     auto it = c->points.find(pts);
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
     if (!c_le32) return fail(VMSM_ERR_INVALID, "null argument");
+    if (it->second.curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "fold is defined for the Ed25519 path only");
     if (half == 0 || 2 * half > it->second.n) return fail(VMSM_ERR_INVALID, "fold: need 2*half <= length");
     int32_t rc = ensure_tmp(c, half);
     if (rc) return rc;
@@ -1033,12 +1220,39 @@ int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le
 int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const uint8_t *scalars_le32, uint64_t n,
                      uint8_t *out_affine) {
     GET_CTX(ctx);
-    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "curve %d not supported yet", curve);
+    if (curve < VMSM_CURVE_ED25519 || curve > VMSM_CURVE_BN256_G2) return fail(VMSM_ERR_UNSUPPORTED, "unknown curve %d", curve);
     if (n > 64) return fail(VMSM_ERR_INVALID, "lincomb takes at most 64 terms");
     if (!out_affine || (n && (!affine || !scalars_le32))) return fail(VMSM_ERR_INVALID, "null argument");
     int32_t rc = ensure_stage(c, 64);
     if (rc) return rc;
     CudaBE be(c);
+    if (curve != VMSM_CURVE_ED25519) {
+        size_t wb = wire_bytes(curve);
+        if (n) {
+            be.note(cudaMemcpyAsync(c->small_w_wire, affine, n * wb, cudaMemcpyHostToDevice, c->stream));
+            be.note(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
+            be.zero(c->err_word, 4);
+            if (curve == VMSM_CURVE_BN256_G1) {
+                KUploadW<FpBN> k = {(const waff<FpBN> *)c->small_w_wire, (waff<FpBN> *)c->small_w_base, c->err_word, c->check_points ? 1u : 0u};
+                be.launch(k, (uint32_t)n);
+            } else {
+                KUploadW<Fp2BN> k = {(const waff<Fp2BN> *)c->small_w_wire, (waff<Fp2BN> *)c->small_w_base, c->err_word, c->check_points ? 1u : 0u};
+                be.launch(k, (uint32_t)n);
+            }
+        }
+        if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "lincomb: %s", cudaGetErrorString(be.err));
+        PointSet tmp{};
+        tmp.curve = curve;
+        tmp.n = n;
+        tmp.w_wire = c->small_w_wire;
+        tmp.w_base = c->small_w_base;
+        rc = w_run_msm_any(c, tmp, 0, c->stage_scalars, n, kSlots - 1);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(c->pin + 64, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (n && *reinterpret_cast<uint32_t *>(c->pin + 64)) return fail(VMSM_ERR_POINT, "invalid point in lincomb input");
+        return fetch_slot(c, kSlots - 1, out_affine);
+    }
     if (n) {
         be.note(cudaMemcpyAsync(c->small_aff, affine, n * sizeof(ge_aff), cudaMemcpyHostToDevice, c->stream));
         be.note(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));

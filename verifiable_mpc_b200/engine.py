@@ -11,6 +11,11 @@ from ._lib import VmsmError, check
 
 ED_P = 2**255 - 19
 ED_L = 2**252 + 27742317777372353535851937790883648493
+BN_U = 1868033 ** 3
+BN_P = 36 * BN_U ** 4 + 36 * BN_U ** 3 + 24 * BN_U ** 2 + 6 * BN_U + 1
+BN_N = 36 * BN_U ** 4 + 36 * BN_U ** 3 + 18 * BN_U ** 2 + 6 * BN_U + 1
+ORDERS = {_lib.CURVE_ED25519: ED_L, _lib.CURVE_BN256_G1: BN_N, _lib.CURVE_BN256_G2: BN_N}
+WIRE_BYTES = {_lib.CURVE_ED25519: 64, _lib.CURVE_BN256_G1: 64, _lib.CURVE_BN256_G2: 128}
 
 
 def _buf(data):
@@ -44,6 +49,42 @@ def unpack_points(raw):
             for i in range(0, len(raw), 64)]
 
 
+# BN256 wire forms (include/vmsm.h): G1 = x || y (64 B), G2 = x.re || x.im || y.re || y.im (128 B), identity = zeros;
+# host-side points are None (identity), (x, y) for G1 and ((xre, xim), (yre, yim)) for G2.
+def pack_points_bn(pts, curve):
+    out = []
+    for p in pts:
+        if p is None:
+            out.append(bytes(WIRE_BYTES[curve]))
+        elif curve == _lib.CURVE_BN256_G2:
+            out.append(b"".join(int(v).to_bytes(32, "little") for v in (p[0][0], p[0][1], p[1][0], p[1][1])))
+        else:
+            out.append(int(p[0]).to_bytes(32, "little") + int(p[1]).to_bytes(32, "little"))
+    return b"".join(out)
+
+
+def unpack_points_bn(raw, curve):
+    wb = WIRE_BYTES[curve]
+    out = []
+    for i in range(0, len(raw), wb):
+        v = [int.from_bytes(raw[i + 32 * k:i + 32 * k + 32], "little") for k in range(wb // 32)]
+        if not any(v):
+            out.append(None)
+        elif curve == _lib.CURVE_BN256_G2:
+            out.append(((v[0], v[1]), (v[2], v[3])))
+        else:
+            out.append((v[0], v[1]))
+    return out
+
+
+def pack_any(pts, curve):
+    return pack_points(pts) if curve == _lib.CURVE_ED25519 else pack_points_bn(pts, curve)
+
+
+def unpack_any(raw, curve):
+    return unpack_points(raw) if curve == _lib.CURVE_ED25519 else unpack_points_bn(raw, curve)
+
+
 class DevicePoints:
     """A device-resident vector of group elements (a generator list ``g`` / ``g_hat``)."""
 
@@ -55,12 +96,13 @@ class DevicePoints:
 
     def download(self, off=0, n=None):
         n = self.n - off if n is None else n
-        out = ctypes.create_string_buffer(max(1, 64 * n))
+        wb = WIRE_BYTES[self.curve]
+        out = ctypes.create_string_buffer(max(1, wb * n))
         check(self.ctx.lib.vmsm_points_download(self.ctx.h, self.handle, off, n, out))
-        return out.raw[:64 * n]
+        return out.raw[:wb * n]
 
     def tolist(self, off=0, n=None):
-        return unpack_points(self.download(off, n))
+        return unpack_any(self.download(off, n), self.curve)
 
     def fold(self, c):
         """In place ``P[j] = c*P[j] + P[half+j]`` (compressed_pivot.py:64); the vector shrinks to half."""
@@ -171,9 +213,9 @@ class Context:
     # -- points
     def upload_points(self, pts, curve=_lib.CURVE_ED25519):
         """``pts``: bytes (n*64, canonical affine LE) or a list of (x, y) ints."""
-        raw = pts if isinstance(pts, (bytes, bytearray)) or hasattr(pts, "nbytes") else pack_points(pts)
+        raw = pts if isinstance(pts, (bytes, bytearray)) or hasattr(pts, "nbytes") else pack_any(pts, curve)
         nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
-        n = nbytes // 64
+        n = nbytes // WIRE_BYTES[curve]
         p, keep = _buf(raw)
         h = ctypes.c_uint64()
         check(self.lib.vmsm_points_upload(self.h, curve, p, n, ctypes.byref(h)))
@@ -182,7 +224,8 @@ class Context:
     def fixed_base(self, scalars=None, seed=0, n=None, curve=_lib.CURVE_ED25519):
         """``g_i = r_i * B`` on the device: explicit scalars (ints or packed bytes) or ``synth(seed, i)``."""
         if scalars is not None:
-            raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars)
+            raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else \
+                pack_scalars(scalars, ORDERS[curve])
             nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
             n = nbytes // 32
             p, keep = _buf(raw)
@@ -193,8 +236,8 @@ class Context:
         return DevicePoints(self, h.value, n, curve)
 
     # -- scalars
-    def upload_scalars(self, scalars):
-        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars)
+    def upload_scalars(self, scalars, order=ED_L):
+        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars, order)
         nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
         n = nbytes // 32
         p, keep = _buf(raw)
@@ -210,25 +253,27 @@ class Context:
     # -- MSM
     def msm(self, points, scalars, off=0, n=None):
         """End to end: host scalars (ints / packed bytes / numpy uint8) -> canonical affine (x, y)."""
-        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars)
+        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else \
+            pack_scalars(scalars, ORDERS[points.curve])
         nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
         if n is None:
             n = nbytes // 32
         p, keep = _buf(raw)
-        out = ctypes.create_string_buffer(64)
+        out = ctypes.create_string_buffer(WIRE_BYTES[points.curve])
         check(self.lib.vmsm_msm(self.h, points.handle, off, n, p, out))
-        return unpack_points(out.raw)[0]
+        return unpack_any(out.raw, points.curve)[0]
 
     def msm_ext(self, points, off, n, extra, extra_off, n_extra, scalars):
         """Pedersen form in one pass: sum_{i<n} s_i P[off+i] + sum_{j<n_extra} s_{n+j} E[extra_off+j]."""
-        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else pack_scalars(scalars)
+        raw = scalars if isinstance(scalars, (bytes, bytearray)) or hasattr(scalars, "nbytes") else \
+            pack_scalars(scalars, ORDERS[points.curve])
         nbytes = raw.nbytes if hasattr(raw, "nbytes") else len(raw)
         if nbytes != 32 * (n + n_extra):
             raise ValueError("need n + n_extra scalars")
         p, keep = _buf(raw)
-        out = ctypes.create_string_buffer(64)
+        out = ctypes.create_string_buffer(WIRE_BYTES[points.curve])
         check(self.lib.vmsm_msm_ext(self.h, points.handle, off, n, extra.handle, extra_off, n_extra, p, out))
-        return unpack_points(out.raw)[0]
+        return unpack_any(out.raw, points.curve)[0]
 
     def concat(self, a, a_off, a_n, b=None, b_off=0, b_n=0):
         """Device-side copy: a[a_off:a_off+a_n] || b[b_off:b_off+b_n] as a new DevicePoints."""
@@ -271,10 +316,10 @@ class Context:
             n = min(points.n - poff, scalars.n - soff)
         check(self.lib.vmsm_msm_dev_shard(self.h, points.handle, poff, n, scalars.handle, soff, slot, seq))
 
-    def result(self, slot=0):
-        out = ctypes.create_string_buffer(64)
+    def result(self, slot=0, curve=_lib.CURVE_ED25519):
+        out = ctypes.create_string_buffer(128)
         check(self.lib.vmsm_result_affine(self.h, slot, out))
-        return unpack_points(out.raw)[0]
+        return unpack_any(out.raw[:WIRE_BYTES[curve]], curve)[0]
 
     def result_extended(self, slot=0):
         out = ctypes.create_string_buffer(128)
@@ -284,9 +329,9 @@ class Context:
     def lincomb(self, pts, scalars, curve=_lib.CURVE_ED25519):
         """sum_i s_i * P_i for a handful (<= 64) of host points; returns canonical affine (x, y)."""
         n = len(pts)
-        out = ctypes.create_string_buffer(64)
-        check(self.lib.vmsm_lincomb(self.h, curve, pack_points(pts), pack_scalars(scalars), n, out))
-        return unpack_points(out.raw)[0]
+        out = ctypes.create_string_buffer(WIRE_BYTES[curve])
+        check(self.lib.vmsm_lincomb(self.h, curve, pack_any(pts, curve), pack_scalars(scalars, ORDERS[curve]), n, out))
+        return unpack_any(out.raw, curve)[0]
 
     def selftest_fe(self, op, a, b):
         n = len(a)

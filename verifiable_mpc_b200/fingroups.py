@@ -14,7 +14,7 @@ Single operations cost a kernel launch each -- they are meant for the O(log N) g
 import functools
 
 from . import _lib
-from .engine import ED_L, ED_P, default_context, unpack_points
+from .engine import BN_N, BN_P, ED_L, ED_P, default_context, unpack_points
 from .finfields import GF
 
 BX = 15112221349535400772501151409588531511454012693041857206046113283949847762202
@@ -201,10 +201,110 @@ def _ed25519_class(coordinates):
     return cls
 
 
+# ---------------------------------------------------------------------------------------------- BN256 G1 / G2
+class BN256Point(EllipticCurvePoint):
+    """A point of BN256 (G1, over Fp) or of its sextic twist (G2, over Fp2 = Fp[i]/(i^2+1)): the groups the
+    Pinocchio prover works in (demos/demo_zkp_pynocchio.py:27-29).  Host side: ``pt`` is None (identity), ``(x, y)``
+    for G1 or ``((x_re, x_im), (y_re, y_im))`` for G2, canonical; every group operation is a device call."""
+    __slots__ = ("pt",)
+    order = BN_N
+    curve_id = _lib.CURVE_BN256_G1
+    context = None
+
+    def __init__(self, value=None, check=True):
+        if value is None:
+            self.pt = None
+            return
+        raise NotImplementedError("construct BN256 points with from_affine() or from group.generator")
+
+    @classmethod
+    def _ctx(cls):
+        return cls.context or default_context()
+
+    @classmethod
+    def _make(cls, pt):
+        obj = cls.__new__(cls)
+        obj.pt = pt
+        return obj
+
+    from_affine = _make
+
+    def affine(self):
+        return self.pt
+
+    def normalize(self):
+        return self
+
+    def __repr__(self):
+        if self.pt is None:
+            return "[1, 1, 0]"
+        x, y = self.pt
+        return f"[{list(x) if isinstance(x, tuple) else x}, {list(y) if isinstance(y, tuple) else y}, 1]"
+
+    def __eq__(self, other):
+        if not isinstance(other, type(self)):
+            return NotImplemented
+        return self.pt == other.pt
+
+    def __hash__(self):
+        return hash(self.pt)
+
+    @classmethod
+    def operation(cls, a, b):
+        return cls._make(cls._ctx().lincomb([a.pt, b.pt], [1, 1], curve=cls.curve_id))
+
+    @classmethod
+    def operation2(cls, a):
+        return cls._make(cls._ctx().lincomb([a.pt], [2], curve=cls.curve_id))
+
+    @classmethod
+    def inversion(cls, a):
+        if a.pt is None:
+            return a
+        x, y = a.pt
+        ny = tuple((-v) % BN_P for v in y) if isinstance(y, tuple) else (-y) % BN_P
+        return cls._make((x, ny))
+
+    @classmethod
+    def equality(cls, a, b):
+        return a == b
+
+    @classmethod
+    def repeat(cls, a, n):
+        return cls._make(cls._ctx().lincomb([a.pt], [int(n) % BN_N], curve=cls.curve_id))
+
+    @classmethod
+    def lincomb(cls, points, scalars):
+        return cls._make(cls._ctx().lincomb([p.pt for p in points], [int(s) % BN_N for s in scalars], curve=cls.curve_id))
+
+
+_BN_G1 = (1, BN_P - 2)
+_BN_G2 = ((64746500191241794695844075326670126197795977525365406531717464316923369116492,
+           21167961636542580255011770066570541300993051739349375019639421053990175267184),
+          (17778617556404439934652658462602675281523610326338642107814333856843981424549,
+           20666913350058776956210519119118544732556678129809273996262322366050359951122))
+
+
+@functools.lru_cache(maxsize=None)
+def _bn256_class(curvename, coordinates):
+    twist = curvename == "BN256_twist"
+    cls = type(f"E({curvename}){coordinates}", (BN256Point,), {"__slots__": ()})
+    cls.curve_id = _lib.CURVE_BN256_G2 if twist else _lib.CURVE_BN256_G1
+    cls.curvename = curvename
+    cls.coordinates = coordinates
+    cls.field = None if twist else GF(BN_P)
+    cls.is_additive, cls.is_multiplicative = True, False
+    cls.identity = cls._make(None)
+    cls.generator = cls._make(_BN_G2 if twist else _BN_G1)
+    return cls
+
+
 def EllipticCurve(curvename="Ed25519", coordinates=None):
     if curvename == "Ed25519":
         return _ed25519_class(coordinates or "extended")
-    raise NotImplementedError(f"curve {curvename}: BN256 G1/G2 are the next row of the scope table (DESIGN.md)")
+    if curvename in ("BN256", "BN256_twist"):
+        return _bn256_class(curvename, coordinates or "jacobian")
+    raise NotImplementedError(f"curve {curvename} is not part of the engine")
 
 
 class DevicePointList:

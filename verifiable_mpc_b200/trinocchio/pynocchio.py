@@ -1,0 +1,96 @@
+"""GPU-backed twin of the PROVER step of ``verifiable_mpc/trinocchio/pynocchio.py``: ``compute_proof`` (:228-273).
+
+The reference builds eight lists ``[int(c[i]) * evalkey[key_i] ...]`` (one Python double-and-add per term, six over
+BN256 G1 and one over G2 for the mid-wire indices, one over G1 for the quotient polynomial h) and sums each with
+``apply_to_list(point_add, ...)`` (:82-91), then adds up to nine single scalar multiplications for the zero-knowledge
+shifts.  Here every one of the eight proof elements is ONE device MSM (libvmsm.so, Pippenger over BN256 Jacobian
+arithmetic) with the zero-knowledge terms riding along as extra terms of the same MSM.  Same signature, same proof
+keys; key generation and the pairing-based ``verify`` stay the reference's (north_star: "pairing verify unchanged").
+"""
+from .. import _lib
+from ..engine import BN_N, pack_scalars
+
+# (proof key, evalkey key template for mid index i, delta terms [(delta attribute, evalkey key)])
+_MID_SUMS = (
+    ("r_v*v_mid*g1", "r_v*v{i}*g1", (("v", "r_v*t*g1"),)),
+    ("r_w*w_mid*g2", "r_w*w{i}*g2", (("w", "r_w*t*g2"),)),
+    ("r_y*y_mid*g1", "r_y*y{i}*g1", (("y", "r_y*t*g1"),)),
+    ("r_v*alpha_v*v_mid*g1", "r_v*alpha_v*v{i}*g1", (("v", "r_v*alpha_v*t*g1"),)),
+    ("r_w*alpha_w*w_mid*g1", "r_w*alpha_w*w{i}*g1", (("w", "r_w*alpha_w*t*g1"),)),
+    ("r_y*alpha_y*y_mid*g1", "r_y*alpha_y*y{i}*g1", (("y", "r_y*alpha_y*t*g1"),)),
+    ("r_v*beta*v_mid+r_w*beta*w_mid+r_y*beta*y_mid*g1", "r_v*beta*v+r_w*beta*w+r_y*beta*y{i}_g1",
+     (("v", "r_v*beta*t*g1"), ("w", "r_w*beta*t*g1"), ("y", "r_y*beta*t*g1"))),
+)
+
+
+def apply_to_list(op, inputs):
+    """Binary-tree application (reference :82-91); kept for callers that import it from this module."""
+    n = len(inputs)
+    if n == 1:
+        return inputs[0]
+    return op(apply_to_list(op, inputs[: n // 2]), apply_to_list(op, inputs[n // 2:]))
+
+
+def point_add(a, b):
+    return a @ b
+
+
+def _msm(points, scalars):
+    """sum_i scalars[i] * points[i] on the device; points are group elements of one BN256 group."""
+    group = type(points[0])
+    ctx = group._ctx()
+    dev = ctx.upload_points([p.affine() for p in points], curve=group.curve_id)
+    try:
+        return group._make(ctx.msm(dev, pack_scalars(scalars, BN_N)))
+    finally:
+        dev.free()
+
+
+class PreparedEvalKey:
+    """The base vectors of the eight sums uploaded ONCE (they only depend on the QAP and the evaluation key), so a
+    prover that produces many proofs for the same circuit pays H2D for the witness scalars only."""
+
+    def __init__(self, qap, evalkey, h_len):
+        self.indices_mid = list(qap.indices_mid)
+        self.h_len = h_len
+        self.groups, self.bases = {}, {}
+        for name, template, deltas in _MID_SUMS:
+            pts = [evalkey[template.format(i=i)] for i in self.indices_mid] + [evalkey[k] for _, k in deltas]
+            self._put(name, pts)
+        self._put("h*g1", [evalkey["s^" + str(i) + "*g1"] for i in range(h_len)])
+
+    def _put(self, name, pts):
+        group = type(pts[0])
+        self.groups[name] = group
+        self.bases[name] = group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id)
+
+
+def compute_proof(qap, c, h, evalkey, deltas=None):
+    """Pinocchio proof elements for witness ``c`` and quotient polynomial ``h`` (reference :228-273).
+
+    ``evalkey``: the reference's dict of group elements, or a ``PreparedEvalKey`` (bases resident on the device).
+    """
+    prepared = evalkey if isinstance(evalkey, PreparedEvalKey) else None
+    mid = prepared.indices_mid if prepared else list(qap.indices_mid)
+    c_mid = [int(c[i]) for i in mid]
+    proof = {}
+    for name, template, delta_terms in _MID_SUMS:
+        scalars = list(c_mid)
+        if deltas is not None:
+            scalars += [int(getattr(deltas, attr)) for attr, _ in delta_terms]
+        if prepared:
+            group, dev = prepared.groups[name], prepared.bases[name]
+            proof[name] = group._make(group._ctx().msm(dev, pack_scalars(scalars, BN_N), n=len(scalars)))
+        else:
+            pts = [evalkey[template.format(i=i)] for i in mid]
+            if deltas is not None:
+                pts += [evalkey[k] for _, k in delta_terms]
+            proof[name] = _msm(pts, scalars)
+    h_scalars = [int(h.coeffs[i]) for i in range(0, len(h))]
+    if prepared:
+        group, dev = prepared.groups["h*g1"], prepared.bases["h*g1"]
+        assert len(h_scalars) <= prepared.h_len, "Not enough generators."
+        proof["h*g1"] = group._make(group._ctx().msm(dev, pack_scalars(h_scalars, BN_N), n=len(h_scalars)))
+    else:
+        proof["h*g1"] = _msm([evalkey["s^" + str(i) + "*g1"] for i in range(0, len(h))], h_scalars)
+    return proof
