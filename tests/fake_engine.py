@@ -93,6 +93,17 @@ class FakeContext:
         sc = _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else [int(s) % E.L for s in scalars]
         return E.msm_naive(sc, points.pts[off:off + len(sc)])
 
+    def msm_async(self, points, ptr, off, n, slot):
+        import ctypes
+
+        raw = ctypes.string_at(ptr, 32 * n) if n else b""
+        if not hasattr(self, "_slots"):
+            self._slots = {}
+        self._slots[slot] = self.msm(points, raw, off=off)
+
+    def result(self, slot=0, curve=0):
+        return self._slots[slot]
+
     def concat(self, a, a_off, a_n, b=None, b_off=0, b_n=0):
         pts = a.pts[a_off:a_off + a_n] + (b.pts[b_off:b_off + b_n] if b is not None else [])
         return FakePoints(self, pts)

@@ -11,8 +11,9 @@
 
 namespace vmsm {
 
-// The Montgomery multiplication is a real function on the device (not inlined): a G2 point addition contains 48 of
-// them and ptxas needs tens of minutes for the fully inlined kernels; a call costs a few cycles against ~300.
+// Code-size control.  The base-field multiplication is inlined, but the Fp2 multiplication / squaring, the field
+// inversion and the point operations of bn256.cuh are real functions on the device: a fully inlined G2 point addition
+// contains 48 Montgomery multiplications and ptxas needs tens of minutes for such kernels.
 #if defined(__CUDACC__)
 #define VMSM_HD_NOINLINE static __host__ __device__ __noinline__
 #else
@@ -40,6 +41,23 @@ VMSM_HD fbn fbn_zero() {
 VMSM_HD fbn fbn_cond_sub_p(const fbn &a, uint32_t carry_in) {
     const fbn p = fbn_p();
     fbn d;
+#if defined(__CUDA_ARCH__)
+    uint32_t nb;  // 0 - borrow: 0 when a >= p, 0xffffffff when a < p
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]),
+          "=r"(d.v[7]), "=r"(nb)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(p.v[0]), "r"(p.v[1]), "r"(p.v[2]), "r"(p.v[3]), "r"(p.v[4]), "r"(p.v[5]), "r"(p.v[6]), "r"(p.v[7]));
+    bool use = carry_in != 0 || nb == 0;
+#else
     int64_t bw = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -48,6 +66,7 @@ VMSM_HD fbn fbn_cond_sub_p(const fbn &a, uint32_t carry_in) {
         bw >>= 32;
     }
     bool use = carry_in != 0 || bw == 0;
+#endif
     fbn r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = use ? d.v[i] : a.v[i];
@@ -56,6 +75,23 @@ VMSM_HD fbn fbn_cond_sub_p(const fbn &a, uint32_t carry_in) {
 
 VMSM_HD fbn fbn_add(const fbn &a, const fbn &b) {
     fbn s;
+#if defined(__CUDA_ARCH__)
+    uint32_t c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]),
+          "=r"(s.v[7]), "=r"(c)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    return fbn_cond_sub_p(s, c);
+#else
     uint64_t c = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -64,11 +100,42 @@ VMSM_HD fbn fbn_add(const fbn &a, const fbn &b) {
         c >>= 32;
     }
     return fbn_cond_sub_p(s, (uint32_t)c);
+#endif
 }
 
 VMSM_HD fbn fbn_sub(const fbn &a, const fbn &b) {
     const fbn p = fbn_p();
     fbn d;
+#if defined(__CUDA_ARCH__)
+    uint32_t m;  // 0xffffffff on borrow
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]),
+          "=r"(d.v[7]), "=r"(m)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    fbn r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(d.v[0]), "r"(d.v[1]), "r"(d.v[2]), "r"(d.v[3]), "r"(d.v[4]), "r"(d.v[5]), "r"(d.v[6]), "r"(d.v[7]),
+          "r"(p.v[0] & m), "r"(p.v[1] & m), "r"(p.v[2] & m), "r"(p.v[3] & m), "r"(p.v[4] & m), "r"(p.v[5] & m),
+          "r"(p.v[6] & m), "r"(p.v[7] & m));
+    return r;
+#else
     int64_t bw = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -86,6 +153,7 @@ VMSM_HD fbn fbn_sub(const fbn &a, const fbn &b) {
         c >>= 32;
     }
     return r;
+#endif
 }
 
 VMSM_HD fbn fbn_neg(const fbn &a) { return fbn_sub(fbn_zero(), a); }
@@ -169,7 +237,7 @@ VMSM_HD fbn fbn_redc(uint32_t *t) {
 #endif
 }
 
-VMSM_HD_NOINLINE fbn fbn_mul(const fbn &a, const fbn &b) {
+VMSM_HD fbn fbn_mul(const fbn &a, const fbn &b) {
     uint32_t t[16];
     mp_mul8(a.v, b.v, t);
     return fbn_redc(t);
@@ -223,15 +291,15 @@ VMSM_HD f2bn f2bn_select(bool c, const f2bn &a, const f2bn &b) {
     f2bn r = {fbn_select(c, a.c0, b.c0), fbn_select(c, a.c1, b.c1)};
     return r;
 }
-// Karatsuba: 3 base-field multiplications
-VMSM_HD f2bn f2bn_mul(const f2bn &a, const f2bn &b) {
+// Karatsuba: 3 base-field multiplications (a real function on the device, see VMSM_HD_NOINLINE)
+VMSM_HD_NOINLINE f2bn f2bn_mul(const f2bn &a, const f2bn &b) {
     fbn t0 = fbn_mul(a.c0, b.c0), t1 = fbn_mul(a.c1, b.c1);
     fbn t2 = fbn_mul(fbn_add(a.c0, a.c1), fbn_add(b.c0, b.c1));
     f2bn r = {fbn_sub(t0, t1), fbn_sub(fbn_sub(t2, t0), t1)};
     return r;
 }
 // (a0 + a1 i)^2 = (a0+a1)(a0-a1) + 2 a0 a1 i : 2 multiplications
-VMSM_HD f2bn f2bn_sqr(const f2bn &a) {
+VMSM_HD_NOINLINE f2bn f2bn_sqr(const f2bn &a) {
     fbn m = fbn_mul(a.c0, a.c1);
     f2bn r = {fbn_mul(fbn_add(a.c0, a.c1), fbn_sub(a.c0, a.c1)), fbn_dbl(m)};
     return r;

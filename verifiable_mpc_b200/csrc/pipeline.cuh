@@ -47,7 +47,8 @@ struct Workspace {
 // so the last window that holds bit (scalar_bits-2) sees r = (scalar_bits-1) mod c live bits and its 2^(r-1) buckets
 // are 2^(c-r) times fuller than average (r = 0: a carry-only window, one bucket with n/2 entries).  The long-bucket
 // path keeps such cases correct and bounded; the chooser simply avoids paying for them (measured: profiles/r01).
-inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits, bool avoid_skew = true) {
+inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits, bool avoid_skew = true, double madd = 504.0,
+                              double add = 648.0 * 1.3) {
     if (n == 0) return 4;
     double best = 0;
     uint32_t best_c = 0;
@@ -56,7 +57,7 @@ inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits, bool avoid_skew 
         if (avoid_skew && (r == 0 || c - r > 4)) continue;
         double W = (double)((scalar_bits + 1 + c - 1) / c);
         double NB = (double)(1u << (c - 1));
-        double cost = (double)n * W * 504.0 + W * NB * 2.0 * 648.0 * 1.3 + (W - 1) * c * 464.0;
+        double cost = (double)n * W * madd + W * NB * 2.0 * add + (W - 1) * c * 464.0;
         if (!best_c || cost < best) {
             best = cost;
             best_c = c;
@@ -233,9 +234,12 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
 // Same sequence as msm_run for the Weierstrass groups; everything on the main stream (these MSMs are 2^14-sized).
 template <class BE, class F>
 int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases, const uint32_t *scalars, uint32_t n,
-              wjac<F> *out_jac, waff<F> *out_wire, const waff<F> *extra = nullptr, uint32_t n_extra = 0) {
+              wjac<F> *out_jac, waff<F> *out_wire, const waff<F> *extra = nullptr, uint32_t n_extra = 0,
+              uint32_t seq = 0) {
     const uint32_t scalar_bits = 256, n_main = n - n_extra;
-    uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits, false);
+    // Jacobian costs in field multiplications (mixed addition 7M+4S, addition 11M+5S); the long-bucket path makes any
+    // window safe, so skewed top windows are allowed here (these MSMs are small and latency matters more)
+    uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits, false, 11.0, 16.0 * 0.6);
     if (c > 16) c = 16;
     MsmGeom g = make_geom(n, c, scalar_bits);
     uint32_t R = 1u << opt.reduce_log2r;
@@ -275,24 +279,32 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         }
     }
     be.phase_mark(PH_ACCUMULATE);
+    // leaf level on the main stream; the latency-bound rest (upper levels, Horner, inversion) on the side stream so
+    // that it overlaps the head of the next MSM (the eight MSMs of a Pinocchio proof are independent)
+    const int par = (int)(seq & 1);
+    be.head_wait_tail(par);
     const wjac<F> *inS = (const wjac<F> *)ws.buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;
+    bool in_tail = false;
     do {
         uint32_t cnt_out = (cnt + R - 1) / R;
-        KReduceW<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[0][pp], (wjac<F> *)ws.nodeT[0][pp], cnt, cnt_out, R, log2s};
+        if (log2s && !in_tail) be.tail_begin(), in_tail = true;
+        KReduceW<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[par][pp], (wjac<F> *)ws.nodeT[par][pp], cnt, cnt_out, R, log2s};
         be.launch(k6, g.W * cnt_out);
-        inS = (const wjac<F> *)ws.nodeS[0][pp];
-        inT = (const wjac<F> *)ws.nodeT[0][pp];
+        inS = (const wjac<F> *)ws.nodeS[par][pp];
+        inT = (const wjac<F> *)ws.nodeT[par][pp];
         pp ^= 1;
         cnt = cnt_out;
         log2s += opt.reduce_log2r;
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
+    if (!in_tail) be.tail_begin(), in_tail = true;
     KFinalW<F> k7 = {inS, inT, out_jac, out_wire, g.W, g.c};
     be.launch(k7, 32);
     be.phase_mark(PH_FINAL);
     be.result_ready();
+    be.tail_end(par);
     be.phase_end();
     return 0;
 }

@@ -528,7 +528,7 @@ int32_t w_run_msm(Ctx *c, const PointSet &ps, uint64_t off, const uint32_t *scal
     MsmOptions opt = c->opt;
     int rc = msm_run_w<CudaBE, F>(be, c->ws, opt, (const waff<F> *)ps.w_base + off, scalars, (uint32_t)n_total,
                                   (wjac<F> *)(c->res_w_dev + 192 * slot), (waff<F> *)(c->res_w_host + 128 * slot),
-                                  extra ? (const waff<F> *)extra->w_base + extra_off : nullptr, n_extra);
+                                  extra ? (const waff<F> *)extra->w_base + extra_off : nullptr, n_extra, c->msm_seq++);
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
     return VMSM_OK;
@@ -1144,7 +1144,6 @@ int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, con
     if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "Not enough generators.");
     if (n && !scalars_le32) return fail(VMSM_ERR_INVALID, "null argument");
     if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
-    if (it->second.curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "vmsm_msm_async: Ed25519 only");
     const int b = (int)(c->async_seq++ & 1);
     if ((n ? n : 1) > c->astage_cap[b]) {
         if (c->astage[b]) cudaFree(c->astage[b]);  // synchronises the device
@@ -1159,7 +1158,8 @@ int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, con
     if (n) CU(cudaMemcpyAsync(c->astage[b], scalars_le32, n * 32, cudaMemcpyHostToDevice, c->copy));
     CU(cudaEventRecord(c->ev_copied[b], c->copy));
     CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-    int32_t rc = run_msm(c, it->second.niels + off, c->astage[b], n, slot);
+    int32_t rc = it->second.curve == VMSM_CURVE_ED25519 ? run_msm(c, it->second.niels + off, c->astage[b], n, slot)
+                                                        : w_run_msm_any(c, it->second, off, c->astage[b], n, slot);
     if (rc) return rc;
     CU(cudaEventRecord(c->ev_consumed[b], c->stream));
     c->astage_used[b] = true;

@@ -69,28 +69,53 @@ def compute_proof(qap, c, h, evalkey, deltas=None):
     """Pinocchio proof elements for witness ``c`` and quotient polynomial ``h`` (reference :228-273).
 
     ``evalkey``: the reference's dict of group elements, or a ``PreparedEvalKey`` (bases resident on the device).
+    All eight MSMs are issued asynchronously (the witness scalars are packed once and shared by the seven mid-wire
+    sums) and fetched afterwards, so their latency-bound tails overlap on the device.
     """
+    import ctypes
+
     prepared = evalkey if isinstance(evalkey, PreparedEvalKey) else None
     mid = prepared.indices_mid if prepared else list(qap.indices_mid)
-    c_mid = [int(c[i]) for i in mid]
-    proof = {}
-    for name, template, delta_terms in _MID_SUMS:
-        scalars = list(c_mid)
+    c_mid_raw = pack_scalars([int(c[i]) for i in mid], BN_N)
+    h_scalars = [int(h.coeffs[i]) for i in range(0, len(h))]
+    if prepared:
+        assert len(h_scalars) <= prepared.h_len, "Not enough generators."
+
+    jobs = []  # (name, group, device points, owned?, scalar bytes)
+    # the G2 sum first: its tail is the longest and then overlaps the other seven
+    order = sorted(_MID_SUMS, key=lambda t: not t[0].endswith("g2"))
+    for name, template, delta_terms in order:
+        raw = c_mid_raw
         if deltas is not None:
-            scalars += [int(getattr(deltas, attr)) for attr, _ in delta_terms]
+            raw = raw + pack_scalars([int(getattr(deltas, attr)) for attr, _ in delta_terms], BN_N)
         if prepared:
-            group, dev = prepared.groups[name], prepared.bases[name]
-            proof[name] = group._make(group._ctx().msm(dev, pack_scalars(scalars, BN_N), n=len(scalars)))
+            jobs.append((name, prepared.groups[name], prepared.bases[name], False, raw))
         else:
             pts = [evalkey[template.format(i=i)] for i in mid]
             if deltas is not None:
                 pts += [evalkey[k] for _, k in delta_terms]
-            proof[name] = _msm(pts, scalars)
-    h_scalars = [int(h.coeffs[i]) for i in range(0, len(h))]
+            group = type(pts[0])
+            dev = group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id)
+            jobs.append((name, group, dev, True, raw))
+    raw_h = pack_scalars(h_scalars, BN_N)
     if prepared:
-        group, dev = prepared.groups["h*g1"], prepared.bases["h*g1"]
-        assert len(h_scalars) <= prepared.h_len, "Not enough generators."
-        proof["h*g1"] = group._make(group._ctx().msm(dev, pack_scalars(h_scalars, BN_N), n=len(h_scalars)))
+        jobs.append(("h*g1", prepared.groups["h*g1"], prepared.bases["h*g1"], False, raw_h))
     else:
-        proof["h*g1"] = _msm([evalkey["s^" + str(i) + "*g1"] for i in range(0, len(h))], h_scalars)
-    return proof
+        pts = [evalkey["s^" + str(i) + "*g1"] for i in range(0, len(h))]
+        group = type(pts[0])
+        jobs.append(("h*g1", group, group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id), True, raw_h))
+
+    proof, keep = {}, []
+    try:
+        for slot, (name, group, dev, owned, raw) in enumerate(jobs):
+            buf = ctypes.create_string_buffer(raw, len(raw)) if raw else ctypes.create_string_buffer(1)
+            keep.append(buf)
+            group._ctx().msm_async(dev, ctypes.cast(buf, ctypes.c_void_p), 0, len(raw) // 32, slot)
+        for slot, (name, group, dev, owned, raw) in enumerate(jobs):
+            proof[name] = group._make(group._ctx().result(slot, curve=group.curve_id))
+    finally:
+        for name, group, dev, owned, raw in jobs:
+            if owned:
+                dev.free()
+    # same key order as the reference's dict
+    return {name: proof[name] for name in [t[0] for t in _MID_SUMS] + ["h*g1"]}
