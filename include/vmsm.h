@@ -49,6 +49,8 @@ extern "C" {
 #define VMSM_OPT_CAP_FACTOR 8 /* per-thread bucket cap = max(64, factor * average bucket population) (default 8) */
 #define VMSM_OPT_SHARD_SEQ 9 /* non-zero: the NEXT vmsm_msm_dev / vmsm_msm_async call is one shard of a multi-GPU MSM
                                with this sequence number (see the mailbox functions); clears itself */
+#define VMSM_OPT_ASYNC_SORT 10 /* 1 (default) = run the counting sort of the next MSM on a side stream under the
+                                 accumulate kernel of the previous one (CSR lists double-buffered) */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */
@@ -56,10 +58,11 @@ extern "C" {
 #define VMSM_PHASE_SCAN 1
 #define VMSM_PHASE_SCATTER 2
 #define VMSM_PHASE_ORDER 3
-#define VMSM_PHASE_ACCUMULATE 4
-#define VMSM_PHASE_REDUCE 5
-#define VMSM_PHASE_FINAL 6
-#define VMSM_PHASE_COUNT 7
+#define VMSM_PHASE_HANDOFF 4 /* sorted lists waiting for the main stream (previous MSM's accumulate kernel) */
+#define VMSM_PHASE_ACCUMULATE 5
+#define VMSM_PHASE_REDUCE 6
+#define VMSM_PHASE_FINAL 7
+#define VMSM_PHASE_COUNT 8
 
 int32_t vmsm_version(void);
 const char *vmsm_last_error(void);

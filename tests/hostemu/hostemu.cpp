@@ -38,6 +38,9 @@ struct HostBE {
     }
     uint32_t overflow_warps() { return 3; }
     uint32_t combine_threads() { return 5; }
+    void sort_begin(int) {}
+    void sort_end(int) {}
+    void acc_done(int) {}
     void after_final(ge_ext *, ge_aff *) {}
     void result_ready() {}
     void head_wait_tail(int) {}

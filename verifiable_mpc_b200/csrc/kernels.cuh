@@ -284,8 +284,11 @@ struct KAccumulate {
         ge_ext acc = ge_identity();
         if (cnt) {
             uint32_t e = idx[pos];
-            for (uint32_t k = 0; k < cnt; k++) {
-                uint32_t en = (k + 1 < cnt) ? idx[pos + k + 1] : 0u;  // index prefetch: one load ahead of the gather
+            uint32_t en = cnt > 1 ? idx[pos + 1] : 0u;
+            acc = ge_from_niels(ld_niels(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);  // first base: 1M instead of 7M
+            e = en;
+            for (uint32_t k = 1; k < cnt; k++) {
+                en = (k + 1 < cnt) ? idx[pos + k + 1] : 0u;  // index prefetch: one load ahead of the gather
                 ge_niels q = ld_niels(base_ptr(e & 0x7fffffffu));
                 acc = ge_madd(acc, q, (e >> 31) != 0);
                 e = en;

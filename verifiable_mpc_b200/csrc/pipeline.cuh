@@ -12,10 +12,11 @@ enum Phase {
     PH_SCAN = 1,
     PH_SCATTER = 2,
     PH_ORDER = 3,
-    PH_ACCUMULATE = 4,
-    PH_REDUCE = 5,
-    PH_FINAL = 6,
-    PH_COUNT = 7
+    PH_HANDOFF = 4,  // sort stream -> main stream: time the sorted lists wait for the previous MSM's accumulate kernel
+    PH_ACCUMULATE = 5,
+    PH_REDUCE = 6,
+    PH_FINAL = 7,
+    PH_COUNT = 8
 };
 
 struct MsmOptions {
@@ -27,8 +28,13 @@ struct MsmOptions {
 };
 
 struct Workspace {
-    uint32_t *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *order = nullptr;  // W*NB each
-    uint32_t *idx = nullptr;                                                              // W*n
+    // outputs of the counting sort, double-buffered by MSM parity: the sort of MSM k+1 (atomics-bound) runs on its
+    // own stream underneath the accumulate kernel of MSM k (integer-pipe-bound)
+    uint32_t *counts_[2] = {nullptr, nullptr}, *offsets_[2] = {nullptr, nullptr}, *cursor_[2] = {nullptr, nullptr},
+             *order_[2] = {nullptr, nullptr};  // W*NB each
+    uint32_t *idx_[2] = {nullptr, nullptr};    // W*n
+    int cur = 0;                               // parity in use by the MSM being issued
+
     void *buckets = nullptr;  // W*NB accumulator points (ge_ext for Ed25519, wjac<F> for BN256): sized in bytes
     // bucket-tree levels: [parity of the MSM sequence number][ping-pong].  Two parities because the latency-bound tail
     // of one MSM (upper tree levels + Horner) runs on a side stream underneath the head of the next MSM.
@@ -85,21 +91,27 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
     }
     elem_bytes = ws.elem_bytes;
     if (nb > ws.cap_buckets) {
-        be.free(ws.counts), be.free(ws.offsets), be.free(ws.cursor), be.free(ws.order), be.free(ws.buckets);
+        be.free(ws.buckets);
         ws.cap_buckets = 0;
-        ws.counts = (uint32_t *)be.alloc(nb * 4);
-        ws.offsets = (uint32_t *)be.alloc(nb * 4);
-        ws.cursor = (uint32_t *)be.alloc(nb * 4);
-        ws.order = (uint32_t *)be.alloc(nb * 4);
         ws.buckets = be.alloc(nb * elem_bytes);
-        if (!ws.counts || !ws.offsets || !ws.cursor || !ws.order || !ws.buckets) return -1;
+        if (!ws.buckets) return -1;
+        for (int k = 0; k < 2; k++) {
+            be.free(ws.counts_[k]), be.free(ws.offsets_[k]), be.free(ws.cursor_[k]), be.free(ws.order_[k]);
+            ws.counts_[k] = (uint32_t *)be.alloc(nb * 4);
+            ws.offsets_[k] = (uint32_t *)be.alloc(nb * 4);
+            ws.cursor_[k] = (uint32_t *)be.alloc(nb * 4);
+            ws.order_[k] = (uint32_t *)be.alloc(nb * 4);
+            if (!ws.counts_[k] || !ws.offsets_[k] || !ws.cursor_[k] || !ws.order_[k]) return -1;
+        }
         ws.cap_buckets = nb;
     }
     if (ni > ws.cap_idx) {
-        be.free(ws.idx);
         ws.cap_idx = 0;
-        ws.idx = (uint32_t *)be.alloc((ni ? ni : 1) * 4);
-        if (!ws.idx) return -1;
+        for (int k = 0; k < 2; k++) {
+            be.free(ws.idx_[k]);
+            ws.idx_[k] = (uint32_t *)be.alloc((ni ? ni : 1) * 4);
+            if (!ws.idx_[k]) return -1;
+        }
         ws.cap_idx = ni;
     }
     size_t nt = ni / 32 + 64;  // >= sum over long buckets of their task counts (cap >= 64, segments >= 256)
@@ -131,8 +143,9 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
 
 template <class BE>
 void ws_release(BE &be, Workspace &ws) {
-    be.free(ws.counts), be.free(ws.offsets), be.free(ws.cursor), be.free(ws.order), be.free(ws.buckets);
-    be.free(ws.idx);
+    be.free(ws.buckets);
+    for (int k = 0; k < 2; k++)
+        be.free(ws.counts_[k]), be.free(ws.offsets_[k]), be.free(ws.cursor_[k]), be.free(ws.order_[k]), be.free(ws.idx_[k]);
     be.free(ws.ctl), be.free(ws.tasks), be.free(ws.longs), be.free(ws.partials);
     for (int par = 0; par < 2; par++)
         for (int k = 0; k < 2; k++) be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
@@ -151,34 +164,40 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     uint32_t R = 1u << opt.reduce_log2r;
     if (ws_ensure(be, ws, g, R)) return -1;
     uint32_t nbuckets = g.W * g.NB;
+    const int par = (int)(seq & 1);
+    uint32_t *counts = ws.counts_[par], *offsets = ws.offsets_[par], *cursor = ws.cursor_[par], *idx = ws.idx_[par];
 
+    // counting sort of (window, |digit|) -> CSR lists, on the sort stream (double-buffered by parity)
+    be.sort_begin(par);
     be.phase_begin();
-    be.zero(ws.counts, (size_t)nbuckets * 4);
+    be.zero(counts, (size_t)nbuckets * 4);
     if (n) {
-        KDigitsHist k1 = {scalars, ws.counts, g};
+        KDigitsHist k1 = {scalars, counts, g};
         be.launch(k1, n);
     }
     be.phase_mark(PH_DIGITS);
-    be.scan_offsets(ws.counts, ws.offsets, ws.cursor, g);
+    be.scan_offsets(counts, offsets, cursor, g);
     be.phase_mark(PH_SCAN);
     if (n) {
-        KScatter k3 = {scalars, ws.cursor, ws.idx, g};
+        KScatter k3 = {scalars, cursor, idx, g};
         be.launch(k3, n);
     }
     be.phase_mark(PH_SCATTER);
     const uint32_t *order = nullptr;
-    if (opt.sort_buckets && be.order_buckets(ws.counts, ws.order, nbuckets, n)) order = ws.order;
+    if (opt.sort_buckets && be.order_buckets(counts, ws.order_[par], nbuckets, n)) order = ws.order_[par];
     be.phase_mark(PH_ORDER);
+    be.sort_end(par);
+    be.phase_mark(PH_HANDOFF);
     {
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < 64) cap = 64;
         be.zero(ws.ctl, sizeof(OverflowCtl));
-        KAccumulate k5 = {bases, ws.offsets, ws.counts, ws.idx, order, (ge_ext *)ws.buckets, nbuckets, cap, ws.ctl, ws.tasks,
+        KAccumulate k5 = {bases, offsets, counts, idx, order, (ge_ext *)ws.buckets, nbuckets, cap, ws.ctl, ws.tasks,
                           ws.longs, extra, n_main};
         be.launch(k5, nbuckets);
         if (n > cap) {  // otherwise no bucket can be long
             const uint32_t ow = be.overflow_warps();
-            KOverflow ko = {bases, ws.idx, ws.ctl, ws.tasks, (ge_ext *)ws.partials, ow, extra, n_main};
+            KOverflow ko = {bases, idx, ws.ctl, ws.tasks, (ge_ext *)ws.partials, ow, extra, n_main};
             be.launch(ko, ow * 32);
             const uint32_t ct = be.combine_threads();
             KCombine kc = {ws.ctl, ws.longs, (const ge_ext *)ws.partials, (ge_ext *)ws.buckets, ct};
@@ -188,7 +207,6 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_ACCUMULATE);
     // bucket tree: throughput-bound leaf level(s) on the main stream, then the latency-bound tail (quad-cooperative
     // levels + Horner) which the CUDA backend runs on a side stream so that it overlaps the next MSM's head
-    const int par = (int)(seq & 1);
     be.head_wait_tail(par);
     const ge_ext *inS = (const ge_ext *)ws.buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
@@ -205,6 +223,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
             KReduce k6 = {inS, inT, (ge_ext *)ws.nodeS[par][pp], (ge_ext *)ws.nodeT[par][pp], cnt, cnt_out, R, log2s};
             be.launch(k6, nodes);
         }
+        if (log2s == 0) be.acc_done(par);  // the CSR lists of this parity are free again once the buckets are consumed
         inS = (const ge_ext *)ws.nodeS[par][pp];
         inT = (const ge_ext *)ws.nodeT[par][pp];
         pp ^= 1;
@@ -245,33 +264,38 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     uint32_t R = 1u << opt.reduce_log2r;
     if (ws_ensure(be, ws, g, R, sizeof(wjac<F>))) return -1;
     uint32_t nbuckets = g.W * g.NB;
+    const int par = (int)(seq & 1);
+    uint32_t *counts = ws.counts_[par], *offsets = ws.offsets_[par], *cursor = ws.cursor_[par], *idx = ws.idx_[par];
+    be.sort_begin(par);
     be.phase_begin();
-    be.zero(ws.counts, (size_t)nbuckets * 4);
+    be.zero(counts, (size_t)nbuckets * 4);
     if (n) {
-        KDigitsHist k1 = {scalars, ws.counts, g};
+        KDigitsHist k1 = {scalars, counts, g};
         be.launch(k1, n);
     }
     be.phase_mark(PH_DIGITS);
-    be.scan_offsets(ws.counts, ws.offsets, ws.cursor, g);
+    be.scan_offsets(counts, offsets, cursor, g);
     be.phase_mark(PH_SCAN);
     if (n) {
-        KScatter k3 = {scalars, ws.cursor, ws.idx, g};
+        KScatter k3 = {scalars, cursor, idx, g};
         be.launch(k3, n);
     }
     be.phase_mark(PH_SCATTER);
     const uint32_t *order = nullptr;
-    if (opt.sort_buckets && be.order_buckets(ws.counts, ws.order, nbuckets, n)) order = ws.order;
+    if (opt.sort_buckets && be.order_buckets(counts, ws.order_[par], nbuckets, n)) order = ws.order_[par];
     be.phase_mark(PH_ORDER);
+    be.sort_end(par);
+    be.phase_mark(PH_HANDOFF);
     {
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < 64) cap = 64;
         be.zero(ws.ctl, sizeof(OverflowCtl));
-        KAccumulateW<F> k5 = {bases, ws.offsets, ws.counts, ws.idx, order, (wjac<F> *)ws.buckets, nbuckets, cap, ws.ctl,
+        KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)ws.buckets, nbuckets, cap, ws.ctl,
                               ws.tasks, ws.longs, extra, n_main};
         be.launch(k5, nbuckets);
         if (n > cap) {
             const uint32_t ow = be.overflow_warps();
-            KOverflowW<F> ko = {bases, ws.idx, ws.ctl, ws.tasks, (wjac<F> *)ws.partials, ow, extra, n_main};
+            KOverflowW<F> ko = {bases, idx, ws.ctl, ws.tasks, (wjac<F> *)ws.partials, ow, extra, n_main};
             be.launch(ko, ow * 32);
             const uint32_t ct = be.combine_threads();
             KCombineW<F> kc = {ws.ctl, ws.longs, (const wjac<F> *)ws.partials, (wjac<F> *)ws.buckets, ct};
@@ -281,7 +305,6 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     be.phase_mark(PH_ACCUMULATE);
     // leaf level on the main stream; the latency-bound rest (upper levels, Horner, inversion) on the side stream so
     // that it overlaps the head of the next MSM (the eight MSMs of a Pinocchio proof are independent)
-    const int par = (int)(seq & 1);
     be.head_wait_tail(par);
     const wjac<F> *inS = (const wjac<F> *)ws.buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
@@ -292,6 +315,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         if (log2s && !in_tail) be.tail_begin(), in_tail = true;
         KReduceW<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[par][pp], (wjac<F> *)ws.nodeT[par][pp], cnt, cnt_out, R, log2s};
         be.launch(k6, g.W * cnt_out);
+        if (log2s == 0) be.acc_done(par);
         inS = (const wjac<F> *)ws.nodeS[par][pp];
         inT = (const wjac<F> *)ws.nodeT[par][pp];
         pp ^= 1;

@@ -215,6 +215,11 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;  // main stream: everything except MSM tails
     cudaStream_t tail = nullptr;    // side stream: upper bucket-tree levels + Horner of the previous MSM(s)
+    cudaStream_t sort = nullptr;    // side stream: counting sort (digits, scan, scatter, order) of the NEXT MSM
+    cudaEvent_t ev_sorted[2] = {nullptr, nullptr}, ev_acc_done[2] = {nullptr, nullptr}, ev_sort_in = nullptr;
+    bool acc_pending[2] = {false, false};
+    bool async_sort = true;
+    cudaEvent_t scalars_ready = nullptr;  // set by the entry point when the scalars of the next MSM are still in flight
     cudaEvent_t ev_head = nullptr, ev_tail[2] = {nullptr, nullptr};
     bool tail_pending[2] = {false, false};
     int last_tail = -1;
@@ -293,6 +298,28 @@ struct CudaBE {
     void head_wait_tail(int par) {
         if (c->tail_pending[par]) note(cudaStreamWaitEvent(c->stream, c->ev_tail[par], 0));
     }
+    // counting sort on its own stream: ordered after whatever produced the scalars on the main stream (H2D, synth)
+    // and after the accumulate kernel that last read this parity's CSR lists
+    void sort_begin(int par) {
+        if (!c->async_sort) return;
+        // order the sort after the copy that produces its scalars -- NOT after the main stream as a whole, or it
+        // would wait for the previous MSM's accumulate kernel, which is exactly what it is meant to run under
+        if (c->scalars_ready) note(cudaStreamWaitEvent(c->sort, c->scalars_ready, 0));
+        c->scalars_ready = nullptr;
+        if (c->acc_pending[par]) note(cudaStreamWaitEvent(c->sort, c->ev_acc_done[par], 0));
+        cur = c->sort;
+    }
+    void sort_end(int par) {
+        if (!c->async_sort) return;
+        note(cudaEventRecord(c->ev_sorted[par], c->sort));
+        note(cudaStreamWaitEvent(c->stream, c->ev_sorted[par], 0));
+        cur = c->stream;
+    }
+    void acc_done(int par) {
+        if (!c->async_sort) return;
+        note(cudaEventRecord(c->ev_acc_done[par], c->stream));
+        c->acc_pending[par] = true;
+    }
     void after_final(ge_ext *out_ext, ge_aff *out_aff) {
         if (!c->shard_seq || !c->mailbox) return;
         MailSlot *box = c->mailbox + (size_t)c->cur_slot * c->mb_world;
@@ -343,17 +370,17 @@ struct CudaBE {
     }
     void scan_offsets(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g) {
         uint32_t tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
-        vmsm_scan_offsets<<<g.W * tiles, SCAN_TILE, 0, c->stream>>>(counts, offsets, cursor, g, tiles);
+        vmsm_scan_offsets<<<g.W * tiles, SCAN_TILE, 0, cur>>>(counts, offsets, cursor, g, tiles);
         c->launches++;
         note(cudaGetLastError());
     }
     bool order_buckets(const uint32_t *counts, uint32_t *order, uint32_t nb, uint32_t n) {
         if (nb < 8192 || n == 0) return false;  // too few buckets for ordering to matter
-        note(cudaMemsetAsync(c->order_bins, 0, ORDER_BINS * 4, c->stream));
+        note(cudaMemsetAsync(c->order_bins, 0, ORDER_BINS * 4, cur));
         uint32_t grid = (nb + ORDER_TILE - 1) / ORDER_TILE;
-        vmsm_order_hist<<<grid, 256, 0, c->stream>>>(counts, nb, c->order_bins);
-        vmsm_order_scan<<<1, ORDER_BINS, 0, c->stream>>>(c->order_bins);
-        vmsm_order_scatter<<<grid, 256, 0, c->stream>>>(counts, nb, c->order_bins, order);
+        vmsm_order_hist<<<grid, 256, 0, cur>>>(counts, nb, c->order_bins);
+        vmsm_order_scan<<<1, ORDER_BINS, 0, cur>>>(c->order_bins);
+        vmsm_order_scatter<<<grid, 256, 0, cur>>>(counts, nb, c->order_bins, order);
         c->launches += 3;
         note(cudaGetLastError());
         return true;
@@ -368,7 +395,7 @@ struct CudaBE {
             c->ev_pool.push_back(es);
         }
         c->ev_cur = (int)c->ev_used++;
-        note(cudaEventRecord(c->ev_pool[c->ev_cur].ev[0], c->stream));
+        note(cudaEventRecord(c->ev_pool[c->ev_cur].ev[0], cur));
     }
     void phase_mark(int ph) {
         if (c->ev_cur >= 0) note(cudaEventRecord(c->ev_pool[c->ev_cur].ev[ph + 1], cur));
@@ -597,6 +624,16 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(cudaStreamCreateWithPriority(&c->tail, cudaStreamNonBlocking, hi));
     }
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->sort, cudaStreamNonBlocking, hi));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_sort_in, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&c->ev_sorted[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_acc_done[k], cudaEventDisableTiming));
+    }
     CU(cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_tail[0], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_tail[1], cudaEventDisableTiming));
@@ -639,6 +676,7 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
 int32_t vmsm_ctx_destroy(uint64_t ctx) {
     GET_CTX(ctx);
     cudaStreamSynchronize(c->copy);
+    cudaStreamSynchronize(c->sort);
     cudaStreamSynchronize(c->tail);
     cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 2; k++) cudaFree(c->astage[k]), cudaEventDestroy(c->ev_copied[k]), cudaEventDestroy(c->ev_consumed[k]);
@@ -665,6 +703,9 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     cudaEventDestroy(c->t0), cudaEventDestroy(c->t1);
     cudaEventDestroy(c->ev_head), cudaEventDestroy(c->ev_tail[0]), cudaEventDestroy(c->ev_tail[1]);
     cudaStreamDestroy(c->tail);
+    cudaStreamDestroy(c->sort);
+    cudaEventDestroy(c->ev_sort_in);
+    for (int k = 0; k < 2; k++) cudaEventDestroy(c->ev_sorted[k]), cudaEventDestroy(c->ev_acc_done[k]);
     cudaStreamDestroy(c->stream);
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -704,6 +745,9 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             return VMSM_OK;
         case VMSM_OPT_ASYNC_TAIL:
             c->async_tail = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_ASYNC_SORT:
+            c->async_sort = value != 0;
             return VMSM_OK;
         case VMSM_OPT_QUAD_THRESHOLD:
             if (value < 0 || value > (1 << 24)) return fail(VMSM_ERR_INVALID, "quad threshold out of range");
@@ -970,6 +1014,8 @@ int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uin
     int32_t rc = ensure_stage(c, n ? n : 1);
     if (rc) return rc;
     if (n) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_sort_in, c->stream));
+    c->scalars_ready = c->ev_sort_in;
     if (it->second.curve == VMSM_CURVE_ED25519) rc = run_msm(c, it->second.niels + off, c->stage_scalars, n, kSlots - 1);
     else rc = w_run_msm_any(c, it->second, off, c->stage_scalars, n, kSlots - 1);
     if (rc) return rc;
@@ -990,6 +1036,8 @@ int32_t vmsm_msm_ext(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint6
     int32_t rc = ensure_stage(c, tot ? tot : 1);
     if (rc) return rc;
     if (tot) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, tot * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_sort_in, c->stream));
+    c->scalars_ready = c->ev_sort_in;
     if (it->second.curve != ie->second.curve) return fail(VMSM_ERR_INVALID, "point vectors are on different curves");
     if (it->second.curve == VMSM_CURVE_ED25519)
         rc = run_msm(c, it->second.niels + off, c->stage_scalars, tot, kSlots - 1, ie->second.niels + extra_off,
@@ -1157,11 +1205,13 @@ int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, con
     if (c->astage_used[b]) CU(cudaStreamWaitEvent(c->copy, c->ev_consumed[b], 0));
     if (n) CU(cudaMemcpyAsync(c->astage[b], scalars_le32, n * 32, cudaMemcpyHostToDevice, c->copy));
     CU(cudaEventRecord(c->ev_copied[b], c->copy));
-    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    if (c->async_sort) c->scalars_ready = c->ev_copied[b];  // only the sort stream reads the scalars
+    else CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
     int32_t rc = it->second.curve == VMSM_CURVE_ED25519 ? run_msm(c, it->second.niels + off, c->astage[b], n, slot)
                                                         : w_run_msm_any(c, it->second, off, c->astage[b], n, slot);
     if (rc) return rc;
-    CU(cudaEventRecord(c->ev_consumed[b], c->stream));
+    // the scalars are read by the counting sort only: the staging buffer is free again once that is done
+    CU(cudaEventRecord(c->ev_consumed[b], c->async_sort ? c->sort : c->stream));
     c->astage_used[b] = true;
     return VMSM_OK;
 }
@@ -1246,6 +1296,8 @@ int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const u
         tmp.n = n;
         tmp.w_wire = c->small_w_wire;
         tmp.w_base = c->small_w_base;
+        CU(cudaEventRecord(c->ev_sort_in, c->stream));
+        c->scalars_ready = c->ev_sort_in;
         rc = w_run_msm_any(c, tmp, 0, c->stage_scalars, n, kSlots - 1);
         if (rc) return rc;
         CU(cudaMemcpyAsync(c->pin + 64, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1261,6 +1313,8 @@ int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const u
         be.launch(k, (uint32_t)n);
     }
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "lincomb: %s", cudaGetErrorString(be.err));
+    CU(cudaEventRecord(c->ev_sort_in, c->stream));
+    c->scalars_ready = c->ev_sort_in;
     rc = run_msm(c, c->small_niels, c->stage_scalars, n, kSlots - 1);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->pin + 64, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
