@@ -44,7 +44,7 @@ struct HostBE {
     void after_final(ge_ext *, ge_aff *) {}
     void result_ready() {}
     void head_wait_tail(int) {}
-    void tail_begin() {}
+    void tail_begin(int) {}
     void tail_end(int) {}
     void phase_begin() {}
     void phase_mark(int) {}

@@ -19,6 +19,11 @@ enum Phase {
     PH_COUNT = 8
 };
 
+// number of MSM tails (upper tree levels + Horner + inversion) that may be in flight at once, each on its own side
+// stream with its own node buffers: the tails are latency-bound single-warp work, so several of them overlap freely
+// (the eight MSMs of a Pinocchio proof, back-to-back commitments)
+enum { kTailWays = 4 };
+
 struct MsmOptions {
     uint32_t window_bits = 0;  // 0 = auto
     uint32_t reduce_log2r = 3;
@@ -38,7 +43,7 @@ struct Workspace {
     void *buckets = nullptr;  // W*NB accumulator points (ge_ext for Ed25519, wjac<F> for BN256): sized in bytes
     // bucket-tree levels: [parity of the MSM sequence number][ping-pong].  Two parities because the latency-bound tail
     // of one MSM (upper tree levels + Horner) runs on a side stream underneath the head of the next MSM.
-    void *nodeS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *nodeT[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    void *nodeS[kTailWays][2] = {}, *nodeT[kTailWays][2] = {};
     // long-bucket overflow (kernels.cuh: KOverflow / KCombine)
     OverflowCtl *ctl = nullptr;
     OverflowTask *tasks = nullptr;
@@ -126,7 +131,7 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
         ws.cap_tasks = nt;
     }
     if (nn > ws.cap_nodes) {
-        for (int par = 0; par < 2; par++)
+        for (int par = 0; par < kTailWays; par++)
             for (int k = 0; k < 2; k++) {
                 be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
                 ws.nodeS[par][k] = be.alloc(nn * elem_bytes);
@@ -147,7 +152,7 @@ void ws_release(BE &be, Workspace &ws) {
     for (int k = 0; k < 2; k++)
         be.free(ws.counts_[k]), be.free(ws.offsets_[k]), be.free(ws.cursor_[k]), be.free(ws.order_[k]), be.free(ws.idx_[k]);
     be.free(ws.ctl), be.free(ws.tasks), be.free(ws.longs), be.free(ws.partials);
-    for (int par = 0; par < 2; par++)
+    for (int par = 0; par < kTailWays; par++)
         for (int k = 0; k < 2; k++) be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
     ws = Workspace();
 }
@@ -207,7 +212,8 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_ACCUMULATE);
     // bucket tree: throughput-bound leaf level(s) on the main stream, then the latency-bound tail (quad-cooperative
     // levels + Horner) which the CUDA backend runs on a side stream so that it overlaps the next MSM's head
-    be.head_wait_tail(par);
+    const int tw = (int)(seq % kTailWays);
+    be.head_wait_tail(tw);
     const ge_ext *inS = (const ge_ext *)ws.buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;
@@ -216,16 +222,16 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         uint32_t cnt_out = (cnt + R - 1) / R;
         uint32_t nodes = g.W * cnt_out;
         if (nodes <= opt.quad_threshold) {
-            if (!in_tail) be.tail_begin(), in_tail = true;
-            KReduceQ k6 = {inS, inT, (ge_ext *)ws.nodeS[par][pp], (ge_ext *)ws.nodeT[par][pp], cnt, cnt_out, R, log2s, nodes};
+            if (!in_tail) be.tail_begin(tw), in_tail = true;
+            KReduceQ k6 = {inS, inT, (ge_ext *)ws.nodeS[tw][pp], (ge_ext *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s, nodes};
             be.launch(k6, (4 * nodes + 31) & ~31u);
         } else {
-            KReduce k6 = {inS, inT, (ge_ext *)ws.nodeS[par][pp], (ge_ext *)ws.nodeT[par][pp], cnt, cnt_out, R, log2s};
+            KReduce k6 = {inS, inT, (ge_ext *)ws.nodeS[tw][pp], (ge_ext *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s};
             be.launch(k6, nodes);
         }
         if (log2s == 0) be.acc_done(par);  // the CSR lists of this parity are free again once the buckets are consumed
-        inS = (const ge_ext *)ws.nodeS[par][pp];
-        inT = (const ge_ext *)ws.nodeT[par][pp];
+        inS = (const ge_ext *)ws.nodeS[tw][pp];
+        inT = (const ge_ext *)ws.nodeT[tw][pp];
         pp ^= 1;
         cnt = cnt_out;
         log2s += opt.reduce_log2r;
@@ -233,7 +239,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_REDUCE);
     {
         if (opt.quad_threshold) {
-            if (!in_tail) be.tail_begin(), in_tail = true;
+            if (!in_tail) be.tail_begin(tw), in_tail = true;
             KFinalQ k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
             be.launch(k7, 32);
         } else {
@@ -244,7 +250,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_FINAL);
     be.after_final(out_ext, out_aff);  // multi-GPU: push this partial to the owner's mailbox / gather on the owner
     be.result_ready();
-    if (in_tail) be.tail_end(par);
+    if (in_tail) be.tail_end(tw);
     be.phase_end();
     return 0;
 }
@@ -305,30 +311,31 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     be.phase_mark(PH_ACCUMULATE);
     // leaf level on the main stream; the latency-bound rest (upper levels, Horner, inversion) on the side stream so
     // that it overlaps the head of the next MSM (the eight MSMs of a Pinocchio proof are independent)
-    be.head_wait_tail(par);
+    const int tw = (int)(seq % kTailWays);
+    be.head_wait_tail(tw);
     const wjac<F> *inS = (const wjac<F> *)ws.buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;
     bool in_tail = false;
     do {
         uint32_t cnt_out = (cnt + R - 1) / R;
-        if (log2s && !in_tail) be.tail_begin(), in_tail = true;
-        KReduceW<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[par][pp], (wjac<F> *)ws.nodeT[par][pp], cnt, cnt_out, R, log2s};
+        if (log2s && !in_tail) be.tail_begin(tw), in_tail = true;
+        KReduceW<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[tw][pp], (wjac<F> *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s};
         be.launch(k6, g.W * cnt_out);
         if (log2s == 0) be.acc_done(par);
-        inS = (const wjac<F> *)ws.nodeS[par][pp];
-        inT = (const wjac<F> *)ws.nodeT[par][pp];
+        inS = (const wjac<F> *)ws.nodeS[tw][pp];
+        inT = (const wjac<F> *)ws.nodeT[tw][pp];
         pp ^= 1;
         cnt = cnt_out;
         log2s += opt.reduce_log2r;
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
-    if (!in_tail) be.tail_begin(), in_tail = true;
+    if (!in_tail) be.tail_begin(tw), in_tail = true;
     KFinalW<F> k7 = {inS, inT, out_jac, out_wire, g.W, g.c};
     be.launch(k7, 32);
     be.phase_mark(PH_FINAL);
     be.result_ready();
-    be.tail_end(par);
+    be.tail_end(tw);
     be.phase_end();
     return 0;
 }

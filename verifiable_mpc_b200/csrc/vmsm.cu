@@ -214,15 +214,14 @@ constexpr uint32_t kSlots = 64;
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;  // main stream: everything except MSM tails
-    cudaStream_t tail = nullptr;    // side stream: upper bucket-tree levels + Horner of the previous MSM(s)
+    cudaStream_t tails[kTailWays] = {};  // side streams: upper bucket-tree levels + Horner of the previous MSMs
     cudaStream_t sort = nullptr;    // side stream: counting sort (digits, scan, scatter, order) of the NEXT MSM
     cudaEvent_t ev_sorted[2] = {nullptr, nullptr}, ev_acc_done[2] = {nullptr, nullptr}, ev_sort_in = nullptr;
     bool acc_pending[2] = {false, false};
     bool async_sort = true;
     cudaEvent_t scalars_ready = nullptr;  // set by the entry point when the scalars of the next MSM are still in flight
-    cudaEvent_t ev_head = nullptr, ev_tail[2] = {nullptr, nullptr};
-    bool tail_pending[2] = {false, false};
-    int last_tail = -1;
+    cudaEvent_t ev_head = nullptr, ev_tail[kTailWays] = {};
+    bool tail_pending[kTailWays] = {};
     bool async_tail = true;
     uint32_t msm_seq = 0;
     // asynchronous end-to-end path (vmsm_msm_async): H2D of the scalars on a copy stream into one of two staging
@@ -331,17 +330,16 @@ struct CudaBE {
         }
     }
     void result_ready() { note(cudaEventRecord(c->ev_slot[c->cur_slot], cur)); }
-    void tail_begin() {
+    void tail_begin(int way) {
         if (!c->async_tail) return;
         note(cudaEventRecord(c->ev_head, c->stream));
-        note(cudaStreamWaitEvent(c->tail, c->ev_head, 0));
-        cur = c->tail;
+        note(cudaStreamWaitEvent(c->tails[way], c->ev_head, 0));
+        cur = c->tails[way];
     }
-    void tail_end(int par) {
+    void tail_end(int way) {
         if (!c->async_tail) return;
-        note(cudaEventRecord(c->ev_tail[par], c->tail));
-        c->tail_pending[par] = true;
-        c->last_tail = par;
+        note(cudaEventRecord(c->ev_tail[way], c->tails[way]));
+        c->tail_pending[way] = true;
         cur = c->stream;
     }
     void note(cudaError_t e) {
@@ -405,8 +403,12 @@ struct CudaBE {
 
 // make the main stream wait for every MSM tail issued so far (tails are ordered on the side stream)
 cudaError_t join_tail(Ctx *c) {
-    if (c->last_tail < 0) return cudaSuccess;
-    return cudaStreamWaitEvent(c->stream, c->ev_tail[c->last_tail], 0);
+    for (int w = 0; w < kTailWays; w++)
+        if (c->tail_pending[w]) {
+            cudaError_t e = cudaStreamWaitEvent(c->stream, c->ev_tail[w], 0);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
 }
 
 int32_t harvest_phases(Ctx *c) {
@@ -622,7 +624,7 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     {
         int lo = 0, hi = 0;  // hi = numerically smallest = greatest priority
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU(cudaStreamCreateWithPriority(&c->tail, cudaStreamNonBlocking, hi));
+        for (int w = 0; w < kTailWays; w++) CU(cudaStreamCreateWithPriority(&c->tails[w], cudaStreamNonBlocking, hi));
     }
     {
         int lo = 0, hi = 0;
@@ -635,8 +637,7 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
         CU(cudaEventCreateWithFlags(&c->ev_acc_done[k], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_tail[0], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_tail[1], cudaEventDisableTiming));
+    for (int w = 0; w < kTailWays; w++) CU(cudaEventCreateWithFlags(&c->ev_tail[w], cudaEventDisableTiming));
     CU(cudaMalloc(&c->order_bins, ORDER_BINS * 4));
     CU(cudaMalloc(&c->err_word, 16));
     CU(cudaMalloc(&c->fb_table, 512 * sizeof(ge_niels)));
@@ -677,7 +678,7 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     GET_CTX(ctx);
     cudaStreamSynchronize(c->copy);
     cudaStreamSynchronize(c->sort);
-    cudaStreamSynchronize(c->tail);
+    for (int w = 0; w < kTailWays; w++) cudaStreamSynchronize(c->tails[w]);
     cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 2; k++) cudaFree(c->astage[k]), cudaEventDestroy(c->ev_copied[k]), cudaEventDestroy(c->ev_consumed[k]);
     for (uint32_t k = 0; k < kSlots; k++) cudaEventDestroy(c->ev_slot[k]);
@@ -701,8 +702,8 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (auto &es : c->ev_pool)
         for (auto &e : es.ev) cudaEventDestroy(e);
     cudaEventDestroy(c->t0), cudaEventDestroy(c->t1);
-    cudaEventDestroy(c->ev_head), cudaEventDestroy(c->ev_tail[0]), cudaEventDestroy(c->ev_tail[1]);
-    cudaStreamDestroy(c->tail);
+    cudaEventDestroy(c->ev_head);
+    for (int w = 0; w < kTailWays; w++) cudaEventDestroy(c->ev_tail[w]), cudaStreamDestroy(c->tails[w]);
     cudaStreamDestroy(c->sort);
     cudaEventDestroy(c->ev_sort_in);
     for (int k = 0; k < 2; k++) cudaEventDestroy(c->ev_sorted[k]), cudaEventDestroy(c->ev_acc_done[k]);
