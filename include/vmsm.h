@@ -92,6 +92,12 @@ int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t 
  * g_hat = g + [h] of compressed_pivot.py:137 and the private copy a prover folds in place. */
 int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_n, uint64_t b, uint64_t b_off,
                            uint64_t b_n, uint64_t *out);
+/* Decimal transcript text of a point range, formatted on the device: "[x0, y0, 1], [x1, y1, 1], ..." -- exactly what
+ * repr() of the list of normalised group elements has between its outer brackets, which is what enters the
+ * Fiat-Shamir pre-image of every folding round (compressed_pivot.py:51-59 via pivot.py:131-136).  `cap` >= 176 * n
+ * always suffices; *len receives the number of bytes written (no terminator).  Ed25519 only. */
+int32_t vmsm_points_text(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *out, uint64_t cap,
+                         uint64_t *len);
 int32_t vmsm_points_count(uint64_t ctx, uint64_t pts, uint64_t *n);
 int32_t vmsm_points_free(uint64_t ctx, uint64_t pts);
 

@@ -160,6 +160,15 @@ void hostemu_synth_scalars(uint64_t seed, uint32_t n, uint8_t *out) {
 
 uint32_t hostemu_choose_window(uint64_t n) { return choose_window(n, 253); }
 
+// transcript text of n points: slots + lens as KPointText writes them
+void hostemu_point_text(const uint8_t *affine, uint32_t n, uint8_t *slots, uint32_t *lens) {
+    HostBE be;
+    std::vector<ge_aff> aff(n ? n : 1);
+    memcpy(aff.data(), affine, (size_t)n * 64);
+    KPointText k = {aff.data(), slots, lens, n};
+    be.launch(k, n);
+}
+
 // ---- BN256: field ops (plain in, plain out), MSM and fixed-base for G1 (g2 = 0) / G2 (g2 = 1)
 void hostemu_fbn_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out) {
     fbn x, y, r;

@@ -271,3 +271,16 @@ def test_multi_gpu_mailbox_shards(ctx):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_points_text_on_device(ctx, known_points):
+    """vmsm_points_text: the generators' decimal text for the Fiat-Shamir pre-image, formatted by the GPU."""
+    _, pts = known_points
+    cases = pts[:50] + [E.IDENTITY, (1, 0), (P - 1, 0)] if False else pts[:50] + [E.IDENTITY]
+    dev = ctx.upload_points(cases)
+    want = ", ".join(f"[{x}, {y}, 1]" for x, y in cases)
+    assert dev.text() == want
+    assert dev.text(3, 4) == ", ".join(f"[{x}, {y}, 1]" for x, y in cases[3:7])
+    assert dev.text(0, 0) == ""
+    big = ctx.fixed_base(seed=0x5EEE, n=5000)
+    assert big.text() == ", ".join(f"[{x}, {y}, 1]" for x, y in big.tolist())

@@ -165,3 +165,15 @@ def test_numpy_synth_matches_oracle_prng():
         assert int.from_bytes(a[i].tobytes(), "little") == prng.scalar(0x5EED, i)
     b = synth.scalars_ed25519(0x5EED, 8, start=1000)
     assert (b[0] == a[1000]).all()
+
+
+def test_point_text_matches_python_repr(hostemu, known_points):
+    """KPointText: the decimal text of the Fiat-Shamir pre-image, byte for byte what Python prints."""
+    _, pts = known_points
+    cases = pts[:20] + [E.IDENTITY, (0, 1), (1, 0), (10**9, 10**18 - 1), (10**9 - 1, 10**9), (P - 1, 2**255 - 20)]
+    n = len(cases)
+    slots = ctypes.create_string_buffer(176 * n)
+    lens = (ctypes.c_uint32 * n)()
+    hostemu.hostemu_point_text(b"".join(E.point_to_bytes(p) for p in cases), n, slots, lens)
+    got = "".join(slots.raw[176 * i: 176 * i + lens[i]].decode() for i in range(n))
+    assert got == ", ".join(f"[{x}, {y}, 1]" for x, y in cases)

@@ -666,6 +666,91 @@ struct KSynthScalars {
     }
 };
 
+// ---------------------------------------------------------------------------------------------- transcript text
+// The Fiat-Shamir pre-image of every folding round contains the decimal text of ALL current generators
+// (compressed_pivot.py:51-59 hashes str([A, B, g_hat, k, Q, L_tilde]); pivot.py:131-136).  Formatting 2*N 255-bit
+// integers in Python dominated the prover's latency, so the device emits the text itself: one slot per point holding
+// "[x, y, 1]" (the repr of a normalised point) and its length; a scan + compaction then produces the exact
+// ", "-joined string that repr(list_of_points) has between its brackets.
+#define VMSM_TEXT_SLOT 176  // >= 1 + 78 + 2 + 78 + 4
+
+// decimal digits of a 256-bit value (8 limbs, little-endian), most significant first; returns the digit count
+VMSM_HD uint32_t fe_to_decimal(const fe &v, uint8_t *out) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = v.v[i];
+    uint32_t chunks[9];  // base 10^9, least significant first
+    int nchunks = 0;
+    for (int pass = 0; pass < 9; pass++) {
+        uint64_t rem = 0;
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            uint64_t cur = (rem << 32) | w[i];
+            w[i] = (uint32_t)(cur / 1000000000u);
+            rem = cur % 1000000000u;
+            any |= w[i];
+        }
+        chunks[nchunks++] = (uint32_t)rem;
+        if (!any) break;
+    }
+    uint32_t len = 0;
+    for (int k = nchunks - 1; k >= 0; k--) {
+        uint32_t c = chunks[k];
+        uint8_t d[9];
+        for (int j = 8; j >= 0; j--) {
+            d[j] = (uint8_t)('0' + c % 10u);
+            c /= 10u;
+        }
+        int start = 0;
+        if (k == nchunks - 1)
+            while (start < 8 && d[start] == '0') start++;  // no leading zeros on the top chunk (keeps a lone "0")
+        for (int j = start; j < 9; j++) out[len++] = d[j];
+    }
+    return len;
+}
+
+struct KPointText {
+    enum { kBlock = 128 };
+    const ge_aff *aff;
+    uint8_t *slots;  // n x VMSM_TEXT_SLOT
+    uint32_t *lens;  // n, length of "[x, y, 1]" plus 2 for the ", " separator that follows all but the last
+    uint32_t n;
+    VMSM_HD void operator()(uint32_t tid) const {
+        ge_aff a = ld_aff(aff + tid);
+        uint8_t *o = slots + (size_t)tid * VMSM_TEXT_SLOT;
+        uint32_t len = 0;
+        o[len++] = '[';
+        len += fe_to_decimal(a.x, o + len);
+        o[len++] = ',';
+        o[len++] = ' ';
+        len += fe_to_decimal(a.y, o + len);
+        o[len++] = ',';
+        o[len++] = ' ';
+        o[len++] = '1';
+        o[len++] = ']';
+        if (tid + 1 < n) {
+            o[len++] = ',';
+            o[len++] = ' ';
+        }
+        lens[tid] = len;
+    }
+};
+
+struct KTextCompact {
+    enum { kBlock = 128 };
+    const uint8_t *slots;
+    const uint32_t *lens;
+    const uint64_t *offsets;  // exclusive prefix of lens
+    uint8_t *out;
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint8_t *s = slots + (size_t)tid * VMSM_TEXT_SLOT;
+        uint8_t *d = out + offsets[tid];
+        uint32_t len = lens[tid];
+        for (uint32_t i = 0; i < len; i++) d[i] = s[i];
+    }
+};
+
 // device self-test of fe25519.cuh (vmsm_selftest_fe): results are canonicalised
 struct KSelfTestFe {
     enum { kBlock = 128 };

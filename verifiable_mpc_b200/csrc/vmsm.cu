@@ -98,6 +98,36 @@ __global__ void __launch_bounds__(SCAN_TILE) vmsm_scan_offsets(const uint32_t *_
     }
 }
 
+// Exclusive prefix sums of n 32-bit lengths into 64-bit offsets (transcript text compaction): per-block sums,
+// one block scanning the block sums, then a per-block scan with the block's base.  Returns the total in totals[nblk].
+__global__ void __launch_bounds__(1024) vmsm_lens_block_sums(const uint32_t *__restrict__ lens, uint32_t n,
+                                                             uint64_t *__restrict__ sums) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t total;
+    uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    block_scan_1024(i < n ? lens[i] : 0u, ws, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void vmsm_lens_scan_sums(uint64_t *sums, uint32_t nblk) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint64_t run = 0;
+    for (uint32_t b = 0; b < nblk; b++) {
+        uint64_t v = sums[b];
+        sums[b] = run;
+        run += v;
+    }
+    sums[nblk] = run;
+}
+__global__ void __launch_bounds__(1024) vmsm_lens_offsets(const uint32_t *__restrict__ lens, uint32_t n,
+                                                          const uint64_t *__restrict__ sums,
+                                                          uint64_t *__restrict__ offsets) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t total;
+    uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    uint32_t excl = block_scan_1024(i < n ? lens[i] : 0u, ws, &total);
+    if (i < n) offsets[i] = sums[blockIdx.x] + excl;
+}
+
 // Counting sort of bucket ids by population, largest first (keys clamped to ORDER_BINS-1).
 #define ORDER_BINS 1024
 #define ORDER_TILE 2048  // buckets per block (256 threads x 8)
@@ -917,6 +947,55 @@ int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t 
     }
     CU(cudaStreamSynchronize(c->stream));
     return VMSM_OK;
+}
+
+int32_t vmsm_points_text(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *out, uint64_t cap,
+                         uint64_t *len) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (it->second.curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "points_text: Ed25519 only");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "range out of bounds");
+    if (!len || (n && !out)) return fail(VMSM_ERR_INVALID, "null argument");
+    *len = 0;
+    if (!n) return VMSM_OK;
+    if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "too many points");
+    uint32_t nblk = (uint32_t)((n + 1023) / 1024);
+    uint8_t *slots = nullptr, *text = nullptr;
+    uint32_t *lens = nullptr;
+    uint64_t *offsets = nullptr, *sums = nullptr;
+    cudaError_t e = cudaMalloc(&slots, n * VMSM_TEXT_SLOT);
+    if (e == cudaSuccess) e = cudaMalloc(&text, n * VMSM_TEXT_SLOT);
+    if (e == cudaSuccess) e = cudaMalloc(&lens, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&offsets, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&sums, (nblk + 1) * 8);
+    int32_t rc = VMSM_OK;
+    if (e != cudaSuccess) rc = fail(VMSM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    if (!rc) {
+        CudaBE be(c);
+        KPointText kt = {it->second.aff + off, slots, lens, (uint32_t)n};
+        be.launch(kt, (uint32_t)n);
+        vmsm_lens_block_sums<<<nblk, 1024, 0, c->stream>>>(lens, (uint32_t)n, sums);
+        vmsm_lens_scan_sums<<<1, 32, 0, c->stream>>>(sums, nblk);
+        vmsm_lens_offsets<<<nblk, 1024, 0, c->stream>>>(lens, (uint32_t)n, sums, offsets);
+        c->launches += 3;
+        KTextCompact kc = {slots, lens, offsets, text};
+        be.launch(kc, (uint32_t)n);
+        be.note(cudaMemcpyAsync(c->pin, sums + nblk, 8, cudaMemcpyDeviceToHost, c->stream));
+        be.note(cudaStreamSynchronize(c->stream));
+        if (be.err != cudaSuccess) rc = fail(VMSM_ERR_CUDA, "points_text: %s", cudaGetErrorString(be.err));
+    }
+    if (!rc) {
+        uint64_t total = *reinterpret_cast<uint64_t *>(c->pin);
+        *len = total;
+        if (total > cap) rc = fail(VMSM_ERR_INVALID, "text buffer too small: need %llu bytes", (unsigned long long)total);
+        else {
+            e = cudaMemcpy(out, text, total, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = fail(VMSM_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFree(slots), cudaFree(text), cudaFree(lens), cudaFree(offsets), cudaFree(sums);
+    return rc;
 }
 
 int32_t vmsm_points_count(uint64_t ctx, uint64_t pts, uint64_t *n) {

@@ -349,7 +349,10 @@ class DevicePointList:
         return list(self)
 
     def __repr__(self):
-        # byte-identical to repr(list of points); straight from the downloaded 64-byte encodings
+        # byte-identical to repr(list of points).  The decimal text is produced on the device (vmsm_points_text);
+        # formatting 2n 255-bit integers in Python used to dominate the prover's latency.
+        if hasattr(self.dev, "text"):
+            return "[" + self.dev.text(self.off, self.n) + "]"
         raw = self.dev.download(self.off, self.n)
         fb = int.from_bytes
         return "[" + ", ".join([f"[{fb(raw[i:i + 32], 'little')}, {fb(raw[i + 32:i + 64], 'little')}, 1]"
