@@ -310,7 +310,9 @@ def run_gpu(args, rank, world, dist):
                 "d2h_bytes_per_step": 64 * world, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "Context.msm_async(points, pinned_scalars, slot) + Context.result(slot), pipelined three deep"},
         "roofline": {"bound": "imad", "kernel": "vmsm_kernel<KAccumulate>", "achieved": achieved, "peak": peak_tlps,
-                     "unit": "T limb-products/s", "frac": (achieved / peak_tlps) if achieved else None, "traffic": None,
+                     "unit": "T limb-products/s", "frac": (achieved / peak_tlps) if achieved else None,
+                     "traffic": _ncu_traffic_bytes() if args.log2n == 20 else None, "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/)",
+                     "algorithmic_gather_bytes_per_launch": n * W_c * 96,
                      "peak_source": "measured live: vmsm_microbench_imad (independent carry-chained IMAD.WIDE.U32 multiply-accumulate chains, all SMs; every IMAD.WIDE form is half-rate on B200)",
                      "kernel_ms": acc_ms, "algorithmic_lp_per_launch": acc_lp,
                      "whole_msm_frac": msm_frac, "whole_msm_lp_per_point": lp_per_point(n),
@@ -328,6 +330,32 @@ def run_gpu(args, rank, world, dist):
                                 "sample": f"{cores} processes x {args.cpu_points} terms ({dt:.1f} s) of the same MSM with the "
                                           "pure-Python restatement of pivot.vector_commitment (oracle/ed25519.py)"}
     print(json.dumps(line), flush=True)
+
+
+def _ncu_traffic_bytes():
+    """DRAM bytes per KAccumulate launch from the committed `ncu --set full` capture (profiles/), or None."""
+    import csv
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "ncu_full_KAccumulate.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr = rows[0]
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            tot = []
+            for r in rows[1:]:
+                if not r:
+                    continue
+                b = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    col = [i for i, h in enumerate(hdr) if h.startswith(key)][0]
+                    b += float(r[col]) * unit[hdr[col].split("[")[1].rstrip("]")]
+                tot.append(b)
+            if tot:
+                return sum(tot) / len(tot)
+        except Exception:
+            continue
+    return None
 
 
 def _choose_window(n):

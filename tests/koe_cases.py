@@ -1,0 +1,37 @@
+"""Shared helper: rebuild the KoE golden case with the PRODUCT's group / field types and run the prover twin."""
+import json
+import os
+
+from pynocchio_cases import dec
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "koe_proof.json")
+
+
+def check_koe(g1_group, g2_group):
+    from verifiable_mpc_b200.ac20 import knowledge_of_exponent as twin
+    from verifiable_mpc_b200.ac20 import pivot
+    from verifiable_mpc_b200.finfields import GF
+
+    gold = json.load(open(GOLDEN))
+    for grp in (g1_group, g2_group):
+        grp.is_additive, grp.is_multiplicative = False, True
+    try:
+        gf = GF(g1_group.order)
+        pp = {"pp_lhs": [g1_group._make(dec(p)) for p in gold["pp_lhs"]],
+              "pp_rhs": [g2_group._make(dec(p)) for p in gold["pp_rhs"]]}
+        x = [gf(int(v, 16)) for v in gold["x"]]
+        gamma = gf(int(gold["gamma"], 16))
+        L = pivot.LinearForm([gf(int(v, 16)) for v in gold["L"]])
+        proof, u = twin.opening_linear_form_prover(L, x, gamma, pp)
+        assert u.value == int(gold["u"], 16)
+        assert sorted(proof) == sorted(gold["proof"])
+        for key, val in gold["proof"].items():
+            assert proof[key].affine() == dec(val), key
+        P, pi = twin.restriction_argument_prover(range(len(x)), x, gamma, pp)
+        assert P == proof["P"] and pi == proof["pi"]
+        # group-type operators in multiplicative notation
+        assert (pp["pp_lhs"][0] ** 3) * pp["pp_lhs"][0] == pp["pp_lhs"][0] ** 4
+        return proof, u, L, pp
+    finally:
+        for grp in (g1_group, g2_group):
+            grp.is_additive, grp.is_multiplicative = True, False

@@ -284,3 +284,38 @@ def test_points_text_on_device(ctx, known_points):
     assert dev.text(0, 0) == ""
     big = ctx.fixed_base(seed=0x5EEE, n=5000)
     assert big.text() == ", ".join(f"[{x}, {y}, 1]" for x, y in big.tolist())
+
+
+def test_abi_error_paths(ctx, known_points):
+    """Status codes instead of crashes: bad handles, ranges, slots, options, mixed curves, Ed25519-only calls."""
+    import ctypes
+
+    from verifiable_mpc_b200 import VmsmError, _lib
+
+    lib, h = ctx.lib, ctx.h
+    _, pts = known_points
+    dev = ctx.upload_points(pts[:8])
+    out = ctypes.create_string_buffer(128)
+    sc = b"\x01" + bytes(31)
+    assert lib.vmsm_msm(h, 987654, 0, 1, sc, out) == _lib.ERR_INVALID
+    assert lib.vmsm_msm(h, dev.handle, 8, 1, sc, out) == _lib.ERR_INVALID
+    assert lib.vmsm_msm(h, dev.handle, 0, 1, None, out) == _lib.ERR_INVALID
+    assert lib.vmsm_msm(12345, dev.handle, 0, 1, sc, out) == _lib.ERR_INVALID
+    assert b"context" in lib.vmsm_last_error()
+    assert lib.vmsm_points_download(h, dev.handle, 4, 5, out) == _lib.ERR_INVALID
+    assert lib.vmsm_fold(h, dev.handle, 5, sc) == _lib.ERR_INVALID
+    assert lib.vmsm_result_affine(h, 64, out) == _lib.ERR_INVALID
+    assert lib.vmsm_ctx_set_option(h, 999, 1) == _lib.ERR_INVALID
+    assert lib.vmsm_ctx_set_option(h, _lib.OPT_WINDOW_BITS, 40) == _lib.ERR_INVALID
+    assert lib.vmsm_lincomb(h, 0, None, None, 65, out) == _lib.ERR_INVALID
+    assert lib.vmsm_points_upload(h, 7, sc, 0, ctypes.byref(ctypes.c_uint64())) == _lib.ERR_UNSUPPORTED
+    bn = ctx.fixed_base(seed=1, n=4, curve=1)
+    assert lib.vmsm_fold(h, bn.handle, 2, sc) == _lib.ERR_UNSUPPORTED
+    with pytest.raises(VmsmError):
+        ctx.msm_ext(dev, 0, 2, bn, 0, 1, [1, 2, 3])  # mixed curves
+    with pytest.raises(VmsmError):
+        ctx.msm_dev_shard(dev, ctx.upload_scalars([1] * 8), slot=1, seq=1)  # no mailbox on this context
+    # the context is still healthy afterwards
+    assert ctx.msm(dev, [1] * 8) == E.msm_naive([1] * 8, pts[:8])
+    dev.free()
+    assert lib.vmsm_points_free(h, dev.handle) == _lib.ERR_INVALID

@@ -1,0 +1,89 @@
+"""GPU-backed twin of the PROVER side of ``verifiable_mpc/ac20/knowledge_of_exponent.py`` (KoE pivot over BN256).
+
+``restriction_argument_prover`` (:75-91): two multi-exponentiations with the same exponents, one over the G1 powers
+``pp_lhs`` and one over the G2 powers ``pp_rhs``;  ``opening_linear_form_prover`` (:101-131): a 2n-term G1
+multi-exponentiation with the coefficients of c(X) = (gamma + x_1 X + ...)(L_n + L_{n-1} X + ...).  Each becomes ONE
+device MSM (libvmsm.so on the BN256 curves).  The polynomial product and the pairing-based verifier stay host-side /
+the reference's; ``linear_form_R`` offers the verifier's n-term G2 product (:146) as a device MSM as well.
+Same names, arguments and return values as the reference functions.
+"""
+from ..engine import BN_N, pack_scalars
+from . import pivot
+
+
+def _msm(points, scalars):
+    group = type(points[0])
+    ctx = group._ctx()
+    dev = ctx.upload_points([p.affine() for p in points], curve=group.curve_id)
+    try:
+        return group._make(ctx.msm(dev, pack_scalars(scalars, BN_N)))
+    finally:
+        dev.free()
+
+
+def list_mul(x):
+    return _msm(list(x), [1] * len(x))
+
+
+def vector_commitment(x, gamma, g, h):
+    """``h**gamma * prod g[i]**x[i]`` over a BN256 group (reference :29-38)."""
+    assert len(g) >= len(x), "Not enough generators."
+    return _msm(list(g[: len(x)]) + [h], [int(v) for v in x] + [int(gamma)])
+
+
+def restriction_argument_prover(S, x, gamma, pp):
+    """Restriction argument [Gro10], prover: (P, pi) over the S-indices of x (reference :75-91)."""
+    S = list(S)
+    scalars = [int(gamma)] + [int(x[i]) for i in S]
+    P = _msm([pp["pp_lhs"][0]] + [pp["pp_lhs"][i + 1] for i in S], scalars)
+    pi = _msm([pp["pp_rhs"][0]] + [pp["pp_rhs"][i + 1] for i in S], scalars)
+    return P, pi
+
+
+def _poly_mul_mod(a, b, q):
+    out = [0] * (len(a) + len(b) - 1)
+    for i, ai in enumerate(a):
+        if ai:
+            for j, bj in enumerate(b):
+                out[i + j] = (out[i + j] + ai * bj) % q
+    return out
+
+
+def opening_linear_form_prover(L, x, gamma, pp, P=None, pi=None):
+    """ZK argument of knowledge for the opening of a linear form (reference :101-131)."""
+    proof = {}
+    n = len(x)
+    S = range(n)
+    assert 2 * n - 1 <= len(pp["pp_lhs"]), \
+        "Requirement does not hold: 2*len(x)-1 <= number of generators in first group."
+    if P is None:
+        P, pi = restriction_argument_prover(S, x, gamma, pp)
+    proof["P"] = P
+    proof["pi"] = pi
+    u = L(x)
+    L_linear, u_linear = pivot.affine_to_linear(L, u, n)
+    q = BN_N
+    lhs = [int(gamma) % q] + [int(x_i) % q for x_i in x]
+    rhs = [int(L_linear.coeffs[n - (j + 1)]) % q for j in range(n)]
+    c_bar = _poly_mul_mod(lhs, rhs, q)
+    assert int(u_linear) % q == c_bar[n], "L(x) not equal to n-th coefficient of c_poly"
+    c_bar[n] = 0
+    assert len(pp["pp_lhs"]) == 2 * n
+    proof["Q"] = _msm(list(pp["pp_lhs"]), [-c for c in c_bar])
+    return proof, u
+
+
+def linear_form_R(L, pp, u):
+    """The verifier's ``R = prod pp_rhs[j] ** L_linear.coeffs[n-(j+1)]`` (reference :146) as one G2 MSM."""
+    n = len(L.coeffs)
+    L_linear, _ = pivot.affine_to_linear(L, u, n)
+    return _msm(list(pp["pp_rhs"][:n]), [int(L_linear.coeffs[n - (j + 1)]) for j in range(n)])
+
+
+def prove_nullity_koe(pp, lin_forms, x, gamma, gf, P, pi):
+    """Nullity protocol on top of the linear-form opening (reference :152-162)."""
+    rho = pivot.fiat_shamir_hash([P, lin_forms], gf.order)
+    L = sum((linform_i) * (rho ** i) for i, linform_i in enumerate(lin_forms))
+    L = pivot.LinearForm([gf(c) if isinstance(c, int) else c for c in L.coeffs])
+    proof, u = opening_linear_form_prover(L, x, gamma, pp, P, pi)
+    return proof, L, u
