@@ -61,3 +61,29 @@ def test_compressed_pivot_1024(gpu_group):
     assert len([k for k in proof if k.startswith("B")]) == 9
     assert cp.protocol_5_verifier(generators, P, L, y, proof, gf) is True
     assert cp.protocol_5_verifier(generators, P, L, y + 1, proof, gf) is False
+
+
+def test_compressed_pivot_2p16(gpu_group):
+    """BASELINE config 3 size: N = 2^16 generators, 15 folding rounds, prover and verifier on the device."""
+    from verifiable_mpc_b200.ac20 import compressed_pivot as cp
+    from verifiable_mpc_b200.ac20 import generators as gens
+    from verifiable_mpc_b200.ac20 import pivot
+
+    group, gf = gpu_group
+    rng = random.Random(2016)
+    n = (1 << 16) - 1
+    gens.prng = rng
+    generators = gens.create_generators(n, group)
+    x = [gf(rng.randrange(gf.order)) for _ in range(n)]
+    x[:64] = [gf(rng.randrange(2)) for _ in range(64)]  # some boolean witnesses, as real circuits have
+    gamma = gf(rng.randrange(gf.order))
+    L = pivot.LinearForm([gf(rng.randrange(gf.order)) for _ in range(n)])
+    y = L(x)
+    P = pivot.vector_commitment(x, gamma, generators["g"], generators["h"])
+    cp.prng = rng
+    proof = cp.protocol_5_prover(generators, P, L, y, x, gamma, gf)
+    assert len([k for k in proof if k.startswith("B")]) == 15 and len(proof["z_prime"]) == 2
+    assert cp.protocol_5_verifier(generators, P, L, y, proof, gf) is True
+    bad = dict(proof)
+    bad["A7"] = proof["B7"]
+    assert cp.protocol_5_verifier(generators, P, L, y, bad, gf) is False

@@ -36,8 +36,11 @@ def _all_in_field(values, gf):
     return all(type(v) is gf for v in values)
 
 
-def _signed_text(ints, q):
-    """repr of a list of gf elements (signed representatives, as MPyC prints them) from their residues."""
+def _field_text(ints, q, signed=True):
+    """repr of a list of gf elements from their residues: signed representatives when the field class is signed
+    (MPyC's default and what int(element) returns), plain residues otherwise."""
+    if not signed:
+        return "[" + ", ".join([str(v) for v in ints]) + "]"
     half = q >> 1
     return "[" + ", ".join([str(v - q if v > half else v) for v in ints]) + "]"
 
@@ -55,13 +58,13 @@ class _Verbatim:
 
 class _IntForm:
     """Stand-in for a LinearForm over gf inside the round loop: residues + the exact repr of the real thing."""
-    __slots__ = ("ints", "q")
+    __slots__ = ("ints", "q", "signed")
 
-    def __init__(self, ints, q):
-        self.ints, self.q = ints, q
+    def __init__(self, ints, q, signed=True):
+        self.ints, self.q, self.signed = ints, q, signed
 
     def __repr__(self):
-        return f"{_signed_text(self.ints, self.q)}, 0"
+        return f"{_field_text(self.ints, self.q, self.signed)}, 0"
 
 
 def _dot(a, b, q):
@@ -144,7 +147,7 @@ def _protocol_4_prover_ints(g_hat, k, Q, coeffs, z, gf, proof, round_i):
         B = pivot.vector_commitment(z_r, _dot(coeffs[:half], z_r, q), g_hat[:half], k)
         proof["A" + str(round_i)] = A
         proof["B" + str(round_i)] = B
-        c = _fold_challenge(A, B, g_hat, k, Q, _IntForm(coeffs, q), q)
+        c = _fold_challenge(A, B, g_hat, k, Q, _IntForm(coeffs, q, bool(gf.is_signed)), q)
         g_hat = _fold_generators(g_hat, c)
         Q = group.lincomb([A, Q, B], [1, c, c ** 2])
         coeffs = [(l * c + r) % q for l, r in zip(coeffs[:half], coeffs[half:])]
@@ -162,7 +165,7 @@ def _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i):
         half = len(g_hat) // 2
         A = proof["A" + str(round_i)]
         B = proof["B" + str(round_i)]
-        c = _fold_challenge(A, B, g_hat, k, Q, _IntForm(coeffs, q), q)
+        c = _fold_challenge(A, B, g_hat, k, Q, _IntForm(coeffs, q, bool(gf.is_signed)), q)
         g_hat = _fold_generators(g_hat, c)
         Q = group.lincomb([A, Q, B], [1, c, c ** 2])
         coeffs = [(l * c + r) % q for l, r in zip(coeffs[:half], coeffs[half:])]
@@ -174,7 +177,29 @@ def _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i):
         round_i += 1
 
 
-def _first_challenges(t, A, generators, P, L, y, order):
+def _to_linear(L, y, n, gf):
+    """pivot.affine_to_linear without evaluating L on n zeros one coefficient at a time: when every coefficient
+    lives in gf, L(0, ..., 0) is gf(0) + L.constant (what the reference's sum() produces)."""
+    if FAST_INT_PATH and _all_in_field(L.coeffs, gf):
+        constant = gf(0) + L.constant
+        return L - constant, y - constant
+    return pivot.affine_to_linear(L, y, n)
+
+
+class _FormText:
+    """repr-compatible stand-in for an affine form with gf coefficients: same text, built from the residues."""
+    __slots__ = ("form", "q", "signed")
+
+    def __init__(self, form, q, signed):
+        self.form, self.q, self.signed = form, q, signed
+
+    def __repr__(self):
+        return f"{_field_text([c.value for c in self.form.coeffs], self.q, self.signed)}, {str(self.form.constant)}"
+
+
+def _first_challenges(t, A, generators, P, L, y, order, gf=None):
+    if FAST_INT_PATH and gf is not None and gf.order == order and _all_in_field(L.coeffs, gf):
+        L = _FormText(L, order, bool(gf.is_signed))
     input_list = [t, A.normalize(), generators, P.normalize(), L, y]
     logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
     # str(input_list + [b] + [tag]) for b = 0, 1 share everything but one character: build the O(N) text once
@@ -200,7 +225,7 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     group = type(h)
     proof = {}
     n = len(x)
-    L, y = pivot.affine_to_linear(L, y, n)
+    L, y = _to_linear(L, y, n, gf)
     assert bin(n + 1).count("1") == 1, \
         "This implementation requires n+1 to be power of 2 (else, use padding with zeros)."
     order = gf.order
@@ -213,18 +238,21 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     A = pivot.vector_commitment(r, rho, g, h)
     proof["t"] = t
     proof["A"] = A
-    c0, c1 = _first_challenges(t, A, generators, P, L, y, order)
-    z = [gf(c0 * x_i.value + r_i) for x_i, r_i in zip(x, r)] if fast else [c0 * x_i + r_i for x_i, r_i in zip(x, r)]
+    c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf)
     phi = gf(c0 * gamma + rho)
-    z_hat = z + [phi]
+    if fast:
+        zi = [(c0 * x_i.value + r_i) % order for x_i, r_i in zip(x, r)] + [phi.value]
+    else:
+        z = [c0 * x_i + r_i for x_i, r_i in zip(x, r)]
+        z_hat = z + [phi]
     g_hat = _g_hat(g, h, group)
     logger_cp.debug("Calculate Q.")
     Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
-    if FAST_INT_PATH and _all_in_field(L.coeffs, gf) and _all_in_field(z_hat, gf):
+    if fast:
         # same values as the generic lines below; the appended coefficient 0 prints as "0" either way
-        coeffs = [cf.value * c1 % order for cf in L.coeffs] + [0]
-        zi = [v.value for v in z_hat]
-        assert _dot([cf.value for cf in L.coeffs], zi[:-1], order) * c1 % order == _dot(coeffs, zi, order)
+        lc = [cf.value for cf in L.coeffs]
+        coeffs = [v * c1 % order for v in lc] + [0]
+        assert _dot(lc, zi[:-1], order) * c1 % order == _dot(coeffs, zi, order)
         return _protocol_4_prover_ints(g_hat, k, Q, coeffs, zi, gf, proof, 0)
     L_tilde = pivot.LinearForm(L.coeffs + [0]) * c1
     assert L(z) * c1 == L_tilde(z_hat)
@@ -262,10 +290,10 @@ def protocol_5_verifier(generators, P, L, y, proof, gf):
     g, h, k = generators["g"], generators["h"], generators["k"]
     group = type(h)
     order = gf.order
-    L, y = pivot.affine_to_linear(L, y, len(g))
+    L, y = _to_linear(L, y, len(g), gf)
     logger_cp.debug("Load from proof: t, A.")
     t, A = proof["t"], proof["A"]
-    c0, c1 = _first_challenges(t, A, generators, P, L, y, order)
+    c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf)
     g_hat = _g_hat(g, h, group)
     Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
     if FAST_INT_PATH and _all_in_field(L.coeffs, gf):
