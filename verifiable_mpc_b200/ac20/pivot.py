@@ -15,89 +15,15 @@ from random import SystemRandom
 
 from .. import fingroups
 from ..engine import pack_scalars
-from ..finfields import FiniteFieldElement as _OwnFieldElement
 from ..fingroups import DevicePointList, EllipticCurvePoint as EllipticCurveElement
 
-try:  # real MPyC field / secure types are accepted when installed (the reference's own types)
-    from mpyc.finfields import FiniteFieldElement as _MpycFieldElement
-    from mpyc.sectypes import SecureObject
-    _FIELD_TYPES = (_OwnFieldElement, _MpycFieldElement)
-except Exception:  # MPyC absent: only this package's fields and plain ints
-    class SecureObject:  # placeholder so isinstance checks read like the reference's
-        pass
-    _FIELD_TYPES = (_OwnFieldElement,)
+from .forms import FIELD_TYPES as _FIELD_TYPES
+from .forms import AffineForm, LinearForm, SecureObject  # noqa: F401  (the reference exports them from pivot)
 
 prng = SystemRandom()
 
 logger_piv = logging.getLogger("pivot")
 logger_piv.setLevel(logging.INFO)
-
-
-def _is_scalar(v):
-    return isinstance(v, (int, SecureObject) + _FIELD_TYPES)
-
-
-class AffineForm:
-    """f(x) = <coeffs, x> + constant over the scalar field (host-side bookkeeping, as in the reference)."""
-
-    def __init__(self, coeffs, constant):
-        self.coeffs = coeffs
-        self.constant = constant
-
-    def _combine(self, other):
-        if isinstance(other, AffineForm):
-            assert len(self) == len(other), "Length of linear forms to add not consistent."
-            return [a + b for a, b in zip(self.coeffs, other.coeffs)], self.constant + other.constant
-        if _is_scalar(other):
-            return self.coeffs, self.constant + other
-        return None
-
-    def __add__(self, other):
-        res = self._combine(other)
-        if res is None:
-            raise NotImplementedError(f"Addition of form not defined for type: {type(other)}")
-        return type(self)(*res)
-
-    def __radd__(self, other):
-        return self if other == 0 else self.__add__(other)
-
-    def __sub__(self, other):
-        return self + (-1) * other
-
-    def __mul__(self, other):
-        if not isinstance(other, (int,) + _FIELD_TYPES):
-            raise NotImplementedError(f"Multiplication of form not defined for type: {type(other)}")
-        return type(self)([c * other for c in self.coeffs], self.constant * other)
-
-    __rmul__ = __mul__
-
-    def __len__(self):
-        return len(self.coeffs)
-
-    def __eq__(self, other):
-        return self.coeffs == other.coeffs
-
-    def __repr__(self):
-        return f"{str(self.coeffs)}, {str(self.constant)}"
-
-    def eval(self, values):
-        assert len(values) == len(self.coeffs), "Length of inputs to be equal to coefficients of linear form."
-        return sum([c * v for c, v in zip(self.coeffs, values)]) + self.constant
-
-    __call__ = eval
-
-
-class LinearForm(AffineForm):
-    """Affine form whose constant is pinned to 0; sums fall back to AffineForm like the reference's."""
-
-    def __init__(self, coeffs, constant=0):
-        super().__init__(coeffs, 0)
-
-    def __add__(self, other):
-        res = self._combine(other)
-        if res is None:
-            raise NotImplementedError
-        return AffineForm(*res)
 
 
 def _int(value):
