@@ -124,7 +124,9 @@ int32_t vmsm_msm_ext(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint6
  * `scalars_le32` must stay valid until the result has been fetched. */
 int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
                        uint32_t slot);
-/* device resident, asynchronous on the context's stream: result goes to result slot `slot` (0..62) */
+/* device resident, asynchronous on the context's streams: result goes to result slot `slot` (0..62).  A slot must not
+ * be targeted again before its result has been fetched (vmsm_result_affine) or the context synchronised: consecutive
+ * MSMs finish on different side streams. */
 int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
                      uint32_t slot);
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine);      /* synchronises */

@@ -319,3 +319,23 @@ def test_abi_error_paths(ctx, known_points):
     assert ctx.msm(dev, [1] * 8) == E.msm_naive([1] * 8, pts[:8])
     dev.free()
     assert lib.vmsm_points_free(h, dev.handle) == _lib.ERR_INVALID
+
+
+@pytest.mark.parametrize("logn", [8, 12, 14])
+def test_back_to_back_msms_in_flight(ctx, logn):
+    """Stress of the stream pipeline (sort stream / main stream / four tail streams): 40 different MSMs issued
+    without any synchronisation in between, every result checked afterwards."""
+    n = 1 << logn
+    dev = ctx.fixed_base(seed=0x5EEE, n=n)
+    dl = [prng.scalar(0x5EEE, i) for i in range(n)]
+    nsets = 8
+    scs, want = [], []
+    for k in range(nsets):
+        sc = [prng.scalar(0x3000 + k, i) for i in range(n)]
+        scs.append(ctx.upload_scalars(sc))
+        want.append(E.msm_known_dlog(sc, dl))
+    for rep in range(3):
+        for j in range(40):
+            ctx.msm_dev(dev, scs[j % nsets], slot=j)
+        for j in range(40):
+            assert ctx.result(j) == want[j % nsets], (rep, j)

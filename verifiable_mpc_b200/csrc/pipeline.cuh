@@ -222,7 +222,9 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         uint32_t cnt_out = (cnt + R - 1) / R;
         uint32_t nodes = g.W * cnt_out;
         if (nodes <= opt.quad_threshold) {
-            if (!in_tail) be.tail_begin(tw), in_tail = true;
+            // the leaf level always stays on the main stream: it reads `buckets`, which the next MSM's accumulate
+            // kernel (main stream) overwrites -- only levels that read the per-way node buffers may move to a tail
+            if (!in_tail && log2s) be.tail_begin(tw), in_tail = true;
             KReduceQ k6 = {inS, inT, (ge_ext *)ws.nodeS[tw][pp], (ge_ext *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s, nodes};
             be.launch(k6, (4 * nodes + 31) & ~31u);
         } else {
