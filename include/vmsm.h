@@ -98,6 +98,10 @@ int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_
  * always suffices; *len receives the number of bytes written (no terminator).  Ed25519 only. */
 int32_t vmsm_points_text(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *out, uint64_t cap,
                          uint64_t *len);
+/* same, without the copy: *text points into a page-locked buffer owned by the context, valid until the next
+ * vmsm_points_text* call on it. */
+int32_t vmsm_points_text_ptr(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t **text,
+                             uint64_t *len);
 int32_t vmsm_points_count(uint64_t ctx, uint64_t pts, uint64_t *n);
 int32_t vmsm_points_free(uint64_t ctx, uint64_t pts);
 

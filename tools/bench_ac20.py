@@ -48,6 +48,7 @@ def main():
         return wrapper
 
     pivot.fiat_shamir_hash = timed("hash", orig_hash)
+    pivot.fiat_shamir_prefix = timed("hash", pivot.fiat_shamir_prefix)  # transcript text (device + host) + SHA-256
     pivot.vector_commitment = timed("commit", orig_vc)
     cp._fold_generators = timed("fold", orig_fold)
     group.lincomb = classmethod(timed("lincomb", orig_lin))

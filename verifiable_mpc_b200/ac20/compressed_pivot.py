@@ -45,17 +45,6 @@ def _field_text(ints, q, signed=True):
     return "[" + ", ".join([str(v - q if v > half else v) for v in ints]) + "]"
 
 
-class _Verbatim:
-    """An object whose str() is a precomputed pre-image (fiat_shamir_hash hashes str(input_list))."""
-    __slots__ = ("text",)
-
-    def __init__(self, text):
-        self.text = text
-
-    def __str__(self):
-        return self.text
-
-
 class _IntForm:
     """Stand-in for a LinearForm over gf inside the round loop: residues + the exact repr of the real thing."""
     __slots__ = ("ints", "q", "signed")
@@ -83,8 +72,9 @@ def _private_device_list(g_hat, group):
 
 def _fold_challenge(A, B, g_hat, k, Q, L_tilde, order):
     input_list = [A.normalize(), B.normalize(), g_hat, k, Q.normalize(), L_tilde]
-    logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
-    c = pivot.fiat_shamir_hash(input_list, order)
+    if logger_cp_hin.isEnabledFor(logging.DEBUG):
+        logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
+    c = pivot.fiat_shamir_hash_items(input_list, order)
     logger_cp_hout.debug(f"After hash, hash=\n{c}")
     return c
 
@@ -201,11 +191,12 @@ def _first_challenges(t, A, generators, P, L, y, order, gf=None):
     if FAST_INT_PATH and gf is not None and gf.order == order and _all_in_field(L.coeffs, gf):
         L = _FormText(L, order, bool(gf.is_signed))
     input_list = [t, A.normalize(), generators, P.normalize(), L, y]
-    logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
-    # str(input_list + [b] + [tag]) for b = 0, 1 share everything but one character: build the O(N) text once
-    body = ", ".join([repr(item) for item in input_list])
-    c0 = pivot.fiat_shamir_hash(_Verbatim(f"[{body}, 0, {_TAG!r}]"), order)
-    c1 = pivot.fiat_shamir_hash(_Verbatim(f"[{body}, 1, {_TAG!r}]"), order)
+    if logger_cp_hin.isEnabledFor(logging.DEBUG):
+        logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
+    # str(input_list + [b] + [tag]) for b = 0, 1 share everything but one character: hash the O(N) prefix once
+    prefix = pivot.fiat_shamir_prefix(input_list)
+    c0 = pivot.fiat_shamir_finish(prefix, [0, _TAG], order)
+    c1 = pivot.fiat_shamir_finish(prefix, [1, _TAG], order)
     logger_cp_hout.debug(f"After hash, hash=\n{c0}, {c1}")
     return c0, c1
 

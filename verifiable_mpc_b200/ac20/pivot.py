@@ -40,6 +40,48 @@ def fiat_shamir_hash(input_list, order):
     return int.from_bytes(digest, "little") % order
 
 
+def _feed_repr(h, item):
+    """h.update(repr(item).encode()) without building the large strings: device-resident generator lists offer
+    ``repr_bytes()`` (decimal text produced on the GPU); dicts (the ``generators`` argument) are walked."""
+    rb = getattr(item, "repr_bytes", None)
+    if rb is not None:
+        h.update(rb())
+    elif type(item) is dict:
+        h.update(b"{")
+        for i, (key, value) in enumerate(item.items()):
+            h.update((", " if i else "").encode() + repr(key).encode("utf-8") + b": ")
+            _feed_repr(h, value)
+        h.update(b"}")
+    else:
+        h.update(repr(item).encode("utf-8"))
+
+
+def fiat_shamir_prefix(items):
+    """SHA-256 state after ``"[" + ", ".join(repr(i) for i in items)`` -- the shared part of str(list) pre-images."""
+    h = hashlib.sha256()
+    h.update(b"[")
+    for i, item in enumerate(items):
+        if i:
+            h.update(b", ")
+        _feed_repr(h, item)
+    return h
+
+
+def fiat_shamir_finish(h, tail_items, order):
+    """Challenge from a prefix state plus the remaining list items (the state is copied, so it can be reused)."""
+    h = h.copy()
+    for item in tail_items:
+        h.update(b", ")
+        _feed_repr(h, item)
+    h.update(b"]")
+    return int.from_bytes(h.digest(), "little") % order
+
+
+def fiat_shamir_hash_items(items, order):
+    """Same value as ``fiat_shamir_hash(items, order)``, computed incrementally (no O(N) Python str)."""
+    return fiat_shamir_finish(fiat_shamir_prefix(items), [], order)
+
+
 def list_mul(x):
     """Product of a list of group elements: one device call per 64 elements instead of len(x)-1 host operations."""
     rettype = type(x[0])
@@ -104,7 +146,7 @@ def prove_linear_form_eval(g, h, P, L, y, x, gamma, gf):
     t = L(r)
     A = vector_commitment(r, rho, g, h)
     logger_piv.debug(f"Prover computed A={A}.")
-    c = fiat_shamir_hash([t, A.normalize(), g, h, P.normalize(), L, y], gf.order)
+    c = fiat_shamir_hash_items([t, A.normalize(), g, h, P.normalize(), L, y], gf.order)
     z = [c * x_i + r_i for x_i, r_i in zip(x, r)]
     phi = (c * gamma + rho) % gf.order
     return z, phi, c
@@ -117,7 +159,7 @@ def verify_linear_form_proof(g, h, P, L, y, z, phi, c):
     A_check = group.lincomb([vector_commitment(z, phi, g, h), P], [1, -int(c)])
     t_check = L(z) - c * y
     order = type(t_check).order
-    hash_check = fiat_shamir_hash([t_check, A_check.normalize(), g, h, P.normalize(), L, y], order)
+    hash_check = fiat_shamir_hash_items([t_check, A_check.normalize(), g, h, P.normalize(), L, y], order)
     logger_piv.debug(f"Value of c         ={c}")
     logger_piv.debug(f"Value of hash_check={hash_check}")
     return c == hash_check

@@ -66,6 +66,9 @@ inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits, bool avoid_skew 
     for (uint32_t c = 3; c <= 17; c++) {
         uint32_t r = (scalar_bits - 1) % c;
         if (avoid_skew && (r == 0 || c - r > 4)) continue;
+        // below c = 11 every size measured (2^6 .. 2^16) is latency-bound and c = 11 was fastest or tied
+        // (profiles/r01/sweep_tiny_windows.jsonl): few entries per bucket, short serial chains
+        if (avoid_skew && c < 11) continue;
         double W = (double)((scalar_bits + 1 + c - 1) / c);
         double NB = (double)(1u << (c - 1));
         double cost = (double)n * W * madd + W * NB * 2.0 * add + (W - 1) * c * 464.0;

@@ -271,6 +271,11 @@ struct Ctx {
     int32_t slot_curve[64] = {0};
     void *fbw_table[2] = {nullptr, nullptr};  // fixed-base tables for G1 / G2 (520 entries), built on first use
     void *small_w_wire = nullptr, *small_w_base = nullptr;  // lincomb scratch, 64 x 128 B each
+    // transcript text scratch (vmsm_points_text): grow-only device buffers and a pinned host buffer
+    uint8_t *txt_slots = nullptr, *txt_text = nullptr, *txt_host = nullptr;
+    uint32_t *txt_lens = nullptr;
+    uint64_t *txt_offsets = nullptr, *txt_sums = nullptr;
+    size_t txt_cap = 0;
     uint32_t *res_status_host = nullptr;  // pinned + mapped, kSlots words: 0 ok, 1 = a multi-GPU partial timed out
     // multi-GPU mailbox (kernels.cuh: KPushPartial / KGatherPartials)
     MailSlot *mailbox = nullptr;  // [kSlots][mb_world]; owner: local allocation, others: peer mapping
@@ -714,6 +719,8 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (uint32_t k = 0; k < kSlots; k++) cudaEventDestroy(c->ev_slot[k]);
     cudaFreeHost(c->res_aff_host);
     cudaFreeHost(c->res_status_host);
+    cudaFree(c->txt_slots), cudaFree(c->txt_text), cudaFree(c->txt_lens), cudaFree(c->txt_offsets), cudaFree(c->txt_sums);
+    if (c->txt_host) cudaFreeHost(c->txt_host);
     cudaFree(c->res_w_dev), cudaFreeHost(c->res_w_host), cudaFree(c->fbw_table[0]), cudaFree(c->fbw_table[1]);
     cudaFree(c->small_w_wire), cudaFree(c->small_w_base);
     if (c->mailbox) {
@@ -949,53 +956,69 @@ int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t 
     return VMSM_OK;
 }
 
-int32_t vmsm_points_text(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *out, uint64_t cap,
-                         uint64_t *len) {
-    GET_CTX(ctx);
+static int32_t points_text_impl(Ctx *c, uint64_t pts, uint64_t off, uint64_t n, uint64_t *len) {
     auto it = c->points.find(pts);
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
     if (it->second.curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "points_text: Ed25519 only");
     if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "range out of bounds");
-    if (!len || (n && !out)) return fail(VMSM_ERR_INVALID, "null argument");
     *len = 0;
     if (!n) return VMSM_OK;
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "too many points");
+    if (n > c->txt_cap) {
+        cudaFree(c->txt_slots), cudaFree(c->txt_text), cudaFree(c->txt_lens), cudaFree(c->txt_offsets), cudaFree(c->txt_sums);
+        if (c->txt_host) cudaFreeHost(c->txt_host);
+        c->txt_slots = c->txt_text = c->txt_host = nullptr;
+        c->txt_lens = nullptr;
+        c->txt_offsets = c->txt_sums = nullptr;
+        c->txt_cap = 0;
+        size_t cap = n + n / 4 + 1024;
+        CU(cudaMalloc(&c->txt_slots, cap * VMSM_TEXT_SLOT));
+        CU(cudaMalloc(&c->txt_text, cap * VMSM_TEXT_SLOT));
+        CU(cudaMalloc(&c->txt_lens, cap * 4));
+        CU(cudaMalloc(&c->txt_offsets, cap * 8));
+        CU(cudaMalloc(&c->txt_sums, (cap / 1024 + 2) * 8));
+        CU(cudaHostAlloc(&c->txt_host, cap * VMSM_TEXT_SLOT, cudaHostAllocDefault));
+        c->txt_cap = cap;
+    }
     uint32_t nblk = (uint32_t)((n + 1023) / 1024);
-    uint8_t *slots = nullptr, *text = nullptr;
-    uint32_t *lens = nullptr;
-    uint64_t *offsets = nullptr, *sums = nullptr;
-    cudaError_t e = cudaMalloc(&slots, n * VMSM_TEXT_SLOT);
-    if (e == cudaSuccess) e = cudaMalloc(&text, n * VMSM_TEXT_SLOT);
-    if (e == cudaSuccess) e = cudaMalloc(&lens, n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&offsets, n * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&sums, (nblk + 1) * 8);
-    int32_t rc = VMSM_OK;
-    if (e != cudaSuccess) rc = fail(VMSM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
-    if (!rc) {
-        CudaBE be(c);
-        KPointText kt = {it->second.aff + off, slots, lens, (uint32_t)n};
-        be.launch(kt, (uint32_t)n);
-        vmsm_lens_block_sums<<<nblk, 1024, 0, c->stream>>>(lens, (uint32_t)n, sums);
-        vmsm_lens_scan_sums<<<1, 32, 0, c->stream>>>(sums, nblk);
-        vmsm_lens_offsets<<<nblk, 1024, 0, c->stream>>>(lens, (uint32_t)n, sums, offsets);
-        c->launches += 3;
-        KTextCompact kc = {slots, lens, offsets, text};
-        be.launch(kc, (uint32_t)n);
-        be.note(cudaMemcpyAsync(c->pin, sums + nblk, 8, cudaMemcpyDeviceToHost, c->stream));
-        be.note(cudaStreamSynchronize(c->stream));
-        if (be.err != cudaSuccess) rc = fail(VMSM_ERR_CUDA, "points_text: %s", cudaGetErrorString(be.err));
-    }
-    if (!rc) {
-        uint64_t total = *reinterpret_cast<uint64_t *>(c->pin);
-        *len = total;
-        if (total > cap) rc = fail(VMSM_ERR_INVALID, "text buffer too small: need %llu bytes", (unsigned long long)total);
-        else {
-            e = cudaMemcpy(out, text, total, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) rc = fail(VMSM_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
-        }
-    }
-    cudaFree(slots), cudaFree(text), cudaFree(lens), cudaFree(offsets), cudaFree(sums);
-    return rc;
+    CudaBE be(c);
+    KPointText kt = {it->second.aff + off, c->txt_slots, c->txt_lens, (uint32_t)n};
+    be.launch(kt, (uint32_t)n);
+    vmsm_lens_block_sums<<<nblk, 1024, 0, c->stream>>>(c->txt_lens, (uint32_t)n, c->txt_sums);
+    vmsm_lens_scan_sums<<<1, 32, 0, c->stream>>>(c->txt_sums, nblk);
+    vmsm_lens_offsets<<<nblk, 1024, 0, c->stream>>>(c->txt_lens, (uint32_t)n, c->txt_sums, c->txt_offsets);
+    c->launches += 3;
+    KTextCompact kc = {c->txt_slots, c->txt_lens, c->txt_offsets, c->txt_text};
+    be.launch(kc, (uint32_t)n);
+    be.note(cudaMemcpyAsync(c->pin, c->txt_sums + nblk, 8, cudaMemcpyDeviceToHost, c->stream));
+    be.note(cudaStreamSynchronize(c->stream));
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "points_text: %s", cudaGetErrorString(be.err));
+    uint64_t total = *reinterpret_cast<uint64_t *>(c->pin);
+    CU(cudaMemcpyAsync(c->txt_host, c->txt_text, total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *len = total;
+    return VMSM_OK;
+}
+
+int32_t vmsm_points_text(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *out, uint64_t cap,
+                         uint64_t *len) {
+    GET_CTX(ctx);
+    if (!len || (n && !out)) return fail(VMSM_ERR_INVALID, "null argument");
+    int32_t rc = points_text_impl(c, pts, off, n, len);
+    if (rc) return rc;
+    if (*len > cap) return fail(VMSM_ERR_INVALID, "text buffer too small: need %llu bytes", (unsigned long long)*len);
+    if (*len) memcpy(out, c->txt_host, *len);
+    return VMSM_OK;
+}
+
+int32_t vmsm_points_text_ptr(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t **text,
+                             uint64_t *len) {
+    GET_CTX(ctx);
+    if (!len || !text) return fail(VMSM_ERR_INVALID, "null argument");
+    int32_t rc = points_text_impl(c, pts, off, n, len);
+    if (rc) return rc;
+    *text = c->txt_host;
+    return VMSM_OK;
 }
 
 int32_t vmsm_points_count(uint64_t ctx, uint64_t pts, uint64_t *n) {

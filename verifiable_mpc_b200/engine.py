@@ -104,14 +104,15 @@ class DevicePoints:
     def tolist(self, off=0, n=None):
         return unpack_any(self.download(off, n), self.curve)
 
-    def text(self, off=0, n=None):
-        """``"[x0, y0, 1], [x1, y1, 1], ..."`` formatted on the device (the inside of repr(list of points))."""
+    def text_bytes(self, off=0, n=None):
+        """``b"[x0, y0, 1], [x1, y1, 1], ..."`` formatted on the device (the inside of repr(list of points))."""
         n = self.n - off if n is None else n
-        cap = max(1, 176 * n)
-        out = ctypes.create_string_buffer(cap)
-        ln = ctypes.c_uint64()
-        check(self.ctx.lib.vmsm_points_text(self.ctx.h, self.handle, off, n, out, cap, ctypes.byref(ln)))
-        return out.raw[:ln.value].decode("ascii")
+        ptr, ln = ctypes.c_void_p(), ctypes.c_uint64()
+        check(self.ctx.lib.vmsm_points_text_ptr(self.ctx.h, self.handle, off, n, ctypes.byref(ptr), ctypes.byref(ln)))
+        return ctypes.string_at(ptr, ln.value) if ln.value else b""
+
+    def text(self, off=0, n=None):
+        return self.text_bytes(off, n).decode("ascii")
 
     def fold(self, c):
         """In place ``P[j] = c*P[j] + P[half+j]`` (compressed_pivot.py:64); the vector shrinks to half."""

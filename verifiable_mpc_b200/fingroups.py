@@ -358,6 +358,12 @@ class DevicePointList:
         return "[" + ", ".join([f"[{fb(raw[i:i + 32], 'little')}, {fb(raw[i + 32:i + 64], 'little')}, 1]"
                                 for i in range(0, len(raw), 64)]) + "]"
 
+    def repr_bytes(self):
+        """repr(self).encode() without ever building the str (fed straight into the incremental hash)."""
+        if hasattr(self.dev, "text_bytes"):
+            return b"[" + self.dev.text_bytes(self.off, self.n) + b"]"
+        return repr(self).encode("utf-8")
+
     def __eq__(self, other):
         if isinstance(other, DevicePointList):
             return self.affine_list() == other.affine_list()
