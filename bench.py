@@ -24,6 +24,7 @@ METRIC = "ed25519_msm_points_per_s"
 UNIT = "points/s"
 SEED_SCALARS, SEED_BASES = 0x5EED, 0x5EEE
 NSETS = 3  # distinct (bases, scalars) sets rotated between steps so no step finds its inputs in L2
+E2E_DEPTH = 4  # MSMs in flight in the end-to-end loop
 
 # SURVEY.md 8(d)/App. E work model: limb products per point at the LP-minimising window c*(n)
 M, S = 72, 44
@@ -156,6 +157,8 @@ def run_gpu(args, rank, world, dist):
     n = 1 << args.log2n
     if args.window:
         ctx.set_option(_lib.OPT_WINDOW_BITS, args.window)
+    if args.sort_blocks >= 0:
+        ctx.set_option(_lib.OPT_SORT_BLOCKS, args.sort_blocks)
     ctx.set_option(_lib.OPT_PHASE_TIMING, 1)
 
     # inputs: NSETS distinct (bases, scalars) sets per rank, all resident in HBM before the timed region.
@@ -259,17 +262,18 @@ def run_gpu(args, rank, world, dist):
 
     # end-to-end through the public host API: every step copies that step's scalars from pinned host memory to the
     # device (H2D on the library's copy stream) and reads the resulting group element back on the host (the final
-    # kernel writes it into mapped pinned memory).  Steps are pipelined three deep: the host fetches result s-2 after
-    # issuing step s, so the copy and the counting sort of step s overlap the accumulate kernel of step s-1.
+    # kernel writes it into mapped pinned memory).  Steps are pipelined E2E_DEPTH deep: the host fetches result s-3 after
+    # issuing step s, so the copy and the counting sort of step s overlap the accumulate kernels of earlier steps.
     def e2e_loop(steps):
         last = None
+        lag = E2E_DEPTH - 1
         for s in range(steps):
             issue("async", s % NSETS, s % 48)
-            if s >= 2:
-                last = combine((s - 2) % 48)
-        if steps >= 2:
-            combine((steps - 2) % 48)
-        return combine((steps - 1) % 48)
+            if s >= lag:
+                last = combine((s - lag) % 48)
+        for s in range(max(steps - lag, 0), steps):
+            last = combine(s % 48)
+        return last
 
     e2e_loop(min(args.warmup, 3))
     barrier()
@@ -308,7 +312,7 @@ def run_gpu(args, rank, world, dist):
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": total_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world,
                 "d2h_bytes_per_step": 64 * world, "ms_per_step": 1e3 * e2e_s / args.steps,
-                "api": "Context.msm_async(points, pinned_scalars, slot) + Context.result(slot), pipelined three deep"},
+                "api": "Context.msm_async(points, pinned_scalars, slot) + Context.result(slot), pipelined %d deep" % E2E_DEPTH},
         "roofline": {"bound": "imad", "kernel": "vmsm_kernel<KAccumulate>", "achieved": achieved, "peak": peak_tlps,
                      "unit": "T limb-products/s", "frac": (achieved / peak_tlps) if achieved else None,
                      "traffic": _ncu_traffic_bytes() if args.log2n == 20 else None, "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/)",
@@ -379,6 +383,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--sort-blocks", type=int, default=-1, help="experiment: VMSM_OPT_SORT_BLOCKS (-1 = library default)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-check", dest="check", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

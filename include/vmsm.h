@@ -51,6 +51,11 @@ extern "C" {
                                with this sequence number (see the mailbox functions); clears itself */
 #define VMSM_OPT_ASYNC_SORT 10 /* 1 (default) = run the counting sort of the next MSM on a side stream under the
                                  accumulate kernel of the previous one (CSR lists double-buffered) */
+#define VMSM_OPT_SORT_BLOCKS 11 /* thread blocks of the digit-histogram and scatter kernels when they run on the sort
+                                  stream (grid-stride); small = a thin slice of every SM for longer, so the sort
+                                  shares the SMs with the accumulate kernel instead of displacing it (used only
+                                  while the previous MSM is still accumulating); default = the SM count, 0 = always
+                                  one thread per scalar */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */

@@ -21,6 +21,10 @@ struct HostBE {
     void launch(const F &f, uint32_t n) {
         for (uint32_t t = 0; t < n; t++) f(t);
     }
+    template <class F>
+    void launch_sort(const F &f, uint32_t n) {
+        launch(f, n);
+    }
     void scan_offsets(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g) {
         for (uint32_t w = 0; w < g.W; w++) {
             uint32_t run = w * g.n;

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--radix", type=int, nargs="+", default=[3])
     ap.add_argument("--cap", type=int, nargs="+", default=[0])
     ap.add_argument("--async-tail", type=int, nargs="+", default=[1])
+    ap.add_argument("--sort-blocks", type=int, nargs="+", default=[-1])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -32,7 +33,10 @@ def main():
         sets = [(ctx.fixed_base(seed=0x5EEE + 16 * k, n=n), ctx.synth_scalars(0x5EED + 16 * k, n)) for k in range(3)]
         for c in args.windows:
             for sort in args.sort:
-                for radix, cap, at in [(r, cp, a) for r in args.radix for cp in args.cap for a in args.async_tail]:
+                for radix, cap, at, sb in [(r, cp, a, b) for r in args.radix for cp in args.cap for a in args.async_tail
+                                           for b in args.sort_blocks]:
+                    if sb >= 0:
+                        ctx.set_option(_lib.OPT_SORT_BLOCKS, sb)
                     if cap:
                         ctx.set_option(_lib.OPT_CAP_FACTOR, cap)
                     ctx.set_option(_lib.OPT_ASYNC_TAIL, at)
@@ -48,7 +52,7 @@ def main():
                         ctx.msm_dev(*sets[s % 3], slot=s % 32)
                     ms = ctx.timer_stop() / args.steps
                     ph, calls = ctx.phase_times()
-                    rec = {"log2n": logn, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "ms": ms, "Mpts_s": n / ms / 1e3,
+                    rec = {"log2n": logn, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "Mpts_s": n / ms / 1e3,
                            "imad_peak_tlps": peak, "phase_ms": {k: round(v / calls, 5) for k, v in ph.items()}}
                     print(json.dumps(rec), flush=True)
                     if out:

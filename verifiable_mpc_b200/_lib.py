@@ -7,13 +7,14 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvmsm.so")
+LIB_PATH = os.environ.get("VMSM_LIB") or os.path.join(_HERE, "libvmsm.so")  # VMSM_LIB: A/B builds of the same ABI
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_POINT, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TIMEOUT = -1, -2, -3, -4, -5, -6
 CURVE_ED25519, CURVE_BN256_G1, CURVE_BN256_G2 = 0, 1, 2
 OPT_WINDOW_BITS, OPT_PHASE_TIMING, OPT_SORT_BUCKETS, OPT_CHECK_POINTS, OPT_REDUCE_RADIX = 1, 2, 3, 4, 5
 OPT_QUAD_THRESHOLD, OPT_ASYNC_TAIL, OPT_CAP_FACTOR, OPT_SHARD_SEQ, OPT_ASYNC_SORT = 6, 7, 8, 9, 10
+OPT_SORT_BLOCKS = 11
 PHASES = ("digits", "scan", "scatter", "order", "handoff", "accumulate", "reduce", "final")
 
 

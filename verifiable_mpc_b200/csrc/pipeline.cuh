@@ -40,9 +40,11 @@ struct Workspace {
     uint32_t *idx_[2] = {nullptr, nullptr};    // W*n
     int cur = 0;                               // parity in use by the MSM being issued
 
-    void *buckets = nullptr;  // W*NB accumulator points (ge_ext for Ed25519, wjac<F> for BN256): sized in bytes
-    // bucket-tree levels: [parity of the MSM sequence number][ping-pong].  Two parities because the latency-bound tail
-    // of one MSM (upper tree levels + Horner) runs on a side stream underneath the head of the next MSM.
+    // W*NB accumulator points (ge_ext for Ed25519, wjac<F> for BN256), sized in bytes; one set per tail way, because
+    // the whole bucket tree of MSM k (leaf level included) runs on side stream k % kTailWays underneath the accumulate
+    // kernels of the MSMs that follow
+    void *buckets_[kTailWays] = {};
+    // bucket-tree levels: [tail way][ping-pong]
     void *nodeS[kTailWays][2] = {}, *nodeT[kTailWays][2] = {};
     // long-bucket overflow (kernels.cuh: KOverflow / KCombine)
     OverflowCtl *ctl = nullptr;
@@ -99,10 +101,12 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
     }
     elem_bytes = ws.elem_bytes;
     if (nb > ws.cap_buckets) {
-        be.free(ws.buckets);
         ws.cap_buckets = 0;
-        ws.buckets = be.alloc(nb * elem_bytes);
-        if (!ws.buckets) return -1;
+        for (int k = 0; k < kTailWays; k++) {
+            be.free(ws.buckets_[k]);
+            ws.buckets_[k] = be.alloc(nb * elem_bytes);
+            if (!ws.buckets_[k]) return -1;
+        }
         for (int k = 0; k < 2; k++) {
             be.free(ws.counts_[k]), be.free(ws.offsets_[k]), be.free(ws.cursor_[k]), be.free(ws.order_[k]);
             ws.counts_[k] = (uint32_t *)be.alloc(nb * 4);
@@ -151,7 +155,7 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
 
 template <class BE>
 void ws_release(BE &be, Workspace &ws) {
-    be.free(ws.buckets);
+    for (int k = 0; k < kTailWays; k++) be.free(ws.buckets_[k]);
     for (int k = 0; k < 2; k++)
         be.free(ws.counts_[k]), be.free(ws.offsets_[k]), be.free(ws.cursor_[k]), be.free(ws.order_[k]), be.free(ws.idx_[k]);
     be.free(ws.ctl), be.free(ws.tasks), be.free(ws.longs), be.free(ws.partials);
@@ -181,14 +185,14 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.zero(counts, (size_t)nbuckets * 4);
     if (n) {
         KDigitsHist k1 = {scalars, counts, g};
-        be.launch(k1, n);
+        be.launch_sort(k1, n);
     }
     be.phase_mark(PH_DIGITS);
     be.scan_offsets(counts, offsets, cursor, g);
     be.phase_mark(PH_SCAN);
     if (n) {
         KScatter k3 = {scalars, cursor, idx, g};
-        be.launch(k3, n);
+        be.launch_sort(k3, n);
     }
     be.phase_mark(PH_SCATTER);
     const uint32_t *order = nullptr;
@@ -196,11 +200,16 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_ORDER);
     be.sort_end(par);
     be.phase_mark(PH_HANDOFF);
+    // this MSM's buckets, bucket tree and Horner chain live in the buffers of tail way `tw`: wait until the MSM that
+    // used them kTailWays issues ago has left them
+    const int tw = (int)(seq % kTailWays);
+    be.head_wait_tail(tw);
+    void *const buckets = ws.buckets_[tw];
     {
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < 64) cap = 64;
         be.zero(ws.ctl, sizeof(OverflowCtl));
-        KAccumulate k5 = {bases, offsets, counts, idx, order, (ge_ext *)ws.buckets, nbuckets, cap, ws.ctl, ws.tasks,
+        KAccumulate k5 = {bases, offsets, counts, idx, order, (ge_ext *)buckets, nbuckets, cap, ws.ctl, ws.tasks,
                           ws.longs, extra, n_main};
         be.launch(k5, nbuckets);
         if (n > cap) {  // otherwise no bucket can be long
@@ -208,33 +217,28 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
             KOverflow ko = {bases, idx, ws.ctl, ws.tasks, (ge_ext *)ws.partials, ow, extra, n_main};
             be.launch(ko, ow * 32);
             const uint32_t ct = be.combine_threads();
-            KCombine kc = {ws.ctl, ws.longs, (const ge_ext *)ws.partials, (ge_ext *)ws.buckets, ct};
+            KCombine kc = {ws.ctl, ws.longs, (const ge_ext *)ws.partials, (ge_ext *)buckets, ct};
             be.launch(kc, ct);
         }
     }
+    be.acc_done(par);  // the CSR lists of this parity are free again
     be.phase_mark(PH_ACCUMULATE);
-    // bucket tree: throughput-bound leaf level(s) on the main stream, then the latency-bound tail (quad-cooperative
-    // levels + Horner) which the CUDA backend runs on a side stream so that it overlaps the next MSM's head
-    const int tw = (int)(seq % kTailWays);
-    be.head_wait_tail(tw);
-    const ge_ext *inS = (const ge_ext *)ws.buckets, *inT = nullptr;
+    // bucket tree (S,T radix-R levels, quad-cooperative once few nodes remain) + Horner over the windows: on the CUDA
+    // backend all of it runs on side stream `tw`, underneath the accumulate kernels of the following MSMs
+    be.tail_begin(tw);
+    const ge_ext *inS = (const ge_ext *)buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;
-    bool in_tail = false;
     do {
         uint32_t cnt_out = (cnt + R - 1) / R;
         uint32_t nodes = g.W * cnt_out;
         if (nodes <= opt.quad_threshold) {
-            // the leaf level always stays on the main stream: it reads `buckets`, which the next MSM's accumulate
-            // kernel (main stream) overwrites -- only levels that read the per-way node buffers may move to a tail
-            if (!in_tail && log2s) be.tail_begin(tw), in_tail = true;
             KReduceQ k6 = {inS, inT, (ge_ext *)ws.nodeS[tw][pp], (ge_ext *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s, nodes};
             be.launch(k6, (4 * nodes + 31) & ~31u);
         } else {
             KReduce k6 = {inS, inT, (ge_ext *)ws.nodeS[tw][pp], (ge_ext *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s};
             be.launch(k6, nodes);
         }
-        if (log2s == 0) be.acc_done(par);  // the CSR lists of this parity are free again once the buckets are consumed
         inS = (const ge_ext *)ws.nodeS[tw][pp];
         inT = (const ge_ext *)ws.nodeT[tw][pp];
         pp ^= 1;
@@ -244,7 +248,6 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_REDUCE);
     {
         if (opt.quad_threshold) {
-            if (!in_tail) be.tail_begin(tw), in_tail = true;
             KFinalQ k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
             be.launch(k7, 32);
         } else {
@@ -255,7 +258,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_FINAL);
     be.after_final(out_ext, out_aff);  // multi-GPU: push this partial to the owner's mailbox / gather on the owner
     be.result_ready();
-    if (in_tail) be.tail_end(tw);
+    be.tail_end(tw);
     be.phase_end();
     return 0;
 }
@@ -282,14 +285,14 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     be.zero(counts, (size_t)nbuckets * 4);
     if (n) {
         KDigitsHist k1 = {scalars, counts, g};
-        be.launch(k1, n);
+        be.launch_sort(k1, n);
     }
     be.phase_mark(PH_DIGITS);
     be.scan_offsets(counts, offsets, cursor, g);
     be.phase_mark(PH_SCAN);
     if (n) {
         KScatter k3 = {scalars, cursor, idx, g};
-        be.launch(k3, n);
+        be.launch_sort(k3, n);
     }
     be.phase_mark(PH_SCATTER);
     const uint32_t *order = nullptr;
@@ -297,11 +300,14 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     be.phase_mark(PH_ORDER);
     be.sort_end(par);
     be.phase_mark(PH_HANDOFF);
+    const int tw = (int)(seq % kTailWays);
+    be.head_wait_tail(tw);
+    void *const buckets = ws.buckets_[tw];
     {
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < 64) cap = 64;
         be.zero(ws.ctl, sizeof(OverflowCtl));
-        KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)ws.buckets, nbuckets, cap, ws.ctl,
+        KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl,
                               ws.tasks, ws.longs, extra, n_main};
         be.launch(k5, nbuckets);
         if (n > cap) {
@@ -309,25 +315,22 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
             KOverflowW<F> ko = {bases, idx, ws.ctl, ws.tasks, (wjac<F> *)ws.partials, ow, extra, n_main};
             be.launch(ko, ow * 32);
             const uint32_t ct = be.combine_threads();
-            KCombineW<F> kc = {ws.ctl, ws.longs, (const wjac<F> *)ws.partials, (wjac<F> *)ws.buckets, ct};
+            KCombineW<F> kc = {ws.ctl, ws.longs, (const wjac<F> *)ws.partials, (wjac<F> *)buckets, ct};
             be.launch(kc, ct);
         }
     }
+    be.acc_done(par);
     be.phase_mark(PH_ACCUMULATE);
-    // leaf level on the main stream; the latency-bound rest (upper levels, Horner, inversion) on the side stream so
-    // that it overlaps the head of the next MSM (the eight MSMs of a Pinocchio proof are independent)
-    const int tw = (int)(seq % kTailWays);
-    be.head_wait_tail(tw);
-    const wjac<F> *inS = (const wjac<F> *)ws.buckets, *inT = nullptr;
+    // bucket tree, Horner and inversion on side stream `tw`, underneath the heads of the following MSMs (the eight
+    // MSMs of a Pinocchio proof are independent)
+    be.tail_begin(tw);
+    const wjac<F> *inS = (const wjac<F> *)buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;
-    bool in_tail = false;
     do {
         uint32_t cnt_out = (cnt + R - 1) / R;
-        if (log2s && !in_tail) be.tail_begin(tw), in_tail = true;
         KReduceW<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[tw][pp], (wjac<F> *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s};
         be.launch(k6, g.W * cnt_out);
-        if (log2s == 0) be.acc_done(par);
         inS = (const wjac<F> *)ws.nodeS[tw][pp];
         inT = (const wjac<F> *)ws.nodeT[tw][pp];
         pp ^= 1;
@@ -335,7 +338,6 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         log2s += opt.reduce_log2r;
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
-    if (!in_tail) be.tail_begin(tw), in_tail = true;
     KFinalW<F> k7 = {inS, inT, out_jac, out_wire, g.W, g.c};
     be.launch(k7, 32);
     be.phase_mark(PH_FINAL);

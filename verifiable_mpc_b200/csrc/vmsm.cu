@@ -47,6 +47,18 @@ __global__ void __launch_bounds__(F::kBlock, min_blocks<F>::value) vmsm_kernel(c
     if (tid < n) f(tid);
 }
 
+// grid-stride variant for the per-scalar kernels of the counting sort when they run underneath an accumulate kernel.
+// Deliberately plain: batching the scatter's atomics / prefetching the next scalar made the sort itself ~30 % faster
+// but slowed the accumulate kernel it shares the memory system with by more (profiles/r01/sweep_sort_blocks.jsonl).
+template <class F>
+__global__ void __launch_bounds__(F::kBlock) vmsm_kernel_strided(const F f, uint32_t n) {
+    const uint32_t stride = gridDim.x * (uint32_t)F::kBlock;
+    for (uint32_t tid = blockIdx.x * (uint32_t)F::kBlock + threadIdx.x; tid < n; tid += stride) {
+        f(tid);
+        if (tid + stride < tid) break;
+    }
+}
+
 // Exclusive scan of the bucket populations, one block per (window, tile of 1024 buckets).  Each block first sums
 // the tiles before it in the same window (coalesced re-read of at most NB counters from L2), then scans its own
 // tile: one launch, W * NB / 1024 blocks, no inter-block dependency.  Offsets are absolute positions in idx.
@@ -249,6 +261,7 @@ struct Ctx {
     cudaEvent_t ev_sorted[2] = {nullptr, nullptr}, ev_acc_done[2] = {nullptr, nullptr}, ev_sort_in = nullptr;
     bool acc_pending[2] = {false, false};
     bool async_sort = true;
+    uint32_t sort_blocks = 0;
     cudaEvent_t scalars_ready = nullptr;  // set by the entry point when the scalars of the next MSM are still in flight
     cudaEvent_t ev_head = nullptr, ev_tail[kTailWays] = {};
     bool tail_pending[kTailWays] = {};
@@ -329,6 +342,7 @@ struct CudaBE {
     uint32_t overflow_warps() { return 148u * 8u * 4u; }  // 8 blocks of 4 warps per SM, grid-stride over the tasks
     uint32_t combine_threads() { return 148u * 128u; }
     // the node buffers of parity `par` may still be read by the tail of the MSM two calls ago
+    bool thin_sort = false;
     void head_wait_tail(int par) {
         if (c->tail_pending[par]) note(cudaStreamWaitEvent(c->stream, c->ev_tail[par], 0));
     }
@@ -341,6 +355,9 @@ struct CudaBE {
         if (c->scalars_ready) note(cudaStreamWaitEvent(c->sort, c->scalars_ready, 0));
         c->scalars_ready = nullptr;
         if (c->acc_pending[par]) note(cudaStreamWaitEvent(c->sort, c->ev_acc_done[par], 0));
+        // is the previous MSM still accumulating?  Then this sort runs underneath it and should stay thin; a lone MSM
+        // (or the first of a burst) gets the whole machine
+        thin_sort = c->acc_pending[par ^ 1] && cudaEventQuery(c->ev_acc_done[par ^ 1]) == cudaErrorNotReady;
         cur = c->sort;
     }
     void sort_end(int par) {
@@ -398,6 +415,15 @@ struct CudaBE {
         if (!n) return;
         uint32_t grid = (n + F::kBlock - 1) / F::kBlock;
         vmsm_kernel<F><<<grid, F::kBlock, 0, cur>>>(f, n);
+        c->launches++;
+        note(cudaGetLastError());
+    }
+    // per-scalar kernels of the counting sort: on the sort stream they run as a thin grid-stride slice of every SM
+    template <class F>
+    void launch_sort(const F &f, uint32_t n) {
+        uint32_t grid = (n + F::kBlock - 1) / F::kBlock;
+        if (!c->async_sort || !thin_sort || !c->sort_blocks || grid <= c->sort_blocks) return launch(f, n);
+        vmsm_kernel_strided<F><<<c->sort_blocks, F::kBlock, 0, cur>>>(f, n);
         c->launches++;
         note(cudaGetLastError());
     }
@@ -655,6 +681,8 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
                     prop.major, prop.minor);
     Ctx *c = new Ctx();
     c->device = device;
+    // one block of the sort kernels per SM: measured best at 2^14 .. 2^22 (profiles/r01/sweep_sort_blocks.jsonl)
+    c->sort_blocks = (uint32_t)prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;  // hi = numerically smallest = greatest priority
@@ -786,6 +814,10 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             return VMSM_OK;
         case VMSM_OPT_ASYNC_SORT:
             c->async_sort = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_SORT_BLOCKS:
+            if (value < 0 || value > (1 << 20)) return fail(VMSM_ERR_INVALID, "sort blocks out of range");
+            c->sort_blocks = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_QUAD_THRESHOLD:
             if (value < 0 || value > (1 << 24)) return fail(VMSM_ERR_INVALID, "quad threshold out of range");
