@@ -116,6 +116,31 @@ int32_t vmsm_scalars_synth(uint64_t ctx, int32_t curve, uint64_t seed, uint64_t 
 int32_t vmsm_scalars_download(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t n, uint8_t *le32_out);
 int32_t vmsm_scalars_free(uint64_t ctx, uint64_t sc);
 
+/* Scalar vectors modulo the Ed25519 group order l: the halving of the witness and of the linear form that accompanies
+ * every generator fold, without leaving HBM.  Entries must be reduced (< l).
+ * vmsm_scalars_fold, in place on sc[0 .. 2*half), result in sc[0 .. half):
+ *   VMSM_FOLD_WITNESS  z'_j = z_j + c * z_{half+j}      compressed_pivot.py:76  (z_prime)
+ *   VMSM_FOLD_FORM     L'_j = c * L_j + L_{half+j}      compressed_pivot.py:68-73 (L_prime), :189-193 (verifier)
+ * vmsm_scalars_dot: sum_i a[aoff+i] * b[boff+i] mod l -- L_tilde([0]*half + z_L), L_tilde(z_R + [0]*half), :41-42.
+ * vmsm_scalars_text_ptr: "v0, v1, ..." as MPyC prints field elements (is_signed: representatives in (-l/2, l/2]),
+ *   the coefficient text of L_tilde in the Fiat-Shamir pre-image, :51-54; *text as for vmsm_points_text_ptr.
+ * vmsm_scalars_axpy, the same element-wise operations on two vectors (ranges must not overlap):
+ *   VMSM_AXPY_ADD_SCALED  dst_j = dst_j + c * src_j      z = r + c0 * x, phi = rho + c0 * gamma   :134-135
+ *   VMSM_AXPY_SCALE_ADD   dst_j = c * dst_j + src_j
+ *   VMSM_AXPY_SCALE       dst_j = c * dst_j              L_tilde = (L.coeffs + [0]) * c1           :141, :236 */
+#define VMSM_FOLD_WITNESS 0
+#define VMSM_FOLD_FORM 1
+#define VMSM_AXPY_ADD_SCALED 0
+#define VMSM_AXPY_SCALE_ADD 1
+#define VMSM_AXPY_SCALE 2
+int32_t vmsm_scalars_fold(uint64_t ctx, uint64_t sc, uint64_t half, const uint8_t *c_le32, int32_t mode);
+int32_t vmsm_scalars_axpy(uint64_t ctx, uint64_t dst, uint64_t doff, uint64_t src, uint64_t soff, uint64_t n,
+                          const uint8_t *c_le32, int32_t mode);
+int32_t vmsm_scalars_dot(uint64_t ctx, uint64_t a, uint64_t aoff, uint64_t b, uint64_t boff, uint64_t n,
+                         uint8_t *out_le32);
+int32_t vmsm_scalars_text_ptr(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t n, int32_t is_signed,
+                              const uint8_t **text, uint64_t *len);
+
 /* ---- multi-scalar multiplication -------------------------------------------------------------------------
  * out = sum_{i<n} s_i * P[off + i].  Replaces pivot.vector_commitment / list_mul
  * (verifiable_mpc/ac20/pivot.py:139-145, :26-28; call sites compressed_pivot.py:41-42,110,193,
@@ -138,6 +163,11 @@ int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, con
  * MSMs finish on different side streams. */
 int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
                      uint32_t slot);
+/* As vmsm_msm_dev with n_extra more terms whose scalars come from the host (the k^{L(z)} factor of the cross terms):
+ * A_i = g_R^{z_L} * k^{L_R(z_L)} with z resident in HBM -- verifiable_mpc/ac20/compressed_pivot.py:41-42.  Ed25519. */
+int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
+                         uint64_t extra_pts, uint64_t extra_off, uint64_t n_extra, const uint8_t *extra_scalars_le32,
+                         uint32_t slot);
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine);      /* synchronises */
 int32_t vmsm_result_extended(uint64_t ctx, uint32_t slot, uint8_t *out_extended);  /* synchronises */
 

@@ -41,6 +41,45 @@ def _unpack_scalars(raw):
     return [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
 
 
+class FakeScalars:
+    """Device-resident scalar vector modulo the Ed25519 group order, on Python ints."""
+
+    def __init__(self, ctx, vals):
+        self.ctx, self.vals, self.handle = ctx, [int(v) % E.L for v in vals], 1
+
+    @property
+    def n(self):
+        return len(self.vals)
+
+    def tolist(self, off=0, n=None):
+        n = len(self.vals) - off if n is None else n
+        return self.vals[off:off + n]
+
+    def fold(self, half, c, mode):
+        c = int(c) % E.L
+        lo, hi = self.vals[:half], self.vals[half:2 * half]
+        assert len(hi) == half
+        new = [(a + c * b) % E.L for a, b in zip(lo, hi)] if mode == 0 else [(c * a + b) % E.L for a, b in zip(lo, hi)]
+        self.vals[:half] = new
+
+    def axpy(self, c, src=None, mode=0, off=0, soff=0, n=None):
+        c = int(c) % E.L
+        n = len(self.vals) - off if n is None else n
+        d = self.vals[off:off + n]
+        s = src.vals[soff:soff + n] if src is not None else [0] * n
+        assert len(d) == n and len(s) == n
+        new = [(a + c * b) % E.L for a, b in zip(d, s)] if mode == 0 else \
+            [(c * a + b) % E.L for a, b in zip(d, s)] if mode == 1 else [c * a % E.L for a in d]
+        self.vals[off:off + n] = new
+
+    def text_bytes(self, off=0, n=None, signed=True):
+        vals = self.tolist(off, n)
+        return ", ".join(str(v - E.L if signed and v > (E.L >> 1) else v) for v in vals).encode()
+
+    def free(self):
+        self.handle = 0
+
+
 class FakeBNPoints:
     def __init__(self, ctx, pts, curve):
         self.ctx, self.pts, self.handle, self.curve = ctx, list(pts), 1, curve
@@ -92,6 +131,31 @@ class FakeContext:
             return BN.msm_naive(F, sc, points.pts[off:off + len(sc)])
         sc = _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else [int(s) % E.L for s in scalars]
         return E.msm_naive(sc, points.pts[off:off + len(sc)])
+
+    def upload_scalars(self, scalars, order=E.L):
+        assert order == E.L
+        return FakeScalars(self, _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else scalars)
+
+    def scalars_dot(self, a, aoff, b, boff, n):
+        assert aoff + n <= a.n and boff + n <= b.n
+        return sum(x * y for x, y in zip(a.vals[aoff:aoff + n], b.vals[boff:boff + n])) % E.L
+
+    def msm_dev_ext(self, points, poff, n, scalars, soff, extra, extra_off, extra_scalars, slot=0):
+        FakeContext.calls += 1
+        assert poff + n <= points.n and soff + n <= scalars.n
+        sc = scalars.vals[soff:soff + n] + [int(s) % E.L for s in extra_scalars]
+        bases = points.pts[poff:poff + n] + extra.pts[extra_off:extra_off + len(extra_scalars)]
+        if not hasattr(self, "_slots"):
+            self._slots = {}
+        self._slots[slot] = E.msm_naive(sc, bases)
+
+    def msm_dev(self, points, scalars, slot=0, poff=0, soff=0, n=None):
+        FakeContext.calls += 1
+        if n is None:
+            n = min(points.n - poff, scalars.n - soff)
+        if not hasattr(self, "_slots"):
+            self._slots = {}
+        self._slots[slot] = E.msm_naive(scalars.vals[soff:soff + n], points.pts[poff:poff + n])
 
     def msm_async(self, points, ptr, off, n, slot):
         import ctypes

@@ -173,6 +173,45 @@ void hostemu_point_text(const uint8_t *affine, uint32_t n, uint8_t *slots, uint3
     be.launch(k, n);
 }
 
+// ---- scalar vectors modulo the Ed25519 group order (sc25519.cuh), the launch sequences of vmsm.cu
+void hostemu_scalars_fold(uint32_t *v, uint32_t half, const uint8_t *c_le32, int mode) {
+    HostBE be;
+    scl cs;
+    memcpy(cs.v, c_le32, 32);
+    KScalarAxpy k = {v, v + 8ull * half, scl_to_mont(cs), mode};
+    be.launch(k, half);
+}
+
+void hostemu_scalars_axpy(uint32_t *dst, const uint32_t *src, uint32_t n, const uint8_t *c_le32, int mode) {
+    HostBE be;
+    scl cs;
+    memcpy(cs.v, c_le32, 32);
+    KScalarAxpy k = {dst, src, scl_to_mont(cs), mode};
+    be.launch(k, n);
+}
+
+void hostemu_scalars_dot(const uint32_t *a, const uint32_t *b, uint32_t n, uint8_t *out_le32) {
+    HostBE be;
+    memset(out_le32, 0, 32);
+    if (!n) return;
+    uint32_t T = n < 4096 ? n : 4096u, T2 = T < 64 ? T : 64u;
+    std::vector<uint32_t> scratch((4096 + 64 + 1) * 8 + 16);
+    uint32_t *p1 = (uint32_t *)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15), *p2 = p1 + 4096 * 8, *p3 = p2 + 64 * 8;
+    KScalarDotPartial k1 = {a, b, n, T, p1};
+    be.launch(k1, T);
+    KScalarSum k2 = {p1, T, T2, p2, 0};
+    be.launch(k2, T2);
+    KScalarSum k3 = {p2, T2, 1, p3, 1};
+    be.launch(k3, 1);
+    memcpy(out_le32, p3, 32);
+}
+
+void hostemu_scalar_text(const uint32_t *v, uint32_t n, int is_signed, uint8_t *slots, uint32_t *lens) {
+    HostBE be;
+    KScalarText k = {v, slots, lens, n, is_signed};
+    be.launch(k, n);
+}
+
 // ---- BN256: field ops (plain in, plain out), MSM and fixed-base for G1 (g2 = 0) / G2 (g2 = 1)
 void hostemu_fbn_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out) {
     fbn x, y, r;

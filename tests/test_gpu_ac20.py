@@ -27,6 +27,16 @@ def test_twin_matches_reference_fixture(gpu_group, idx):
     check_case(load_cases()[idx], group, gf)
 
 
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_twin_device_scalar_path_matches_reference_fixture(gpu_group, idx, monkeypatch):
+    """Witness and linear form halved on the device from the first round on (threshold lowered to 2)."""
+    from verifiable_mpc_b200.ac20 import compressed_pivot as cp
+
+    group, gf = gpu_group
+    monkeypatch.setattr(cp, "DEVICE_SCALAR_MIN", 2)
+    check_case(load_cases()[idx], group, gf)
+
+
 def test_group_ops_on_device(gpu_group):
     from oracle import ed25519 as E
 
@@ -61,6 +71,22 @@ def test_compressed_pivot_1024(gpu_group):
     assert len([k for k in proof if k.startswith("B")]) == 9
     assert cp.protocol_5_verifier(generators, P, L, y, proof, gf) is True
     assert cp.protocol_5_verifier(generators, P, L, y + 1, proof, gf) is False
+    # the same statement with the witness / form algebra on host integers and on field-element objects: one proof
+    for dev_path, fast in ((False, True), (False, False)):
+        old = (cp.DEVICE_SCALAR_PATH, cp.FAST_INT_PATH)
+        cp.DEVICE_SCALAR_PATH, cp.FAST_INT_PATH = dev_path, fast
+        try:
+            rng2 = random.Random(77)
+            gens.prng = rng2
+            gens.create_generators(n, group)
+            [rng2.randrange(gf.order) for _ in range(2 * n + 1)]  # x, gamma, L: replay the draws made above
+            cp.prng = rng2
+            other = cp.protocol_5_prover(generators, P, L, y, x, gamma, gf)
+            assert sorted(other) == sorted(proof)
+            assert all(other[k] == proof[k] for k in proof)
+            assert cp.protocol_5_verifier(generators, P, L, y, proof, gf) is True
+        finally:
+            cp.DEVICE_SCALAR_PATH, cp.FAST_INT_PATH = old
 
 
 def test_compressed_pivot_2p16(gpu_group):

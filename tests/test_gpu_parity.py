@@ -286,6 +286,76 @@ def test_points_text_on_device(ctx, known_points):
     assert big.text() == ", ".join(f"[{x}, {y}, 1]" for x, y in big.tolist())
 
 
+def test_scalar_vectors_on_device(ctx, known_points):
+    """vmsm_scalars_fold / _dot / _text_ptr and vmsm_msm_dev_ext: the witness / linear-form side of a folding round,
+    against Python integers and the oracle."""
+    from verifiable_mpc_b200 import VmsmError, _lib
+
+    dlogs, pts = known_points
+    L = E.L
+    rng = random.Random(99)
+    edge = [0, 1, L - 1, L >> 1, (L >> 1) + 1, 2**252, 2**252 - 1, 10**9, 10**9 - 1]
+    for n in (2, 18, 1000, 70000):
+        vals = (edge + [rng.randrange(L) for _ in range(n)])[:n]
+        other = [rng.randrange(L) for _ in range(n)]
+        a, b = ctx.upload_scalars(vals), ctx.upload_scalars(other)
+        assert a.tolist() == vals
+        want = ", ".join(str(v - L if v > (L >> 1) else v) for v in vals)
+        assert a.text_bytes().decode() == want
+        assert a.text_bytes(signed=False).decode() == ", ".join(map(str, vals))
+        assert a.text_bytes(1, 1).decode() == str(vals[1] - L if vals[1] > (L >> 1) else vals[1])
+        assert ctx.scalars_dot(a, 0, b, 0, n) == sum(x * y for x, y in zip(vals, other)) % L
+        half = n // 2
+        assert ctx.scalars_dot(a, half, b, 0, half) == sum(x * y for x, y in zip(vals[half:], other[:half])) % L
+        c = rng.randrange(L)
+        a.fold(half, c, _lib.FOLD_WITNESS)
+        b.fold(half, c, _lib.FOLD_FORM)
+        assert a.tolist(0, half) == [(x + c * y) % L for x, y in zip(vals[:half], vals[half:2 * half])]
+        assert b.tolist(0, half) == [(c * x + y) % L for x, y in zip(other[:half], other[half:2 * half])]
+        # element-wise forms on two vectors: z = r + c0*x, L_tilde = c1*L, and c*dst + src
+        now_a, now_b = a.tolist(), b.tolist()
+        a.axpy(c, b, _lib.AXPY_ADD_SCALED)
+        assert a.tolist() == [(x + c * y) % L for x, y in zip(now_a, now_b)]
+        b.axpy(c, None, _lib.AXPY_SCALE, off=1, n=n - 1)
+        assert b.tolist() == now_b[:1] + [c * y % L for y in now_b[1:]]
+        now_a, now_b = a.tolist(), b.tolist()
+        a.axpy(L - 1, b, _lib.AXPY_SCALE_ADD)
+        assert a.tolist() == [((L - 1) * x + y) % L for x, y in zip(now_a, now_b)]
+        a.free(), b.free()
+    assert ctx.scalars_dot(ctx.upload_scalars([5]), 0, ctx.upload_scalars([7]), 0, 0) == 0
+
+    # A_i = g_R^{z_L} * k^{s}: z read in place at an offset, the extra scalar from the host, two MSMs in flight,
+    # then the fold overwrites z while nothing may still be reading it
+    n = 64
+    g = ctx.upload_points(pts[:n])
+    k = ctx.upload_points([pts[n]])
+    z_vals = [rng.randrange(L) for _ in range(n)]
+    z = ctx.upload_scalars(z_vals)
+    half = n // 2
+    for rnd in range(4):
+        s_a, s_b = rng.randrange(L), rng.randrange(L)
+        ctx.msm_dev_ext(g, half, half, z, 0, k, 0, [s_a], slot=0)
+        ctx.msm_dev_ext(g, 0, half, z, half, k, 0, [s_b], slot=1)
+        c = rng.randrange(L)
+        z.fold(half, c, _lib.FOLD_WITNESS)  # issued while both MSMs are in flight
+        assert ctx.result(0) == E.msm_naive(z_vals[:half] + [s_a], pts[half:n] + [pts[n]])
+        assert ctx.result(1) == E.msm_naive(z_vals[half:] + [s_b], pts[:half] + [pts[n]])
+        z_vals = [(x + c * y) % L for x, y in zip(z_vals[:half], z_vals[half:])] + z_vals[half:]
+        assert z.tolist() == z_vals
+    with pytest.raises(VmsmError):
+        z.fold(n, 1, _lib.FOLD_WITNESS)
+    with pytest.raises(VmsmError):
+        z.fold(1, 1, 7)
+    with pytest.raises(VmsmError):
+        z.axpy(1, z, _lib.AXPY_ADD_SCALED, off=0, soff=1, n=8)  # overlapping ranges
+    with pytest.raises(VmsmError):
+        z.axpy(1, z, 9)
+    with pytest.raises(VmsmError):
+        ctx.scalars_dot(z, 1, z, 0, n)
+    with pytest.raises(VmsmError):
+        ctx.msm_dev_ext(g, 1, n, z, 0, k, 0, [1], slot=0)
+
+
 def test_abi_error_paths(ctx, known_points):
     """Status codes instead of crashes: bad handles, ranges, slots, options, mixed curves, Ed25519-only calls."""
     import ctypes

@@ -177,3 +177,76 @@ def test_point_text_matches_python_repr(hostemu, known_points):
     hostemu.hostemu_point_text(b"".join(E.point_to_bytes(p) for p in cases), n, slots, lens)
     got = "".join(slots.raw[176 * i: 176 * i + lens[i]].decode() for i in range(n))
     assert got == ", ".join(f"[{x}, {y}, 1]" for x, y in cases)
+
+
+# ---- scalar vectors modulo the group order (sc25519.cuh): witness / linear-form halving, cross terms, text
+def _aligned_scalars(vals):
+    """n x 32 bytes, 16-byte aligned (the kernels use 128-bit loads)."""
+    import numpy as np
+    arr = np.zeros(len(vals) * 8 + 4, dtype=np.uint32)
+    off = (-arr.ctypes.data % 16) // 4
+    view = arr[off:off + len(vals) * 8]
+    view[:] = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint32)
+    return view
+
+
+def _edge_scalars(n, seed):
+    import random
+    rng = random.Random(seed)
+    L = E.L
+    vals = [0, 1, L - 1, L >> 1, (L >> 1) + 1, 2**252, 2**252 - 1, 10**9, 10**9 - 1, 2**32 - 1, 2**32]
+    vals += [rng.randrange(L) for _ in range(n - len(vals))]
+    return vals[:n]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_scalars_fold(hostemu, mode):
+    """KScalarFold against Python ints: z' = z_L + c z_R (mode 0) and L' = c L_L + L_R (mode 1), edge values included."""
+    L = E.L
+    for half, c in ((1, 0), (7, 1), (16, L - 1), (33, 0x1234567890ABCDEF << 180)):
+        vals = _edge_scalars(2 * half, half) if half > 5 else [L - 1, 5][:2 * half] + [3] * max(0, 2 * half - 2)
+        v = _aligned_scalars(vals)
+        hostemu.hostemu_scalars_fold(v.ctypes.data_as(ctypes.c_void_p), half, (c % L).to_bytes(32, "little"), mode)
+        got = [int.from_bytes(v[8 * i:8 * i + 8].tobytes(), "little") for i in range(half)]
+        lo, hi = vals[:half], vals[half:2 * half]
+        exp = [(a + c * b) % L for a, b in zip(lo, hi)] if mode == 0 else [(c * a + b) % L for a, b in zip(lo, hi)]
+        assert got == exp
+
+
+def test_scalars_axpy(hostemu):
+    L = E.L
+    n = 23
+    d_vals, s_vals = _edge_scalars(n, 1), list(reversed(_edge_scalars(n, 2)))
+    for mode, c in ((0, 5), (1, L - 1), (2, 2**251 + 12345), (2, 0)):
+        d, sv = _aligned_scalars(d_vals), _aligned_scalars(s_vals)
+        hostemu.hostemu_scalars_axpy(d.ctypes.data_as(ctypes.c_void_p), sv.ctypes.data_as(ctypes.c_void_p), n,
+                                     c.to_bytes(32, "little"), mode)
+        got = [int.from_bytes(d[8 * i:8 * i + 8].tobytes(), "little") for i in range(n)]
+        exp = [(a + c * b) % L for a, b in zip(d_vals, s_vals)] if mode == 0 else \
+            [(c * a + b) % L for a, b in zip(d_vals, s_vals)] if mode == 1 else [c * a % L for a in d_vals]
+        assert got == exp
+
+
+def test_scalars_dot(hostemu):
+    L = E.L
+    for n in (0, 1, 2, 63, 64, 65, 300, 5000):
+        a_vals, b_vals = _edge_scalars(max(n, 11), n)[:n], list(reversed(_edge_scalars(max(n, 11), n + 1)))[:n]
+        a, b = _aligned_scalars(a_vals or [0]), _aligned_scalars(b_vals or [0])
+        out = ctypes.create_string_buffer(32)
+        hostemu.hostemu_scalars_dot(a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), n, out)
+        assert int.from_bytes(out.raw, "little") == sum(x * y for x, y in zip(a_vals, b_vals)) % L
+
+
+@pytest.mark.parametrize("signed", [0, 1])
+def test_scalar_text_matches_python_repr(hostemu, signed):
+    """KScalarText: the coefficient text of L_tilde exactly as MPyC prints (signed) field elements."""
+    L = E.L
+    vals = _edge_scalars(40, 5)
+    n = len(vals)
+    v = _aligned_scalars(vals)
+    slots = ctypes.create_string_buffer(96 * n)
+    lens = (ctypes.c_uint32 * n)()
+    hostemu.hostemu_scalar_text(v.ctypes.data_as(ctypes.c_void_p), n, signed, slots, lens)
+    got = "".join(slots.raw[96 * i: 96 * i + lens[i]].decode() for i in range(n))
+    exp = ", ".join(str(x - L if signed and x > (L >> 1) else x) for x in vals)
+    assert got == exp

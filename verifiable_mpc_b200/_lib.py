@@ -15,6 +15,8 @@ CURVE_ED25519, CURVE_BN256_G1, CURVE_BN256_G2 = 0, 1, 2
 OPT_WINDOW_BITS, OPT_PHASE_TIMING, OPT_SORT_BUCKETS, OPT_CHECK_POINTS, OPT_REDUCE_RADIX = 1, 2, 3, 4, 5
 OPT_QUAD_THRESHOLD, OPT_ASYNC_TAIL, OPT_CAP_FACTOR, OPT_SHARD_SEQ, OPT_ASYNC_SORT = 6, 7, 8, 9, 10
 OPT_SORT_BLOCKS = 11
+FOLD_WITNESS, FOLD_FORM = 0, 1
+AXPY_ADD_SCALED, AXPY_SCALE_ADD, AXPY_SCALE = 0, 1, 2
 PHASES = ("digits", "scan", "scatter", "order", "handoff", "accumulate", "reduce", "final")
 
 
@@ -62,6 +64,11 @@ SIGNATURES = {
     "vmsm_msm_dev_shard": [_u64, _u64, _u64, _u64, _u64, _u64, _u32, _u32],
     "vmsm_msm_async": [_u64, _u64, _u64, _u64, _p, _u32],
     "vmsm_msm_dev": [_u64, _u64, _u64, _u64, _u64, _u64, _u32],
+    "vmsm_msm_dev_ext": [_u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _p, _u32],
+    "vmsm_scalars_fold": [_u64, _u64, _u64, _p, _i32],
+    "vmsm_scalars_axpy": [_u64, _u64, _u64, _u64, _u64, _u64, _p, _i32],
+    "vmsm_scalars_dot": [_u64, _u64, _u64, _u64, _u64, _u64, _p],
+    "vmsm_scalars_text_ptr": [_u64, _u64, _u64, _u64, _i32, ctypes.POINTER(_p), _pu64],
     "vmsm_result_affine": [_u64, _u32, _p],
     "vmsm_result_extended": [_u64, _u32, _p],
     "vmsm_fold": [_u64, _u64, _u64, _p],

@@ -11,6 +11,8 @@ import logging
 from random import SystemRandom
 
 from . import pivot
+from .. import _lib
+from ..engine import ED_L
 from ..fingroups import DevicePointList
 
 prng = SystemRandom()
@@ -33,7 +35,7 @@ FAST_INT_PATH = True
 
 
 def _all_in_field(values, gf):
-    return all(type(v) is gf for v in values)
+    return set(map(type, values)) <= {gf}
 
 
 def _field_text(ints, q, signed=True):
@@ -102,7 +104,7 @@ def protocol_4_prover(g_hat, k, Q, L_tilde, z_hat, gf, proof=None, round_i=0):
     order = k.order
     if (FAST_INT_PATH and isinstance(L_tilde, pivot.LinearForm) and gf.order == order
             and _all_in_field(L_tilde.coeffs, gf) and _all_in_field(z_hat, gf)):
-        return _protocol_4_prover_ints(g_hat, k, Q, [c.value for c in L_tilde.coeffs], [z.value for z in z_hat], gf,
+        return _protocol_4_prover_fast(g_hat, k, Q, [c.value for c in L_tilde.coeffs], [z.value for z in z_hat], gf,
                                        proof, round_i)
     while True:
         half = len(g_hat) // 2
@@ -160,11 +162,120 @@ def _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i):
         Q = group.lincomb([A, Q, B], [1, c, c ** 2])
         coeffs = [(l * c + r) % q for l, r in zip(coeffs[:half], coeffs[half:])]
         if len(g_hat) <= 2:
-            z_prime = proof["z_prime"]
-            gamma = int(sum([gf(cf) * zp for cf, zp in zip(coeffs, z_prime)]) + 0)
-            Q_check = pivot.vector_commitment(z_prime, gamma, g_hat, k)
-            return Q_check == Q
+            return _final_check(g_hat, k, Q, coeffs, gf, proof)
         round_i += 1
+
+
+def _final_check(g_hat, k, Q, coeffs, gf, proof):
+    z_prime = proof["z_prime"]
+    gamma = int(sum([gf(cf) * zp for cf, zp in zip(coeffs, z_prime)]) + 0)
+    Q_check = pivot.vector_commitment(z_prime, gamma, g_hat, k)
+    return Q_check == Q
+
+
+# Device-resident witness and linear form.  Above DEVICE_SCALAR_MIN entries the round loop keeps z and the coefficients
+# of L_tilde in HBM next to the generators: the cross terms L_R(z_L), L_L(z_R) are device dot products, A_i / B_i read
+# z in place, the halvings z' = z_L + c z_R and L' = c L_L + L_R are one kernel each, and the decimal text of L_tilde
+# for the next challenge is produced on the device like that of g_hat.  Per round the host only hashes.  Below the
+# threshold (a few rounds, a few hundred scalars in total) the vectors come back and the integer loop finishes.
+DEVICE_SCALAR_PATH = True
+DEVICE_SCALAR_MIN = 256
+
+
+class _DevForm:
+    """The form whose coefficients live on the device, for the Fiat-Shamir pre-image ("[coeffs], constant")."""
+    __slots__ = ("sc", "n", "signed", "constant")
+
+    def __init__(self, sc, n, signed, constant="0"):
+        self.sc, self.n, self.signed, self.constant = sc, n, signed, str(constant)
+
+    def repr_bytes(self):
+        return b"[" + self.sc.text_bytes(0, self.n, self.signed) + b"], " + self.constant.encode("ascii")
+
+    def __repr__(self):
+        return self.repr_bytes().decode("ascii")
+
+
+def _use_device_scalars(g_hat, q):
+    n = len(g_hat)
+    return (DEVICE_SCALAR_PATH and isinstance(g_hat, DevicePointList) and n > DEVICE_SCALAR_MIN and n & (n - 1) == 0
+            and q == ED_L)
+
+
+def _protocol_4_prover_fast(g_hat, k, Q, coeffs, z, gf, proof, round_i):
+    q = k.order
+    if not _use_device_scalars(g_hat, q) or len(z) != len(g_hat) or len(coeffs) != len(g_hat):
+        return _protocol_4_prover_ints(g_hat, k, Q, coeffs, z, gf, proof, round_i)
+    ctx = g_hat.dev.ctx
+    return _protocol_4_prover_dev(g_hat, k, Q, ctx.upload_scalars(coeffs, q), ctx.upload_scalars(z, q), gf, proof, round_i)
+
+
+def _protocol_4_prover_dev(g_hat, k, Q, Ld, zd, gf, proof, round_i):
+    """Round loop with L_tilde (Ld) and z_hat (zd) resident on the device; takes ownership of both vectors."""
+    group = type(k)
+    q = k.order
+    ctx = g_hat.dev.ctx
+    signed = bool(gf.is_signed)
+    kd = pivot._device_single(group, k)
+    try:
+        n = len(g_hat)
+        while n > DEVICE_SCALAR_MIN:
+            half = n // 2
+            logger_cp.debug("Calculate A_i, B_i.")
+            s_a = ctx.scalars_dot(Ld, half, zd, 0, half)  # L_tilde([0]*half + z_L)
+            s_b = ctx.scalars_dot(Ld, 0, zd, half, half)  # L_tilde(z_R + [0]*half)
+            ctx.msm_dev_ext(g_hat.dev, g_hat.off + half, half, zd, 0, kd, 0, [s_a], slot=0)
+            ctx.msm_dev_ext(g_hat.dev, g_hat.off, half, zd, half, kd, 0, [s_b], slot=1)
+            A, B = group._make(ctx.result(0)), group._make(ctx.result(1))
+            proof["A" + str(round_i)] = A
+            proof["B" + str(round_i)] = B
+            c = _fold_challenge(A, B, g_hat, k, Q, _DevForm(Ld, n, signed), q)
+            g_hat = _fold_generators(g_hat, c)
+            Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+            Ld.fold(half, c, _lib.FOLD_FORM)
+            zd.fold(half, c, _lib.FOLD_WITNESS)
+            n = half
+            if n <= 2:
+                proof["z_prime"] = [gf(v) for v in zd.tolist(0, n)]
+                return proof
+            round_i += 1
+        coeffs, z = Ld.tolist(0, n), zd.tolist(0, n)
+    finally:
+        zd.free()
+        Ld.free()
+    return _protocol_4_prover_ints(g_hat, k, Q, coeffs, z, gf, proof, round_i)
+
+
+def _protocol_4_verifier_fast(g_hat, k, Q, coeffs, gf, proof, round_i):
+    q = k.order
+    if not _use_device_scalars(g_hat, q) or len(coeffs) != len(g_hat):
+        return _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i)
+    return _protocol_4_verifier_dev(g_hat, k, Q, g_hat.dev.ctx.upload_scalars(coeffs, q), gf, proof, round_i)
+
+
+def _protocol_4_verifier_dev(g_hat, k, Q, Ld, gf, proof, round_i):
+    """Verifier rounds with L_tilde resident on the device; takes ownership of Ld."""
+    group = type(k)
+    q = k.order
+    signed = bool(gf.is_signed)
+    try:
+        n = len(g_hat)
+        while n > DEVICE_SCALAR_MIN:
+            half = n // 2
+            A = proof["A" + str(round_i)]
+            B = proof["B" + str(round_i)]
+            c = _fold_challenge(A, B, g_hat, k, Q, _DevForm(Ld, n, signed), q)
+            g_hat = _fold_generators(g_hat, c)
+            Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+            Ld.fold(half, c, _lib.FOLD_FORM)
+            n = half
+            if n <= 2:
+                return _final_check(g_hat, k, Q, Ld.tolist(0, n), gf, proof)
+            round_i += 1
+        coeffs = Ld.tolist(0, n)
+    finally:
+        Ld.free()
+    return _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i)
 
 
 def _to_linear(L, y, n, gf):
@@ -187,8 +298,10 @@ class _FormText:
         return f"{_field_text([c.value for c in self.form.coeffs], self.q, self.signed)}, {str(self.form.constant)}"
 
 
-def _first_challenges(t, A, generators, P, L, y, order, gf=None):
-    if FAST_INT_PATH and gf is not None and gf.order == order and _all_in_field(L.coeffs, gf):
+def _first_challenges(t, A, generators, P, L, y, order, gf=None, L_text=None):
+    if L_text is not None:
+        L = L_text
+    elif FAST_INT_PATH and gf is not None and gf.order == order and _all_in_field(L.coeffs, gf):
         L = _FormText(L, order, bool(gf.is_signed))
     input_list = [t, A.normalize(), generators, P.normalize(), L, y]
     if logger_cp_hin.isEnabledFor(logging.DEBUG):
@@ -210,6 +323,43 @@ def _g_hat(g, h, group):
     return out
 
 
+def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
+    """protocol_5_prover with every length-n vector on the device: r_ext = r + [rho], x_ext = x + [gamma] and
+    L_ext = L.coeffs + [0] are uploaded once; t = <L, r>, A = g_hat^{r_ext}, z_hat = r_ext + c0 x_ext (its last entry
+    is phi = rho + c0 gamma) and L_tilde = c1 L_ext are device operations.  Same values, same transcript."""
+    k = generators["k"]
+    group = type(k)
+    order = gf.order
+    n = len(x)
+    ctx = g_hat.dev.ctx
+    proof = {}
+    zd = ctx.upload_scalars(r + [rho], order)
+    xd = ctx.upload_scalars([v.value for v in x] + [pivot._int(gamma)], order)
+    Ld = ctx.upload_scalars([cf.value for cf in L.coeffs] + [0], order)
+    try:
+        t = gf(ctx.scalars_dot(Ld, 0, zd, 0, n)) + L.constant
+        logger_cp.debug("Calculate A.")
+        ctx.msm_dev(g_hat.dev, zd, slot=0, poff=g_hat.off, soff=0, n=n + 1)  # h**rho * prod g_i**r_i
+        A = group._make(ctx.result(0))
+        proof["t"] = t
+        proof["A"] = A
+        c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf,
+                                   L_text=_DevForm(Ld, n, bool(gf.is_signed), L.constant))
+        zd.axpy(c0, xd, _lib.AXPY_ADD_SCALED)
+        logger_cp.debug("Calculate Q.")
+        Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
+        l_z = ctx.scalars_dot(Ld, 0, zd, 0, n)
+        Ld.axpy(c1, None, _lib.AXPY_SCALE)
+        assert l_z * c1 % order == ctx.scalars_dot(Ld, 0, zd, 0, n + 1)  # L(z) * c1 == L_tilde(z_hat)
+    except BaseException:
+        zd.free()
+        Ld.free()
+        raise
+    finally:
+        xd.free()
+    return _protocol_4_prover_dev(g_hat, k, Q, Ld, zd, gf, proof, 0)
+
+
 def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     """Compressed Sigma-protocol Pi_c, prover (reference :89-145)."""
     g, h, k = generators["g"], generators["h"], generators["k"]
@@ -220,10 +370,15 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     assert bin(n + 1).count("1") == 1, \
         "This implementation requires n+1 to be power of 2 (else, use padding with zeros)."
     order = gf.order
-    r = [prng.randrange(order) for _ in range(n)]
+    r = pivot.random_residues(prng, order, n)
     rho = prng.randrange(order)
     logger_cp.debug("Calculate t.")
     fast = FAST_INT_PATH and _all_in_field(L.coeffs, gf) and _all_in_field(x, gf) and L.constant == 0
+    if fast and len(L.coeffs) == n:
+        g_hat = _g_hat(g, h, group)
+        if _use_device_scalars(g_hat, order):
+            return _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho)
+        del g_hat
     t = gf(_dot([cf.value for cf in L.coeffs], r, order)) + L.constant if fast else L(r)
     logger_cp.debug("Calculate A.")
     A = pivot.vector_commitment(r, rho, g, h)
@@ -244,7 +399,7 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
         lc = [cf.value for cf in L.coeffs]
         coeffs = [v * c1 % order for v in lc] + [0]
         assert _dot(lc, zi[:-1], order) * c1 % order == _dot(coeffs, zi, order)
-        return _protocol_4_prover_ints(g_hat, k, Q, coeffs, zi, gf, proof, 0)
+        return _protocol_4_prover_fast(g_hat, k, Q, coeffs, zi, gf, proof, 0)
     L_tilde = pivot.LinearForm(L.coeffs + [0]) * c1
     assert L(z) * c1 == L_tilde(z_hat)
     return protocol_4_prover(g_hat, k, Q, L_tilde, z_hat, gf, proof)
@@ -257,7 +412,7 @@ def protocol_4_verifier(g_hat, k, Q, L_tilde, gf, proof, round_i=0):
     order = k.order
     if (FAST_INT_PATH and isinstance(L_tilde, pivot.LinearForm) and gf.order == order
             and _all_in_field(L_tilde.coeffs, gf)):
-        return _protocol_4_verifier_ints(g_hat, k, Q, [c.value for c in L_tilde.coeffs], gf, proof, round_i)
+        return _protocol_4_verifier_fast(g_hat, k, Q, [c.value for c in L_tilde.coeffs], gf, proof, round_i)
     while True:
         half = len(g_hat) // 2
         logger_cp.debug("Load from proof: A_i, B_i.")
@@ -284,11 +439,23 @@ def protocol_5_verifier(generators, P, L, y, proof, gf):
     L, y = _to_linear(L, y, len(g), gf)
     logger_cp.debug("Load from proof: t, A.")
     t, A = proof["t"], proof["A"]
-    c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf)
     g_hat = _g_hat(g, h, group)
+    if (FAST_INT_PATH and _all_in_field(L.coeffs, gf) and len(L.coeffs) + 1 == len(g_hat)
+            and _use_device_scalars(g_hat, order)):
+        Ld = g_hat.dev.ctx.upload_scalars([cf.value for cf in L.coeffs] + [0], order)
+        try:
+            c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf,
+                                       L_text=_DevForm(Ld, len(L.coeffs), bool(gf.is_signed), L.constant))
+            Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
+            Ld.axpy(c1, None, _lib.AXPY_SCALE)
+        except BaseException:
+            Ld.free()
+            raise
+        return _protocol_4_verifier_dev(g_hat, k, Q, Ld, gf, proof, 0)
+    c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf)
     Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
     if FAST_INT_PATH and _all_in_field(L.coeffs, gf):
         coeffs = [cf.value * c1 % order for cf in L.coeffs] + [0]
-        return _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, 0)
+        return _protocol_4_verifier_fast(g_hat, k, Q, coeffs, gf, proof, 0)
     L_tilde = pivot.LinearForm(L.coeffs + [0]) * c1
     return protocol_4_verifier(g_hat, k, Q, L_tilde, gf, proof)

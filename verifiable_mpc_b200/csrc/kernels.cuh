@@ -746,8 +746,9 @@ struct KTextCompact {
     const uint32_t *lens;
     const uint64_t *offsets;  // exclusive prefix of lens
     uint8_t *out;
+    uint32_t slot;  // bytes per slot
     VMSM_HD void operator()(uint32_t tid) const {
-        const uint8_t *s = slots + (size_t)tid * VMSM_TEXT_SLOT;
+        const uint8_t *s = slots + (size_t)tid * slot;
         uint8_t *d = out + offsets[tid];
         uint32_t len = lens[tid];
         for (uint32_t i = 0; i < len; i++) d[i] = s[i];

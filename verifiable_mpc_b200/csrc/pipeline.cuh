@@ -4,6 +4,7 @@
 #include <stddef.h>
 #include "kernels.cuh"
 #include "kernels_w.cuh"
+#include "sc25519.cuh"
 
 namespace vmsm {
 

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <set>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/vmsm.h"
@@ -274,6 +275,15 @@ struct Ctx {
     size_t astage_cap[2] = {0, 0};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     bool astage_used[2] = {false, false};
+    // freed point / scalar vectors are kept for reuse: cudaFree synchronises the whole device and was measured at up to
+    // 0.18 s per call inside a proof (a prover frees its private copy of g_hat at the end of every proof)
+    std::multimap<size_t, void *> pool;
+    std::unordered_map<void *, size_t> pool_size;
+    size_t pool_bytes = 0;
+    // device-resident scalar vectors (vmsm_scalars_fold / _dot): written on the main stream, read by the copy stream
+    cudaEvent_t ev_sc_written = nullptr;
+    bool sc_dirty = false;
+    uint32_t *dot_scratch = nullptr;  // 4096 + 64 + 1 partial sums
     uint32_t async_seq = 0;
     cudaEvent_t ev_slot[64] = {nullptr};
     uint32_t cur_slot = 0;
@@ -497,6 +507,60 @@ int32_t ensure_stage(Ctx *c, size_t n_scalars) {
     c->stage_cap = n_scalars;
     return VMSM_OK;
 }
+// ---- cached device allocations for point / scalar vectors (context of the calling entry point)
+static thread_local Ctx *tl_ctx = nullptr;
+constexpr size_t kPoolCapBytes = 16ull << 30;
+
+static size_t pool_round(size_t bytes) {
+    if (bytes < 512) bytes = 512;
+    if (bytes <= (1u << 20)) {
+        size_t p = 512;
+        while (p < bytes) p <<= 1;
+        return p;
+    }
+    return (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+}
+
+template <class T>
+static cudaError_t pool_alloc(T **p, size_t bytes) {
+    Ctx *c = tl_ctx;
+    bytes = pool_round(bytes);
+    auto it = c->pool.lower_bound(bytes);
+    if (it != c->pool.end() && it->first <= bytes + bytes / 4) {
+        *p = (T *)it->second;
+        c->pool_bytes -= it->first;
+        c->pool.erase(it);
+        return cudaSuccess;
+    }
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess && !c->pool.empty()) {  // out of memory with blocks parked in the pool: give them back, retry
+        for (auto &kv : c->pool) cudaFree(kv.second), c->pool_size.erase(kv.second);
+        c->pool.clear();
+        c->pool_bytes = 0;
+        cudaGetLastError();
+        e = cudaMalloc(&q, bytes);
+    }
+    if (e != cudaSuccess) return e;
+    c->pool_size[q] = bytes;
+    *p = (T *)q;
+    return cudaSuccess;
+}
+
+// the caller has already made sure no stream still uses the block
+static void pool_free(void *p) {
+    if (!p) return;
+    Ctx *c = tl_ctx;
+    auto it = c->pool_size.find(p);
+    if (it == c->pool_size.end() || c->pool_bytes + it->second > kPoolCapBytes) {
+        if (it != c->pool_size.end()) c->pool_size.erase(it);
+        cudaFree(p);
+        return;
+    }
+    c->pool.insert({it->second, p});
+    c->pool_bytes += it->second;
+}
+
 int32_t ensure_tmp(Ctx *c, size_t n_pts) {
     if (n_pts <= c->tmp_cap) return VMSM_OK;
     if (c->tmp_ext) cudaFree(c->tmp_ext);
@@ -535,10 +599,10 @@ int32_t w_new_pointset(int32_t curve, uint64_t n, PointSet *ps) {
     ps->aff = nullptr;
     ps->niels = nullptr;
     ps->w_wire = ps->w_base = nullptr;
-    CU(cudaMalloc(&ps->w_wire, (n ? n : 1) * sizeof(waff<F>)));
-    cudaError_t e = cudaMalloc(&ps->w_base, (n ? n : 1) * sizeof(waff<F>));
+    CU(pool_alloc(&ps->w_wire, (n ? n : 1) * sizeof(waff<F>)));
+    cudaError_t e = pool_alloc(&ps->w_base, (n ? n : 1) * sizeof(waff<F>));
     if (e != cudaSuccess) {
-        cudaFree(ps->w_wire);
+        pool_free(ps->w_wire);
         return fail(VMSM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
     }
     return VMSM_OK;
@@ -557,7 +621,7 @@ int32_t w_upload(Ctx *c, int32_t curve, const uint8_t *wire, uint64_t n, PointSe
     be.note(cudaStreamSynchronize(c->stream));
     uint32_t ew = *reinterpret_cast<uint32_t *>(c->pin);
     if (be.err != cudaSuccess || ew) {
-        cudaFree(ps->w_wire), cudaFree(ps->w_base);
+        pool_free(ps->w_wire), pool_free(ps->w_base);
         if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "upload: %s", cudaGetErrorString(be.err));
         return fail(VMSM_ERR_POINT, "invalid point in upload (%s%s)", (ew & 1) ? "non-canonical coordinate " : "",
                     (ew & 2) ? "not on curve" : "");
@@ -592,7 +656,7 @@ int32_t w_fixed_base(Ctx *c, int32_t curve, const uint8_t *scalars, uint64_t see
     }
     if (!rc) rc = ensure_tmp(c, (n * sizeof(wjac<F>) + sizeof(ge_ext) - 1) / sizeof(ge_ext));
     if (rc) {
-        cudaFree(ps->w_wire), cudaFree(ps->w_base);
+        pool_free(ps->w_wire), pool_free(ps->w_base);
         return rc;
     }
     CudaBE be(c);
@@ -602,7 +666,7 @@ int32_t w_fixed_base(Ctx *c, int32_t curve, const uint8_t *scalars, uint64_t see
     be.launch(kn, (uint32_t)n);
     be.note(cudaStreamSynchronize(c->stream));
     if (be.err != cudaSuccess) {
-        cudaFree(ps->w_wire), cudaFree(ps->w_base);
+        pool_free(ps->w_wire), pool_free(ps->w_base);
         return fail(VMSM_ERR_CUDA, "fixed_base: %s", cudaGetErrorString(be.err));
     }
     return VMSM_OK;
@@ -647,6 +711,7 @@ int32_t fetch_slot(Ctx *c, uint32_t slot, uint8_t *out) {
 #define GET_CTX(h)                                                        \
     Ctx *c = get_ctx(h);                                                  \
     if (!c) return fail(VMSM_ERR_INVALID, "invalid context handle");      \
+    tl_ctx = c;                                                           \
     CU(cudaSetDevice(c->device))
 
 // ------------------------------------------------------------------------------------------------ C ABI
@@ -701,6 +766,8 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     }
     CU(cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
     for (int w = 0; w < kTailWays; w++) CU(cudaEventCreateWithFlags(&c->ev_tail[w], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_sc_written, cudaEventDisableTiming));
+    CU(cudaMalloc(&c->dot_scratch, (4096 + 64 + 1) * 32));
     CU(cudaMalloc(&c->order_bins, ORDER_BINS * 4));
     CU(cudaMalloc(&c->err_word, 16));
     CU(cudaMalloc(&c->fb_table, 512 * sizeof(ge_niels)));
@@ -747,6 +814,8 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (uint32_t k = 0; k < kSlots; k++) cudaEventDestroy(c->ev_slot[k]);
     cudaFreeHost(c->res_aff_host);
     cudaFreeHost(c->res_status_host);
+    cudaEventDestroy(c->ev_sc_written);
+    cudaFree(c->dot_scratch);
     cudaFree(c->txt_slots), cudaFree(c->txt_text), cudaFree(c->txt_lens), cudaFree(c->txt_offsets), cudaFree(c->txt_sums);
     if (c->txt_host) cudaFreeHost(c->txt_host);
     cudaFree(c->res_w_dev), cudaFreeHost(c->res_w_host), cudaFree(c->fbw_table[0]), cudaFree(c->fbw_table[1]);
@@ -759,6 +828,7 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (auto &kv : c->points)
         cudaFree(kv.second.aff), cudaFree(kv.second.niels), cudaFree(kv.second.w_wire), cudaFree(kv.second.w_base);
     for (auto &kv : c->scalars) cudaFree(kv.second.data);
+    for (auto &kv : c->pool) cudaFree(kv.second);
     CudaBE be(c);
     ws_release(be, c->ws);
     cudaFree(c->order_bins), cudaFree(c->err_word), cudaFree(c->fb_table), cudaFree(c->res_ext), cudaFree(c->res_aff);
@@ -874,10 +944,10 @@ static int32_t new_pointset(Ctx *c, int32_t curve, uint64_t n, PointSet *ps) {
     ps->aff = nullptr;
     ps->niels = nullptr;
     ps->w_wire = ps->w_base = nullptr;
-    CU(cudaMalloc(&ps->aff, (n ? n : 1) * sizeof(ge_aff)));
-    cudaError_t e = cudaMalloc(&ps->niels, (n ? n : 1) * sizeof(ge_niels));
+    CU(pool_alloc(&ps->aff, (n ? n : 1) * sizeof(ge_aff)));
+    cudaError_t e = pool_alloc(&ps->niels, (n ? n : 1) * sizeof(ge_niels));
     if (e != cudaSuccess) {
-        cudaFree(ps->aff);
+        pool_free(ps->aff);
         return fail(VMSM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
     }
     return VMSM_OK;
@@ -910,7 +980,7 @@ int32_t vmsm_points_upload(uint64_t ctx, int32_t curve, const uint8_t *affine, u
         be.note(cudaStreamSynchronize(c->stream));
         uint32_t ew = *reinterpret_cast<uint32_t *>(c->pin);
         if (be.err != cudaSuccess || ew) {
-            cudaFree(ps.aff), cudaFree(ps.niels);
+            pool_free(ps.aff), pool_free(ps.niels);
             if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "upload: %s", cudaGetErrorString(be.err));
             return fail(VMSM_ERR_POINT, "invalid point in upload (%s%s)", (ew & 1) ? "non-canonical coordinate " : "",
                         (ew & 2) ? "not on curve" : "");
@@ -952,7 +1022,7 @@ int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scala
         }
         if (!rc) rc = ensure_tmp(c, n);
         if (rc) {
-            cudaFree(ps.aff), cudaFree(ps.niels);
+            pool_free(ps.aff), pool_free(ps.niels);
             return rc;
         }
         CudaBE be(c);
@@ -962,7 +1032,7 @@ int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scala
         be.launch(kn, (uint32_t)n);
         be.note(cudaStreamSynchronize(c->stream));
         if (be.err != cudaSuccess) {
-            cudaFree(ps.aff), cudaFree(ps.niels);
+            pool_free(ps.aff), pool_free(ps.niels);
             return fail(VMSM_ERR_CUDA, "fixed_base: %s", cudaGetErrorString(be.err));
         }
     }
@@ -988,6 +1058,45 @@ int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t 
     return VMSM_OK;
 }
 
+// grow-only scratch of the text pipeline, sized for n slots of VMSM_TEXT_SLOT bytes
+static int32_t text_ensure(Ctx *c, uint64_t n) {
+    if (n <= c->txt_cap) return VMSM_OK;
+    cudaFree(c->txt_slots), cudaFree(c->txt_text), cudaFree(c->txt_lens), cudaFree(c->txt_offsets), cudaFree(c->txt_sums);
+    if (c->txt_host) cudaFreeHost(c->txt_host);
+    c->txt_slots = c->txt_text = c->txt_host = nullptr;
+    c->txt_lens = nullptr;
+    c->txt_offsets = c->txt_sums = nullptr;
+    c->txt_cap = 0;
+    size_t cap = n + n / 4 + 1024;
+    CU(cudaMalloc(&c->txt_slots, cap * VMSM_TEXT_SLOT));
+    CU(cudaMalloc(&c->txt_text, cap * VMSM_TEXT_SLOT));
+    CU(cudaMalloc(&c->txt_lens, cap * 4));
+    CU(cudaMalloc(&c->txt_offsets, cap * 8));
+    CU(cudaMalloc(&c->txt_sums, (cap / 1024 + 2) * 8));
+    CU(cudaHostAlloc(&c->txt_host, cap * VMSM_TEXT_SLOT, cudaHostAllocDefault));
+    c->txt_cap = cap;
+    return VMSM_OK;
+}
+
+// slots + lens (already launched on the main stream) -> ", "-joined text in c->txt_host; *len = its length
+static int32_t text_finish(Ctx *c, CudaBE &be, uint64_t n, uint32_t slot_bytes, uint64_t *len) {
+    uint32_t nblk = (uint32_t)((n + 1023) / 1024);
+    vmsm_lens_block_sums<<<nblk, 1024, 0, c->stream>>>(c->txt_lens, (uint32_t)n, c->txt_sums);
+    vmsm_lens_scan_sums<<<1, 32, 0, c->stream>>>(c->txt_sums, nblk);
+    vmsm_lens_offsets<<<nblk, 1024, 0, c->stream>>>(c->txt_lens, (uint32_t)n, c->txt_sums, c->txt_offsets);
+    c->launches += 3;
+    KTextCompact kc = {c->txt_slots, c->txt_lens, c->txt_offsets, c->txt_text, slot_bytes};
+    be.launch(kc, (uint32_t)n);
+    be.note(cudaMemcpyAsync(c->pin, c->txt_sums + nblk, 8, cudaMemcpyDeviceToHost, c->stream));
+    be.note(cudaStreamSynchronize(c->stream));
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "text: %s", cudaGetErrorString(be.err));
+    uint64_t total = *reinterpret_cast<uint64_t *>(c->pin);
+    CU(cudaMemcpyAsync(c->txt_host, c->txt_text, total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *len = total;
+    return VMSM_OK;
+}
+
 static int32_t points_text_impl(Ctx *c, uint64_t pts, uint64_t off, uint64_t n, uint64_t *len) {
     auto it = c->points.find(pts);
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
@@ -996,40 +1105,12 @@ static int32_t points_text_impl(Ctx *c, uint64_t pts, uint64_t off, uint64_t n, 
     *len = 0;
     if (!n) return VMSM_OK;
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "too many points");
-    if (n > c->txt_cap) {
-        cudaFree(c->txt_slots), cudaFree(c->txt_text), cudaFree(c->txt_lens), cudaFree(c->txt_offsets), cudaFree(c->txt_sums);
-        if (c->txt_host) cudaFreeHost(c->txt_host);
-        c->txt_slots = c->txt_text = c->txt_host = nullptr;
-        c->txt_lens = nullptr;
-        c->txt_offsets = c->txt_sums = nullptr;
-        c->txt_cap = 0;
-        size_t cap = n + n / 4 + 1024;
-        CU(cudaMalloc(&c->txt_slots, cap * VMSM_TEXT_SLOT));
-        CU(cudaMalloc(&c->txt_text, cap * VMSM_TEXT_SLOT));
-        CU(cudaMalloc(&c->txt_lens, cap * 4));
-        CU(cudaMalloc(&c->txt_offsets, cap * 8));
-        CU(cudaMalloc(&c->txt_sums, (cap / 1024 + 2) * 8));
-        CU(cudaHostAlloc(&c->txt_host, cap * VMSM_TEXT_SLOT, cudaHostAllocDefault));
-        c->txt_cap = cap;
-    }
-    uint32_t nblk = (uint32_t)((n + 1023) / 1024);
+    int32_t rc = text_ensure(c, n);
+    if (rc) return rc;
     CudaBE be(c);
     KPointText kt = {it->second.aff + off, c->txt_slots, c->txt_lens, (uint32_t)n};
     be.launch(kt, (uint32_t)n);
-    vmsm_lens_block_sums<<<nblk, 1024, 0, c->stream>>>(c->txt_lens, (uint32_t)n, c->txt_sums);
-    vmsm_lens_scan_sums<<<1, 32, 0, c->stream>>>(c->txt_sums, nblk);
-    vmsm_lens_offsets<<<nblk, 1024, 0, c->stream>>>(c->txt_lens, (uint32_t)n, c->txt_sums, c->txt_offsets);
-    c->launches += 3;
-    KTextCompact kc = {c->txt_slots, c->txt_lens, c->txt_offsets, c->txt_text};
-    be.launch(kc, (uint32_t)n);
-    be.note(cudaMemcpyAsync(c->pin, c->txt_sums + nblk, 8, cudaMemcpyDeviceToHost, c->stream));
-    be.note(cudaStreamSynchronize(c->stream));
-    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "points_text: %s", cudaGetErrorString(be.err));
-    uint64_t total = *reinterpret_cast<uint64_t *>(c->pin);
-    CU(cudaMemcpyAsync(c->txt_host, c->txt_text, total, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    *len = total;
-    return VMSM_OK;
+    return text_finish(c, be, n, VMSM_TEXT_SLOT, len);
 }
 
 int32_t vmsm_points_text(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *out, uint64_t cap,
@@ -1066,7 +1147,7 @@ int32_t vmsm_points_free(uint64_t ctx, uint64_t pts) {
     auto it = c->points.find(pts);
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(it->second.aff), cudaFree(it->second.niels), cudaFree(it->second.w_wire), cudaFree(it->second.w_base);
+    pool_free(it->second.aff), pool_free(it->second.niels), pool_free(it->second.w_wire), pool_free(it->second.w_base);
     c->points.erase(it);
     return VMSM_OK;
 }
@@ -1076,12 +1157,12 @@ int32_t vmsm_scalars_upload(uint64_t ctx, const uint8_t *le32, uint64_t n, uint6
     GET_CTX(ctx);
     if (!sc || (n && !le32)) return fail(VMSM_ERR_INVALID, "null argument");
     ScalarSet ss{n, nullptr};
-    CU(cudaMalloc(&ss.data, (n ? n : 1) * 32));
+    CU(pool_alloc(&ss.data, (n ? n : 1) * 32));
     if (n) {
         cudaError_t e = cudaMemcpyAsync(ss.data, le32, n * 32, cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) {
-            cudaFree(ss.data);
+            pool_free(ss.data);
             return fail(VMSM_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
         }
     }
@@ -1097,7 +1178,7 @@ int32_t vmsm_scalars_synth(uint64_t ctx, int32_t curve, uint64_t seed, uint64_t 
     if (curve < VMSM_CURVE_ED25519 || curve > VMSM_CURVE_BN256_G2) return fail(VMSM_ERR_UNSUPPORTED, "unknown curve %d", curve);
     if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
     ScalarSet ss{n, nullptr};
-    CU(cudaMalloc(&ss.data, (n ? n : 1) * 32));
+    CU(pool_alloc(&ss.data, (n ? n : 1) * 32));
     CudaBE be(c);
     if (curve == VMSM_CURVE_ED25519) {
         KSynthScalars k = {ss.data, seed};
@@ -1108,7 +1189,7 @@ int32_t vmsm_scalars_synth(uint64_t ctx, int32_t curve, uint64_t seed, uint64_t 
     }
     be.note(cudaStreamSynchronize(c->stream));
     if (be.err != cudaSuccess) {
-        cudaFree(ss.data);
+        pool_free(ss.data);
         return fail(VMSM_ERR_CUDA, "synth: %s", cudaGetErrorString(be.err));
     }
     uint64_t id = c->next_id++;
@@ -1133,7 +1214,9 @@ int32_t vmsm_scalars_free(uint64_t ctx, uint64_t sc) {
     auto it = c->scalars.find(sc);
     if (it == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(it->second.data);
+    CU(cudaStreamSynchronize(c->copy));  // msm_dev_ext stages device scalars on the copy stream
+    CU(cudaStreamSynchronize(c->sort));
+    pool_free(it->second.data);
     c->scalars.erase(it);
     return VMSM_OK;
 }
@@ -1214,7 +1297,7 @@ int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_
             if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t *)ps.w_base + a_n * wb, (const uint8_t *)pb.w_base + b_off * wb, b_n * wb, cudaMemcpyDeviceToDevice, c->stream);
         }
         if (e != cudaSuccess) {
-            cudaFree(ps.w_wire), cudaFree(ps.w_base);
+            pool_free(ps.w_wire), pool_free(ps.w_base);
             return fail(VMSM_ERR_CUDA, "concat: %s", cudaGetErrorString(e));
         }
         uint64_t idw = c->next_id++;
@@ -1234,7 +1317,7 @@ int32_t vmsm_points_concat(uint64_t ctx, uint64_t a, uint64_t a_off, uint64_t a_
         be.launch(k, (uint32_t)b_n);
     }
     if (be.err != cudaSuccess) {
-        cudaFree(ps.aff), cudaFree(ps.niels);
+        pool_free(ps.aff), pool_free(ps.niels);
         return fail(VMSM_ERR_CUDA, "concat: %s", cudaGetErrorString(be.err));
     }
     uint64_t id = c->next_id++;
@@ -1361,8 +1444,165 @@ int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint
     if (poff > it->second.n || n > it->second.n - poff) return fail(VMSM_ERR_INVALID, "Not enough generators.");
     if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
     if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    // the sort stream reads the scalars in place: order it after a fold kernel that may have just written them
+    if (c->sc_dirty && c->async_sort && !c->scalars_ready) c->scalars_ready = c->ev_sc_written;
     if (it->second.curve != VMSM_CURVE_ED25519) return w_run_msm_any(c, it->second, poff, is->second.data + soff * 8, n, slot);
     return run_msm(c, it->second.niels + poff, is->second.data + soff * 8, n, slot);
+}
+
+// ---- device-resident scalar vectors modulo the Ed25519 group order (witness / linear-form halving)
+static bool scalar_below_l(const uint8_t *le32, scl *out) {
+    memcpy(out->v, le32, 32);
+    return scl_gt(scl_l(), *out);
+}
+
+// a kernel on the main stream is about to overwrite scalars that earlier MSMs may still be reading on the copy /
+// sort streams: order it after them
+static void scalars_write_barrier(Ctx *c) {
+    for (int k = 0; k < 2; k++) {
+        if (c->astage_used[k]) cudaStreamWaitEvent(c->stream, c->ev_copied[k], 0);
+        cudaStreamWaitEvent(c->stream, c->ev_sorted[k], 0);  // no-op until first recorded
+    }
+}
+
+int32_t vmsm_scalars_fold(uint64_t ctx, uint64_t sc, uint64_t half, const uint8_t *c_le32, int32_t mode) {
+    GET_CTX(ctx);
+    auto it = c->scalars.find(sc);
+    if (it == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (!c_le32) return fail(VMSM_ERR_INVALID, "null argument");
+    if (mode != VMSM_FOLD_WITNESS && mode != VMSM_FOLD_FORM) return fail(VMSM_ERR_INVALID, "unknown fold mode %d", mode);
+    if (half == 0 || 2 * half > it->second.n) return fail(VMSM_ERR_INVALID, "fold: need 2*half <= length");
+    scl cs;
+    if (!scalar_below_l(c_le32, &cs)) return fail(VMSM_ERR_INVALID, "challenge is not reduced modulo the group order");
+    scalars_write_barrier(c);
+    CudaBE be(c);
+    KScalarAxpy k = {it->second.data, it->second.data + 8ull * half, scl_to_mont(cs), mode};
+    be.launch(k, (uint32_t)half);
+    be.note(cudaEventRecord(c->ev_sc_written, c->stream));
+    c->sc_dirty = true;
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "scalars_fold: %s", cudaGetErrorString(be.err));
+    return VMSM_OK;
+}
+
+int32_t vmsm_scalars_axpy(uint64_t ctx, uint64_t dst, uint64_t doff, uint64_t src, uint64_t soff, uint64_t n,
+                          const uint8_t *c_le32, int32_t mode) {
+    GET_CTX(ctx);
+    auto id = c->scalars.find(dst);
+    if (id == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (!c_le32) return fail(VMSM_ERR_INVALID, "null argument");
+    if (mode < VMSM_AXPY_ADD_SCALED || mode > VMSM_AXPY_SCALE) return fail(VMSM_ERR_INVALID, "unknown axpy mode %d", mode);
+    if (doff > id->second.n || n > id->second.n - doff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+    const uint32_t *sp = nullptr;
+    if (mode != VMSM_AXPY_SCALE) {
+        auto is = c->scalars.find(src);
+        if (is == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+        if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+        if (src == dst && soff < doff + n && doff < soff + n && soff != doff + n && doff != soff + n)
+            return fail(VMSM_ERR_INVALID, "axpy: source and destination ranges overlap");
+        sp = is->second.data + soff * 8;
+    }
+    scl cs;
+    if (!scalar_below_l(c_le32, &cs)) return fail(VMSM_ERR_INVALID, "constant is not reduced modulo the group order");
+    if (!n) return VMSM_OK;
+    if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
+    scalars_write_barrier(c);
+    CudaBE be(c);
+    KScalarAxpy k = {id->second.data + doff * 8, sp, scl_to_mont(cs), mode};
+    be.launch(k, (uint32_t)n);
+    be.note(cudaEventRecord(c->ev_sc_written, c->stream));
+    c->sc_dirty = true;
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "scalars_axpy: %s", cudaGetErrorString(be.err));
+    return VMSM_OK;
+}
+
+int32_t vmsm_scalars_dot(uint64_t ctx, uint64_t a, uint64_t aoff, uint64_t b, uint64_t boff, uint64_t n,
+                         uint8_t *out_le32) {
+    GET_CTX(ctx);
+    auto ia = c->scalars.find(a), ib = c->scalars.find(b);
+    if (ia == c->scalars.end() || ib == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (!out_le32) return fail(VMSM_ERR_INVALID, "null argument");
+    if (aoff > ia->second.n || n > ia->second.n - aoff || boff > ib->second.n || n > ib->second.n - boff)
+        return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+    if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
+    memset(out_le32, 0, 32);
+    if (!n) return VMSM_OK;
+    CudaBE be(c);
+    uint32_t T = n < 4096 ? (uint32_t)n : 4096u, T2 = T < 64 ? T : 64u;
+    uint32_t *p1 = c->dot_scratch, *p2 = p1 + 4096 * 8, *p3 = p2 + 64 * 8;
+    KScalarDotPartial k1 = {ia->second.data + aoff * 8, ib->second.data + boff * 8, (uint32_t)n, T, p1};
+    be.launch(k1, T);
+    KScalarSum k2 = {p1, T, T2, p2, 0};
+    be.launch(k2, T2);
+    KScalarSum k3 = {p2, T2, 1, p3, 1};
+    be.launch(k3, 1);
+    be.note(cudaMemcpyAsync(c->pin, p3, 32, cudaMemcpyDeviceToHost, c->stream));
+    be.note(cudaStreamSynchronize(c->stream));
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "scalars_dot: %s", cudaGetErrorString(be.err));
+    memcpy(out_le32, c->pin, 32);
+    return VMSM_OK;
+}
+
+int32_t vmsm_scalars_text_ptr(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t n, int32_t is_signed,
+                              const uint8_t **text, uint64_t *len) {
+    GET_CTX(ctx);
+    if (!len || !text) return fail(VMSM_ERR_INVALID, "null argument");
+    auto it = c->scalars.find(sc);
+    if (it == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+    *len = 0;
+    *text = nullptr;
+    if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
+    int32_t rc = text_ensure(c, n ? n : 1);
+    if (rc) return rc;
+    *text = c->txt_host;
+    if (!n) return VMSM_OK;
+    CudaBE be(c);
+    KScalarText kt = {it->second.data + off * 8, c->txt_slots, c->txt_lens, (uint32_t)n, is_signed};
+    be.launch(kt, (uint32_t)n);
+    return text_finish(c, be, n, VMSM_SCALAR_TEXT_SLOT, len);
+}
+
+int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
+                         uint64_t extra_pts, uint64_t extra_off, uint64_t n_extra, const uint8_t *extra_scalars_le32,
+                         uint32_t slot) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    auto ie = c->points.find(extra_pts);
+    if (it == c->points.end() || ie == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    auto is = c->scalars.find(sc);
+    if (is == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (it->second.curve != VMSM_CURVE_ED25519 || ie->second.curve != VMSM_CURVE_ED25519)
+        return fail(VMSM_ERR_UNSUPPORTED, "msm_dev_ext: Ed25519 only");
+    if (poff > it->second.n || n > it->second.n - poff) return fail(VMSM_ERR_INVALID, "Not enough generators.");
+    if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+    if (extra_off > ie->second.n || n_extra > ie->second.n - extra_off)
+        return fail(VMSM_ERR_INVALID, "extra range out of bounds");
+    if (n_extra && !extra_scalars_le32) return fail(VMSM_ERR_INVALID, "null argument");
+    if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    const uint64_t tot = n + n_extra;
+    const int b = (int)(c->async_seq++ & 1);
+    if ((tot ? tot : 1) > c->astage_cap[b]) {
+        if (c->astage[b]) cudaFree(c->astage[b]);  // synchronises the device
+        c->astage[b] = nullptr;
+        c->astage_cap[b] = 0;
+        CU(cudaMalloc(&c->astage[b], (tot ? tot : 1) * 32));
+        c->astage_cap[b] = tot ? tot : 1;
+        c->astage_used[b] = false;
+    }
+    // staging on the copy stream: after the kernel that last wrote the device scalars, and after the MSM that last
+    // read this staging buffer
+    if (c->sc_dirty) CU(cudaStreamWaitEvent(c->copy, c->ev_sc_written, 0));
+    if (c->astage_used[b]) CU(cudaStreamWaitEvent(c->copy, c->ev_consumed[b], 0));
+    if (n) CU(cudaMemcpyAsync(c->astage[b], is->second.data + soff * 8, n * 32, cudaMemcpyDeviceToDevice, c->copy));
+    if (n_extra) CU(cudaMemcpyAsync(c->astage[b] + n * 8, extra_scalars_le32, n_extra * 32, cudaMemcpyHostToDevice, c->copy));
+    CU(cudaEventRecord(c->ev_copied[b], c->copy));
+    if (c->async_sort) c->scalars_ready = c->ev_copied[b];
+    else CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    int32_t rc = run_msm(c, it->second.niels + poff, c->astage[b], tot, slot, ie->second.niels + extra_off, (uint32_t)n_extra);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_consumed[b], c->async_sort ? c->sort : c->stream));
+    c->astage_used[b] = true;
+    return VMSM_OK;
 }
 
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine) {

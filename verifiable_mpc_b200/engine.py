@@ -36,6 +36,12 @@ def _buf(data):
 def pack_scalars(xs, order=ED_L):
     """Iterable of Python ints (negative / unreduced allowed, as the reference passes them: pivot.py:119-128,
     compressed_pivot.py:66,134) -> n*32 bytes little-endian, reduced below the group order."""
+    if type(xs) is list and xs:
+        try:  # a list of residues already in [0, order): no per-element int() and %
+            if min(xs) >= 0 and max(xs) < order:
+                return b"".join([x.to_bytes(32, "little") for x in xs])
+        except (TypeError, AttributeError):
+            pass
     return b"".join((int(x) % order).to_bytes(32, "little") for x in xs)
 
 
@@ -146,6 +152,28 @@ class DeviceScalars:
         out = ctypes.create_string_buffer(max(1, 32 * n))
         check(self.ctx.lib.vmsm_scalars_download(self.ctx.h, self.handle, off, n, out))
         return out.raw[:32 * n]
+
+    def tolist(self, off=0, n=None):
+        raw = self.download(off, n)
+        return [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
+
+    def fold(self, half, c, mode):
+        """In place on [0, 2*half): FOLD_WITNESS v[j] += c*v[half+j]; FOLD_FORM v[j] = c*v[j] + v[half+j] (mod l)."""
+        check(self.ctx.lib.vmsm_scalars_fold(self.ctx.h, self.handle, half, (int(c) % ED_L).to_bytes(32, "little"), mode))
+
+    def axpy(self, c, src=None, mode=_lib.AXPY_ADD_SCALED, off=0, soff=0, n=None):
+        """Element-wise on the device: self += c*src (ADD_SCALED), self = c*self + src (SCALE_ADD), self *= c (SCALE)."""
+        n = self.n - off if n is None else n
+        check(self.ctx.lib.vmsm_scalars_axpy(self.ctx.h, self.handle, off, src.handle if src is not None else 0, soff, n,
+                                             (int(c) % ED_L).to_bytes(32, "little"), mode))
+
+    def text_bytes(self, off=0, n=None, signed=True):
+        """b"v0, v1, ..." -- the residues as MPyC prints them (signed representatives unless ``signed`` is False)."""
+        n = self.n - off if n is None else n
+        ptr, ln = ctypes.c_void_p(), ctypes.c_uint64()
+        check(self.ctx.lib.vmsm_scalars_text_ptr(self.ctx.h, self.handle, off, n, 1 if signed else 0,
+                                                 ctypes.byref(ptr), ctypes.byref(ln)))
+        return ctypes.string_at(ptr, ln.value) if ln.value else b""
 
     def free(self):
         if self.handle and self.ctx.h:
@@ -306,6 +334,19 @@ class Context:
         if n is None:
             n = min(points.n - poff, scalars.n - soff)
         check(self.lib.vmsm_msm_dev(self.h, points.handle, poff, n, scalars.handle, soff, slot))
+
+    def msm_dev_ext(self, points, poff, n, scalars, soff, extra, extra_off, extra_scalars, slot=0):
+        """Asynchronous ``sum_{i<n} s[soff+i] P[poff+i] + sum_j e_j E[extra_off+j]`` with s resident on the device and
+        the few extra scalars e_j (ints) from the host; fetch with ``result(slot)``."""
+        raw = pack_scalars(extra_scalars, ORDERS[points.curve])
+        check(self.lib.vmsm_msm_dev_ext(self.h, points.handle, poff, n, scalars.handle, soff, extra.handle, extra_off,
+                                        len(extra_scalars), raw, slot))
+
+    def scalars_dot(self, a, aoff, b, boff, n):
+        """sum_i a[aoff+i] * b[boff+i] modulo the Ed25519 group order, computed on the device."""
+        out = ctypes.create_string_buffer(32)
+        check(self.lib.vmsm_scalars_dot(self.h, a.handle, aoff, b.handle, boff, n, out))
+        return int.from_bytes(out.raw, "little")
 
     # -- multi-GPU shards (one context per GPU; rank 0 owns the mailbox)
     def mailbox_create(self, world):
