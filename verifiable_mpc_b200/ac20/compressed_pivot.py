@@ -4,8 +4,9 @@ Same signatures, proof-dict keys ("t", "A", "A{i}", "B{i}", "z_prime") and Fiat-
 (compressed_pivot.py:29-239), so a proof made here verifies with the reference's verifier running on
 group types that print canonical affine coordinates, and vice versa.  Per folding round the device does: two
 (half+1)-term MSMs (A_i, B_i), one 3-term combination (Q'), and ONE fold kernel over the generator vector kept in
-HBM (``g'_j = c * g_j + g_{half+j}``, compressed_pivot.py:64 / :178).  The host keeps the scalar-field algebra and
-hashing, and downloads the folded generators once per round because their decimal text is part of the next hash.
+HBM (``g'_j = c * g_j + g_{half+j}``, compressed_pivot.py:64 / :178), and -- above DEVICE_SCALAR_MIN entries -- the
+halving of the witness and of the linear form, their cross terms and their decimal text (csrc/sc25519.cuh).  The host
+draws the randomness, hashes the transcript bytes the device formats, and finishes the last few rounds on integers.
 """
 import logging
 from random import SystemRandom
