@@ -299,6 +299,13 @@ def run_gpu(args, rank, world, dist):
     acc_lp = n * W_c * MADD
     achieved = acc_lp / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
     msm_frac = value / world * lp_per_point(n) / (peak_tlps * 1e12)
+    # HBM-side view of the counting sort (SURVEY 8d asks for GB/s next to the integer roofline): per scalar it reads the
+    # 32-byte scalar twice (histogram, scatter) and writes W 4-byte index entries, plus three passes over the counters
+    sp = {k: v / max(serial_calls, 1) for k, v in serial_phases.items()}
+    sort_ms = sp["digits"] + sp["scan"] + sp["scatter"] + sp["order"]
+    sort_bytes = n * (32 + 32 + 4 * W_c) + 3 * 4 * W_c * (1 << (c_auto - 1))
+    hbm_peak, hbm_src = _hbm_peak_gbs()
+    sort_gbs = sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -325,7 +332,12 @@ def run_gpu(args, rank, world, dist):
                                     "consecutive MSMs, so its per-phase times are not additive",
                      "serial_ms_per_step": serial_ms, "kernel_share_of_serial_step": acc_ms / serial_ms,
                      "phase_ms": {k: v / max(serial_calls, 1) for k, v in serial_phases.items()},
-                     "overlapped_phase_ms": {k: v / max(calls, 1) for k, v in phases.items()}},
+                     "overlapped_phase_ms": {k: v / max(calls, 1) for k, v in phases.items()},
+                     "hbm_phases": {"counting_sort": {
+                         "algorithmic_bytes": sort_bytes, "ms": sort_ms, "GB_s": sort_gbs, "hbm_peak_GB_s": hbm_peak,
+                         "frac": (sort_gbs / hbm_peak) if sort_gbs else None, "peak_source": hbm_src,
+                         "note": "bound by L2 atomics (16 fetch-and-adds per scalar), not by HBM bandwidth; in the "
+                                 "headline loop it runs as a thin slice under the accumulate kernel"}}},
     }
     if args.cpu_baseline:
         cores = os.cpu_count() or 1
@@ -334,6 +346,15 @@ def run_gpu(args, rank, world, dist):
                                 "sample": f"{cores} processes x {args.cpu_points} terms ({dt:.1f} s) of the same MSM with the "
                                           "pure-Python restatement of pivot.vector_commitment (oracle/ed25519.py)"}
     print(json.dumps(line), flush=True)
+
+
+def _hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the recipe's figure."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s; MEASURED_PEAKS.json absent)"
 
 
 def _ncu_traffic_bytes():

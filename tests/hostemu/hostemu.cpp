@@ -194,9 +194,15 @@ void hostemu_scalars_dot(const uint32_t *a, const uint32_t *b, uint32_t n, uint8
     HostBE be;
     memset(out_le32, 0, 32);
     if (!n) return;
-    uint32_t T = n < 4096 ? n : 4096u, T2 = T < 64 ? T : 64u;
-    std::vector<uint32_t> scratch((4096 + 64 + 1) * 8 + 16);
-    uint32_t *p1 = (uint32_t *)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15), *p2 = p1 + 4096 * 8, *p3 = p2 + 64 * 8;
+    const uint32_t kT1 = 1u << 16, kT2 = 256;  // stage sizes as vmsm.cu (dot_stage_sizes)
+    uint64_t t = n / 16;
+    if (t < 64) t = n < 64 ? n : 64;
+    if (t > kT1) t = kT1;
+    uint32_t t2 = 1;
+    while ((uint64_t)t2 * t2 < t && t2 < kT2) t2 <<= 1;
+    uint32_t T = (uint32_t)t, T2 = t2 < t ? t2 : (uint32_t)t;
+    std::vector<uint32_t> scratch((kT1 + kT2 + 1) * 8 + 16);
+    uint32_t *p1 = (uint32_t *)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15), *p2 = p1 + kT1 * 8, *p3 = p2 + kT2 * 8;
     KScalarDotPartial k1 = {a, b, n, T, p1};
     be.launch(k1, T);
     KScalarSum k2 = {p1, T, T2, p2, 0};

@@ -229,7 +229,7 @@ def test_scalars_axpy(hostemu):
 
 def test_scalars_dot(hostemu):
     L = E.L
-    for n in (0, 1, 2, 63, 64, 65, 300, 5000):
+    for n in (0, 1, 2, 63, 64, 65, 255, 256, 257, 300, 5000, 66000):
         a_vals, b_vals = _edge_scalars(max(n, 11), n)[:n], list(reversed(_edge_scalars(max(n, 11), n + 1)))[:n]
         a, b = _aligned_scalars(a_vals or [0]), _aligned_scalars(b_vals or [0])
         out = ctypes.create_string_buffer(32)

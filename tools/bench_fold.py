@@ -9,6 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from verifiable_mpc_b200 import Context  # noqa: E402
 
+import time  # noqa: E402
+
+from verifiable_mpc_b200 import _lib  # noqa: E402
+
 LP_FOLD = 253 * (4 * 72 + 4 * 44) + 85 * 504 + 504  # doublings + NAF additions + final addition (limb products)
 
 
@@ -37,6 +41,47 @@ def main():
         print(json.dumps(rec), flush=True)
         if out:
             out.write(json.dumps(rec) + "\n")
+    # the field-vector halvings that accompany every generator fold (z' = z_L + c z_R, L' = c L_L + L_R), the cross-term
+    # dot product and the coefficient text: HBM-side figures.  Algorithmic bytes per output element:
+    # fold 64 B read + 32 B written, dot 64 B read, text 32 B read + ~78 B written.
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm = 6650.0
+    for lg in args.log2half:
+        half = 1 << lg
+        sc = ctx.synth_scalars(0x5EED, 2 * half)
+        other = ctx.synth_scalars(0x5EEF, 2 * half)
+        res = {}
+        for name, fn, nbytes in (
+                ("scalars_fold", lambda: sc.fold(half, c, _lib.FOLD_WITNESS), 96 * half),
+                ("scalars_dot", lambda: ctx.scalars_dot(sc, 0, other, half, half), 64 * half)):
+            fn()
+            ctx.sync()
+            best = None
+            for rep in range(5):
+                ctx.sync()
+                if name == "scalars_dot":  # synchronous call (returns the value): wall clock around it
+                    t0 = time.perf_counter()
+                    fn()
+                    ms = (time.perf_counter() - t0) * 1e3
+                else:
+                    ctx.timer_start()
+                    fn()
+                    ms = ctx.timer_stop()
+                best = ms if best is None else min(best, ms)
+            res[name] = {"ms": best, "GB_s": nbytes / (best * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (best * 1e-3) / 1e9 / hbm}
+        sc.text_bytes(0, half)  # first call of a new maximum size allocates the (pinned) text buffers
+        t0 = time.perf_counter()
+        txt = sc.text_bytes(0, half)
+        ms = (time.perf_counter() - t0) * 1e3
+        res["scalars_text"] = {"ms_incl_d2h": ms, "bytes_out": len(txt)}
+        rec = {"bench": "scalar_vectors", "half": half, "hbm_peak_GB_s": hbm, **res}
+        print(json.dumps(rec), flush=True)
+        if out:
+            out.write(json.dumps(rec) + "\n")
+        sc.free()
+        other.free()
     ctx.close()
 
 

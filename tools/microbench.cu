@@ -110,6 +110,49 @@ __global__ void k_imad_wide_cc(uint32_t *out, uint32_t a, uint32_t b, long long 
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// 4b) FP64 FMA chains: would the double-precision pipe be a second multiplier for 26-bit limb products?
+__global__ void k_dfma(double *out, uint32_t a, uint32_t b, long long *cycles) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 1.0 + 1e-9 * (double)(a + threadIdx.x + i);
+    double y = 1.0 + 1e-12 * (double)b;
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = fma(acc[i], y, acc[(i + 1) & 7]);
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// 4c) both at once: 4 IMAD.WIDE chains and 4 DFMA chains per thread (do the two pipes run concurrently?)
+__global__ void k_dfma_imad(double *out, uint32_t a, uint32_t b, long long *cycles) {
+    double acc[4];
+    uint64_t iac[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[i] = 1.0 + 1e-9 * (double)(a + threadIdx.x + i), iac[i] = a + threadIdx.x + i;
+    double y = 1.0 + 1e-12 * (double)b;
+    uint32_t yi = b | 1u;
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            acc[i] = fma(acc[i], y, acc[(i + 1) & 3]);
+            iac[i] = (uint64_t)((uint32_t)iac[i] + (uint32_t)(iac[i] >> 32)) * yi;
+        }
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) s += acc[i] + (double)(iac[i] & 0xffff);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 // 5) dependent field multiplications, 2 independent chains per thread
 __global__ void k_fe_mul(fe *out, const fe *in, int iters, long long *cycles) {
     fe a = in[0], b = in[1];
@@ -230,6 +273,8 @@ int main() {
         run("imad_lo_u32", blocks, threads, 8.0 * ITERS, 0.5, cyc, [&] { k_imad_lo<<<blocks, threads>>>((uint32_t *)out, 12345, 6789, cyc); });
         run("iadd64_pairs", blocks, threads, 8.0 * ITERS, 0.0, cyc, [&] { k_iadd64<<<blocks, threads>>>((uint64_t *)out, 12345, 6789, cyc); });
         run("imad_wide_carry_chain", blocks, threads, 8.0 * ITERS, 1.0, cyc, [&] { k_imad_wide_cc<<<blocks, threads>>>((uint32_t *)out, 12345, 6789, cyc); });
+        run("dfma_fp64", blocks, threads, 8.0 * ITERS, 0.0, cyc, [&] { k_dfma<<<blocks, threads>>>((double *)out, 12345, 6789, cyc); });
+        run("dfma_plus_imad_wide_4and4", blocks, threads, 8.0 * ITERS, 0.5, cyc, [&] { k_dfma_imad<<<blocks, threads>>>((double *)out, 12345, 6789, cyc); });
     }
     const int it = 512;
     for (int threads = 128; threads <= 512; threads *= 2) {

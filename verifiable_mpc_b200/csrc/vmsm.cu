@@ -253,6 +253,16 @@ struct EventSet {
 };
 
 constexpr uint32_t kSlots = 64;
+constexpr uint32_t kDotT1 = 1u << 16, kDotT2 = 256;  // most partial-sum threads of vmsm_scalars_dot
+inline void dot_stage_sizes(uint64_t n, uint32_t *T, uint32_t *T2) {
+    uint64_t t = n / 16;
+    if (t < 64) t = n < 64 ? n : 64;
+    if (t > kDotT1) t = kDotT1;
+    uint32_t t2 = 1;
+    while ((uint64_t)t2 * t2 < t && t2 < kDotT2) t2 <<= 1;
+    *T = (uint32_t)t;
+    *T2 = t2 < t ? t2 : (uint32_t)t;
+}
 
 struct Ctx {
     int device = 0;
@@ -283,7 +293,7 @@ struct Ctx {
     // device-resident scalar vectors (vmsm_scalars_fold / _dot): written on the main stream, read by the copy stream
     cudaEvent_t ev_sc_written = nullptr;
     bool sc_dirty = false;
-    uint32_t *dot_scratch = nullptr;  // 4096 + 64 + 1 partial sums
+    uint32_t *dot_scratch = nullptr;  // kDotT1 + kDotT2 + 1 partial sums
     uint32_t async_seq = 0;
     cudaEvent_t ev_slot[64] = {nullptr};
     uint32_t cur_slot = 0;
@@ -767,7 +777,7 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     CU(cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
     for (int w = 0; w < kTailWays; w++) CU(cudaEventCreateWithFlags(&c->ev_tail[w], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_sc_written, cudaEventDisableTiming));
-    CU(cudaMalloc(&c->dot_scratch, (4096 + 64 + 1) * 32));
+    CU(cudaMalloc(&c->dot_scratch, (kDotT1 + kDotT2 + 1) * 32));
     CU(cudaMalloc(&c->order_bins, ORDER_BINS * 4));
     CU(cudaMalloc(&c->err_word, 16));
     CU(cudaMalloc(&c->fb_table, 512 * sizeof(ge_niels)));
@@ -1527,8 +1537,11 @@ int32_t vmsm_scalars_dot(uint64_t ctx, uint64_t a, uint64_t aoff, uint64_t b, ui
     memset(out_le32, 0, 32);
     if (!n) return VMSM_OK;
     CudaBE be(c);
-    uint32_t T = n < 4096 ? (uint32_t)n : 4096u, T2 = T < 64 ? T : 64u;
-    uint32_t *p1 = c->dot_scratch, *p2 = p1 + 4096 * 8, *p3 = p2 + 64 * 8;
+    // three latency-bound stages (T threads multiply and pre-sum n/T terms, T2 threads sum T/T2 of those, one thread
+    // finishes): keep the three serial chains of comparable length
+    uint32_t T, T2;
+    dot_stage_sizes(n, &T, &T2);
+    uint32_t *p1 = c->dot_scratch, *p2 = p1 + kDotT1 * 8, *p3 = p2 + kDotT2 * 8;
     KScalarDotPartial k1 = {ia->second.data + aoff * 8, ib->second.data + boff * 8, (uint32_t)n, T, p1};
     be.launch(k1, T);
     KScalarSum k2 = {p1, T, T2, p2, 0};
