@@ -68,6 +68,7 @@ struct KAccumulateW {
     LongBucket *longs;
     const waff<F> *extra;
     uint32_t n_main;
+    uint32_t seg_min;  // shortest overflow segment (a multiple of 32)
     VMSM_HD const waff<F> *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
     VMSM_HD void operator()(uint32_t tid) const {
         uint32_t b = order ? order[tid] : tid;
@@ -75,7 +76,7 @@ struct KAccumulateW {
         if (cnt > cap) {
             uint32_t over = cnt - cap;
             uint32_t seg = (over + 63) / 64;
-            if (seg < 256) seg = 256;
+            if (seg < seg_min) seg = seg_min;
             seg = (seg + 31) & ~31u;
             uint32_t ntask = (over + seg - 1) / seg;
             uint32_t base = VMSM_ATOMIC_ADD(&ctl->ntasks, ntask);

@@ -23,7 +23,7 @@ enum Phase {
 // number of MSM tails (upper tree levels + Horner + inversion) that may be in flight at once, each on its own side
 // stream with its own node buffers: the tails are latency-bound single-warp work, so several of them overlap freely
 // (the eight MSMs of a Pinocchio proof, back-to-back commitments)
-enum { kTailWays = 4 };
+enum { kTailWays = 8, kTailWaysEd = 4, kTailWaysBN = 8 };
 
 struct MsmOptions {
     uint32_t window_bits = 0;  // 0 = auto
@@ -53,6 +53,7 @@ struct Workspace {
     LongBucket *longs = nullptr;
     void *partials = nullptr;
     size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0, cap_tasks = 0;  // element counts
+    int ways = 0;  // tail ways that have buckets / node buffers (grows to the largest count requested)
     size_t elem_bytes = 0;  // size of one accumulator point the point buffers were allocated for
 };
 
@@ -93,9 +94,14 @@ inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits) {
 }
 
 template <class BE>
-int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_bytes = sizeof(ge_ext)) {
+int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_bytes = sizeof(ge_ext),
+              uint32_t cap_floor = 64, uint32_t seg_floor = 256, int ways = kTailWaysEd) {
     size_t nb = (size_t)g.W * g.NB, ni = (size_t)g.W * g.n, nn = (size_t)g.W * ((g.NB + R - 1) / R);
     if (nn < g.W) nn = g.W;
+    if (ways > ws.ways) {  // more MSM tails in flight than before: (re)allocate the per-way buffers
+        ws.cap_buckets = ws.cap_nodes = 0;
+        ws.ways = ways;
+    }
     if (elem_bytes > ws.elem_bytes) {  // a wider accumulator type than before: regrow the point buffers
         ws.cap_buckets = ws.cap_nodes = ws.cap_tasks = 0;
         ws.elem_bytes = elem_bytes;
@@ -103,7 +109,7 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
     elem_bytes = ws.elem_bytes;
     if (nb > ws.cap_buckets) {
         ws.cap_buckets = 0;
-        for (int k = 0; k < kTailWays; k++) {
+        for (int k = 0; k < ws.ways; k++) {
             be.free(ws.buckets_[k]);
             ws.buckets_[k] = be.alloc(nb * elem_bytes);
             if (!ws.buckets_[k]) return -1;
@@ -127,7 +133,9 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
         }
         ws.cap_idx = ni;
     }
-    size_t nt = ni / 32 + 64;  // >= sum over long buckets of their task counts (cap >= 64, segments >= 256)
+    // >= sum over long buckets of their task counts: at most ni / cap_floor long buckets, each with one partly filled
+    // segment, plus ni / seg_floor full segments
+    size_t nt = ni / cap_floor + ni / seg_floor + 64;
     if (nt > ws.cap_tasks) {
         be.free(ws.ctl), be.free(ws.tasks), be.free(ws.longs), be.free(ws.partials);
         ws.cap_tasks = 0;
@@ -139,7 +147,7 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
         ws.cap_tasks = nt;
     }
     if (nn > ws.cap_nodes) {
-        for (int par = 0; par < kTailWays; par++)
+        for (int par = 0; par < ws.ways; par++)
             for (int k = 0; k < 2; k++) {
                 be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
                 ws.nodeS[par][k] = be.alloc(nn * elem_bytes);
@@ -203,7 +211,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.phase_mark(PH_HANDOFF);
     // this MSM's buckets, bucket tree and Horner chain live in the buffers of tail way `tw`: wait until the MSM that
     // used them kTailWays issues ago has left them
-    const int tw = (int)(seq % kTailWays);
+    const int tw = (int)(seq % kTailWaysEd);
     be.head_wait_tail(tw);
     void *const buckets = ws.buckets_[tw];
     {
@@ -275,9 +283,16 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     // window safe, so skewed top windows are allowed here (these MSMs are small and latency matters more)
     uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits, false, 11.0, 16.0 * 0.6);
     if (c > 16) c = 16;
+    // 2^9 .. 2^16 terms are latency-bound on this curve (few, expensive additions per thread): c = 13 gives 20 x 4096
+    // short bucket chains and a bucket tree of exactly four full radix-8 levels; measured fastest or tied at 2^10, 2^12,
+    // 2^14 and 2^16 on G1 and G2 (profiles/r01/bn256_msm_v5_windows.jsonl), 35 % faster than the work-minimising c = 11
+    if (!opt.window_bits && n >= 512 && n <= (1u << 16)) c = 13;
     MsmGeom g = make_geom(n, c, scalar_bits);
     uint32_t R = 1u << opt.reduce_log2r;
-    if (ws_ensure(be, ws, g, R, sizeof(wjac<F>))) return -1;
+    // long-bucket granularity for this curve: additions are 3-9x dearer than on Ed25519 and the MSMs are small, so a
+    // bucket's own thread takes at most max(16, ...) entries and overflow segments may be as short as one warp pass
+    const uint32_t kCapFloor = 16, kSegFloor = 32;
+    if (ws_ensure(be, ws, g, R, sizeof(wjac<F>), kCapFloor, kSegFloor, kTailWaysBN)) return -1;
     uint32_t nbuckets = g.W * g.NB;
     const int par = (int)(seq & 1);
     uint32_t *counts = ws.counts_[par], *offsets = ws.offsets_[par], *cursor = ws.cursor_[par], *idx = ws.idx_[par];
@@ -301,15 +316,16 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     be.phase_mark(PH_ORDER);
     be.sort_end(par);
     be.phase_mark(PH_HANDOFF);
-    const int tw = (int)(seq % kTailWays);
+    // eight tails in flight: a lone tail on this curve takes 1.5 ms (G1) to 3.6 ms (G2), the head 0.3-1 ms
+    const int tw = (int)(seq % kTailWaysBN);
     be.head_wait_tail(tw);
     void *const buckets = ws.buckets_[tw];
     {
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
-        if (cap < 64) cap = 64;
+        if (cap < kCapFloor) cap = kCapFloor;
         be.zero(ws.ctl, sizeof(OverflowCtl));
         KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl,
-                              ws.tasks, ws.longs, extra, n_main};
+                              ws.tasks, ws.longs, extra, n_main, kSegFloor};
         be.launch(k5, nbuckets);
         if (n > cap) {
             const uint32_t ow = be.overflow_warps();
