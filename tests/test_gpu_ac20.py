@@ -113,3 +113,13 @@ def test_compressed_pivot_2p16(gpu_group):
     bad = dict(proof)
     bad["A7"] = proof["B7"]
     assert cp.protocol_5_verifier(generators, P, L, y, bad, gf) is False
+
+
+def test_mpc_share_local_commitments(gpu_group):
+    """Three parties, each with its own context (its own GPU when the box has several): local MSM over its Shamir
+    shares scaled by its Lagrange coefficient on the device; the product of the three factors is the commitment."""
+    from mpc_cases import check_share_local_commitments
+
+    group, gf = gpu_group
+    check_share_local_commitments(group, gf, n=33)
+    check_share_local_commitments(group, gf, n=1023, m=5, t=2, seed=9)

@@ -78,3 +78,19 @@ def test_rank_slice_properties():
             sl = [rank_slice(n, world, r) for r in range(world)]
             assert sl[0][0] == 0 and sum(c for _, c in sl) == n
             assert max(c for _, c in sl) - min(c for _, c in sl) <= 1
+
+
+def test_three_party_share_local_commitment_over_gloo():
+    """tools/demo_mpc_parties.py with three processes (the CPU oracle standing in for each party's GPU): Shamir shares,
+    per-party local MSM, exchange of the factors, product == commitment with the known discrete logs."""
+    port = 29900 + os.getpid() % 90
+    procs = []
+    for rank in range(3):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="3", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   PYTHONPATH=ROOT)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "demo_mpc_parties.py"), "--log2n", "4",
+                                       "--fake"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0, err[-2000:]
+    assert '"matches_known_dlog": true' in outs[0][0]

@@ -4,6 +4,7 @@ This is the layer the reference-facing modules (``verifiable_mpc_b200.ac20.pivot
 touches group elements goes through libvmsm.so on the GPU; Python only marshals integers <-> little-endian bytes.
 """
 import ctypes
+import itertools
 import os
 
 from . import _lib
@@ -33,13 +34,16 @@ def _buf(data):
     raise TypeError(f"unsupported buffer type {type(data)}")
 
 
+_REPEAT_32, _REPEAT_LITTLE = itertools.repeat(32), itertools.repeat("little")
+
+
 def pack_scalars(xs, order=ED_L):
     """Iterable of Python ints (negative / unreduced allowed, as the reference passes them: pivot.py:119-128,
     compressed_pivot.py:66,134) -> n*32 bytes little-endian, reduced below the group order."""
     if type(xs) is list and xs:
         try:  # a list of residues already in [0, order): no per-element int() and %
             if min(xs) >= 0 and max(xs) < order:
-                return b"".join([x.to_bytes(32, "little") for x in xs])
+                return b"".join(map(int.to_bytes, xs, _REPEAT_32, _REPEAT_LITTLE))
         except (TypeError, AttributeError):
             pass
     return b"".join((int(x) % order).to_bytes(32, "little") for x in xs)
