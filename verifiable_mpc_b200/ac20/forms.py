@@ -6,18 +6,29 @@ forms); re-exported by ``verifiable_mpc_b200.ac20.pivot`` under the reference's 
 """
 from ..finfields import FiniteFieldElement as _OwnFieldElement
 
-try:  # real MPyC field / secure types are accepted when installed (the reference's own types)
-    from mpyc.finfields import FiniteFieldElement as _MpycFieldElement
-    from mpyc.sectypes import SecureObject
-    FIELD_TYPES = (_OwnFieldElement, _MpycFieldElement)
-except Exception:  # MPyC absent: only this package's fields and plain ints
-    class SecureObject:  # placeholder so isinstance checks read like the reference's
-        pass
-    FIELD_TYPES = (_OwnFieldElement,)
+import sys
+
+
+class SecureObject:
+    """Placeholder exported under the reference's name; real MPyC secure objects are recognised by `secure_types()`."""
+
+
+def field_types():
+    """Field-element classes accepted as scalars: this package's, and MPyC's when `mpyc.finfields` is loaded -- looked
+    up at call time, so it does not matter whether MPyC (or a look-alike) was imported before or after this package."""
+    mod = sys.modules.get("mpyc.finfields")
+    t = getattr(mod, "FiniteFieldElement", None) if mod is not None else None
+    return (_OwnFieldElement, t) if isinstance(t, type) else (_OwnFieldElement,)
+
+
+def secure_types():
+    mod = sys.modules.get("mpyc.sectypes")
+    t = getattr(mod, "SecureObject", None) if mod is not None else None
+    return (SecureObject, t) if isinstance(t, type) else (SecureObject,)
 
 
 def _is_scalar(v):
-    return isinstance(v, (int, SecureObject) + FIELD_TYPES)
+    return isinstance(v, (int,) + secure_types() + field_types())
 
 
 class AffineForm:
@@ -48,7 +59,7 @@ class AffineForm:
         return self + (-1) * other
 
     def __mul__(self, other):
-        if not isinstance(other, (int,) + FIELD_TYPES):
+        if not isinstance(other, (int,) + field_types()):
             raise NotImplementedError(f"Multiplication of form not defined for type: {type(other)}")
         return type(self)([c * other for c in self.coeffs], self.constant * other)
 

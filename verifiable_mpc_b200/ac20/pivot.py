@@ -17,7 +17,7 @@ from .. import fingroups
 from ..engine import pack_scalars
 from ..fingroups import DevicePointList, EllipticCurvePoint as EllipticCurveElement
 
-from .forms import FIELD_TYPES as _FIELD_TYPES
+from .forms import field_types as _field_types, secure_types as _secure_types
 from .forms import AffineForm, LinearForm, SecureObject  # noqa: F401  (the reference exports them from pivot)
 
 prng = SystemRandom()
@@ -48,9 +48,9 @@ def random_residues(rng, order, n):
 
 def _int(value):
     """Field elements -> ints (signed representative, as MPyC's int()); ints and secure objects pass through."""
-    if isinstance(value, (int, SecureObject)):
+    if isinstance(value, (int,) + _secure_types()):
         return value
-    if isinstance(value, _FIELD_TYPES):
+    if isinstance(value, _field_types()):
         return int(value)
     raise NotImplementedError
 
