@@ -196,6 +196,14 @@ def run_gpu(args, rank, world, dist):
         else:
             ctx.msm_async(bases[k], host_scal[k].ptr, 0, n, slot=slot)
 
+    def recycle_slots(s):
+        """Result slots / mailbox entries are reused every 48 steps.  A single GPU needs nothing (an unread result is
+        simply overwritten); with a mailbox a rank may not push step s into an entry the owner has not yet gathered
+        for step s - 48, so once per 48 steps the owner drains its pipeline and every rank waits for it."""
+        if dist is not None and s and s % 48 == 0:
+            ctx.sync()
+            dist.barrier()
+
     def combine(slot):
         """Owner: the sum over all ranks (gathered on the device); other ranks: their own partial."""
         return ctx.result(slot)
@@ -212,8 +220,8 @@ def run_gpu(args, rank, world, dist):
     barrier()
     tm0 = time.perf_counter()
     ctx.timer_start()
-    assert args.steps <= 48, "result slots / mailbox entries are reused every 48 steps"
     for s in range(args.steps):
+        recycle_slots(s)
         issue("dev", s % NSETS, s % 48)
     ms = ctx.timer_stop()
     barrier()
@@ -233,7 +241,7 @@ def run_gpu(args, rank, world, dist):
         issue("dev", w % NSETS, 0)
     ctx.sync()
     ctx.phase_times()
-    serial_steps = min(args.steps, 10)
+    serial_steps = max(1, min(args.steps, 10))
     ctx.timer_start()
     for s in range(serial_steps):
         issue("dev", s % NSETS, s % 48)
@@ -268,6 +276,7 @@ def run_gpu(args, rank, world, dist):
         last = None
         lag = E2E_DEPTH - 1
         for s in range(steps):
+            recycle_slots(s)
             issue("async", s % NSETS, s % 48)
             if s >= lag:
                 last = combine((s - lag) % 48)
@@ -400,7 +409,7 @@ def _choose_window(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--window", type=int, default=0)

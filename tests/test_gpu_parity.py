@@ -409,3 +409,27 @@ def test_back_to_back_msms_in_flight(ctx, logn):
             ctx.msm_dev(dev, scs[j % nsets], slot=j)
         for j in range(40):
             assert ctx.result(j) == want[j % nsets], (rep, j)
+
+
+@pytest.mark.parametrize("sort_blocks", [0, 1, 7, 148, 100000])
+def test_thin_counting_sort_grid(ctx, sort_blocks):
+    """VMSM_OPT_SORT_BLOCKS: the per-scalar sort kernels of an MSM issued while the previous one is still accumulating
+    run grid-stride with this many blocks; every setting must give the same results (2^14 terms = 64 full blocks)."""
+    from verifiable_mpc_b200 import _lib
+
+    n = 1 << 14
+    dev = ctx.fixed_base(seed=0x5EEE, n=n)
+    dl = [prng.scalar(0x5EEE, i) for i in range(n)]
+    scs, want = [], []
+    for k in range(3):
+        sc = [prng.scalar(0x4000 + k, i) for i in range(n - k)]  # ragged lengths: the stride loop's tail
+        scs.append(ctx.upload_scalars(sc))
+        want.append(E.msm_known_dlog(sc, dl[:n - k]))
+    ctx.set_option(_lib.OPT_SORT_BLOCKS, sort_blocks)
+    try:
+        for j in range(12):
+            ctx.msm_dev(dev, scs[j % 3], slot=j, n=n - j % 3)
+        for j in range(12):
+            assert ctx.result(j) == want[j % 3], j
+    finally:
+        ctx.set_option(_lib.OPT_SORT_BLOCKS, 148)
