@@ -56,6 +56,8 @@ extern "C" {
                                   shares the SMs with the accumulate kernel instead of displacing it (used only
                                   while the previous MSM is still accumulating); default = the SM count, 0 = always
                                   one thread per scalar */
+#define VMSM_OPT_FOLD_QUAD_MAX 12 /* generator folds of at most this many outputs use the 4-lanes-per-element kernel
+                                    (latency-bound rounds); 0 = never */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */
@@ -195,6 +197,12 @@ int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le
  * compressed_pivot.py:66; Q = A * P^c0 * k^(...), :140).  n <= 64. */
 int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const uint8_t *scalars_le32, uint64_t n,
                      uint8_t *out_affine);
+
+/* Asynchronous form (Ed25519): the result is fetched with vmsm_result_affine(slot), so Q' of round i is computed
+ * underneath the folds and the A/B commitments of round i+1 and only awaited by the next challenge hash.  An invalid
+ * input point surfaces as VMSM_ERR_POINT from that fetch. */
+int32_t vmsm_lincomb_async(uint64_t ctx, int32_t curve, const uint8_t *affine, const uint8_t *scalars_le32, uint64_t n,
+                           uint32_t slot);
 
 /* ---- pinned host memory for the end-to-end path (H2D of scalars straight from page-locked memory) -------- */
 int32_t vmsm_host_alloc(uint64_t bytes, void **ptr);

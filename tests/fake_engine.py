@@ -172,6 +172,12 @@ class FakeContext:
         pts = a.pts[a_off:a_off + a_n] + (b.pts[b_off:b_off + b_n] if b is not None else [])
         return FakePoints(self, pts)
 
+    def lincomb_async(self, pts, scalars, slot, curve=0):
+        assert curve == 0
+        if not hasattr(self, "_slots"):
+            self._slots = {}
+        self._slots[slot] = self.lincomb(pts, scalars)
+
     def lincomb(self, pts, scalars, curve=0):
         FakeContext.calls += 1
         if curve:

@@ -22,8 +22,12 @@ def gpu_group(ctx):
 
 
 @pytest.mark.parametrize("idx", [0, 1, 2])
-def test_twin_matches_reference_fixture(gpu_group, idx):
+def test_twin_matches_reference_fixture(gpu_group, idx, monkeypatch):
+    """Host-integer round loop (the device-resident scalar path is exercised by the next test)."""
+    from verifiable_mpc_b200.ac20 import compressed_pivot as cp
+
     group, gf = gpu_group
+    monkeypatch.setattr(cp, "DEVICE_SCALAR_PATH", False)
     check_case(load_cases()[idx], group, gf)
 
 
@@ -34,6 +38,7 @@ def test_twin_device_scalar_path_matches_reference_fixture(gpu_group, idx, monke
 
     group, gf = gpu_group
     monkeypatch.setattr(cp, "DEVICE_SCALAR_MIN", 2)
+    monkeypatch.setattr(cp, "DEVICE_SCALAR_MIN_PROVER", 2)
     check_case(load_cases()[idx], group, gf)
 
 

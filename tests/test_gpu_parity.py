@@ -356,6 +356,32 @@ def test_scalar_vectors_on_device(ctx, known_points):
         ctx.msm_dev_ext(g, 1, n, z, 0, k, 0, [1], slot=0)
 
 
+def test_lincomb_async(ctx, known_points):
+    """vmsm_lincomb_async: several small combinations in flight (more than the staging ring holds), results fetched
+    out of order; an invalid input point surfaces as VMSM_ERR_POINT when its slot is fetched."""
+    from verifiable_mpc_b200 import VmsmError
+
+    dlogs, pts = known_points
+    rng = random.Random(4)
+    jobs = []
+    for j in range(20):
+        m = 1 + j % 5
+        ps = [pts[rng.randrange(len(pts))] for _ in range(m)]
+        sc = [rng.randrange(E.L) for _ in range(m)]
+        ctx.lincomb_async(ps, sc, slot=j)
+        jobs.append((ps, sc))
+    for j in reversed(range(20)):
+        ps, sc = jobs[j]
+        assert ctx.result(j) == E.msm_naive(sc, ps), j
+    ctx.lincomb_async([], [], slot=3)
+    assert ctx.result(3) == E.IDENTITY
+    ctx.lincomb_async([pts[0], (5, 7)], [1, 1], slot=4)  # (5, 7) is not on the curve
+    with pytest.raises(VmsmError):
+        ctx.result(4)
+    ctx.lincomb_async([pts[0]], [2], slot=4)  # the slot is usable again
+    assert ctx.result(4) == E.scalar_mul(pts[0], 2)
+
+
 def test_abi_error_paths(ctx, known_points):
     """Status codes instead of crashes: bad handles, ranges, slots, options, mixed curves, Ed25519-only calls."""
     import ctypes

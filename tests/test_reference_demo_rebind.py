@@ -86,6 +86,7 @@ def test_reference_demo_with_rebound_pivot_gives_the_same_proof(device_scalar_mi
     for name in ("protocol_4_prover", "protocol_4_verifier", "protocol_5_prover", "protocol_5_verifier"):
         monkeypatch.setattr(rcp, name, getattr(gcp, name))
     monkeypatch.setattr(gcp, "DEVICE_SCALAR_MIN", device_scalar_min)
+    monkeypatch.setattr(gcp, "DEVICE_SCALAR_MIN_PROVER", device_scalar_min)
     calls = FakeContext.calls
     seed_all(42)
     monkeypatch.setattr(gcp, "prng", rcp.prng)

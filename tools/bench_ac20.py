@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2n", type=int, nargs="+", default=[10, 13, 16])
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--scalar-min", type=int, default=-1, help="experiment: compressed_pivot.DEVICE_SCALAR_MIN")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -29,6 +30,8 @@ def main():
     from verifiable_mpc_b200.ac20 import pivot
     from verifiable_mpc_b200.finfields import GF
 
+    if args.scalar_min >= 0:
+        cp.DEVICE_SCALAR_MIN = args.scalar_min
     group = fingroups.EllipticCurve("Ed25519", "projective")
     group.is_additive, group.is_multiplicative = False, True
     gf = GF(group.order)

@@ -20,8 +20,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2half", type=int, nargs="+", default=[4, 8, 10, 12, 14, 15, 16, 18])
     ap.add_argument("--out", default="")
+    ap.add_argument("--quad-max", type=int, default=-1, help="experiment: VMSM_OPT_FOLD_QUAD_MAX")
     args = ap.parse_args()
     ctx = Context(0)
+    if args.quad_max >= 0:
+        ctx.set_option(_lib.OPT_FOLD_QUAD_MAX, args.quad_max)
     peak = ctx.imad_peak()
     out = open(args.out, "a") if args.out else None
     c = 0x0EADBEEFCAFEBABE123456789ABCDEF0123456789ABCDEF0123456789ABCDEF % (2**252 + 27742317777372353535851937790883648493)

@@ -15,6 +15,7 @@ CURVE_ED25519, CURVE_BN256_G1, CURVE_BN256_G2 = 0, 1, 2
 OPT_WINDOW_BITS, OPT_PHASE_TIMING, OPT_SORT_BUCKETS, OPT_CHECK_POINTS, OPT_REDUCE_RADIX = 1, 2, 3, 4, 5
 OPT_QUAD_THRESHOLD, OPT_ASYNC_TAIL, OPT_CAP_FACTOR, OPT_SHARD_SEQ, OPT_ASYNC_SORT = 6, 7, 8, 9, 10
 OPT_SORT_BLOCKS = 11
+OPT_FOLD_QUAD_MAX = 12
 FOLD_WITNESS, FOLD_FORM = 0, 1
 AXPY_ADD_SCALED, AXPY_SCALE_ADD, AXPY_SCALE = 0, 1, 2
 PHASES = ("digits", "scan", "scatter", "order", "handoff", "accumulate", "reduce", "final")
@@ -72,6 +73,7 @@ SIGNATURES = {
     "vmsm_result_affine": [_u64, _u32, _p],
     "vmsm_result_extended": [_u64, _u32, _p],
     "vmsm_fold": [_u64, _u64, _u64, _p],
+    "vmsm_lincomb_async": [_u64, _i32, _p, _p, _u64, _u32],
     "vmsm_lincomb": [_u64, _i32, _p, _p, _u64, _p],
     "vmsm_host_alloc": [_u64, ctypes.POINTER(_p)],
     "vmsm_host_free": [_p],

@@ -73,6 +73,34 @@ def _private_device_list(g_hat, group):
     return own
 
 
+_Q_SLOT = 5  # result slot of the asynchronous Q' (the A_i / B_i commitments of the device loop use slots 0 and 1)
+
+
+class _PendingPoint:
+    """Q' = A * Q**c * B**(c**2) issued asynchronously: it is awaited by the next challenge hash (or the final
+    check), so it is computed underneath the generator / witness folds and the next round's commitments."""
+    __slots__ = ("group", "ctx")
+
+    def __init__(self, group, ctx):
+        self.group, self.ctx = group, ctx
+
+    def get(self):
+        return self.group._make(self.ctx.result(_Q_SLOT))
+
+
+def _q_prime(group, A, Q, B, c):
+    ctx = group._ctx()
+    if getattr(group, "curve_id", 0) == 0 and hasattr(ctx, "lincomb_async"):
+        order = group.order
+        ctx.lincomb_async([A.affine(), Q.affine(), B.affine()], [1, c % order, c * c % order], _Q_SLOT)
+        return _PendingPoint(group, ctx)
+    return group.lincomb([A, Q, B], [1, c, c ** 2])
+
+
+def _resolve(Q):
+    return Q.get() if type(Q) is _PendingPoint else Q
+
+
 def _fold_challenge(A, B, g_hat, k, Q, L_tilde, order):
     input_list = [A.normalize(), B.normalize(), g_hat, k, Q.normalize(), L_tilde]
     if logger_cp_hin.isEnabledFor(logging.DEBUG):
@@ -115,11 +143,12 @@ def protocol_4_prover(g_hat, k, Q, L_tilde, z_hat, gf, proof=None, round_i=0):
         B = pivot.vector_commitment(z_r, int(L_tilde(z_r + [0] * half)), g_hat[:half], k)
         proof["A" + str(round_i)] = A
         proof["B" + str(round_i)] = B
+        Q = _resolve(Q)
         c = _fold_challenge(A, B, g_hat, k, Q, L_tilde, order)
         logger_cp.debug("Calculate g_prime.")
         g_hat = _fold_generators(g_hat, c)
         logger_cp.debug("Calculate Q_prime.")
-        Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+        Q = _q_prime(group, A, Q, B, c)
         L_tilde = _fold_forms(L_tilde, c, half, gf)
         z_hat = [l + c * r for l, r in zip(z_l, z_r)]
         if len(z_hat) <= 2:
@@ -140,9 +169,10 @@ def _protocol_4_prover_ints(g_hat, k, Q, coeffs, z, gf, proof, round_i):
         B = pivot.vector_commitment(z_r, _dot(coeffs[:half], z_r, q), g_hat[:half], k)
         proof["A" + str(round_i)] = A
         proof["B" + str(round_i)] = B
+        Q = _resolve(Q)
         c = _fold_challenge(A, B, g_hat, k, Q, _IntForm(coeffs, q, bool(gf.is_signed)), q)
         g_hat = _fold_generators(g_hat, c)
-        Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+        Q = _q_prime(group, A, Q, B, c)
         coeffs = [(l * c + r) % q for l, r in zip(coeffs[:half], coeffs[half:])]
         z = [(l + c * r) % q for l, r in zip(z_l, z_r)]
         if len(z) <= 2:
@@ -158,9 +188,10 @@ def _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i):
         half = len(g_hat) // 2
         A = proof["A" + str(round_i)]
         B = proof["B" + str(round_i)]
+        Q = _resolve(Q)
         c = _fold_challenge(A, B, g_hat, k, Q, _IntForm(coeffs, q, bool(gf.is_signed)), q)
         g_hat = _fold_generators(g_hat, c)
-        Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+        Q = _q_prime(group, A, Q, B, c)
         coeffs = [(l * c + r) % q for l, r in zip(coeffs[:half], coeffs[half:])]
         if len(g_hat) <= 2:
             return _final_check(g_hat, k, Q, coeffs, gf, proof)
@@ -168,6 +199,7 @@ def _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i):
 
 
 def _final_check(g_hat, k, Q, coeffs, gf, proof):
+    Q = _resolve(Q)
     z_prime = proof["z_prime"]
     gamma = int(sum([gf(cf) * zp for cf, zp in zip(coeffs, z_prime)]) + 0)
     Q_check = pivot.vector_commitment(z_prime, gamma, g_hat, k)
@@ -180,7 +212,8 @@ def _final_check(g_hat, k, Q, coeffs, gf, proof):
 # for the next challenge is produced on the device like that of g_hat.  Per round the host only hashes.  Below the
 # threshold (a few rounds, a few hundred scalars in total) the vectors come back and the integer loop finishes.
 DEVICE_SCALAR_PATH = True
-DEVICE_SCALAR_MIN = 256
+DEVICE_SCALAR_MIN = 256          # verifier (no commitments per round: the integer loop is as fast below this)
+DEVICE_SCALAR_MIN_PROVER = 2     # prover: A_i and B_i are issued as an asynchronous pair only on the device path
 
 
 class _DevForm:
@@ -197,15 +230,17 @@ class _DevForm:
         return self.repr_bytes().decode("ascii")
 
 
-def _use_device_scalars(g_hat, q):
+def _use_device_scalars(g_hat, q, min_n=None):
     n = len(g_hat)
-    return (DEVICE_SCALAR_PATH and isinstance(g_hat, DevicePointList) and n > DEVICE_SCALAR_MIN and n & (n - 1) == 0
+    min_n = DEVICE_SCALAR_MIN if min_n is None else min_n
+    return (DEVICE_SCALAR_PATH and isinstance(g_hat, DevicePointList) and n > min_n and n & (n - 1) == 0
             and q == ED_L)
 
 
 def _protocol_4_prover_fast(g_hat, k, Q, coeffs, z, gf, proof, round_i):
     q = k.order
-    if not _use_device_scalars(g_hat, q) or len(z) != len(g_hat) or len(coeffs) != len(g_hat):
+    if (not _use_device_scalars(g_hat, q, DEVICE_SCALAR_MIN_PROVER) or len(z) != len(g_hat)
+            or len(coeffs) != len(g_hat)):
         return _protocol_4_prover_ints(g_hat, k, Q, coeffs, z, gf, proof, round_i)
     ctx = g_hat.dev.ctx
     return _protocol_4_prover_dev(g_hat, k, Q, ctx.upload_scalars(coeffs, q), ctx.upload_scalars(z, q), gf, proof, round_i)
@@ -218,9 +253,10 @@ def _protocol_4_prover_dev(g_hat, k, Q, Ld, zd, gf, proof, round_i):
     ctx = g_hat.dev.ctx
     signed = bool(gf.is_signed)
     kd = pivot._device_single(group, k)
+    min_n = DEVICE_SCALAR_MIN_PROVER
     try:
         n = len(g_hat)
-        while n > DEVICE_SCALAR_MIN:
+        while n > min_n:
             half = n // 2
             logger_cp.debug("Calculate A_i, B_i.")
             s_a = ctx.scalars_dot(Ld, half, zd, 0, half)  # L_tilde([0]*half + z_L)
@@ -230,9 +266,10 @@ def _protocol_4_prover_dev(g_hat, k, Q, Ld, zd, gf, proof, round_i):
             A, B = group._make(ctx.result(0)), group._make(ctx.result(1))
             proof["A" + str(round_i)] = A
             proof["B" + str(round_i)] = B
+            Q = _resolve(Q)
             c = _fold_challenge(A, B, g_hat, k, Q, _DevForm(Ld, n, signed), q)
             g_hat = _fold_generators(g_hat, c)
-            Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+            Q = _q_prime(group, A, Q, B, c)
             Ld.fold(half, c, _lib.FOLD_FORM)
             zd.fold(half, c, _lib.FOLD_WITNESS)
             n = half
@@ -265,9 +302,10 @@ def _protocol_4_verifier_dev(g_hat, k, Q, Ld, gf, proof, round_i):
             half = n // 2
             A = proof["A" + str(round_i)]
             B = proof["B" + str(round_i)]
+            Q = _resolve(Q)
             c = _fold_challenge(A, B, g_hat, k, Q, _DevForm(Ld, n, signed), q)
             g_hat = _fold_generators(g_hat, c)
-            Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+            Q = _q_prime(group, A, Q, B, c)
             Ld.fold(half, c, _lib.FOLD_FORM)
             n = half
             if n <= 2:
@@ -377,7 +415,7 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     fast = FAST_INT_PATH and _all_in_field(L.coeffs, gf) and _all_in_field(x, gf) and L.constant == 0
     if fast and len(L.coeffs) == n:
         g_hat = _g_hat(g, h, group)
-        if _use_device_scalars(g_hat, order):
+        if _use_device_scalars(g_hat, order, DEVICE_SCALAR_MIN_PROVER):
             return _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho)
         del g_hat
     t = gf(_dot([cf.value for cf in L.coeffs], r, order)) + L.constant if fast else L(r)
@@ -419,13 +457,15 @@ def protocol_4_verifier(g_hat, k, Q, L_tilde, gf, proof, round_i=0):
         logger_cp.debug("Load from proof: A_i, B_i.")
         A = proof["A" + str(round_i)]
         B = proof["B" + str(round_i)]
+        Q = _resolve(Q)
         c = _fold_challenge(A, B, g_hat, k, Q, L_tilde, order)
         g_hat = _fold_generators(g_hat, c)
-        Q = group.lincomb([A, Q, B], [1, c, c ** 2])
+        Q = _q_prime(group, A, Q, B, c)
         L_tilde = _fold_forms(L_tilde, c, half, gf)
         if len(g_hat) <= 2:
             z_prime = proof["z_prime"]
             Q_check = pivot.vector_commitment(z_prime, int(L_tilde(z_prime)), g_hat, k)
+            Q = _resolve(Q)
             logger_cp.debug(f"Q_check= {Q_check}")
             logger_cp.debug(f"Q_prime= {Q}")
             return Q_check == Q

@@ -56,6 +56,26 @@ VMSM_D fe quad_add(int q, const fe &p, const fe &r) {
     return fe_mul(u, v);  // X3 = EF, Y3 = GH, Z3 = FG, T3 = EH
 }
 
+// P + Q with Q precomputed (y+x, y-x, 2dxy), Z2 = 1: 2 multiplication slots.  `b` is this lane's operand of the first
+// stage: lane 0: y2-x2, lane 1: y2+x2, lane 2: the constant 2 (D = 2 Z1), lane 3: 2d x2 y2 (see quad_niels_operand).
+VMSM_D fe quad_madd(int q, const fe &p, const fe &b) {
+    fe X1 = quad_get(p, 0), Y1 = quad_get(p, 1);
+    fe a = quad_pick(q, fe_sub(Y1, X1), fe_add(Y1, X1), p, p);  // lane 2: Z1, lane 3: T1
+    fe m = fe_mul(a, b);                                         // A, B, D, C
+    fe A = quad_get(m, 0), B = quad_get(m, 1), D = quad_get(m, 2), C = quad_get(m, 3);
+    fe E = fe_sub(B, A), F = fe_sub(D, C), G = fe_add(D, C), H = fe_add(B, A);
+    fe u = quad_pick(q, E, G, F, E);
+    fe v = quad_pick(q, F, H, G, H);
+    return fe_mul(u, v);
+}
+
+// this lane's first-stage operand for adding (neg ? -Q : Q): -Q swaps y+x with y-x and negates 2dxy
+VMSM_D fe quad_niels_operand(int q, const ge_niels &n, bool neg) {
+    fe two = fe_zero();
+    two.v[0] = 2u;
+    return neg ? quad_pick(q, n.ypx, n.ymx, two, fe_neg(n.t2d)) : quad_pick(q, n.ymx, n.ypx, two, n.t2d);
+}
+
 // 2P, 2 multiplication slots
 VMSM_D fe quad_dbl(int q, const fe &p) {
     fe X = quad_get(p, 0), Y = quad_get(p, 1);

@@ -585,6 +585,17 @@ struct KAffToNiels {
     }
 };
 
+// asynchronous calls cannot return a validation error: it is published in the result slot's status word instead
+struct KPublishErr {
+    enum { kBlock = 32 };
+    const uint32_t *err;
+    uint32_t *status;  // mapped host memory
+    uint32_t value;
+    VMSM_HD void operator()(uint32_t tid) const {
+        if (tid == 0 && *err) *status = value;
+    }
+};
+
 // device-side copy of a point range (vmsm_points_concat)
 struct KCopyPoints {
     enum { kBlock = 128 };
@@ -631,6 +642,58 @@ struct KFold {
         }
         acc = ge_madd(acc, ld_niels(niels + half + tid), false);
         st_ext(out + tid, acc);
+    }
+};
+
+// Quad-cooperative, fused twin of KFold + KNormalize for the latency-bound rounds (small halves): four lanes per
+// element, 2 multiplication slots per doubling / mixed addition instead of 8 / 7 dependent multiplications, and the
+// normalisation (one inversion) in the same kernel.  Reads niels[j], niels[half + j], writes aff[j] / niels[j] -- only
+// its own element, so the fold is in place.  Launched with 4 * half threads rounded up to a warp.
+struct KFoldQ {
+    enum { kBlock = 128 };
+    ge_aff *aff;
+    ge_niels *niels;
+    uint32_t half;
+    int32_t top;
+    uint32_t nz[9];
+    uint32_t ng[9];
+    VMSM_HD void operator()(uint32_t tid) const {
+#if defined(__CUDA_ARCH__)
+        const int q = tid & 3;
+        uint32_t j = tid >> 2;
+        const bool live = j < half;
+        if (!live) j = half - 1;
+        const ge_niels p = ld_niels(niels + j);
+        const fe b_pos = quad_niels_operand(q, p, false), b_neg = quad_niels_operand(q, p, true);
+        fe acc = quad_identity(q);
+        for (int32_t i = top; i >= 0; i--) {
+            acc = quad_dbl(q, acc);
+            if ((nz[i >> 5] >> (i & 31)) & 1u) acc = quad_madd(q, acc, ((ng[i >> 5] >> (i & 31)) & 1u) ? b_neg : b_pos);
+        }
+        acc = quad_madd(q, acc, quad_niels_operand(q, ld_niels(niels + half + j), false));
+        const fe zi = fe_inv(quad_get(acc, 2));
+        const fe xy = fe_canon(fe_mul(acc, zi));  // lane 0: x, lane 1: y
+        ge_aff a;
+        a.x = quad_get(xy, 0);
+        a.y = quad_get(xy, 1);
+        if (live && q == 0) {
+            st_aff(aff + j, a);
+            st_niels(niels + j, ge_aff_to_niels(a));
+        }
+#else
+        if ((tid & 3) || (tid >> 2) >= half) return;
+        const uint32_t j = tid >> 2;
+        ge_niels p = ld_niels(niels + j);
+        ge_ext acc = ge_identity();
+        for (int32_t i = top; i >= 0; i--) {
+            acc = ge_dbl(acc);
+            if ((nz[i >> 5] >> (i & 31)) & 1u) acc = ge_madd(acc, p, ((ng[i >> 5] >> (i & 31)) & 1u) != 0);
+        }
+        acc = ge_madd(acc, ld_niels(niels + half + j), false);
+        ge_aff a = ge_ext_to_aff(acc);
+        st_aff(aff + j, a);
+        st_niels(niels + j, ge_aff_to_niels(a));
+#endif
     }
 };
 

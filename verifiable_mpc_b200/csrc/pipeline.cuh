@@ -413,7 +413,17 @@ inline int32_t naf_masks(const uint32_t s_in[8], uint32_t nz[9], uint32_t ng[9])
 
 // In place fold of a point vector held as (aff, niels): P[j] = c*P[j] + P[half+j].  `tmp` holds `half` extended points.
 template <class BE>
-void fold_run(BE &be, ge_aff *aff, ge_niels *niels, ge_ext *tmp, uint32_t half, const uint32_t c[8]) {
+void fold_run(BE &be, ge_aff *aff, ge_niels *niels, ge_ext *tmp, uint32_t half, const uint32_t c[8],
+              uint32_t quad_max_half = 1u << 13) {
+    if (half <= quad_max_half) {  // latency-bound: too few elements to fill the machine with one thread each
+        KFoldQ kq;
+        kq.aff = aff;
+        kq.niels = niels;
+        kq.half = half;
+        kq.top = naf_masks(c, kq.nz, kq.ng);
+        be.launch(kq, (4 * half + 31) & ~31u);
+        return;
+    }
     KFold kf;
     kf.niels = niels;
     kf.out = tmp;

@@ -253,6 +253,7 @@ struct EventSet {
 };
 
 constexpr uint32_t kSlots = 64;
+constexpr uint32_t kLaRing = 8;  // asynchronous small linear combinations in flight
 constexpr uint32_t kDotT1 = 1u << 16, kDotT2 = 256;  // most partial-sum threads of vmsm_scalars_dot
 inline void dot_stage_sizes(uint64_t n, uint32_t *T, uint32_t *T2) {
     uint64_t t = n / 16;
@@ -273,6 +274,7 @@ struct Ctx {
     bool acc_pending[2] = {false, false};
     bool async_sort = true;
     uint32_t sort_blocks = 0;
+    uint32_t fold_quad_max = 1u << 13;  // measured crossover (profiles/r01/fold_kernel_quad.md)
     cudaEvent_t scalars_ready = nullptr;  // set by the entry point when the scalars of the next MSM are still in flight
     cudaEvent_t ev_head = nullptr, ev_tail[kTailWays] = {};
     bool tail_pending[kTailWays] = {};
@@ -285,6 +287,13 @@ struct Ctx {
     size_t astage_cap[2] = {0, 0};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     bool astage_used[2] = {false, false};
+    // vmsm_lincomb_async: a ring of private staging sets (64 points + 64 scalars + error word each)
+    ge_aff *la_aff = nullptr;
+    ge_niels *la_niels = nullptr;
+    uint32_t *la_scalars = nullptr, *la_err = nullptr;
+    cudaEvent_t ev_la_sorted[kLaRing] = {};
+    bool la_used[kLaRing] = {};
+    uint32_t la_seq = 0;
     // freed point / scalar vectors are kept for reuse: cudaFree synchronises the whole device and was measured at up to
     // 0.18 s per call inside a proof (a prover frees its private copy of g_hat at the end of every proof)
     std::multimap<size_t, void *> pool;
@@ -707,8 +716,9 @@ int32_t w_run_msm_any(Ctx *c, const PointSet &ps, uint64_t off, const uint32_t *
 // fetch a finished result slot into `out` (64 B Ed25519 / BN256 G1, 128 B BN256 G2)
 int32_t fetch_slot(Ctx *c, uint32_t slot, uint8_t *out) {
     CU(cudaEventSynchronize(c->ev_slot[slot]));
-    if (c->res_status_host[slot]) {
+    if (uint32_t st = c->res_status_host[slot]) {
         c->res_status_host[slot] = 0;
+        if (st == 2) return fail(VMSM_ERR_POINT, "invalid point in the input of the asynchronous call for slot %u", slot);
         return fail(VMSM_ERR_TIMEOUT, "a multi-GPU partial for slot %u did not arrive", slot);
     }
     if (c->slot_curve[slot] == VMSM_CURVE_ED25519) memcpy(out, c->res_aff_host + slot, sizeof(ge_aff));
@@ -778,6 +788,11 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     for (int w = 0; w < kTailWays; w++) CU(cudaEventCreateWithFlags(&c->ev_tail[w], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_sc_written, cudaEventDisableTiming));
     CU(cudaMalloc(&c->dot_scratch, (kDotT1 + kDotT2 + 1) * 32));
+    CU(cudaMalloc(&c->la_aff, kLaRing * 64 * sizeof(ge_aff)));
+    CU(cudaMalloc(&c->la_niels, kLaRing * 64 * sizeof(ge_niels)));
+    CU(cudaMalloc(&c->la_scalars, kLaRing * 64 * 32));
+    CU(cudaMalloc(&c->la_err, kLaRing * 4));
+    for (uint32_t k = 0; k < kLaRing; k++) CU(cudaEventCreateWithFlags(&c->ev_la_sorted[k], cudaEventDisableTiming));
     CU(cudaMalloc(&c->order_bins, ORDER_BINS * 4));
     CU(cudaMalloc(&c->err_word, 16));
     CU(cudaMalloc(&c->fb_table, 512 * sizeof(ge_niels)));
@@ -826,6 +841,8 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     cudaFreeHost(c->res_status_host);
     cudaEventDestroy(c->ev_sc_written);
     cudaFree(c->dot_scratch);
+    cudaFree(c->la_aff), cudaFree(c->la_niels), cudaFree(c->la_scalars), cudaFree(c->la_err);
+    for (uint32_t k = 0; k < kLaRing; k++) cudaEventDestroy(c->ev_la_sorted[k]);
     cudaFree(c->txt_slots), cudaFree(c->txt_text), cudaFree(c->txt_lens), cudaFree(c->txt_offsets), cudaFree(c->txt_sums);
     if (c->txt_host) cudaFreeHost(c->txt_host);
     cudaFree(c->res_w_dev), cudaFreeHost(c->res_w_host), cudaFree(c->fbw_table[0]), cudaFree(c->fbw_table[1]);
@@ -894,6 +911,10 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             return VMSM_OK;
         case VMSM_OPT_ASYNC_SORT:
             c->async_sort = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_FOLD_QUAD_MAX:
+            if (value < 0 || value > (1 << 26)) return fail(VMSM_ERR_INVALID, "fold quad threshold out of range");
+            c->fold_quad_max = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_SORT_BLOCKS:
             if (value < 0 || value > (1 << 20)) return fail(VMSM_ERR_INVALID, "sort blocks out of range");
@@ -1648,7 +1669,7 @@ int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le
     uint32_t cs[8];
     memcpy(cs, c_le32, 32);
     CudaBE be(c);
-    fold_run(be, it->second.aff, it->second.niels, c->tmp_ext, (uint32_t)half, cs);
+    fold_run(be, it->second.aff, it->second.niels, c->tmp_ext, (uint32_t)half, cs, c->fold_quad_max);
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "fold: %s", cudaGetErrorString(be.err));
     it->second.n = half;
     return VMSM_OK;
@@ -1710,6 +1731,40 @@ int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const u
     CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));
     if (n && *reinterpret_cast<uint32_t *>(c->pin + 64)) return fail(VMSM_ERR_POINT, "invalid point in lincomb input");
     memcpy(out_affine, c->res_aff_host + (kSlots - 1), sizeof(ge_aff));
+    return VMSM_OK;
+}
+
+int32_t vmsm_lincomb_async(uint64_t ctx, int32_t curve, const uint8_t *affine, const uint8_t *scalars_le32, uint64_t n,
+                           uint32_t slot) {
+    GET_CTX(ctx);
+    if (curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "lincomb_async: Ed25519 only");
+    if (n > 64) return fail(VMSM_ERR_INVALID, "lincomb takes at most 64 terms");
+    if (n && (!affine || !scalars_le32)) return fail(VMSM_ERR_INVALID, "null argument");
+    if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    const uint32_t r = c->la_seq++ % kLaRing;
+    ge_aff *aff = c->la_aff + 64 * r;
+    ge_niels *niels = c->la_niels + 64 * r;
+    uint32_t *sc = c->la_scalars + 64 * 8 * r, *err = c->la_err + r;
+    CudaBE be(c);
+    // the staging set may still be read by the sort of the call that used it kLaRing calls ago (its points are read
+    // by that call's accumulate kernel, which precedes this copy on the main stream anyway)
+    if (c->la_used[r]) be.note(cudaStreamWaitEvent(c->stream, c->ev_la_sorted[r], 0));
+    be.zero(err, 4);
+    if (n) {
+        be.note(cudaMemcpyAsync(aff, affine, n * sizeof(ge_aff), cudaMemcpyHostToDevice, c->stream));
+        be.note(cudaMemcpyAsync(sc, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
+        KAffToNiels k = {aff, niels, err, c->check_points ? 1u : 0u};
+        be.launch(k, (uint32_t)n);
+        KPublishErr kp = {err, c->res_status_host + slot, 2u};
+        be.launch(kp, 32);
+    }
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "lincomb_async: %s", cudaGetErrorString(be.err));
+    CU(cudaEventRecord(c->ev_sort_in, c->stream));
+    c->scalars_ready = c->ev_sort_in;
+    int32_t rc = run_msm(c, niels, sc, n, slot);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_la_sorted[r], c->async_sort ? c->sort : c->stream));
+    c->la_used[r] = true;
     return VMSM_OK;
 }
 

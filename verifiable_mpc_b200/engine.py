@@ -388,6 +388,11 @@ class Context:
         check(self.lib.vmsm_lincomb(self.h, curve, pack_any(pts, curve), pack_scalars(scalars, ORDERS[curve]), n, out))
         return unpack_any(out.raw, curve)[0]
 
+    def lincomb_async(self, pts, scalars, slot, curve=_lib.CURVE_ED25519):
+        """As ``lincomb`` but asynchronous (Ed25519): fetch with ``result(slot)``."""
+        check(self.lib.vmsm_lincomb_async(self.h, curve, pack_any(pts, curve), pack_scalars(scalars, ORDERS[curve]),
+                                          len(pts), slot))
+
     def selftest_fe(self, op, a, b):
         n = len(a)
         A = b"".join(int(x).to_bytes(32, "little") for x in a)
