@@ -397,7 +397,7 @@ def _choose_window(n):
     best, best_c = None, 8
     for c in range(3, 18):
         r = 252 % c
-        if r == 0 or c - r > 4 or c < 11:
+        if r == 0 or c - r > 4 or c < 11 or (n >= 49152 and c < 15):
             continue
         W = -(-254 // c)
         cost = n * W * 504.0 + W * (1 << (c - 1)) * 2.0 * 648.0 * 1.3 + (W - 1) * c * 464.0

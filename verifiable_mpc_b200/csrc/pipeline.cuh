@@ -73,6 +73,10 @@ inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits, bool avoid_skew 
         // below c = 11 every size measured (2^6 .. 2^16) is latency-bound and c = 11 was fastest or tied
         // (profiles/r01/sweep_tiny_windows.jsonl): few entries per bucket, short serial chains
         if (avoid_skew && c < 11) continue;
+        // from ~2^15.5 terms the 2^10 buckets of c = 11 hold 64+ entries each and their serial chains bound the
+        // launch; c = 15 (16 x fewer entries per bucket) is 14-36 % faster at 2^16 / 2^17 although the model, which
+        // counts work, not chain length, still prefers 11 there (profiles/r01/sweep_mid_windows.jsonl)
+        if (avoid_skew && n >= 49152 && c < 15) continue;
         double W = (double)((scalar_bits + 1 + c - 1) / c);
         double NB = (double)(1u << (c - 1));
         double cost = (double)n * W * madd + W * NB * 2.0 * add + (W - 1) * c * 464.0;
