@@ -31,4 +31,9 @@ timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k 
     python tools/bench_ac20.py --log2n 16 --repeat 1 > gpurun_out/ncu_full3.log 2>&1
 tail -3 gpurun_out/ncu_full3.log | cut -c1-300
 export_rep prof_ac20
+echo "== ncu full: generator fold kernels (one thread per element at 2^16 outputs, four lanes per element at 2^12)"
+timeout 600 ncu --set full --clock-control none --kernel-name-base demangled -k regex:'KFold|KNormalize' -c 9 -o gpurun_out/prof_fold -f \
+    python tools/bench_fold.py --log2half 12 16 > gpurun_out/ncu_full4.log 2>&1
+tail -2 gpurun_out/ncu_full4.log | cut -c1-200
+export_rep prof_fold
 ls -la gpurun_out
