@@ -109,6 +109,10 @@ int32_t vmsm_points_text(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, u
  * vmsm_points_text* call on it. */
 int32_t vmsm_points_text_ptr(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t **text,
                              uint64_t *len);
+/* canonical wire bytes of a range without a host copy: *affine points into the same context-owned page-locked buffer
+ * as vmsm_points_text_ptr (valid until the next *_ptr call).  Feeds the opt-in binary Fiat-Shamir transcript, which
+ * hashes 64 bytes per generator instead of ~157 characters of decimal text. */
+int32_t vmsm_points_download_ptr(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t **affine);
 int32_t vmsm_points_count(uint64_t ctx, uint64_t pts, uint64_t *n);
 int32_t vmsm_points_free(uint64_t ctx, uint64_t pts);
 
@@ -117,6 +121,7 @@ int32_t vmsm_scalars_upload(uint64_t ctx, const uint8_t *le32, uint64_t n, uint6
 int32_t vmsm_scalars_synth(uint64_t ctx, int32_t curve, uint64_t seed, uint64_t n, uint64_t *sc);
 int32_t vmsm_scalars_download(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t n, uint8_t *le32_out);
 int32_t vmsm_scalars_free(uint64_t ctx, uint64_t sc);
+int32_t vmsm_scalars_download_ptr(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t n, const uint8_t **le32); /* as above */
 
 /* Scalar vectors modulo the Ed25519 group order l: the halving of the witness and of the linear form that accompanies
  * every generator fold, without leaving HBM.  Entries must be reduced (< l).

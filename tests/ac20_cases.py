@@ -77,3 +77,55 @@ def check_case(case, group, gf):
     assert phi == int(case["pivot"]["phi"], 16) and c == int(case["pivot"]["c"], 16)
     assert pivot.verify_linear_form_proof(g, h, P, L, y, z, phi, c) is True
     assert pivot.verify_linear_form_proof(g, h, P, L, y, z, phi + 1, c) is False
+
+
+def check_binary_transcript(group, gf, n=31, seed=3):
+    """Opt-in binary Fiat-Shamir transcript (pivot.TRANSCRIPT = "binary"): prover and verifier of this package agree
+    on it for every representation of the same statement, a proof is bound to the mode it was made in, and the
+    reference mode is left untouched."""
+    from verifiable_mpc_b200.ac20 import compressed_pivot as cp
+    from verifiable_mpc_b200.ac20 import generators as gens
+    from verifiable_mpc_b200.ac20 import pivot
+
+    rng = random.Random(seed)
+    gens.prng = rng
+    generators = gens.create_generators(n, group)
+    x = [gf(rng.randrange(gf.order)) for _ in range(n)]
+    gamma = gf(rng.randrange(gf.order))
+    L = pivot.LinearForm([gf(rng.randrange(gf.order)) for _ in range(n)])
+    y = L(x)
+    P = pivot.vector_commitment(x, gamma, generators["g"], generators["h"])
+    host_generators = dict(generators, g=list(generators["g"]))  # plain Python list of group elements
+    old = (pivot.TRANSCRIPT, cp.DEVICE_SCALAR_MIN, cp.DEVICE_SCALAR_MIN_PROVER, cp.FAST_INT_PATH)
+    try:
+        cp.prng = random.Random(seed + 1)
+        ref_proof = cp.protocol_5_prover(generators, P, L, y, x, gamma, gf)
+        assert cp.protocol_5_verifier(generators, P, L, y, ref_proof, gf) is True
+        pivot.TRANSCRIPT = "binary"
+        proofs = []
+        for dev_min, fast in ((2, True), (1 << 30, True), (1 << 30, False)):  # device scalars / host ints / objects
+            cp.DEVICE_SCALAR_MIN = cp.DEVICE_SCALAR_MIN_PROVER = dev_min
+            cp.FAST_INT_PATH = fast
+            cp.prng = random.Random(seed + 1)
+            proofs.append(cp.protocol_5_prover(generators, P, L, y, x, gamma, gf))
+            for gset in (generators, host_generators):
+                assert cp.protocol_5_verifier(gset, P, L, y, proofs[-1], gf) is True
+        for other in proofs[1:]:
+            assert sorted(other) == sorted(proofs[0]) and all(other[k] == proofs[0][k] for k in other)
+        assert any(proofs[0][k] != ref_proof[k] for k in ref_proof if k not in ("t", "A"))  # different challenges
+        assert cp.protocol_5_verifier(generators, P, L, y, ref_proof, gf) is False   # made for the other transcript
+        assert cp.protocol_5_verifier(generators, P, L, y + 1, proofs[0], gf) is False
+        bad = dict(proofs[0])
+        bad["A0"], bad["B0"] = bad["B0"], bad["A0"]
+        assert cp.protocol_5_verifier(generators, P, L, y, bad, gf) is False
+        # basic pivot in the same mode
+        pivot.prng = random.Random(seed + 2)
+        z, phi, c = pivot.prove_linear_form_eval(generators["g"], generators["h"], P, L, y, x, int(gamma), gf)
+        assert pivot.verify_linear_form_proof(generators["g"], generators["h"], P, L, y, z, phi, c) is True
+        assert pivot.verify_linear_form_proof(host_generators["g"], generators["h"], P, L, y, z, phi, c) is True
+        pivot.TRANSCRIPT = "reference"
+        assert pivot.verify_linear_form_proof(generators["g"], generators["h"], P, L, y, z, phi, c) is False
+        assert cp.protocol_5_verifier(generators, P, L, y, proofs[0], gf) is False
+        assert cp.protocol_5_verifier(generators, P, L, y, ref_proof, gf) is True
+    finally:
+        pivot.TRANSCRIPT, cp.DEVICE_SCALAR_MIN, cp.DEVICE_SCALAR_MIN_PROVER, cp.FAST_INT_PATH = old

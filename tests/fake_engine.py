@@ -55,6 +55,9 @@ class FakeScalars:
         n = len(self.vals) - off if n is None else n
         return self.vals[off:off + n]
 
+    def download(self, off=0, n=None):
+        return b"".join(v.to_bytes(32, "little") for v in self.tolist(off, n))
+
     def fold(self, half, c, mode):
         c = int(c) % E.L
         lo, hi = self.vals[:half], self.vals[half:2 * half]

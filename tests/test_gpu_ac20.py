@@ -128,3 +128,12 @@ def test_mpc_share_local_commitments(gpu_group):
     group, gf = gpu_group
     check_share_local_commitments(group, gf, n=33)
     check_share_local_commitments(group, gf, n=1023, m=5, t=2, seed=9)
+
+
+def test_binary_transcript_mode(gpu_group):
+    """canonical bytes (pinned D2H views of the device vectors) instead of decimal text in the hash."""
+    from ac20_cases import check_binary_transcript
+
+    group, gf = gpu_group
+    check_binary_transcript(group, gf, n=31)
+    check_binary_transcript(group, gf, n=1023, seed=8)

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--log2n", type=int, nargs="+", default=[10, 13, 16])
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--scalar-min", type=int, default=-1, help="experiment: compressed_pivot.DEVICE_SCALAR_MIN")
+    ap.add_argument("--transcript", default="reference", choices=["reference", "binary"],
+                    help="binary: the opt-in canonical-bytes Fiat-Shamir transcript (not verifiable by the reference)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -32,6 +34,7 @@ def main():
 
     if args.scalar_min >= 0:
         cp.DEVICE_SCALAR_MIN = args.scalar_min
+    pivot.TRANSCRIPT = args.transcript
     group = fingroups.EllipticCurve("Ed25519", "projective")
     group.is_additive, group.is_multiplicative = False, True
     gf = GF(group.order)
@@ -52,6 +55,7 @@ def main():
 
     pivot.fiat_shamir_hash = timed("hash", orig_hash)
     pivot.fiat_shamir_prefix = timed("hash", pivot.fiat_shamir_prefix)  # transcript text (device + host) + SHA-256
+    pivot.binary_prefix = timed("hash", pivot.binary_prefix)
     pivot.vector_commitment = timed("commit", orig_vc)
     cp._fold_generators = timed("fold", orig_fold)
     group.lincomb = classmethod(timed("lincomb", orig_lin))
@@ -85,7 +89,7 @@ def main():
             t0 = time.perf_counter()
             ok = cp.protocol_5_verifier(generators, P, L, y, proof, gf)
             t_verify = time.perf_counter() - t0
-            rec = {"N": N, "rounds": logn - 1, "prove_s": t_prove, "verify_s": t_verify, "verified": bool(ok),
+            rec = {"N": N, "transcript": args.transcript, "rounds": logn - 1, "prove_s": t_prove, "verify_s": t_verify, "verified": bool(ok),
                    "create_generators_s": t_gen,
                    "prove_breakdown_s": {k: round(v, 4) for k, v in prove_parts.items()},
                    "prove_host_other_s": round(t_prove - sum(prove_parts.values()), 4),

@@ -49,6 +49,8 @@ SIGNATURES = {
     "vmsm_points_fixed_base": [_u64, _i32, _p, _u64, _u64, _pu64],
     "vmsm_points_download": [_u64, _u64, _u64, _u64, _p],
     "vmsm_points_text": [_u64, _u64, _u64, _u64, _p, _u64, _pu64],
+    "vmsm_points_download_ptr": [_u64, _u64, _u64, _u64, ctypes.POINTER(_p)],
+    "vmsm_scalars_download_ptr": [_u64, _u64, _u64, _u64, ctypes.POINTER(_p)],
     "vmsm_points_text_ptr": [_u64, _u64, _u64, _u64, ctypes.POINTER(_p), _pu64],
     "vmsm_points_count": [_u64, _u64, _pu64],
     "vmsm_points_free": [_u64, _u64],

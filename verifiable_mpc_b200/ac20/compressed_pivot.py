@@ -58,6 +58,9 @@ class _IntForm:
     def __repr__(self):
         return f"{_field_text(self.ints, self.q, self.signed)}, 0"
 
+    def transcript_scalars(self):
+        return len(self.ints), pivot.pack_scalars(self.ints, self.q), 0
+
 
 def _dot(a, b, q):
     return sum(map(int.__mul__, a, b)) % q
@@ -105,7 +108,7 @@ def _fold_challenge(A, B, g_hat, k, Q, L_tilde, order):
     input_list = [A.normalize(), B.normalize(), g_hat, k, Q.normalize(), L_tilde]
     if logger_cp_hin.isEnabledFor(logging.DEBUG):
         logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
-    c = pivot.fiat_shamir_hash_items(input_list, order)
+    c = pivot.transcript_challenge(b"cp-round", input_list, order)
     logger_cp_hout.debug(f"After hash, hash=\n{c}")
     return c
 
@@ -226,6 +229,10 @@ class _DevForm:
     def repr_bytes(self):
         return b"[" + self.sc.text_bytes(0, self.n, self.signed) + b"], " + self.constant.encode("ascii")
 
+    def transcript_scalars(self):
+        view = self.sc.wire_view(0, self.n) if hasattr(self.sc, "wire_view") else self.sc.download(0, self.n)
+        return self.n, view, int(self.constant)
+
     def __repr__(self):
         return self.repr_bytes().decode("ascii")
 
@@ -336,6 +343,9 @@ class _FormText:
     def __repr__(self):
         return f"{_field_text([c.value for c in self.form.coeffs], self.q, self.signed)}, {str(self.form.constant)}"
 
+    def transcript_scalars(self):
+        return len(self.form.coeffs), pivot.pack_scalars([c.value for c in self.form.coeffs], self.q), self.form.constant
+
 
 def _first_challenges(t, A, generators, P, L, y, order, gf=None, L_text=None):
     if L_text is not None:
@@ -346,6 +356,11 @@ def _first_challenges(t, A, generators, P, L, y, order, gf=None, L_text=None):
     if logger_cp_hin.isEnabledFor(logging.DEBUG):
         logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
     # str(input_list + [b] + [tag]) for b = 0, 1 share everything but one character: hash the O(N) prefix once
+    if pivot.TRANSCRIPT == "binary":
+        prefix = pivot.binary_prefix(b"cp-first", input_list, order)
+        c0 = pivot.binary_finish(prefix, [0], order)
+        c1 = pivot.binary_finish(prefix, [1], order)
+        return c0, c1
     prefix = pivot.fiat_shamir_prefix(input_list)
     c0 = pivot.fiat_shamir_finish(prefix, [0, _TAG], order)
     c1 = pivot.fiat_shamir_finish(prefix, [1, _TAG], order)

@@ -60,6 +60,76 @@ def fiat_shamir_hash(input_list, order):
     return int.from_bytes(digest, "little") % order
 
 
+# ---------------------------------------------------------------------------------------------- binary transcript
+# Opt-in alternative to the reference's pre-images (SHA-256 over str(list): ~157 characters of decimal text per
+# generator per round).  TRANSCRIPT = "binary" hashes canonical bytes instead -- 64 bytes x || y per group element,
+# 32 bytes per scalar, every item tagged and length-prefixed, one domain-separation label per call site -- which
+# removes the text formatting and 60 % of the hashing.  It changes every challenge, so prover and verifier must both
+# run this package with the same setting; proofs made in this mode are NOT verifiable by the reference.
+TRANSCRIPT = "reference"
+_BIN_DOMAIN = b"verifiable_mpc_b200 transcript v1\x00"
+
+
+def _feed_binary(h, item, order):
+    """One transcript item: tag byte, 8-byte little-endian count, canonical bytes."""
+    wire = getattr(item, "wire_bytes", None)
+    if wire is not None:  # device-resident generator vector
+        h.update(b"V" + len(item).to_bytes(8, "little"))
+        h.update(wire())
+    elif hasattr(item, "affine"):  # group element
+        x, y = item.affine()
+        h.update(b"P" + int(x).to_bytes(32, "little") + int(y).to_bytes(32, "little"))
+    elif hasattr(item, "transcript_scalars"):  # linear / affine form stand-ins of compressed_pivot
+        n, coeff_bytes, constant = item.transcript_scalars()
+        h.update(b"F" + n.to_bytes(8, "little"))
+        h.update(coeff_bytes)
+        h.update((_int(constant) % order).to_bytes(32, "little"))
+    elif isinstance(item, AffineForm):
+        h.update(b"F" + len(item.coeffs).to_bytes(8, "little"))
+        h.update(pack_scalars([_int(v) for v in item.coeffs], order))
+        h.update((_int(item.constant) % order).to_bytes(32, "little"))
+    elif type(item) is dict:  # the generators argument
+        h.update(b"D" + len(item).to_bytes(8, "little"))
+        for key, value in item.items():
+            h.update(str(key).encode("utf-8") + b"\x00")
+            _feed_binary(h, value, order)
+    elif isinstance(item, (list, tuple)):
+        if item and all(hasattr(v, "affine") for v in item):  # a host list of generators: same bytes as a device vector
+            h.update(b"V" + len(item).to_bytes(8, "little"))
+            h.update(b"".join(int(c).to_bytes(32, "little") for v in item for c in v.affine()))
+            return
+        h.update(b"L" + len(item).to_bytes(8, "little"))
+        for value in item:
+            _feed_binary(h, value, order)
+    elif isinstance(item, (bytes, str)):
+        raw = item.encode("utf-8") if isinstance(item, str) else item
+        h.update(b"T" + len(raw).to_bytes(8, "little") + raw)
+    else:  # scalar: int or field element
+        h.update(b"S" + (_int(item) % order).to_bytes(32, "little"))
+
+
+def binary_prefix(label, items, order):
+    h = hashlib.sha256()
+    h.update(_BIN_DOMAIN + label + b"\x00")
+    for item in items:
+        _feed_binary(h, item, order)
+    return h
+
+
+def binary_finish(h, tail_items, order):
+    h = h.copy()
+    for item in tail_items:
+        _feed_binary(h, item, order)
+    return int.from_bytes(h.digest(), "little") % order
+
+
+def transcript_challenge(label, items, order):
+    """The challenge for one call site: the reference's str(list) pre-image, or the binary encoding when opted in."""
+    if TRANSCRIPT == "binary":
+        return binary_finish(binary_prefix(label, items, order), [], order)
+    return fiat_shamir_hash_items(items, order)
+
+
 def _feed_repr(h, item):
     """h.update(repr(item).encode()) without building the large strings: device-resident generator lists offer
     ``repr_bytes()`` (decimal text produced on the GPU); dicts (the ``generators`` argument) are walked."""
@@ -166,7 +236,7 @@ def prove_linear_form_eval(g, h, P, L, y, x, gamma, gf):
     t = L(r)
     A = vector_commitment(r, rho, g, h)
     logger_piv.debug(f"Prover computed A={A}.")
-    c = fiat_shamir_hash_items([t, A.normalize(), g, h, P.normalize(), L, y], gf.order)
+    c = transcript_challenge(b"pivot", [t, A.normalize(), g, h, P.normalize(), L, y], gf.order)
     z = [c * x_i + r_i for x_i, r_i in zip(x, r)]
     phi = (c * gamma + rho) % gf.order
     return z, phi, c
@@ -179,7 +249,7 @@ def verify_linear_form_proof(g, h, P, L, y, z, phi, c):
     A_check = group.lincomb([vector_commitment(z, phi, g, h), P], [1, -int(c)])
     t_check = L(z) - c * y
     order = type(t_check).order
-    hash_check = fiat_shamir_hash_items([t_check, A_check.normalize(), g, h, P.normalize(), L, y], order)
+    hash_check = transcript_challenge(b"pivot", [t_check, A_check.normalize(), g, h, P.normalize(), L, y], order)
     logger_piv.debug(f"Value of c         ={c}")
     logger_piv.debug(f"Value of hash_check={hash_check}")
     return c == hash_check

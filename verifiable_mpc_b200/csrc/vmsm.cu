@@ -1128,6 +1128,16 @@ static int32_t text_finish(Ctx *c, CudaBE &be, uint64_t n, uint32_t slot_bytes, 
     return VMSM_OK;
 }
 
+// canonical bytes of a device range straight into the context's page-locked buffer (binary transcript mode)
+static int32_t bytes_to_pinned(Ctx *c, const void *dev, size_t nbytes, const uint8_t **ptr) {
+    int32_t rc = text_ensure(c, nbytes / VMSM_TEXT_SLOT + 1);
+    if (rc) return rc;
+    if (nbytes) CU(cudaMemcpyAsync(c->txt_host, dev, nbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *ptr = c->txt_host;
+    return VMSM_OK;
+}
+
 static int32_t points_text_impl(Ctx *c, uint64_t pts, uint64_t off, uint64_t n, uint64_t *len) {
     auto it = c->points.find(pts);
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
@@ -1142,6 +1152,28 @@ static int32_t points_text_impl(Ctx *c, uint64_t pts, uint64_t off, uint64_t n, 
     KPointText kt = {it->second.aff + off, c->txt_slots, c->txt_lens, (uint32_t)n};
     be.launch(kt, (uint32_t)n);
     return text_finish(c, be, n, VMSM_TEXT_SLOT, len);
+}
+
+int32_t vmsm_points_download_ptr(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t **affine) {
+    GET_CTX(ctx);
+    if (!affine) return fail(VMSM_ERR_INVALID, "null argument");
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "range out of bounds");
+    if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "too many points");
+    if (it->second.curve == VMSM_CURVE_ED25519) return bytes_to_pinned(c, it->second.aff + off, n * sizeof(ge_aff), affine);
+    size_t wb = wire_bytes(it->second.curve);
+    return bytes_to_pinned(c, (const uint8_t *)it->second.w_wire + off * wb, n * wb, affine);
+}
+
+int32_t vmsm_scalars_download_ptr(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t n, const uint8_t **le32) {
+    GET_CTX(ctx);
+    if (!le32) return fail(VMSM_ERR_INVALID, "null argument");
+    auto it = c->scalars.find(sc);
+    if (it == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (off > it->second.n || n > it->second.n - off) return fail(VMSM_ERR_INVALID, "range out of bounds");
+    if (n > (1ull << 28)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
+    return bytes_to_pinned(c, it->second.data + off * 8, n * 32, le32);
 }
 
 int32_t vmsm_points_text(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *out, uint64_t cap,

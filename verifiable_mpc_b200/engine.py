@@ -114,6 +114,15 @@ class DevicePoints:
     def tolist(self, off=0, n=None):
         return unpack_any(self.download(off, n), self.curve)
 
+    def wire_view(self, off=0, n=None):
+        """Zero-copy view (ctypes char array over the context's pinned buffer) of the canonical wire bytes of a range;
+        valid until the next ``*_view`` / ``text_bytes`` call on this context."""
+        n = self.n - off if n is None else n
+        ptr = ctypes.c_void_p()
+        check(self.ctx.lib.vmsm_points_download_ptr(self.ctx.h, self.handle, off, n, ctypes.byref(ptr)))
+        nbytes = n * WIRE_BYTES[self.curve]
+        return (ctypes.c_char * nbytes).from_address(ptr.value) if nbytes else b""
+
     def text_bytes(self, off=0, n=None):
         """``b"[x0, y0, 1], [x1, y1, 1], ..."`` formatted on the device (the inside of repr(list of points))."""
         n = self.n - off if n is None else n
@@ -164,6 +173,13 @@ class DeviceScalars:
     def fold(self, half, c, mode):
         """In place on [0, 2*half): FOLD_WITNESS v[j] += c*v[half+j]; FOLD_FORM v[j] = c*v[j] + v[half+j] (mod l)."""
         check(self.ctx.lib.vmsm_scalars_fold(self.ctx.h, self.handle, half, (int(c) % ED_L).to_bytes(32, "little"), mode))
+
+    def wire_view(self, off=0, n=None):
+        """Zero-copy view of n x 32 little-endian bytes (see DevicePoints.wire_view)."""
+        n = self.n - off if n is None else n
+        ptr = ctypes.c_void_p()
+        check(self.ctx.lib.vmsm_scalars_download_ptr(self.ctx.h, self.handle, off, n, ctypes.byref(ptr)))
+        return (ctypes.c_char * (32 * n)).from_address(ptr.value) if n else b""
 
     def axpy(self, c, src=None, mode=_lib.AXPY_ADD_SCALED, off=0, soff=0, n=None):
         """Element-wise on the device: self += c*src (ADD_SCALED), self = c*self + src (SCALE_ADD), self *= c (SCALE)."""

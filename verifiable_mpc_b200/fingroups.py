@@ -364,6 +364,13 @@ class DevicePointList:
             return b"[" + self.dev.text_bytes(self.off, self.n) + b"]"
         return repr(self).encode("utf-8")
 
+    def wire_bytes(self):
+        """Canonical 64-byte encodings x || y of the whole view (binary transcript mode); a zero-copy view of the
+        context's pinned buffer when the engine offers one."""
+        if hasattr(self.dev, "wire_view"):
+            return self.dev.wire_view(self.off, self.n)
+        return self.dev.download(self.off, self.n)
+
     def __eq__(self, other):
         if isinstance(other, DevicePointList):
             return self.affine_list() == other.affine_list()
