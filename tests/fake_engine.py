@@ -116,6 +116,9 @@ class FakeContext:
 
     def fixed_base(self, scalars=None, seed=0, n=None, curve=0):
         sc = _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else [int(s) for s in scalars]
+        if curve:
+            F, G = (BN.FP2, BN.G2) if curve == 2 else (BN.FP, BN.G1)
+            return FakeBNPoints(self, [BN.scalar_mul(F, G, s % BN.N) for s in sc], curve)
         return FakePoints(self, [E.scalar_mul(E.B, s) for s in sc])
 
     def msm_ext(self, points, off, n, extra, extra_off, n_extra, scalars):

@@ -59,17 +59,26 @@ def build(seed=2024):
     proof_nozk = pynocchio.compute_proof(qap, c, (p / qap.t)[0], evalkey, None)
     checks = pynocchio.verify(qap, verikey, proof, c[: qap.out_ix + 1])
     assert all(checks.values()), checks
-    return qap, evalkey, verikey, c, h, (p / qap.t)[0], deltas, proof, proof_nozk
+    return qap, evalkey, verikey, c, h, (p / qap.t)[0], deltas, proof, proof_nozk, td
 
 
 if __name__ == "__main__":
-    qap, evalkey, verikey, c, h, h_nozk, deltas, proof, proof_nozk = build()
+    qap, evalkey, verikey, c, h, h_nozk, deltas, proof, proof_nozk, td = build()
+
+    def poly(p):
+        return [hex(int(v)) for v in p.coeffs]
+
     out = {
         "generator": "tests/golden/make_pynocchio_golden.py: unmodified reference on oracle/mpyc_shim",
         "indices_mid": list(qap.indices_mid), "m": qap.m, "d": qap.d,
         "c": [hex(int(v)) for v in c], "h": [hex(int(v)) for v in h.coeffs], "h_nozk": [hex(int(v)) for v in h_nozk.coeffs],
         "deltas": {"v": hex(deltas.v), "w": hex(deltas.w), "y": hex(deltas.y)},
         "evalkey": {k: enc(v) for k, v in evalkey.items()},
+        # inputs of generate_evalkey (:101-167): the trapdoor and the QAP polynomials it evaluates at s
+        "trapdoor": {k: hex(getattr(td, k)) for k in ("r_v", "r_w", "r_y", "s", "alpha_v", "alpha_w", "alpha_y", "beta", "gamma")},
+        "qap_polys": {"v": {str(i): poly(qap.v[i]) for i in qap.indices_mid},
+                      "w": {str(i): poly(qap.w[i]) for i in qap.indices_mid},
+                      "y": {str(i): poly(qap.y[i]) for i in qap.indices_mid}, "t": poly(qap.t)},
         "proof": {k: enc(v) for k, v in proof.items()},
         "proof_nozk": {k: enc(v) for k, v in proof_nozk.items()},
     }

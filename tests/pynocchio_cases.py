@@ -62,3 +62,47 @@ def check_compute_proof(g1_group, g2_group):
     for key, val in gold["proof"].items():
         assert proof3[key].affine() == dec(val), key
     return proof
+
+
+class _EvalPoly:
+    """QAP polynomial stand-in: coefficients mod n with the reference's ``eval`` (qap_creator.py:47-48,108-109)."""
+
+    def __init__(self, coeffs, order):
+        self.coeffs, self.order = coeffs, order
+
+    def eval(self, x):
+        return sum(c * pow(x, i, self.order) for i, c in enumerate(self.coeffs)) % self.order
+
+
+def check_generate_evalkey(g1_group, g2_group):
+    """generate_evalkey twin (two fixed-base batches) against the evaluation key the unmodified reference produced
+    for the same trapdoor and QAP (tests/golden/pynocchio_proof.json): same keys, same order, same points."""
+    from verifiable_mpc_b200.trinocchio import pynocchio as twin
+
+    gold = load()
+    order = g1_group.order
+
+    class Td:
+        pass
+
+    td = Td()
+    for k, v in gold["trapdoor"].items():
+        setattr(td, k, int(v, 16))
+
+    class Qap:
+        indices_mid = gold["indices_mid"]
+        d = gold["d"]
+        v = {int(i): _EvalPoly([int(c, 16) for c in cs], order) for i, cs in gold["qap_polys"]["v"].items()}
+        w = {int(i): _EvalPoly([int(c, 16) for c in cs], order) for i, cs in gold["qap_polys"]["w"].items()}
+        y = {int(i): _EvalPoly([int(c, 16) for c in cs], order) for i, cs in gold["qap_polys"]["y"].items()}
+        t = _EvalPoly([int(c, 16) for c in gold["qap_polys"]["t"]], order)
+
+    class Gen:
+        g1, g2 = g1_group.generator, g2_group.generator
+
+    key = twin.generate_evalkey(td, Qap, Gen)
+    assert list(key) == list(gold["evalkey"])
+    for name, val in gold["evalkey"].items():
+        assert key[name].affine() == dec(val), name
+        assert isinstance(key[name], g2_group if name.endswith("g2") else g1_group)
+    return key

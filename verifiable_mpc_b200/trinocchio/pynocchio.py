@@ -65,6 +65,70 @@ class PreparedEvalKey:
         self.bases[name] = group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id)
 
 
+def _evalkey_exponents(td, qap, order):
+    """(key, exponent) pairs of every evaluation-key entry, split by group: each entry of the reference's
+    ``generate_evalkey`` (:101-167) is ``int(alpha * poly(s)) * (r * g)`` = a multiple of the group generator, so the
+    whole key is two fixed-base batches.  The polynomial evaluations at the trapdoor point stay the reference's host
+    algebra (one ``poly.eval(s)`` per wire)."""
+    s = td.s
+    mid = list(qap.indices_mid)
+
+    def at_s(poly):
+        return int(poly.eval(s)) % order
+
+    v_s = {i: at_s(qap.v[i]) for i in mid}
+    w_s = {i: at_s(qap.w[i]) for i in mid}
+    y_s = {i: at_s(qap.y[i]) for i in mid}
+    t_s = at_s(qap.t)
+    r_v, r_w, r_y = td.r_v % order, td.r_w % order, td.r_y % order
+    g1, g2 = [], []
+    g1 += [(f"r_v*v{i}*g1", v_s[i] * r_v) for i in mid]
+    g2 += [(f"r_w*w{i}*g2", w_s[i] * r_w) for i in mid]
+    g1 += [(f"r_y*y{i}*g1", y_s[i] * r_y) for i in mid]
+    g1 += [(f"r_v*alpha_v*v{i}*g1", td.alpha_v * v_s[i] % order * r_v) for i in mid]
+    g1 += [(f"r_w*alpha_w*w{i}*g1", td.alpha_w * w_s[i] % order * r_w) for i in mid]
+    g1 += [(f"r_y*alpha_y*y{i}*g1", td.alpha_y * y_s[i] % order * r_y) for i in mid]
+    g1 += [(f"s^{i}*g1", pow(s, i, order)) for i in range(0, qap.d + 1)]
+    g1 += [(f"r_v*beta*v+r_w*beta*w+r_y*beta*y{i}_g1",
+            td.beta * v_s[i] % order * r_v + td.beta * w_s[i] % order * r_w + td.beta * y_s[i] % order * r_y) for i in mid]
+    g1 += [("r_v*t*g1", t_s * r_v), ("r_y*t*g1", t_s * r_y),
+           ("r_v*alpha_v*t*g1", td.alpha_v * t_s % order * r_v), ("r_w*alpha_w*t*g1", td.alpha_w * t_s % order * r_w),
+           ("r_y*alpha_y*t*g1", td.alpha_y * t_s % order * r_y), ("r_v*beta*t*g1", td.beta * t_s % order * r_v),
+           ("r_w*beta*t*g1", td.beta * t_s % order * r_w), ("r_y*beta*t*g1", td.beta * t_s % order * r_y),
+           ("t*g1", t_s)]
+    g2 += [("r_w*t*g2", t_s * r_w)]
+    return [(k, e % order) for k, e in g1], [(k, e % order) for k, e in g2]
+
+
+# the reference's dict order (:155-165): v, w, y, alpha_v, alpha_w, alpha_y, s-powers, beta, then the ZK elements
+_ZK_KEYS = ("r_v*t*g1", "r_w*t*g2", "r_y*t*g1", "r_v*alpha_v*t*g1", "r_w*alpha_w*t*g1", "r_y*alpha_y*t*g1",
+            "r_v*beta*t*g1", "r_w*beta*t*g1", "r_y*beta*t*g1", "t*g1")
+
+
+def generate_evalkey(td, qap, gen):
+    """Public evaluation key (reference :101-167) with the ~8|mid| + d + 11 scalar multiplications done as two
+    fixed-base batches on the device (``vmsm_points_fixed_base`` on BN256 G1 / G2).  ``gen.g1`` / ``gen.g2`` must be the
+    groups' standard generators (what ``Generators(td, group.generator, twist.generator)`` holds, :61-69)."""
+    group1, group2 = type(gen.g1), type(gen.g2)
+    assert gen.g1 == group1.generator and gen.g2 == group2.generator, "fixed-base tables are built for the standard generators"
+    order = group1.order
+    e1, e2 = _evalkey_exponents(td, qap, order)
+    out = {}
+    for group, entries in ((group1, e1), (group2, e2)):
+        dev = group._ctx().fixed_base(scalars=[e for _, e in entries], curve=group.curve_id)
+        try:
+            for (key, _), pt in zip(entries, dev.tolist()):
+                out[key] = group._make(pt)
+        finally:
+            dev.free()
+    mid = list(qap.indices_mid)
+    order_keys = ([f"r_v*v{i}*g1" for i in mid] + [f"r_w*w{i}*g2" for i in mid] + [f"r_y*y{i}*g1" for i in mid]
+                  + [f"r_v*alpha_v*v{i}*g1" for i in mid] + [f"r_w*alpha_w*w{i}*g1" for i in mid]
+                  + [f"r_y*alpha_y*y{i}*g1" for i in mid] + [f"s^{i}*g1" for i in range(0, qap.d + 1)]
+                  + [f"r_v*beta*v+r_w*beta*w+r_y*beta*y{i}_g1" for i in mid] + list(_ZK_KEYS))
+    return {k: out[k] for k in order_keys}
+
+
 def compute_proof(qap, c, h, evalkey, deltas=None):
     """Pinocchio proof elements for witness ``c`` and quotient polynomial ``h`` (reference :228-273).
 
