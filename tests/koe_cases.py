@@ -29,6 +29,17 @@ def check_koe(g1_group, g2_group):
             assert proof[key].affine() == dec(val), key
         P, pi = twin.restriction_argument_prover(range(len(x)), x, gamma, pp)
         assert P == proof["P"] and pi == proof["pi"]
+        # trusted setup twin: seeded like tests/golden/make_koe_golden.py (seed 77, the setup's three draws come first),
+        # it reproduces the reference's public parameters (two fixed-base batches instead of 4n sequential powers)
+        import random
+
+        twin.prng = random.Random(77)
+        pp2 = twin.trusted_setup(g1_group.generator, g2_group.generator, len(x), g1_group.order)
+        assert [p.affine() for p in pp2["pp_lhs"]] == [dec(p) for p in gold["pp_lhs"]]
+        assert [p.affine() for p in pp2["pp_rhs"]] == [dec(p) for p in gold["pp_rhs"]]
+        twin.prng = random.Random(77)  # a base that is not the standard generator takes the per-element path
+        pp3 = twin.trusted_setup(g1_group.generator ** 2, g2_group.generator, 1, g1_group.order)
+        assert pp3["pp_lhs"][0] == pp2["pp_lhs"][0] ** 2 and pp3["pp_rhs"][:2] == pp2["pp_rhs"][:2]
         # group-type operators in multiplicative notation
         assert (pp["pp_lhs"][0] ** 3) * pp["pp_lhs"][0] == pp["pp_lhs"][0] ** 4
         return proof, u, L, pp

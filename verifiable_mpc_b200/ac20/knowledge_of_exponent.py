@@ -7,8 +7,12 @@ device MSM (libvmsm.so on the BN256 curves).  The polynomial product and the pai
 the reference's; ``linear_form_R`` offers the verifier's n-term G2 product (:146) as a device MSM as well.
 Same names, arguments and return values as the reference functions.
 """
+from random import SystemRandom
+
 from ..engine import BN_N, pack_scalars
 from . import pivot
+
+prng = SystemRandom()
 
 
 def _msm(points, scalars):
@@ -29,6 +33,33 @@ def vector_commitment(x, gamma, g, h):
     """``h**gamma * prod g[i]**x[i]`` over a BN256 group (reference :29-38)."""
     assert len(g) >= len(x), "Not enough generators."
     return _msm(list(g[: len(x)]) + [h], [int(v) for v in x] + [int(gamma)])
+
+
+def trusted_setup(_g1, _g2, n, order, progress_bar=False):
+    """Public parameters ``pp_lhs[i] = g1**(z**(i+1))``, ``pp_rhs[i] = g2**(z**(i+1))`` with ``g1 = _g1**g_exp``,
+    ``g2 = _g2**(g_exp*alpha)`` (reference :50-72: 4n sequential scalar multiplications).  Same three draws from
+    ``prng``; the 2n + 2n powers are two fixed-base batches on the device when ``_g1`` / ``_g2`` are the groups'
+    standard generators (how every caller invokes it: circuit_sat_r1cs.py:84-91), otherwise one device call each."""
+    g_exp = prng.randrange(1, order)
+    alpha = prng.randrange(order)
+    z = prng.randrange(order)
+    group1, group2 = type(_g1), type(_g2)
+    e1, e2, zp = [], [], 1
+    for _ in range(2 * n):
+        zp = zp * z % order
+        e1.append(g_exp * zp % order)
+        e2.append(g_exp * alpha % order * zp % order)
+    pp = {}
+    for key, group, base, exps in (("pp_lhs", group1, _g1, e1), ("pp_rhs", group2, _g2, e2)):
+        if base == group.generator:
+            dev = group._ctx().fixed_base(scalars=exps, curve=group.curve_id)
+            try:
+                pp[key] = [group._make(pt) for pt in dev.tolist()]
+            finally:
+                dev.free()
+        else:
+            pp[key] = [group.lincomb([base], [e]) for e in exps]
+    return pp
 
 
 def restriction_argument_prover(S, x, gamma, pp):
