@@ -250,3 +250,17 @@ def test_scalar_text_matches_python_repr(hostemu, signed):
     got = "".join(slots.raw[96 * i: 96 * i + lens[i]].decode() for i in range(n))
     exp = ", ".join(str(x - L if signed and x > (L >> 1) else x) for x in vals)
     assert got == exp
+
+
+def test_bench_window_mirror_matches_library(hostemu):
+    """bench.py reports the window the library will choose (for the roofline arithmetic): the Python mirror must agree
+    with csrc/pipeline.cuh:choose_window at every size the bench or the sweep can be asked for."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sizes = [1, 2, 100] + [1 << k for k in range(4, 27)] + [49151, 49152, 3 << 15, (1 << 20) + 5]
+    for n in sizes:
+        assert bench._choose_window(n) == hostemu.hostemu_choose_window(ctypes.c_uint64(n)), n
