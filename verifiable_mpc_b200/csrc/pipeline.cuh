@@ -48,10 +48,12 @@ struct Workspace {
     // bucket-tree levels: [tail way][ping-pong]
     void *nodeS[kTailWays][2] = {}, *nodeT[kTailWays][2] = {};
     // long-bucket overflow (kernels.cuh: KOverflow / KCombine)
-    OverflowCtl *ctl = nullptr;
-    OverflowTask *tasks = nullptr;
-    LongBucket *longs = nullptr;
-    void *partials = nullptr;
+    // one set per tail way: the overflow / combine kernels of MSM k run on its side stream as well, while the
+    // accumulate kernel of MSM k+1 is already filling the next set
+    OverflowCtl *ctl_[kTailWays] = {};
+    OverflowTask *tasks_[kTailWays] = {};
+    LongBucket *longs_[kTailWays] = {};
+    void *partials_[kTailWays] = {};
     size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0, cap_tasks = 0;  // element counts
     int ways = 0;  // tail ways that have buckets / node buffers (grows to the largest count requested)
     size_t elem_bytes = 0;  // size of one accumulator point the point buffers were allocated for
@@ -103,7 +105,7 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
     size_t nb = (size_t)g.W * g.NB, ni = (size_t)g.W * g.n, nn = (size_t)g.W * ((g.NB + R - 1) / R);
     if (nn < g.W) nn = g.W;
     if (ways > ws.ways) {  // more MSM tails in flight than before: (re)allocate the per-way buffers
-        ws.cap_buckets = ws.cap_nodes = 0;
+        ws.cap_buckets = ws.cap_nodes = ws.cap_tasks = 0;
         ws.ways = ways;
     }
     if (elem_bytes > ws.elem_bytes) {  // a wider accumulator type than before: regrow the point buffers
@@ -141,13 +143,15 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
     // segment, plus ni / seg_floor full segments
     size_t nt = ni / cap_floor + ni / seg_floor + 64;
     if (nt > ws.cap_tasks) {
-        be.free(ws.ctl), be.free(ws.tasks), be.free(ws.longs), be.free(ws.partials);
         ws.cap_tasks = 0;
-        ws.ctl = (OverflowCtl *)be.alloc(sizeof(OverflowCtl));
-        ws.tasks = (OverflowTask *)be.alloc(nt * sizeof(OverflowTask));
-        ws.longs = (LongBucket *)be.alloc(nt * sizeof(LongBucket));
-        ws.partials = be.alloc(nt * elem_bytes);
-        if (!ws.ctl || !ws.tasks || !ws.longs || !ws.partials) return -1;
+        for (int k = 0; k < ws.ways; k++) {
+            be.free(ws.ctl_[k]), be.free(ws.tasks_[k]), be.free(ws.longs_[k]), be.free(ws.partials_[k]);
+            ws.ctl_[k] = (OverflowCtl *)be.alloc(sizeof(OverflowCtl));
+            ws.tasks_[k] = (OverflowTask *)be.alloc(nt * sizeof(OverflowTask));
+            ws.longs_[k] = (LongBucket *)be.alloc(nt * sizeof(LongBucket));
+            ws.partials_[k] = be.alloc(nt * elem_bytes);
+            if (!ws.ctl_[k] || !ws.tasks_[k] || !ws.longs_[k] || !ws.partials_[k]) return -1;
+        }
         ws.cap_tasks = nt;
     }
     if (nn > ws.cap_nodes) {
@@ -171,7 +175,8 @@ void ws_release(BE &be, Workspace &ws) {
     for (int k = 0; k < kTailWays; k++) be.free(ws.buckets_[k]);
     for (int k = 0; k < 2; k++)
         be.free(ws.counts_[k]), be.free(ws.offsets_[k]), be.free(ws.cursor_[k]), be.free(ws.order_[k]), be.free(ws.idx_[k]);
-    be.free(ws.ctl), be.free(ws.tasks), be.free(ws.longs), be.free(ws.partials);
+    for (int k = 0; k < kTailWays; k++)
+        be.free(ws.ctl_[k]), be.free(ws.tasks_[k]), be.free(ws.longs_[k]), be.free(ws.partials_[k]);
     for (int par = 0; par < kTailWays; par++)
         for (int k = 0; k < 2; k++) be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
     ws = Workspace();
@@ -223,24 +228,27 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     {
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < 64) cap = 64;
-        be.zero(ws.ctl, sizeof(OverflowCtl));
-        KAccumulate k5 = {bases, offsets, counts, idx, order, (ge_ext *)buckets, nbuckets, cap, ws.ctl, ws.tasks,
-                          ws.longs, extra, n_main};
+        be.zero(ws.ctl_[tw], sizeof(OverflowCtl));
+        KAccumulate k5 = {bases, offsets, counts, idx, order, (ge_ext *)buckets, nbuckets, cap, ws.ctl_[tw], ws.tasks_[tw],
+                          ws.longs_[tw], extra, n_main};
         be.launch(k5, nbuckets);
+        be.phase_mark(PH_ACCUMULATE);
+        // everything after the accumulate kernel belongs to this MSM's tail: long-bucket overflow tasks, combine, bucket
+        // tree, Horner -- on the CUDA backend on side stream `tw`, so the next MSM's accumulate kernel follows at once
+        be.tail_begin(tw);
         if (n > cap) {  // otherwise no bucket can be long
             const uint32_t ow = be.overflow_warps();
-            KOverflow ko = {bases, idx, ws.ctl, ws.tasks, (ge_ext *)ws.partials, ow, extra, n_main};
+            KOverflow ko = {bases, idx, ws.ctl_[tw], ws.tasks_[tw], (ge_ext *)ws.partials_[tw], ow, extra, n_main};
             be.launch(ko, ow * 32);
+            be.acc_done(par);  // the CSR lists of this parity are free again (the overflow tasks were their last reader)
             const uint32_t ct = be.combine_threads();
-            KCombine kc = {ws.ctl, ws.longs, (const ge_ext *)ws.partials, (ge_ext *)buckets, ct};
+            KCombine kc = {ws.ctl_[tw], ws.longs_[tw], (const ge_ext *)ws.partials_[tw], (ge_ext *)buckets, ct};
             be.launch(kc, ct);
+        } else {
+            be.acc_done(par);
         }
     }
-    be.acc_done(par);  // the CSR lists of this parity are free again
-    be.phase_mark(PH_ACCUMULATE);
-    // bucket tree (S,T radix-R levels, quad-cooperative once few nodes remain) + Horner over the windows: on the CUDA
-    // backend all of it runs on side stream `tw`, underneath the accumulate kernels of the following MSMs
-    be.tail_begin(tw);
+    // bucket tree (S,T radix-R levels, quad-cooperative once few nodes remain) + Horner over the windows
     const ge_ext *inS = (const ge_ext *)buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;
@@ -329,24 +337,26 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     {
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < kCapFloor) cap = kCapFloor;
-        be.zero(ws.ctl, sizeof(OverflowCtl));
-        KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl,
-                              ws.tasks, ws.longs, extra, n_main, kSegFloor};
+        be.zero(ws.ctl_[tw], sizeof(OverflowCtl));
+        KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl_[tw],
+                              ws.tasks_[tw], ws.longs_[tw], extra, n_main, kSegFloor};
         be.launch(k5, nbuckets);
+        be.phase_mark(PH_ACCUMULATE);
+        // overflow tasks, combine, bucket tree, Horner and inversion on side stream `tw`, underneath the heads of the
+        // following MSMs (the eight MSMs of a Pinocchio proof are independent)
+        be.tail_begin(tw);
         if (n > cap) {
             const uint32_t ow = be.overflow_warps();
-            KOverflowW<F> ko = {bases, idx, ws.ctl, ws.tasks, (wjac<F> *)ws.partials, ow, extra, n_main};
+            KOverflowW<F> ko = {bases, idx, ws.ctl_[tw], ws.tasks_[tw], (wjac<F> *)ws.partials_[tw], ow, extra, n_main};
             be.launch(ko, ow * 32);
+            be.acc_done(par);
             const uint32_t ct = be.combine_threads();
-            KCombineW<F> kc = {ws.ctl, ws.longs, (const wjac<F> *)ws.partials, (wjac<F> *)buckets, ct};
+            KCombineW<F> kc = {ws.ctl_[tw], ws.longs_[tw], (const wjac<F> *)ws.partials_[tw], (wjac<F> *)buckets, ct};
             be.launch(kc, ct);
+        } else {
+            be.acc_done(par);
         }
     }
-    be.acc_done(par);
-    be.phase_mark(PH_ACCUMULATE);
-    // bucket tree, Horner and inversion on side stream `tw`, underneath the heads of the following MSMs (the eight
-    // MSMs of a Pinocchio proof are independent)
-    be.tail_begin(tw);
     const wjac<F> *inS = (const wjac<F> *)buckets, *inT = nullptr;
     uint32_t cnt = g.NB, log2s = 0;
     int pp = 0;

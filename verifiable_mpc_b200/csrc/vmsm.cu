@@ -397,7 +397,7 @@ struct CudaBE {
     }
     void acc_done(int par) {
         if (!c->async_sort) return;
-        note(cudaEventRecord(c->ev_acc_done[par], c->stream));
+        note(cudaEventRecord(c->ev_acc_done[par], cur));  // on the stream of the last reader of the CSR lists
         c->acc_pending[par] = true;
     }
     void after_final(ge_ext *out_ext, ge_aff *out_aff) {
