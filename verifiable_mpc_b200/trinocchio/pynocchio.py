@@ -140,45 +140,44 @@ def compute_proof(qap, c, h, evalkey, deltas=None):
 
     prepared = evalkey if isinstance(evalkey, PreparedEvalKey) else None
     mid = prepared.indices_mid if prepared else list(qap.indices_mid)
+    if prepared:
+        assert len(h) <= prepared.h_len, "Not enough generators."
     c_mid_raw = pack_scalars([int(c[i]) for i in mid], BN_N)
-    h_scalars = [int(h.coeffs[i]) for i in range(0, len(h))]
-    if prepared:
-        assert len(h_scalars) <= prepared.h_len, "Not enough generators."
 
-    jobs = []  # (name, group, device points, owned?, scalar bytes)
-    # the G2 sum first: its tail is the longest and then overlaps the other seven
-    order = sorted(_MID_SUMS, key=lambda t: not t[0].endswith("g2"))
-    for name, template, delta_terms in order:
-        raw = c_mid_raw
-        if deltas is not None:
-            raw = raw + pack_scalars([int(getattr(deltas, attr)) for attr, _ in delta_terms], BN_N)
-        if prepared:
-            jobs.append((name, prepared.groups[name], prepared.bases[name], False, raw))
-        else:
-            pts = [evalkey[template.format(i=i)] for i in mid]
-            if deltas is not None:
-                pts += [evalkey[k] for _, k in delta_terms]
-            group = type(pts[0])
-            dev = group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id)
-            jobs.append((name, group, dev, True, raw))
-    raw_h = pack_scalars(h_scalars, BN_N)
-    if prepared:
-        jobs.append(("h*g1", prepared.groups["h*g1"], prepared.bases["h*g1"], False, raw_h))
-    else:
-        pts = [evalkey["s^" + str(i) + "*g1"] for i in range(0, len(h))]
-        group = type(pts[0])
-        jobs.append(("h*g1", group, group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id), True, raw_h))
+    jobs, keep, proof = [], [], {}  # jobs: (name, group, device points, owned?)
 
-    proof, keep = {}, []
+    def issue(name, group, dev, owned, raw):
+        buf = ctypes.create_string_buffer(raw, len(raw)) if raw else ctypes.create_string_buffer(1)
+        keep.append(buf)  # msm_async reads the host buffer until its result is fetched
+        jobs.append((name, group, dev, owned))
+        group._ctx().msm_async(dev, ctypes.cast(buf, ctypes.c_void_p), 0, len(raw) // 32, len(jobs) - 1)
+
     try:
-        for slot, (name, group, dev, owned, raw) in enumerate(jobs):
-            buf = ctypes.create_string_buffer(raw, len(raw)) if raw else ctypes.create_string_buffer(1)
-            keep.append(buf)
-            group._ctx().msm_async(dev, ctypes.cast(buf, ctypes.c_void_p), 0, len(raw) // 32, slot)
-        for slot, (name, group, dev, owned, raw) in enumerate(jobs):
+        # the G2 sum first: its tail is the longest and then overlaps the other seven
+        for name, template, delta_terms in sorted(_MID_SUMS, key=lambda t: not t[0].endswith("g2")):
+            raw = c_mid_raw
+            if deltas is not None:
+                raw = raw + pack_scalars([int(getattr(deltas, attr)) for attr, _ in delta_terms], BN_N)
+            if prepared:
+                issue(name, prepared.groups[name], prepared.bases[name], False, raw)
+            else:
+                pts = [evalkey[template.format(i=i)] for i in mid]
+                if deltas is not None:
+                    pts += [evalkey[k] for _, k in delta_terms]
+                group = type(pts[0])
+                issue(name, group, group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id), True, raw)
+        # the coefficients of h are packed while the device works on the seven sums already issued
+        raw_h = pack_scalars([int(h.coeffs[i]) for i in range(0, len(h))], BN_N)
+        if prepared:
+            issue("h*g1", prepared.groups["h*g1"], prepared.bases["h*g1"], False, raw_h)
+        else:
+            pts = [evalkey["s^" + str(i) + "*g1"] for i in range(0, len(h))]
+            group = type(pts[0])
+            issue("h*g1", group, group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id), True, raw_h)
+        for slot, (name, group, dev, owned) in enumerate(jobs):
             proof[name] = group._make(group._ctx().result(slot, curve=group.curve_id))
     finally:
-        for name, group, dev, owned, raw in jobs:
+        for name, group, dev, owned in jobs:
             if owned:
                 dev.free()
     # same key order as the reference's dict
