@@ -29,6 +29,16 @@ def check_koe(g1_group, g2_group):
             assert proof[key].affine() == dec(val), key
         P, pi = twin.restriction_argument_prover(range(len(x)), x, gamma, pp)
         assert P == proof["P"] and pi == proof["pi"]
+        # the same with the parameters resident on the device, and a non-contiguous index set
+        ppd = twin.PreparedPP(pp)
+        try:
+            proof_d, u_d = twin.opening_linear_form_prover(L, x, gamma, ppd)
+            assert u_d == u and all(proof_d[k] == proof[k] for k in proof)
+            assert twin.linear_form_R(L, ppd, u) == twin.linear_form_R(L, pp, u)
+            S = [0, 2]
+            assert twin.restriction_argument_prover(S, x, gamma, ppd) == twin.restriction_argument_prover(S, x, gamma, pp)
+        finally:
+            ppd.free()
         # trusted setup twin: seeded like tests/golden/make_koe_golden.py (seed 77, the setup's three draws come first),
         # it reproduces the reference's public parameters (two fixed-base batches instead of 4n sequential powers)
         import random

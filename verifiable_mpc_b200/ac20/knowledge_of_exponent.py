@@ -25,6 +25,33 @@ def _msm(points, scalars):
         dev.free()
 
 
+class PreparedPP(dict):
+    """The public parameters of ``trusted_setup`` with ``pp_lhs`` / ``pp_rhs`` ALSO resident on the device, so the
+    prover functions below skip the upload of up to 2n bases per call (they only depend on the setup).  It is the
+    reference's ``pp`` dict (same keys, same lists) and can be passed wherever ``pp`` is expected."""
+
+    def __init__(self, pp):
+        super().__init__(pp)
+        self.dev = {}
+        for key in ("pp_lhs", "pp_rhs"):
+            group = type(pp[key][0])
+            self.dev[key] = group._ctx().upload_points([p.affine() for p in pp[key]], curve=group.curve_id)
+
+    def free(self):
+        for dev in self.dev.values():
+            dev.free()
+        self.dev = {}
+
+
+def _msm_pp(pp, key, first, count, scalars):
+    """sum_j scalars[j] * pp[key][first + j], from the resident copy when ``pp`` is a PreparedPP."""
+    dev = getattr(pp, "dev", {}).get(key)
+    if dev is None:
+        return _msm(list(pp[key][first:first + count]), scalars)
+    group = type(pp[key][0])
+    return group._make(group._ctx().msm(dev, pack_scalars(scalars, BN_N), off=first, n=count))
+
+
 def list_mul(x):
     return _msm(list(x), [1] * len(x))
 
@@ -66,6 +93,8 @@ def restriction_argument_prover(S, x, gamma, pp):
     """Restriction argument [Gro10], prover: (P, pi) over the S-indices of x (reference :75-91)."""
     S = list(S)
     scalars = [int(gamma)] + [int(x[i]) for i in S]
+    if S == list(range(len(S))):  # the usual case (all of x): a contiguous range of the parameters
+        return _msm_pp(pp, "pp_lhs", 0, len(S) + 1, scalars), _msm_pp(pp, "pp_rhs", 0, len(S) + 1, scalars)
     P = _msm([pp["pp_lhs"][0]] + [pp["pp_lhs"][i + 1] for i in S], scalars)
     pi = _msm([pp["pp_rhs"][0]] + [pp["pp_rhs"][i + 1] for i in S], scalars)
     return P, pi
@@ -100,7 +129,7 @@ def opening_linear_form_prover(L, x, gamma, pp, P=None, pi=None):
     assert int(u_linear) % q == c_bar[n], "L(x) not equal to n-th coefficient of c_poly"
     c_bar[n] = 0
     assert len(pp["pp_lhs"]) == 2 * n
-    proof["Q"] = _msm(list(pp["pp_lhs"]), [-c for c in c_bar])
+    proof["Q"] = _msm_pp(pp, "pp_lhs", 0, 2 * n, [-c for c in c_bar])
     return proof, u
 
 
@@ -108,7 +137,7 @@ def linear_form_R(L, pp, u):
     """The verifier's ``R = prod pp_rhs[j] ** L_linear.coeffs[n-(j+1)]`` (reference :146) as one G2 MSM."""
     n = len(L.coeffs)
     L_linear, _ = pivot.affine_to_linear(L, u, n)
-    return _msm(list(pp["pp_rhs"][:n]), [int(L_linear.coeffs[n - (j + 1)]) for j in range(n)])
+    return _msm_pp(pp, "pp_rhs", 0, n, [int(L_linear.coeffs[n - (j + 1)]) for j in range(n)])
 
 
 def prove_nullity_koe(pp, lin_forms, x, gamma, gf, P, pi):
