@@ -9,6 +9,7 @@ halving of the witness and of the linear form, their cross terms and their decim
 draws the randomness, hashes the transcript bytes the device formats, and finishes the last few rounds on integers.
 """
 import logging
+from concurrent.futures import ThreadPoolExecutor
 from random import SystemRandom
 
 from . import pivot
@@ -17,6 +18,11 @@ from ..engine import ED_L
 from ..fingroups import DevicePointList
 
 prng = SystemRandom()
+
+
+def _WORKER():
+    return ThreadPoolExecutor(max_workers=1)
+
 
 logger_cp = logging.getLogger("compressed_pivot")
 logger_cp.setLevel(logging.INFO)
@@ -347,7 +353,10 @@ class _FormText:
         return len(self.form.coeffs), pivot.pack_scalars([c.value for c in self.form.coeffs], self.q), self.form.constant
 
 
-def _first_challenges(t, A, generators, P, L, y, order, gf=None, L_text=None):
+def _first_prefix(t, A, generators, P, L, y, order, gf=None, L_text=None):
+    """The O(N) part of the first pre-image (text or bytes of the generators and of L), hashed once: both challenges
+    share it.  Only device calls and SHA-256 updates, both of which release the GIL -- protocol_5's device front end
+    runs it on a worker thread while the main thread packs the witness."""
     if L_text is not None:
         L = L_text
     elif FAST_INT_PATH and gf is not None and gf.order == order and _all_in_field(L.coeffs, gf):
@@ -355,17 +364,24 @@ def _first_challenges(t, A, generators, P, L, y, order, gf=None, L_text=None):
     input_list = [t, A.normalize(), generators, P.normalize(), L, y]
     if logger_cp_hin.isEnabledFor(logging.DEBUG):
         logger_cp_hin.debug(f"Before fiat_shamir_hash, input_list=\n{input_list}")
-    # str(input_list + [b] + [tag]) for b = 0, 1 share everything but one character: hash the O(N) prefix once
     if pivot.TRANSCRIPT == "binary":
-        prefix = pivot.binary_prefix(b"cp-first", input_list, order)
-        c0 = pivot.binary_finish(prefix, [0], order)
-        c1 = pivot.binary_finish(prefix, [1], order)
-        return c0, c1
-    prefix = pivot.fiat_shamir_prefix(input_list)
+        return "binary", pivot.binary_prefix(b"cp-first", input_list, order)
+    return "reference", pivot.fiat_shamir_prefix(input_list)
+
+
+def _first_finish(state, order):
+    mode, prefix = state
+    if mode == "binary":
+        return pivot.binary_finish(prefix, [0], order), pivot.binary_finish(prefix, [1], order)
+    # str(input_list + [b] + [tag]) for b = 0, 1 share everything but one character
     c0 = pivot.fiat_shamir_finish(prefix, [0, _TAG], order)
     c1 = pivot.fiat_shamir_finish(prefix, [1, _TAG], order)
     logger_cp_hout.debug(f"After hash, hash=\n{c0}, {c1}")
     return c0, c1
+
+
+def _first_challenges(t, A, generators, P, L, y, order, gf=None, L_text=None):
+    return _first_finish(_first_prefix(t, A, generators, P, L, y, order, gf, L_text), order)
 
 
 def _g_hat(g, h, group):
@@ -388,17 +404,28 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
     ctx = g_hat.dev.ctx
     proof = {}
     zd = ctx.upload_scalars(r + [rho], order)
-    xd = ctx.upload_scalars([v.value for v in x] + [pivot._int(gamma)], order)
-    Ld = ctx.upload_scalars([cf.value for cf in L.coeffs] + [0], order)
+    Ld = xd = None
     try:
+        Ld = ctx.upload_scalars([cf.value for cf in L.coeffs] + [0], order)
         t = gf(ctx.scalars_dot(Ld, 0, zd, 0, n)) + L.constant
         logger_cp.debug("Calculate A.")
         ctx.msm_dev(g_hat.dev, zd, slot=0, poff=g_hat.off, soff=0, n=n + 1)  # h**rho * prod g_i**r_i
         A = group._make(ctx.result(0))
         proof["t"] = t
         proof["A"] = A
-        c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf,
-                                   L_text=_DevForm(Ld, n, bool(gf.is_signed), L.constant))
+        # the first pre-image (text of the generators and of L: device calls + SHA-256, no GIL) is hashed on a worker
+        # thread while this thread packs the witness, which is pure Python and touches no device state
+        L_text = _DevForm(Ld, n, bool(gf.is_signed), L.constant)
+        if n >= 4096:  # below that, starting a thread costs more than the overlap returns
+            with _WORKER() as pool:
+                pending = pool.submit(_first_prefix, t, A, generators, P, L, y, order, gf, L_text)
+                x_raw = pivot.pack_scalars([v.value for v in x] + [pivot._int(gamma) % order], order)
+                state = pending.result()
+        else:
+            state = _first_prefix(t, A, generators, P, L, y, order, gf, L_text)
+            x_raw = pivot.pack_scalars([v.value for v in x] + [pivot._int(gamma) % order], order)
+        xd = ctx.upload_scalars(x_raw, order)
+        c0, c1 = _first_finish(state, order)
         zd.axpy(c0, xd, _lib.AXPY_ADD_SCALED)
         logger_cp.debug("Calculate Q.")
         Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
@@ -407,10 +434,12 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
         assert l_z * c1 % order == ctx.scalars_dot(Ld, 0, zd, 0, n + 1)  # L(z) * c1 == L_tilde(z_hat)
     except BaseException:
         zd.free()
-        Ld.free()
+        if Ld is not None:
+            Ld.free()
         raise
     finally:
-        xd.free()
+        if xd is not None:
+            xd.free()
     return _protocol_4_prover_dev(g_hat, k, Q, Ld, zd, gf, proof, 0)
 
 
