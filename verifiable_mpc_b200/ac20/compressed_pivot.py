@@ -20,6 +20,9 @@ from ..fingroups import DevicePointList
 prng = SystemRandom()
 
 
+FIRST_HASH_THREAD_MIN = 4096
+
+
 def _WORKER():
     return ThreadPoolExecutor(max_workers=1)
 
@@ -416,7 +419,7 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
         # the first pre-image (text of the generators and of L: device calls + SHA-256, no GIL) is hashed on a worker
         # thread while this thread packs the witness, which is pure Python and touches no device state
         L_text = _DevForm(Ld, n, bool(gf.is_signed), L.constant)
-        if n >= 4096:  # below that, starting a thread costs more than the overlap returns
+        if n >= FIRST_HASH_THREAD_MIN:  # below that, starting a thread costs more than the overlap returns
             with _WORKER() as pool:
                 pending = pool.submit(_first_prefix, t, A, generators, P, L, y, order, gf, L_text)
                 x_raw = pivot.pack_scalars([v.value for v in x] + [pivot._int(gamma) % order], order)
