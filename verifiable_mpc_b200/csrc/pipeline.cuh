@@ -27,7 +27,9 @@ enum { kTailWays = 8, kTailWaysEd = 4, kTailWaysBN = 8 };
 
 struct MsmOptions {
     uint32_t window_bits = 0;  // 0 = auto
-    uint32_t reduce_log2r = 3;
+    uint32_t reduce_log2r = 3;     // Ed25519 bucket tree: radix 8
+    uint32_t reduce_log2r_w = 2;   // BN256: radix 4 (48 instead of 64 dependent additions down the 4096-bucket tree;
+                                   // G2 2^14-term MSM 1.62 -> 1.54 ms, profiles/r01/bn256_msm_v5_windows.md)
     bool sort_buckets = true;
     uint32_t cap_factor = 8;   // a bucket's own thread sums at most max(64, cap_factor * n / NB) entries (kernels.cuh)
     uint32_t quad_threshold = 16384;  // tree levels with at most this many output nodes run quad-cooperative; 0 = never
@@ -298,11 +300,11 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits, false, 11.0, 16.0 * 0.6);
     if (c > 16) c = 16;
     // 2^9 .. 2^16 terms are latency-bound on this curve (few, expensive additions per thread): c = 13 gives 20 x 4096
-    // short bucket chains and a bucket tree of exactly four full radix-8 levels; measured fastest or tied at 2^10, 2^12,
+    // short bucket chains and a bucket tree of exactly six full radix-4 levels (4096 = 4^6); measured fastest or tied at 2^10, 2^12,
     // 2^14 and 2^16 on G1 and G2 (profiles/r01/bn256_msm_v5_windows.jsonl), 35 % faster than the work-minimising c = 11
     if (!opt.window_bits && n >= 512 && n <= (1u << 16)) c = 13;
     MsmGeom g = make_geom(n, c, scalar_bits);
-    uint32_t R = 1u << opt.reduce_log2r;
+    uint32_t R = 1u << opt.reduce_log2r_w;
     // long-bucket granularity for this curve: additions are 3-9x dearer than on Ed25519 and the MSMs are small, so a
     // bucket's own thread takes at most max(16, ...) entries and overflow segments may be as short as one warp pass
     const uint32_t kCapFloor = 16, kSegFloor = 32;
@@ -368,7 +370,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         inT = (const wjac<F> *)ws.nodeT[tw][pp];
         pp ^= 1;
         cnt = cnt_out;
-        log2s += opt.reduce_log2r;
+        log2s += opt.reduce_log2r_w;
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
     KFinalW<F> k7 = {inS, inT, out_jac, out_wire, g.W, g.c};

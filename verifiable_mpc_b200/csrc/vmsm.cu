@@ -896,7 +896,7 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             return VMSM_OK;
         case VMSM_OPT_REDUCE_RADIX:
             if (value < 1 || value > 6) return fail(VMSM_ERR_INVALID, "reduce radix log2 must be in [1, 6]");
-            c->opt.reduce_log2r = (uint32_t)value;
+            c->opt.reduce_log2r = c->opt.reduce_log2r_w = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_SHARD_SEQ:
             if (value < 0 || value > 0xffffffffll) return fail(VMSM_ERR_INVALID, "shard seq out of range");
