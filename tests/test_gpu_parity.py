@@ -459,3 +459,30 @@ def test_thin_counting_sort_grid(ctx, sort_blocks):
             assert ctx.result(j) == want[j % 3], j
     finally:
         ctx.set_option(_lib.OPT_SORT_BLOCKS, 148)
+
+
+def test_pooled_allocations_are_recycled_safely(ctx, known_points):
+    """Freed point / scalar vectors go to a per-context pool and are handed out again (cudaFree would synchronise the
+    device): many upload / free cycles of mixed sizes with MSMs in between must keep giving correct results, and a
+    freed handle must stay invalid."""
+    from verifiable_mpc_b200 import VmsmError
+
+    dlogs, pts = known_points
+    rng = random.Random(12)
+    for it in range(60):
+        n = rng.choice([1, 3, 17, 64, 200, 300])
+        dev = ctx.upload_points(pts[:n])
+        sc = [rng.randrange(E.L) for _ in range(n)]
+        ds = ctx.upload_scalars(sc)
+        ctx.msm_dev(dev, ds, slot=it % 8)
+        got = ctx.result(it % 8)
+        assert got == E.msm_known_dlog(sc, dlogs[:n]), it
+        assert dev.tolist() == pts[:n] and ds.tolist() == sc
+        handle = dev.handle
+        dev.free()
+        ds.free()
+        if it == 0:
+            stale = type(dev)(ctx, handle, n, 0)
+            with pytest.raises(VmsmError):
+                stale.tolist()
+            stale.handle = 0
