@@ -221,6 +221,153 @@ struct KFinalW {
     }
 };
 
+// ---------------------------------------------------------------------------------------------- lane-cooperative tail
+// Four adjacent lanes share one Jacobian operation of the Horner chain: every lane holds the whole point, the
+// independent field multiplications of a formula stage are spread over the lanes (one each) and the products are
+// broadcast with width-4 shuffles.  A doubling is 3 multiplication latencies instead of 7, a full addition 5 instead
+// of 16.  The operands are identical in the four lanes, so the exceptional-case branches are uniform.
+#if defined(__CUDA_ARCH__)
+template <class T>
+VMSM_D T wq_get(const T &v, int src) {
+    T r;
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(&v);
+    uint32_t *out = reinterpret_cast<uint32_t *>(&r);
+    // only the caller's own quad takes part: quads of one warp may be in different branches (different nodes)
+    const uint32_t mask = 0xfu << (threadIdx.x & 28u);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); i++) out[i] = __shfl_sync(mask, in[i], src, 4);
+    return r;
+}
+template <class T>
+VMSM_D T wq_pick(int q, const T &a0, const T &a1, const T &a2, const T &a3) {
+    T r;
+    const uint32_t *p0 = reinterpret_cast<const uint32_t *>(&a0), *p1 = reinterpret_cast<const uint32_t *>(&a1);
+    const uint32_t *p2 = reinterpret_cast<const uint32_t *>(&a2), *p3 = reinterpret_cast<const uint32_t *>(&a3);
+    uint32_t *out = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); i++) {
+        uint32_t lo = (q & 1) ? p1[i] : p0[i], hi = (q & 1) ? p3[i] : p2[i];
+        out[i] = (q & 2) ? hi : lo;
+    }
+    return r;
+}
+
+// 2P (dbl-2009-l, a = 0): stage 1 {X^2, Y^2, Y*Z}, stage 2 {B^2, (X+B)^2, E^2}, stage 3 E*(D - X3) on every lane
+template <class F>
+static __device__ __noinline__ wjac<F> wq_dbl(int q, const wjac<F> &p) {
+    typedef typename F::T T;
+    T m1 = F::mul(wq_pick(q, p.X, p.Y, p.Y, p.X), wq_pick(q, p.X, p.Y, p.Z, p.X));
+    T A = wq_get(m1, 0), B = wq_get(m1, 1), YZ = wq_get(m1, 2);
+    T E = F::add(F::dbl(A), A);
+    T XB = F::add(p.X, B);
+    T m2 = F::mul(wq_pick(q, B, XB, E, B), wq_pick(q, B, XB, E, B));
+    T C = wq_get(m2, 0), t = wq_get(m2, 1), Fq = wq_get(m2, 2);
+    T D = F::dbl(F::sub(F::sub(t, A), C));
+    wjac<F> r;
+    r.X = F::sub(Fq, F::dbl(D));
+    T C8 = F::dbl(F::dbl(F::dbl(C)));
+    r.Y = F::sub(F::mul(E, F::sub(D, r.X)), C8);
+    r.Z = F::dbl(YZ);
+    return r;
+}
+
+// P + Q (add-2007-bl), five stages
+template <class F>
+static __device__ __noinline__ wjac<F> wq_add(int q, const wjac<F> &p, const wjac<F> &o) {
+    typedef typename F::T T;
+    if (F::is_zero(p.Z)) return o;
+    if (F::is_zero(o.Z)) return p;
+    T m1 = F::mul(wq_pick(q, p.Z, o.Z, p.Y, o.Y), wq_pick(q, p.Z, o.Z, o.Z, p.Z));
+    T Z1Z1 = wq_get(m1, 0), Z2Z2 = wq_get(m1, 1), Y1Z2 = wq_get(m1, 2), Y2Z1 = wq_get(m1, 3);
+    T m2 = F::mul(wq_pick(q, p.X, o.X, Y1Z2, Y2Z1), wq_pick(q, Z2Z2, Z1Z1, Z2Z2, Z1Z1));
+    T U1 = wq_get(m2, 0), U2 = wq_get(m2, 1), S1 = wq_get(m2, 2), S2 = wq_get(m2, 3);
+    T H = F::sub(U2, U1);
+    T rr = F::sub(S2, S1);
+    if (F::is_zero(H)) {
+        if (F::is_zero(rr)) return wq_dbl<F>(q, p);
+        return wj_identity<F>();
+    }
+    T H2 = F::dbl(H), r2 = F::dbl(rr), ZS = F::add(p.Z, o.Z);
+    T m3 = F::mul(wq_pick(q, H2, r2, ZS, H2), wq_pick(q, H2, r2, ZS, H2));
+    T I = wq_get(m3, 0), R2 = wq_get(m3, 1), ZZ = wq_get(m3, 2);
+    T Zt = F::sub(F::sub(ZZ, Z1Z1), Z2Z2);
+    T m4 = F::mul(wq_pick(q, H, U1, Zt, H), wq_pick(q, I, I, H, I));
+    T J = wq_get(m4, 0), V = wq_get(m4, 1);
+    wjac<F> r;
+    r.Z = wq_get(m4, 2);
+    r.X = F::sub(F::sub(R2, J), F::dbl(V));
+    T m5 = F::mul(wq_pick(q, r2, S1, r2, S1), wq_pick(q, F::sub(V, r.X), J, F::sub(V, r.X), J));
+    r.Y = F::sub(wq_get(m5, 0), F::dbl(wq_get(m5, 1)));
+    return r;
+}
+#endif
+
+// Lane-cooperative twin of KReduceW: four lanes per tree node (launched with 4 * nodes threads, a multiple of 4)
+template <class F>
+struct KReduceWQ {
+    enum { kBlock = 128 };
+    const wjac<F> *inS, *inT;
+    wjac<F> *outS, *outT;
+    uint32_t cnt_in, cnt_out, R, log2s;
+    VMSM_HD void operator()(uint32_t tid) const {
+#if defined(__CUDA_ARCH__)
+        const int q = tid & 3;
+        const uint32_t node = tid >> 2;
+        uint32_t w = node / cnt_out, j = node - w * cnt_out;
+        uint32_t first = j * R;
+        uint32_t m = cnt_in - first < R ? cnt_in - first : R;
+        const wjac<F> *s = inS + (size_t)w * cnt_in + first;
+        wjac<F> acc = wj_identity<F>(), run = wj_identity<F>();
+        for (uint32_t i = m - 1; i >= 1; i--) {
+            acc = wq_add<F>(q, acc, ld_obj(s + i));
+            run = wq_add<F>(q, run, acc);
+        }
+        acc = wq_add<F>(q, acc, ld_obj(s));
+        for (uint32_t k = 0; k < log2s; k++) run = wq_dbl<F>(q, run);
+        if (inT) {
+            const wjac<F> *t = inT + (size_t)w * cnt_in + first;
+            for (uint32_t i = 0; i < m; i++) run = wq_add<F>(q, run, ld_obj(t + i));
+        }
+        if (q == 0) {
+            st_obj(outS + (size_t)w * cnt_out + j, acc);
+            st_obj(outT + (size_t)w * cnt_out + j, run);
+        }
+#else
+        if (tid & 3) return;
+        KReduceW<F> k = {inS, inT, outS, outT, cnt_in, cnt_out, R, log2s};
+        k(tid >> 2);
+#endif
+    }
+};
+
+// Lane-cooperative twin of KFinalW (one warp: every quad computes the same chain, lane 0 stores)
+template <class F>
+struct KFinalWQ {
+    enum { kBlock = 32 };
+    const wjac<F> *S, *T;
+    wjac<F> *out_jac;
+    waff<F> *out_wire;
+    uint32_t W, c;
+    VMSM_HD void operator()(uint32_t tid) const {
+#if defined(__CUDA_ARCH__)
+        const int q = tid & 3;
+        wjac<F> acc = wj_identity<F>();
+        for (int32_t w = (int32_t)W - 1; w >= 0; w--) {
+            if (w != (int32_t)W - 1)
+                for (uint32_t k = 0; k < c; k++) acc = wq_dbl<F>(q, acc);
+            acc = wq_add<F>(q, acc, wq_add<F>(q, ld_obj(S + w), ld_obj(T + w)));
+        }
+        if (tid == 0) {
+            st_obj(out_jac, acc);
+            st_obj(out_wire, wa_to_wire(wj_to_aff(acc)));
+        }
+#else
+        KFinalW<F> k = {S, T, out_jac, out_wire, W, c};
+        k(tid);
+#endif
+    }
+};
+
 // upload: wire (plain canonical) -> validation -> Montgomery base
 template <class F>
 struct KUploadW {

@@ -364,8 +364,9 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     int pp = 0;
     do {
         uint32_t cnt_out = (cnt + R - 1) / R;
-        KReduceW<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[tw][pp], (wjac<F> *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s};
-        be.launch(k6, g.W * cnt_out);
+        // four lanes per node: these MSMs are small, the tree is latency-bound at every level
+        KReduceWQ<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[tw][pp], (wjac<F> *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s};
+        be.launch(k6, 4 * g.W * cnt_out);
         inS = (const wjac<F> *)ws.nodeS[tw][pp];
         inT = (const wjac<F> *)ws.nodeT[tw][pp];
         pp ^= 1;
@@ -373,7 +374,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         log2s += opt.reduce_log2r_w;
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
-    KFinalW<F> k7 = {inS, inT, out_jac, out_wire, g.W, g.c};
+    KFinalWQ<F> k7 = {inS, inT, out_jac, out_wire, g.W, g.c};
     be.launch(k7, 32);
     be.phase_mark(PH_FINAL);
     be.result_ready();
