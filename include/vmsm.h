@@ -58,6 +58,8 @@ extern "C" {
                                   one thread per scalar */
 #define VMSM_OPT_FOLD_QUAD_MAX 12 /* generator folds of at most this many outputs use the 4-lanes-per-element kernel
                                     (latency-bound rounds); 0 = never */
+#define VMSM_OPT_BN_QUAD_ACC 13 /* BN256 accumulate kernel with four lanes per bucket: 0 never, 1 (default) for the sizes
+                                  where it was measured faster, 2 always */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--windows", type=int, nargs="+", default=[0])
     ap.add_argument("--radix", type=int, default=-1, help="experiment: VMSM_OPT_REDUCE_RADIX (log2 of the tree radix)")
+    ap.add_argument("--quad-acc", type=int, default=-1, help="experiment: VMSM_OPT_BN_QUAD_ACC")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     from verifiable_mpc_b200 import Context, _lib, fingroups
@@ -27,6 +28,8 @@ def main():
 
     ctx = Context(0)
     ctx.set_option(_lib.OPT_PHASE_TIMING, 1)
+    if args.quad_acc >= 0:
+        ctx.set_option(_lib.OPT_BN_QUAD_ACC, args.quad_acc)
     if args.radix >= 0:
         ctx.set_option(_lib.OPT_REDUCE_RADIX, args.radix)
     out = open(args.out, "a") if args.out else None

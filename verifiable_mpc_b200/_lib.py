@@ -16,6 +16,7 @@ OPT_WINDOW_BITS, OPT_PHASE_TIMING, OPT_SORT_BUCKETS, OPT_CHECK_POINTS, OPT_REDUC
 OPT_QUAD_THRESHOLD, OPT_ASYNC_TAIL, OPT_CAP_FACTOR, OPT_SHARD_SEQ, OPT_ASYNC_SORT = 6, 7, 8, 9, 10
 OPT_SORT_BLOCKS = 11
 OPT_FOLD_QUAD_MAX = 12
+OPT_BN_QUAD_ACC = 13
 FOLD_WITNESS, FOLD_FORM = 0, 1
 AXPY_ADD_SCALED, AXPY_SCALE_ADD, AXPY_SCALE = 0, 1, 2
 PHASES = ("digits", "scan", "scatter", "order", "handoff", "accumulate", "reduce", "final")

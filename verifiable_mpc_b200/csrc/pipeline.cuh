@@ -32,6 +32,7 @@ struct MsmOptions {
                                    // G2 2^14-term MSM 1.62 -> 1.54 ms, profiles/r01/bn256_msm_v5_windows.md)
     bool sort_buckets = true;
     uint32_t cap_factor = 8;   // a bucket's own thread sums at most max(64, cap_factor * n / NB) entries (kernels.cuh)
+    uint32_t w_quad_acc = 1;       // BN256 accumulate with four lanes per bucket: 0 never, 1 by size, 2 always
     uint32_t quad_threshold = 16384;  // tree levels with at most this many output nodes run quad-cooperative; 0 = never
 };
 
@@ -340,9 +341,17 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
         if (cap < kCapFloor) cap = kCapFloor;
         be.zero(ws.ctl_[tw], sizeof(OverflowCtl));
-        KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl_[tw],
-                              ws.tasks_[tw], ws.longs_[tw], extra, n_main, kSegFloor};
-        be.launch(k5, nbuckets);
+        // four lanes per bucket where measured faster (2^15: -8 %, 2^16: -14 %; slower at <= 2^14, where the tails set
+        // the pace, and from 2^17, where the kernel is throughput-bound): profiles/r01/bn256_msm_v5_windows.md
+        if (opt.w_quad_acc == 2 || (opt.w_quad_acc == 1 && n > (1u << 14) && n <= (1u << 16))) {
+            KAccumulateWQ<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl_[tw],
+                                   ws.tasks_[tw], ws.longs_[tw], extra, n_main, kSegFloor};
+            be.launch(k5, 4 * nbuckets);
+        } else {
+            KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl_[tw],
+                                  ws.tasks_[tw], ws.longs_[tw], extra, n_main, kSegFloor};
+            be.launch(k5, nbuckets);
+        }
         be.phase_mark(PH_ACCUMULATE);
         // overflow tasks, combine, bucket tree, Horner and inversion on side stream `tw`, underneath the heads of the
         // following MSMs (the eight MSMs of a Pinocchio proof are independent)

@@ -912,6 +912,10 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
         case VMSM_OPT_ASYNC_SORT:
             c->async_sort = value != 0;
             return VMSM_OK;
+        case VMSM_OPT_BN_QUAD_ACC:
+            if (value < 0 || value > 2) return fail(VMSM_ERR_INVALID, "BN quad accumulate mode out of range");
+            c->opt.w_quad_acc = (uint32_t)value;
+            return VMSM_OK;
         case VMSM_OPT_FOLD_QUAD_MAX:
             if (value < 0 || value > (1 << 26)) return fail(VMSM_ERR_INVALID, "fold quad threshold out of range");
             c->fold_quad_max = (uint32_t)value;
