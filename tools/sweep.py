@@ -21,11 +21,14 @@ def main():
     ap.add_argument("--cap", type=int, nargs="+", default=[0])
     ap.add_argument("--async-tail", type=int, nargs="+", default=[1])
     ap.add_argument("--sort-blocks", type=int, nargs="+", default=[-1])
+    ap.add_argument("--quad-threshold", type=int, default=-1, help="experiment: VMSM_OPT_QUAD_THRESHOLD")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     ctx = Context(0)
     ctx.set_option(_lib.OPT_PHASE_TIMING, 1)
+    if args.quad_threshold >= 0:
+        ctx.set_option(_lib.OPT_QUAD_THRESHOLD, args.quad_threshold)
     peak = ctx.imad_peak()
     out = open(args.out, "a") if args.out else None
     for logn in args.logn:
