@@ -42,6 +42,37 @@ def test_twin_device_scalar_path_matches_reference_fixture(gpu_group, idx, monke
     check_case(load_cases()[idx], group, gf)
 
 
+def test_reference_demo_driver_statement_n128(gpu_group):
+    """BASELINE config 1: the calls demos/demo_zkp_ac20.py --elliptic makes into the pivot (N = 128), on the device,
+    against what the unmodified reference returned for them (tests/golden/ac20_demo_n128.json.gz)."""
+    from ac20_cases import check_demo_case
+
+    group, gf = gpu_group
+    check_demo_case(group, gf)
+
+
+@pytest.mark.parametrize("k", [10, 12, 16])
+def test_twin_matches_reference_at_configured_sizes(gpu_group, k):
+    """N = 2^10, 2^12, 2^16 (BASELINE config 3): commitment and complete proof equal to the unmodified reference's
+    (seeded inputs, tests/golden/ac20_big_<k>.json); device-resident witness / form path, crossing the 256-entry host
+    hand-off and, at 2^16, the 2^13 fold-kernel switch."""
+    from ac20_cases import check_big_case
+
+    group, gf = gpu_group
+    check_big_case(k, group, gf)
+
+
+@pytest.mark.parametrize("k", [10, 12])
+def test_twin_host_integer_path_matches_reference_at_configured_sizes(gpu_group, k, monkeypatch):
+    """Same fixtures through the host-integer round loop (witness / form algebra in Python, MSMs on the device)."""
+    from ac20_cases import check_big_case
+    from verifiable_mpc_b200.ac20 import compressed_pivot as cp
+
+    group, gf = gpu_group
+    monkeypatch.setattr(cp, "DEVICE_SCALAR_PATH", False)
+    check_big_case(k, group, gf)
+
+
 def test_group_ops_on_device(gpu_group):
     from oracle import ed25519 as E
 
@@ -128,6 +159,14 @@ def test_mpc_share_local_commitments(gpu_group):
     group, gf = gpu_group
     check_share_local_commitments(group, gf, n=33)
     check_share_local_commitments(group, gf, n=1023, m=5, t=2, seed=9)
+
+
+def test_list_mul_against_oracle(gpu_group):
+    """pivot.list_mul on the device, expected values computed by oracle/ed25519.py."""
+    from mpc_cases import check_list_mul
+
+    group, gf = gpu_group
+    check_list_mul(group)
 
 
 def test_binary_transcript_mode(gpu_group):

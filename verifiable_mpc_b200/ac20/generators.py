@@ -11,6 +11,10 @@ prng = SystemRandom()
 
 def create_generators(g_length, group, with_k=True, exponents=None):
     """-> {"g": DevicePointList(g_length), "h": group.generator, "k": point}  (``with_k=False``: basic pivot)."""
+    if getattr(group, "curve_id", 0) != 0:
+        # DevicePointList and the fixed-base launch below are the Ed25519 wire format; the reference's loop works for
+        # any group, so say so instead of returning Ed25519 points tagged as another group (ADVICE r1)
+        raise NotImplementedError("create_generators on the device is implemented for the Ed25519 group only")
     ctx = group._ctx()
     if exponents is None:
         exponents = [prng.randrange(1, group.order) for _ in range(g_length)]

@@ -59,6 +59,15 @@ class PreparedEvalKey:
             self._put(name, pts)
         self._put("h*g1", [evalkey["s^" + str(i) + "*g1"] for i in range(h_len)])
 
+    @classmethod
+    def from_device_bases(cls, indices_mid, h_len, groups, bases):
+        """Key whose base vectors are already on the device (``bases[name]``: DevicePoints holding the mid-wire entries
+        followed by the zero-knowledge entries of that sum, in ``_MID_SUMS`` order; ``"h*g1"``: the s-powers), e.g.
+        produced by ``generate_evalkey``-style fixed-base batches without a round trip through host objects."""
+        self = cls.__new__(cls)
+        self.indices_mid, self.h_len, self.groups, self.bases = list(indices_mid), h_len, dict(groups), dict(bases)
+        return self
+
     def _put(self, name, pts):
         group = type(pts[0])
         self.groups[name] = group
