@@ -4,10 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 20] [--impl reference] [--sweep]
 
 N = 1 runs in-process; N > 1 is launched by the driver under torchrun (one rank per GPU; torch.distributed is used
-only for the barrier / max-over-ranks / 128-byte partial exchange -- the data path is libvmsm.so).  A "step" is one
-MSM over one batch of synthetic seeded scalars with the bases resident in HBM.  Multi-GPU: index-range split of ONE
-(N * 2^log2n)-term MSM, every rank computes the partial sum of its slice, rank 0 adds the N partials ("weak" scaling:
-per-GPU work fixed).  Prints ONE JSON line on rank 0.
+only for the barrier / max-over-ranks -- the data path is libvmsm.so, partial results travel GPU -> GPU through a peer
+mailbox).  A "step" is one batch of MSMS_PER_STEP MSMs of 2^log2n terms each over synthetic seeded scalars with the
+bases resident in HBM (a batch, so that the driver's K = 20 steps time ~0.7 s instead of 30 ms).  Multi-GPU: index-range
+split of (N * 2^log2n)-term MSMs, every rank computes the partial sum of its slice, rank 0 adds the N partials
+("weak" scaling: per-GPU work fixed).  Prints ONE JSON line on rank 0.  Beside the headline the same line carries the
+rest of BASELINE.json's metric: `sweep` (2^16, 2^18 points/s and roofline fraction), `fixed_generators` (the same sizes
+over precomputed generator tables), `ac20` (compressed-pivot prove / verify latency at N = 2^16 with a CPU figure) and
+`strong` (one fixed 2^20-term MSM split over the N GPUs).
 """
 import argparse
 import json
@@ -25,6 +29,8 @@ UNIT = "points/s"
 SEED_SCALARS, SEED_BASES = 0x5EED, 0x5EEE
 NSETS = 3  # distinct (bases, scalars) sets rotated between steps so no step finds its inputs in L2
 E2E_DEPTH = 4  # MSMs in flight in the end-to-end loop
+MSMS_PER_STEP = 24  # one step = this many back-to-back MSMs (each over the next of the NSETS input sets)
+STRONG_LOG2N = 20  # the fixed-size MSM of the strong-scaling block
 
 # SURVEY.md 8(d)/App. E work model: limb products per point at the LP-minimising window c*(n)
 M, S = 72, 44
@@ -147,16 +153,145 @@ def dlog_sum(seed_s, seed_r, n, start=0):
     return tot % L
 
 
+def time_msms(ctx, pairs, count, warm=3, pre_issue=None):
+    """ms per MSM of `count` device-resident MSMs issued back to back over the rotating (points, scalars) pairs."""
+    for w in range(warm):
+        ctx.msm_dev(*pairs[w % len(pairs)], slot=0)
+    ctx.sync()
+    ctx.timer_start()
+    for s in range(count):
+        if pre_issue:
+            pre_issue(s)
+        ctx.msm_dev(*pairs[s % len(pairs)], slot=s % 48)
+    return ctx.timer_stop() / count
+
+
+def synth_pairs(ctx, n, nsets, seed_off=0):
+    """`nsets` device-generated (bases g_i = r_i*B, scalars) pairs of n terms; seeds as oracle/prng.py specifies."""
+    return [(ctx.fixed_base(seed=SEED_BASES + seed_off + 16 * k, n=n), ctx.synth_scalars(SEED_SCALARS + seed_off + 16 * k, n))
+            for k in range(nsets)]
+
+
+def sets_beyond_l2(n, bytes_per_term=128):
+    """Enough distinct input sets that a rotation never finds its inputs in the 126 MB L2."""
+    return max(NSETS, -(-160 * (1 << 20) // (n * bytes_per_term)))
+
+
+def sweep_block(ctx, peak_tlps, log2ns=(16, 18)):
+    """Points/s at the other sizes of the metric's range, plain path and over precomputed generator tables; the result
+    of every configuration is checked against the known-dlog identity (plain) / the plain result (tables)."""
+    from verifiable_mpc_b200 import _lib
+
+    out, fixed = [], []
+    for logn in log2ns:
+        n = 1 << logn
+        nsets = sets_beyond_l2(n)
+        pairs = synth_pairs(ctx, n, nsets, seed_off=0x1000 * logn)
+        count = max(48, min(512, (1 << 27) // n))
+        ms = time_msms(ctx, pairs, count)
+        last = (count - 1) % len(pairs)
+        got = ctx.result((count - 1) % 48)
+        e = dlog_sum(SEED_SCALARS + 0x1000 * logn + 16 * last, SEED_BASES + 0x1000 * logn + 16 * last, n)
+        ok = bool(got == ctx.fixed_base(scalars=[e]).tolist()[0])
+        pps = n / (ms * 1e-3)
+        out.append({"log2n": logn, "points_per_s": pps, "ms_per_msm": ms, "msms_timed": count, "input_sets": nsets,
+                    "whole_msm_lp_per_point": lp_per_point(n), "whole_msm_frac": pps * lp_per_point(n) / (peak_tlps * 1e12),
+                    "result_checked_vs_known_dlog": ok})
+        # the same MSMs over tables of 2^(16 w) * g_i (fixed generators): table footprint 16 x 96 B per point
+        psets = pairs[:max(NSETS, -(-160 * (1 << 20) // (n * 16 * 96)))]
+        t0 = time.perf_counter()
+        for pts, _ in psets:
+            pts.precompute()
+        ctx.sync()
+        t_pre = (time.perf_counter() - t0) / len(psets)
+        ms_p = time_msms(ctx, psets, count)
+        lastp = (count - 1) % len(psets)
+        gotp = ctx.result((count - 1) % 48)
+        ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 1 << 30)  # the plain path on the same inputs, for the comparison
+        ctx.msm_dev(*psets[lastp], slot=50)
+        okp = bool(gotp == ctx.result(50))
+        ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 256)
+        ppsp = n / (ms_p * 1e-3)
+        fixed.append({"log2n": logn, "points_per_s": ppsp, "ms_per_msm": ms_p, "table_build_ms": 1e3 * t_pre,
+                      "table_bytes_per_point": 16 * 96, "input_sets": len(psets),
+                      "lp_per_point_executed": (16 * n * MADD) / n,
+                      "frac_of_peak_on_executed_work": ppsp * 16 * MADD / (peak_tlps * 1e12),
+                      "frac_on_survey_work_model": ppsp * lp_per_point(n) / (peak_tlps * 1e12),
+                      "equals_plain_path_result": okp})
+        for pts, sc in pairs:
+            pts.free()
+            sc.free()
+    return out, fixed
+
+
+def ac20_block(ctx):
+    """AC20 compressed-pivot prove / verify latency at N = 2^16 through the reference-facing Python API
+    (protocol_5_prover / protocol_5_verifier twins; host lists of field elements in, proof dict out), wall clock."""
+    from oracle import ed25519 as E
+    from tools import bench_ac20
+    from verifiable_mpc_b200 import fingroups
+    from verifiable_mpc_b200.finfields import GF
+
+    group = fingroups.EllipticCurve("Ed25519", "projective")
+    group.is_additive, group.is_multiplicative = False, True
+    old = fingroups.Ed25519Point.context
+    fingroups.Ed25519Point.context = ctx
+    try:
+        gf = GF(group.order)
+        bench_ac20.measure(group, gf, 12, 1)  # warm-up (pools, pinned buffers, lazy tables)
+        rec = bench_ac20.measure(group, gf, 16, 3)
+        rec_pre = bench_ac20.measure(group, gf, 16, 3, precompute=True)
+    finally:
+        fingroups.Ed25519Point.context = old
+    # CPU figure beside it: the reference's prover is (MSM terms + fold elements) independent double-and-add scalar
+    # multiplications (pivot.py:143, compressed_pivot.py:41-42,64,110) -- operation count x measured cost per operation
+    import random
+    rnd = random.Random(3)
+    pt = E.scalar_mul(E.B, rnd.randrange(E.L))
+    t0 = time.perf_counter()
+    reps = 64
+    for _ in range(reps):
+        E.scalar_mul(pt, rnd.randrange(E.L))
+    t_mul = (time.perf_counter() - t0) / reps
+    N, rounds = 1 << 16, 15
+    msm_terms = N + sum(2 * ((N >> (i + 1)) + 1) for i in range(rounds))
+    fold_elems = N - 2
+    ops = msm_terms + fold_elems + 3 * rounds + 3
+    cores = os.cpu_count() or 1
+    recorded = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "ac20_big_16.json")) as f:
+            recorded = json.load(f)["reference_cpu_seconds"]
+    except Exception:
+        pass
+    return {"N": N, "api": "compressed_pivot.protocol_5_prover / protocol_5_verifier (reference signatures)",
+            "prove_ms": 1e3 * rec["prove_s"], "verify_ms": 1e3 * rec["verify_s"], "verified": rec["verified"],
+            "prove_breakdown_ms": {k: 1e3 * v for k, v in rec["prove_breakdown_s"].items()},
+            "prove_host_other_ms": 1e3 * rec["prove_host_other_s"],
+            "verify_breakdown_ms": {k: 1e3 * v for k, v in rec["verify_breakdown_s"].items()},
+            "transcript": rec["transcript"],
+            "with_generator_table": {"prove_ms": 1e3 * rec_pre["prove_s"], "verify_ms": 1e3 * rec_pre["verify_s"],
+                                     "z_commitment_ms": 1e3 * rec_pre["z_commitment_s"],
+                                     "table_build_ms": 1e3 * (rec_pre["precompute_s"] or 0.0)},
+            "z_commitment_ms": 1e3 * rec["z_commitment_s"],
+            "cpu_baseline": {"kind": "port", "prove_s_1_core": ops * t_mul, "prove_s_all_cores_ideal": ops * t_mul / cores,
+                             "cores": cores, "scalar_mult_ms_1_core": 1e3 * t_mul, "scalar_mults_per_proof": ops,
+                             "recorded_full_run_of_the_unmodified_reference": recorded,
+                             "sample": f"{reps} double-and-add scalar multiplications of oracle/ed25519.py on 1 core x the "
+                                       "reference prover's operation count (N-term announcement, 2 x (half+1) terms and "
+                                       "half fold elements per round); pure-Python ints, no gmpy2 (not installable "
+                                       "here); the recorded run is the whole unmodified protocol_5_prover on the MPyC "
+                                       "look-alike in the build container (tests/golden/make_ac20_big_golden.py 16)"}}
+
+
 def run_gpu(args, rank, world, dist):
-    import ctypes
-
-    import numpy as np
-
+    from tools import dist_util
     from verifiable_mpc_b200 import Context, _lib, shard, synth
 
     local = int(os.environ.get("LOCAL_RANK", rank))
     ctx = Context(local)
     n = 1 << args.log2n
+    R = args.msms_per_step
     if args.window:
         ctx.set_option(_lib.OPT_WINDOW_BITS, args.window)
     if args.sort_blocks >= 0:
@@ -188,21 +323,21 @@ def run_gpu(args, rank, world, dist):
     if dist is not None:
         shard.setup_mailbox(ctx, dist, rank, world)
 
-    def issue(kind, k, slot):
-        """One step on this rank: its shard of the (world * n)-term MSM (or the whole MSM when world == 1)."""
+    def issue(kind, k, slot, pts=None, sc=None):
+        """One MSM on this rank: its shard of the (world * n)-term MSM (or the whole MSM when world == 1)."""
         if dist is not None:
             seq_counter[0] += 1
             ctx.set_option(_lib.OPT_SHARD_SEQ, seq_counter[0])
         if kind == "dev":
-            ctx.msm_dev(bases[k], scal[k], slot=slot)
+            ctx.msm_dev(pts[k] if pts else bases[k], sc[k] if sc else scal[k], slot=slot)
         else:
             ctx.msm_async(bases[k], host_scal[k].ptr, 0, n, slot=slot)
 
-    def recycle_slots(s):
-        """Result slots / mailbox entries are reused every 48 steps.  A single GPU needs nothing (an unread result is
-        simply overwritten); with a mailbox a rank may not push step s into an entry the owner has not yet gathered
-        for step s - 48, so once per 48 steps the owner drains its pipeline and every rank waits for it."""
-        if dist is not None and s and s % 48 == 0:
+    def recycle_slots(i):
+        """Result slots / mailbox entries are reused every 48 MSMs.  A single GPU needs nothing (an unread result is
+        simply overwritten); with a mailbox a rank may not push MSM i into an entry the owner has not yet gathered
+        for MSM i - 48, so once per 48 MSMs the owner drains its pipeline and every rank waits for it."""
+        if dist is not None and i and i % 48 == 0:
             ctx.sync()
             dist.barrier()
 
@@ -210,21 +345,23 @@ def run_gpu(args, rank, world, dist):
         """Owner: the sum over all ranks (gathered on the device); other ranks: their own partial."""
         return ctx.result(slot)
 
-    # warm-up
-    for w in range(args.warmup):
-        issue("dev", w % NSETS, 0)
-        combine(0)
+    # warm-up: W steps of the same shape as the timed ones
+    for w in range(args.warmup * R):
+        recycle_slots(w)
+        issue("dev", w % NSETS, w % 48)
+    combine((args.warmup * R - 1) % 48)
     barrier()
     ctx.phase_times()
     l0 = ctx.launch_count()
 
+    total_msms = args.steps * R
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     tm0 = time.perf_counter()
     ctx.timer_start()
-    for s in range(args.steps):
-        recycle_slots(s)
-        issue("dev", s % NSETS, s % 48)
+    for i in range(total_msms):
+        recycle_slots(i)
+        issue("dev", i % NSETS, i % 48)
     ms = ctx.timer_stop()
     barrier()
     tm1 = time.perf_counter()
@@ -232,8 +369,8 @@ def run_gpu(args, rank, world, dist):
     launches = ctx.launch_count() - l0
     phases, calls = ctx.phase_times()
     if dist is not None:
-        ms = shard.max_over_ranks(dist, ms)
-        launches = shard.sum_over_ranks(dist, launches)
+        ms = dist_util.max_over_ranks(dist, ms)
+        launches = dist_util.sum_over_ranks(dist, launches)
 
     # per-kernel figures for the roofline: the same workload once more with the three streams joined (no overlap of
     # the next MSM's counting sort / the previous MSM's tail with the accumulate kernel), CUDA events around each phase
@@ -243,25 +380,23 @@ def run_gpu(args, rank, world, dist):
         issue("dev", w % NSETS, 0)
     ctx.sync()
     ctx.phase_times()
-    serial_steps = max(1, min(args.steps, 10))
+    serial_msms = 12
     ctx.timer_start()
-    for s in range(serial_steps):
-        issue("dev", s % NSETS, s % 48)
-    serial_ms = ctx.timer_stop() / serial_steps
+    for i in range(serial_msms):
+        issue("dev", i % NSETS, i % 48)
+    serial_ms = ctx.timer_stop() / serial_msms
     serial_phases, serial_calls = ctx.phase_times()
     ctx.set_option(_lib.OPT_ASYNC_SORT, 1)
     ctx.set_option(_lib.OPT_ASYNC_TAIL, 1)
     barrier()
 
-    # correctness of what was just timed: set (steps-1) % NSETS, against the known-dlog identity
-    last = (args.steps - 1) % NSETS
-    got = combine((args.steps - 1) % 48)
+    # correctness of what was just timed: the last MSM's input set, against the known-dlog identity
+    last = (total_msms - 1) % NSETS
+    got = combine((total_msms - 1) % 48)
     checked = None
     if args.check:
         e = dlog_sum(SEED_SCALARS + 16 * last, SEED_BASES + 16 * last, n, start=base_off)
         if dist is not None:
-            import torch
-
             parts = [None] * world
             dist.all_gather_object(parts, e)
             e = sum(parts) % synth.ED_L
@@ -270,39 +405,50 @@ def run_gpu(args, rank, world, dist):
             exp = ctx.fixed_base(scalars=[e]).tolist()[0]
             checked = bool(got == exp)
 
-    # end-to-end through the public host API: every step copies that step's scalars from pinned host memory to the
-    # device (H2D on the library's copy stream) and reads the resulting group element back on the host (the final
-    # kernel writes it into mapped pinned memory).  Steps are pipelined E2E_DEPTH deep: the host fetches result s-3 after
-    # issuing step s, so the copy and the counting sort of step s overlap the accumulate kernels of earlier steps.
-    def e2e_loop(steps):
-        last = None
+    # end-to-end through the public host API: every MSM copies its scalars from pinned host memory to the device (H2D
+    # on the library's copy stream) and its resulting group element is read back on the host (the final kernel writes
+    # it into mapped pinned memory).  MSMs are pipelined E2E_DEPTH deep: the host fetches result i-3 after issuing MSM
+    # i, so the copy and the counting sort of MSM i overlap the accumulate kernels of earlier ones.
+    def e2e_loop(count):
+        last_pt = None
         lag = E2E_DEPTH - 1
-        for s in range(steps):
-            recycle_slots(s)
-            issue("async", s % NSETS, s % 48)
-            if s >= lag:
-                last = combine((s - lag) % 48)
-        for s in range(max(steps - lag, 0), steps):
-            last = combine(s % 48)
-        return last
+        for i in range(count):
+            recycle_slots(i)
+            issue("async", i % NSETS, i % 48)
+            if i >= lag:
+                last_pt = combine((i - lag) % 48)
+        for i in range(max(count - lag, 0), count):
+            last_pt = combine(i % 48)
+        return last_pt
 
-    e2e_loop(min(args.warmup, 3))
+    e2e_loop(min(args.warmup, 3) * R)
     barrier()
     e0 = time.perf_counter()
-    e2e_last = e2e_loop(args.steps)
+    e2e_last = e2e_loop(total_msms)
     barrier()
     e2e_s = time.perf_counter() - e0
     if dist is not None:
-        e2e_s = shard.max_over_ranks(dist, e2e_s)
+        e2e_s = dist_util.max_over_ranks(dist, e2e_s)
     e2e_ok = None
-    if rank == 0 and checked is not None and (args.steps - 1) % NSETS == last:
+    if rank == 0 and checked is not None:
         e2e_ok = bool(e2e_last == got)
+
+    peak_tlps = ctx.imad_peak() if rank == 0 else None
+
+    # ---- strong scaling: ONE fixed 2^20-term MSM split by index range over the `world` GPUs, plain and over
+    # precomputed generator tables (every rank holds the table of its own slice)
+    strong = strong_block(ctx, dist, rank, world, issue_seq=seq_counter, bases_full=bases if args.log2n == STRONG_LOG2N else None,
+                          scal_full=scal if args.log2n == STRONG_LOG2N else None, recycle=recycle_slots, barrier=barrier)
+
+    sweep = fixed = ac20 = None
+    if world == 1 and args.extras:
+        sweep, fixed = sweep_block(ctx, peak_tlps)
+        ac20 = ac20_block(ctx)
 
     if rank != 0:
         return
-    total_pts = world * n * args.steps
+    total_pts = world * n * total_msms
     value = total_pts / (ms * 1e-3)
-    peak_tlps = ctx.imad_peak()
     acc_ms = serial_phases["accumulate"] / max(serial_calls, 1)
     # the accumulate kernel performs exactly one 7M mixed addition per non-zero digit: n * W of them per launch
     c_auto = _choose_window(n) if not args.window else args.window
@@ -322,26 +468,29 @@ def run_gpu(args, rank, world, dist):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"ed25519_msm_2^{args.log2n}", "n_per_gpu": n, "n_total": world * n,
-                   "window_bits": c_auto, "windows": W_c, "bases": "g_i = r_i*B, device generated, niels form resident",
+                   "msms_per_step": R, "ms_per_msm": ms / total_msms,
+                   "step": f"a batch of {R} back-to-back MSMs of 2^{args.log2n} terms per GPU (timed region = steps x {R} MSMs)",
+                   "window_bits": c_auto, "windows": W_c, "bases": "g_i = r_i*B, device generated, niels form resident, no precomputed tables",
                    "l2": f"inputs rotate over {NSETS} distinct (bases, scalars) sets ({NSETS * n * 128 >> 20} MiB) > 126 MB L2",
-                   "multi_gpu": ("index-range split of one N*n-term MSM; partials pushed into rank 0's HBM mailbox over "
+                   "multi_gpu": ("index-range split of N*n-term MSMs; partials pushed into rank 0's HBM mailbox over "
                                  "NVLink peer stores (CUDA IPC), summed by a gather kernel; no NCCL") if world > 1 else "single GPU",
                    "result_checked_vs_known_dlog": checked, "e2e_result_matches": e2e_ok},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": total_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world,
-                "d2h_bytes_per_step": 64 * world, "ms_per_step": 1e3 * e2e_s / args.steps,
+        "e2e": {"value": total_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": R * n * 32 * world,
+                "d2h_bytes_per_step": R * 64 * world, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "Context.msm_async(points, pinned_scalars, slot) + Context.result(slot), pipelined %d deep" % E2E_DEPTH},
         "roofline": {"bound": "imad", "kernel": "vmsm_kernel<KAccumulate>", "achieved": achieved, "peak": peak_tlps,
                      "unit": "T limb-products/s", "frac": (achieved / peak_tlps) if achieved else None,
                      "traffic": _ncu_traffic_bytes() if args.log2n == 20 else None, "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/)",
                      "algorithmic_gather_bytes_per_launch": n * W_c * 96,
                      "peak_source": "measured live: vmsm_microbench_imad (independent carry-chained IMAD.WIDE.U32 multiply-accumulate chains, all SMs; every IMAD.WIDE form is half-rate on B200)",
+                     "imad_wide_tlps": peak_tlps, "imad_nominal_tlps_at_sm_mhz": (148 * 32 * clocks["sm_mhz"] * 1e6 / 1e12) if clocks and clocks.get("sm_mhz") else None,
                      "kernel_ms": acc_ms, "algorithmic_lp_per_launch": acc_lp,
                      "whole_msm_frac": msm_frac, "whole_msm_lp_per_point": lp_per_point(n),
-                     "measured_in": f"{serial_steps} extra steps of the same workload with the library's streams joined "
+                     "measured_in": f"{serial_msms} extra MSMs of the same workload with the library's streams joined "
                                     "(serial), CUDA events around every phase; the headline loop overlaps phases of "
                                     "consecutive MSMs, so its per-phase times are not additive",
-                     "serial_ms_per_step": serial_ms, "kernel_share_of_serial_step": acc_ms / serial_ms,
+                     "serial_ms_per_msm": serial_ms, "kernel_share_of_serial_step": acc_ms / serial_ms,
                      "phase_ms": {k: v / max(serial_calls, 1) for k, v in serial_phases.items()},
                      "overlapped_phase_ms": {k: v / max(calls, 1) for k, v in phases.items()},
                      "hbm_phases": {"counting_sort": {
@@ -349,14 +498,104 @@ def run_gpu(args, rank, world, dist):
                          "frac": (sort_gbs / hbm_peak) if sort_gbs else None, "peak_source": hbm_src,
                          "note": "bound by L2 atomics (16 fetch-and-adds per scalar), not by HBM bandwidth; in the "
                                  "headline loop it runs as a thin slice under the accumulate kernel"}}},
+        "strong": strong,
     }
+    if sweep is not None:
+        line["sweep"] = sweep
+        line["fixed_generators"] = fixed
+        line["ac20"] = ac20
     if args.cpu_baseline:
         cores = os.cpu_count() or 1
         rate, dt = cpu_reference_rate(args.cpu_points, cores)
+        rate1, dt1 = cpu_reference_rate(max(64, args.cpu_points // 4), 1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "one_core_points_per_s": rate1,
                                 "sample": f"{cores} processes x {args.cpu_points} terms ({dt:.1f} s) of the same MSM with the "
-                                          "pure-Python restatement of pivot.vector_commitment (oracle/ed25519.py)"}
+                                          "pure-Python restatement of pivot.vector_commitment (oracle/ed25519.py); "
+                                          f"1 core: {max(64, args.cpu_points // 4)} terms ({dt1:.1f} s); plain Python ints -- "
+                                          "gmpy2 / MPyC are not installable in this image and /root/reference does not "
+                                          "exist on the GPU box"}
     print(json.dumps(line), flush=True)
+
+
+def strong_block(ctx, dist, rank, world, issue_seq, bases_full, scal_full, recycle, barrier):
+    """ms per ONE fixed 2^STRONG_LOG2N-term MSM split by index range over `world` GPUs (pipelined issue, device
+    resident, max over ranks), plain path and over precomputed tables, and the same MSM on one GPU for the ratio."""
+    from tools import dist_util
+    from verifiable_mpc_b200 import _lib, synth
+
+    n_total = 1 << STRONG_LOG2N
+    count = 96
+    own_full = bases_full is None
+
+    def single_gpu_times():
+        nonlocal bases_full, scal_full
+        if own_full:
+            bases_full, scal_full = zip(*synth_pairs(ctx, n_total, NSETS))
+        pairs = list(zip(bases_full, scal_full))
+        t_plain = time_msms(ctx, pairs, count)
+        ref = ctx.result((count - 1) % 48)
+        for pts in bases_full:
+            pts.precompute()
+        ctx.sync()
+        t_pre = time_msms(ctx, pairs, count)
+        same = bool(ctx.result((count - 1) % 48) == ref)
+        return t_plain, t_pre, same
+
+    if world == 1:
+        t_plain, t_pre, same = single_gpu_times()
+        return {"n_total": n_total, "n_gpus": 1, "ms_per_msm": t_plain, "ms_per_msm_generator_tables": t_pre,
+                "x_vs_1_gpu": 1.0, "x_vs_1_gpu_generator_tables": 1.0, "tables_equal_plain_result": same,
+                "msms_timed": count}
+
+    # this rank's slice of the fixed MSM: indices [rank*m, (rank+1)*m) of the same seeded streams as the headline sets
+    m = n_total // world
+    sl_bases, sl_scal = [], []
+    for k in range(NSETS):
+        sl_bases.append(ctx.fixed_base(scalars=synth.scalars_ed25519(SEED_BASES + 16 * k, m, start=rank * m)))
+        sl_scal.append(ctx.upload_scalars(synth.scalars_ed25519(SEED_SCALARS + 16 * k, m, start=rank * m)))
+
+    def shard_issue(i):
+        issue_seq[0] += 1
+        ctx.set_option(_lib.OPT_SHARD_SEQ, issue_seq[0])
+        ctx.msm_dev(sl_bases[i % NSETS], sl_scal[i % NSETS], slot=i % 48)
+
+    def timed_sharded():
+        for i in range(6):
+            shard_issue(i)
+        barrier()
+        ctx.timer_start()
+        for i in range(count):
+            recycle(i)
+            shard_issue(i)
+        t = ctx.timer_stop() / count
+        barrier()
+        return dist_util.max_over_ranks(dist, t), ctx.result((count - 1) % 48)
+
+    t_plain_n, res_plain = timed_sharded()
+    for pts in sl_bases:
+        pts.precompute()
+    ctx.sync()
+    t_pre_n, res_pre = timed_sharded()
+    # the same fixed MSM on ONE GPU (rank 0, which holds indices [0, 2^20) of the same streams), others idle
+    one = None
+    if rank == 0:
+        one = single_gpu_times()
+        ok = None
+        if not own_full or True:
+            ctx.msm_dev(bases_full[(count - 1) % NSETS], scal_full[(count - 1) % NSETS], slot=51)
+            ok = bool(ctx.result(51) == res_plain == res_pre)
+    barrier()
+    if rank != 0:
+        return None
+    t1_plain, t1_pre, same = one
+    return {"n_total": n_total, "n_gpus": world, "terms_per_gpu": m, "ms_per_msm": t_plain_n,
+            "ms_per_msm_generator_tables": t_pre_n, "one_gpu_ms_per_msm": t1_plain,
+            "one_gpu_ms_per_msm_generator_tables": t1_pre, "x_vs_1_gpu": t1_plain / t_plain_n,
+            "x_vs_1_gpu_generator_tables": t1_pre / t_pre_n, "x_generator_tables_vs_1_gpu_plain": t1_plain / t_pre_n,
+            "sharded_result_equals_one_gpu_result": ok, "msms_timed": count,
+            "split": "index range, one slice (and its table) per GPU; 128-byte partials pushed into rank 0's mailbox "
+                     "by each final kernel and summed by its gather kernel (no NCCL, no host hop)"}
 
 
 def _hbm_peak_gbs():
@@ -416,6 +655,8 @@ def main():
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--sort-blocks", type=int, default=-1, help="experiment: VMSM_OPT_SORT_BLOCKS (-1 = library default)")
+    ap.add_argument("--msms-per-step", type=int, default=MSMS_PER_STEP)
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the sweep / AC20 blocks (N = 1)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-check", dest="check", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

@@ -60,6 +60,9 @@ extern "C" {
                                     (latency-bound rounds); 0 = never */
 #define VMSM_OPT_BN_QUAD_ACC 13 /* BN256 accumulate kernel with four lanes per bucket: 0 never, 1 (default) for the sizes
                                   where it was measured faster, 2 always */
+#define VMSM_OPT_PRE_SETS 14 /* MSMs over precomputed bases (vmsm_points_precompute): bucket sets shared by the windows;
+                               0 (default) = chosen from the term count */
+#define VMSM_OPT_PRE_MIN_TERMS 15 /* MSM calls with fewer terms ignore a precomputed table (default 256) */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */
@@ -96,6 +99,14 @@ int32_t vmsm_points_upload(uint64_t ctx, int32_t curve, const uint8_t *affine, u
  * form of create_generators (verifiable_mpc/ac20/circuit_sat_r1cs.py:59-74: g.append(h ** r)). */
 int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scalars, uint64_t seed, uint64_t n,
                                uint64_t *pts);
+/* Table of 2^(c*w) * P_i (w < ceil(254 / c), niels form, c = window_bits or 0 = by size) for a vector of FIXED
+ * generators: the g of create_generators (circuit_sat_r1cs.py:47-93) is made once and then used by every
+ * pivot.vector_commitment of every proof (circuit_sat_cb.py:103, compressed_pivot.py:110).  Every later MSM call on the
+ * vector (any sub-range; extra terms need a table of the same window on their own vector) then runs without a single
+ * doubling: all windows share a few bucket sets, no Horner chain.  Costs W * 96 B per point of HBM and one kernel of
+ * ~250 doublings + W inversions per point.  vmsm_fold drops the table (the folded generators are new points).
+ * Ed25519 only. */
+int32_t vmsm_points_precompute(uint64_t ctx, uint64_t pts, uint32_t window_bits);
 int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *affine_out);
 /* new vector = a[a_off .. a_off+a_n) || b[b_off .. b_off+b_n)  (device-side copy; b_n may be 0: a clone).  The
  * g_hat = g + [h] of compressed_pivot.py:137 and the private copy a prover folds in place. */

@@ -31,8 +31,15 @@ class FakePoints:
         n = len(self.pts) - off if n is None else n
         return self.pts[off:off + n]
 
+    precomputed = False
+
+    def precompute(self, window_bits=0):
+        self.precomputed = True  # values are representation independent: the fake has nothing to build
+        return self
+
     def fold(self, c):
         self.pts = E.fold(self.pts[: 2 * (len(self.pts) // 2)], int(c) % E.L)
+        self.precomputed = False
         return self
 
 

@@ -26,8 +26,8 @@ struct HostBE {
         launch(f, n);
     }
     void scan_offsets(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g) {
-        for (uint32_t w = 0; w < g.W; w++) {
-            uint32_t run = w * g.n;
+        for (uint32_t w = 0; w < g.S; w++) {  // one row per bucket set (S == W unless the bases are precomputed)
+            uint32_t run = geom_set_start(g, w);
             for (uint32_t b = 0; b < g.NB; b++) {
                 offsets[(size_t)w * g.NB + b] = cursor[(size_t)w * g.NB + b] = run;
                 run += counts[(size_t)w * g.NB + b];
@@ -118,6 +118,35 @@ uint32_t hostemu_msm_ext(const uint8_t *affine, uint32_t n_main, const uint8_t *
     ws_release(be, ws);
     memcpy(out_affine, &oa, 64);
     return err;
+}
+
+// MSM over PRECOMPUTED bases (KPrecompute tables for `table_bits`), n_main main terms [off, off + n_main) of a vector
+// of n_pts points plus n_extra extra terms with their own table, `sets` bucket sets (0 = auto); cf. run_msm_ps
+int hostemu_msm_pre(const uint8_t *affine, uint32_t n_pts, uint32_t off, uint32_t n_main, const uint8_t *affine_extra,
+                    uint32_t n_extra, const uint8_t *scalars, uint32_t table_bits, uint32_t sets, uint8_t *out_affine) {
+    HostBE be;
+    const uint32_t W = (253 + table_bits) / table_bits;
+    std::vector<ge_aff> aff(n_pts ? n_pts : 1), affx(n_extra ? n_extra : 1);
+    memcpy(aff.data(), affine, (size_t)n_pts * 64);
+    memcpy(affx.data(), affine_extra, (size_t)n_extra * 64);
+    std::vector<ge_niels> tbl((size_t)W * (n_pts ? n_pts : 1)), tblx((size_t)W * (n_extra ? n_extra : 1));
+    KPrecompute kp = {aff.data(), tbl.data(), n_pts, table_bits, W};
+    be.launch(kp, n_pts);
+    KPrecompute kx = {affx.data(), tblx.data(), n_extra, table_bits, W};
+    be.launch(kx, n_extra);
+    uint32_t n = n_main + n_extra;
+    std::vector<uint32_t> sc((size_t)(n ? n : 1) * 8 + 8);
+    memcpy(sc.data(), scalars, (size_t)n * 32);
+    Workspace ws;
+    MsmOptions opt;
+    opt.pre_sets = sets;
+    PreTable pt = {n_pts, table_bits, W, n_extra ? tblx.data() : nullptr, n_extra};
+    ge_ext oe;
+    ge_aff oa;
+    int rc = msm_run(be, ws, opt, 253, tbl.data() + off, sc.data(), n, &oe, &oa, 0, nullptr, n_extra, &pt);
+    ws_release(be, ws);
+    memcpy(out_affine, &oa, 64);
+    return rc;
 }
 
 void hostemu_fold(const uint8_t *affine, uint32_t n, const uint8_t *c_le32, uint8_t *out_affine) {

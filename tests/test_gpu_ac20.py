@@ -62,6 +62,16 @@ def test_twin_matches_reference_at_configured_sizes(gpu_group, k):
     check_big_case(k, group, gf)
 
 
+@pytest.mark.parametrize("k", [12, 16])
+def test_twin_with_precomputed_generator_table_matches_reference(gpu_group, k):
+    """Fixed generators with a table of 2^(16 w) * g_i (DevicePointList.precompute): the z commitment and the
+    announcement A run without doublings; same commitment, same proof as the unmodified reference."""
+    from ac20_cases import check_big_case
+
+    group, gf = gpu_group
+    check_big_case(k, group, gf, precomputed=True)
+
+
 @pytest.mark.parametrize("k", [10, 12])
 def test_twin_host_integer_path_matches_reference_at_configured_sizes(gpu_group, k, monkeypatch):
     """Same fixtures through the host-integer round loop (witness / form algebra in Python, MSMs on the device)."""

@@ -232,6 +232,31 @@ def test_msm_skewed_scalars(ctx):
         ctx.set_option(_lib.OPT_WINDOW_BITS, 0)
 
 
+def test_fold_and_free_wait_for_msms_in_flight(ctx):
+    """an asynchronous MSM with long buckets still reads its bases on a tail stream (overflow
+    kernel) after the call returns; a fold (rewrites the bases in place) or a free (recycles their memory for the next
+    allocation) issued right behind it must be ordered after that reader.  Results are fetched only afterwards."""
+    n = 1 << 16
+    rnd = random.Random(11)
+    dl = [prng.scalar(0x5EEE, i) for i in range(n)]
+    sc_bits = [rnd.randrange(2) for _ in range(n)]             # two giant buckets -> overflow tasks on the tail stream
+    want = E.msm_known_dlog(sc_bits, dl)
+    c = prng.scalar(0xF01D, 0)
+    for _ in range(3):
+        dev = ctx.fixed_base(seed=0x5EEE, n=n)
+        dsc = ctx.upload_scalars(sc_bits)
+        ctx.msm_dev(dev, dsc, slot=5)
+        dev.fold(c)                                              # in place, main stream
+        ctx.msm_dev(dev, dsc, slot=6, n=n // 2)
+        dev.free()                                               # block goes back to the pool ...
+        other = ctx.fixed_base(seed=0x1234, n=n)                 # ... and is handed out again at once
+        assert ctx.result(5) == want
+        folded_dl = [(c * dl[j] + dl[n // 2 + j]) % E.L for j in range(n // 2)]
+        assert ctx.result(6) == E.msm_known_dlog(sc_bits[:n // 2], folded_dl)
+        other.free()
+        dsc.free()
+
+
 def test_multi_gpu_mailbox_shards(ctx):
     """Index-range split over 3 contexts (all GPUs of the box if there are several, else 3 contexts on GPU 0):
     partials are pushed into the owner's mailbox by the final kernels and summed by the owner's gather kernel."""
@@ -486,3 +511,84 @@ def test_pooled_allocations_are_recycled_safely(ctx, known_points):
             with pytest.raises(VmsmError):
                 stale.tolist()
             stale.handle = 0
+
+
+# ------------------------------------------------------------------------------------------------ precomputed bases
+def test_msm_precomputed_small_matches_oracle(ctx, known_points):
+    """vmsm_points_precompute at sizes the oracle's naive algorithm handles: every table window, every number of
+    bucket sets, sub-ranges, extra terms (table built lazily), edge scalars, repeated / identity / negated bases."""
+    from verifiable_mpc_b200 import _lib
+
+    dl, pts = known_points
+    ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 0)
+    try:
+        n = 300
+        scs = [prng.scalar(0x5EED, i) for i in range(n)]
+        scs[:6] = [0, 1, E.L - 1, 2**252, 2**15, 2**16 - 1]
+        want = E.msm_known_dlog(scs, dl[:n])
+        for cb in (8, 11, 13, 16):
+            dev = ctx.upload_points(pts[:n]).precompute(cb)
+            W = (253 + cb) // cb
+            for sets in sorted({0, 1, 2, 3, W - 1, W}):
+                ctx.set_option(_lib.OPT_PRE_SETS, sets)
+                assert ctx.msm(dev, scs) == want, (cb, sets)
+                assert ctx.msm(dev, scs[:17]) == E.msm_naive(scs[:17], pts[:17]), (cb, sets)
+            ctx.set_option(_lib.OPT_PRE_SETS, 0)
+            # sub-range + extra terms: the one-element vector gets its table on first use
+            extra = ctx.upload_points([pts[200], E.affine_neg(pts[201])])
+            sc2 = scs[10:30] + [prng.scalar(9, 0), prng.scalar(9, 1)]
+            assert ctx.msm_ext(dev, 7, 20, extra, 0, 2, sc2) == E.msm_known_dlog(sc2, dl[7:27] + [dl[200], E.L - dl[201]])
+            dsc = ctx.upload_scalars(scs)
+            ctx.msm_dev_ext(dev, 0, n, dsc, 0, extra, 1, [5], slot=9)
+            assert ctx.result(9) == E.msm_known_dlog(scs + [5], dl[:n] + [E.L - dl[201]])
+            # a fold drops the table and the folded vector still multiplies correctly
+            c = prng.scalar(0xF01D, 1)
+            dev.fold(c)
+            assert not dev.precomputed
+            fdl = [(c * dl[j] + dl[n // 2 + j]) % E.L for j in range(n // 2)]
+            assert ctx.msm(dev, scs[:n // 2]) == E.msm_known_dlog(scs[:n // 2], fdl)
+            dev.free(), extra.free(), dsc.free()
+        pp = [pts[0]] * 5 + [E.IDENTITY] * 3 + [E.affine_neg(pts[0])] * 2
+        sc = [5, 7, 11, 13, 17, 3, 4, 5, 9, 1]
+        dev = ctx.upload_points(pp).precompute(8)
+        assert ctx.msm(dev, sc) == E.msm_naive(sc, pp)
+        assert ctx.msm(dev, [1, 1, 1, 1, 1, 0, 0, 0, 3, 2]) == E.IDENTITY
+        dev.free()
+    finally:
+        ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 256)
+        ctx.set_option(_lib.OPT_PRE_SETS, 0)
+
+
+@pytest.mark.parametrize("logn", [10, 12, 16, 18, 20])
+def test_msm_precomputed_large_known_dlog(ctx, logn):
+    """BASELINE sizes over precomputed bases: known-dlog identity, equality with the plain windowed path on the same
+    inputs, skewed (boolean) scalars through the shared-bucket overflow path, several MSMs in flight."""
+    from verifiable_mpc_b200 import _lib
+
+    n = 1 << logn
+    dev = ctx.fixed_base(seed=0x5EEE, n=n)
+    sc = ctx.synth_scalars(0x5EED, n)
+    ctx.msm_dev(dev, sc, slot=1)
+    plain = ctx.result(1)
+    assert plain == E.scalar_mul(E.B, _dlog_sum(0x5EED, 0x5EEE, n))
+    dev.precompute()
+    try:
+        for sets in ((0, 1, 4) if logn <= 16 else (0, 8)):
+            ctx.set_option(_lib.OPT_PRE_SETS, sets)
+            for j in range(3):
+                ctx.msm_dev(dev, sc, slot=2 + j)
+            assert [ctx.result(2 + j) for j in range(3)] == [plain] * 3, sets
+        ctx.set_option(_lib.OPT_PRE_SETS, 0)
+        m = min(n, 1 << 14)
+        rnd = random.Random(logn)
+        bits = [rnd.randrange(2) for _ in range(m)]
+        dl = [prng.scalar(0x5EEE, i) for i in range(m)]
+        assert ctx.msm(dev, bits) == E.msm_known_dlog(bits, dl)
+        # sub-range starting in the middle of the vector
+        off = n // 2 + 3
+        sub = [prng.scalar(0x77, i) for i in range(1000)]
+        assert ctx.msm(dev, sub, off=off) == E.msm_known_dlog(sub, [prng.scalar(0x5EEE, off + i) for i in range(1000)])
+    finally:
+        ctx.set_option(_lib.OPT_PRE_SETS, 0)
+        dev.free()
+        sc.free()

@@ -264,3 +264,50 @@ def test_bench_window_mirror_matches_library(hostemu):
     sizes = [1, 2, 100] + [1 << k for k in range(4, 27)] + [49151, 49152, 3 << 15, (1 << 20) + 5]
     for n in sizes:
         assert bench._choose_window(n) == hostemu.hostemu_choose_window(ctypes.c_uint64(n)), n
+
+
+def run_msm_pre(lib, pts, off, n_main, extra, scs, table_bits, sets):
+    A = b"".join(E.point_to_bytes(p) for p in pts)
+    X = b"".join(E.point_to_bytes(p) for p in extra)
+    S = b"".join(E.scalar_to_bytes(s) for s in scs)
+    out = ctypes.create_string_buffer(64)
+    rc = lib.hostemu_msm_pre(A, len(pts), off, n_main, X, len(extra), S, table_bits, sets, out)
+    assert rc == 0
+    return E.point_from_bytes(out.raw)
+
+
+@pytest.mark.parametrize("table_bits", [8, 13, 16])
+def test_msm_over_precomputed_bases(hostemu, known_points, table_bits):
+    """Tables of 2^(c*w) * P_i (KPrecompute): windows share bucket sets, no doublings; any number of sets, any
+    sub-range of the vector, extra terms with their own table, edge scalars, repeated / identity / negated bases."""
+    dl, pts = known_points
+    W = (253 + table_bits) // table_bits
+    n = 40
+    scs = [prng.scalar(0x5EED, i) for i in range(n)]
+    scs[:6] = [0, 1, E.L - 1, 2**252, 2**(table_bits - 1), 2**table_bits - 1]
+    want = E.msm_known_dlog(scs, dl[:n])
+    for sets in sorted({0, 1, 2, 3, 5, W - 1, W}):
+        assert run_msm_pre(hostemu, pts[:n], 0, n, [], scs, table_bits, sets) == want, sets
+    # sub-range of a longer vector + two extra terms (the h / k of a commitment)
+    extra = [pts[200], E.affine_neg(pts[201])]
+    sc2 = scs[:20] + [prng.scalar(9, 0), prng.scalar(9, 1)]
+    want2 = E.msm_known_dlog(sc2, dl[7:27] + [dl[200], E.L - dl[201]])
+    for sets in (0, 1, 4):
+        assert run_msm_pre(hostemu, pts[:60], 7, 20, extra, sc2, table_bits, sets) == want2, sets
+    pp = [pts[0]] * 5 + [E.IDENTITY] * 3 + [E.affine_neg(pts[0])] * 2
+    sc = [5, 7, 11, 13, 17, 3, 4, 5, 9, 1]
+    assert run_msm_pre(hostemu, pp, 0, len(pp), [], sc, table_bits, 2) == E.msm_naive(sc, pp)
+    assert run_msm_pre(hostemu, pts[:3], 0, 0, [], [], table_bits, 0) == E.IDENTITY
+
+
+def test_msm_over_precomputed_bases_long_buckets(hostemu):
+    """Boolean / constant scalars over shared bucket sets: every window's entries pile into a few buckets (overflow
+    tasks across windows)."""
+    n = 600
+    base = [E.scalar_mul(E.B, k + 1) for k in range(30)]
+    pts = [base[i % 30] for i in range(n)]
+    rnd = random.Random(4)
+    for sc in ([rnd.randrange(2) for _ in range(n)], [7] * n, [rnd.randrange(1, 4) << 240 for _ in range(n)]):
+        want = E.scalar_mul(E.B, sum(s * (i % 30 + 1) for i, s in enumerate(sc)) % E.L)
+        for sets in (1, 2):
+            assert run_msm_pre(hostemu, pts, 0, n, [], sc, 8, sets) == want

@@ -14,6 +14,7 @@ WORKER = textwrap.dedent("""
     import torch.distributed as dist
     from oracle import ed25519 as E, prng
     from verifiable_mpc_b200 import shard
+    from tools import dist_util
     from fake_engine import FakeContext
 
     class Ctx(FakeContext):
@@ -43,8 +44,8 @@ WORKER = textwrap.dedent("""
     partial = ctx.msm(pts, sc)                      # this rank's slice (oracle arithmetic standing in for the GPU)
     gathered = [None] * world
     dist.all_gather_object(gathered, partial)
-    assert shard.max_over_ranks(dist, float(rank)) == world - 1
-    assert shard.sum_over_ranks(dist, rank + 1) == world * (world + 1) // 2
+    assert dist_util.max_over_ranks(dist, float(rank)) == world - 1
+    assert dist_util.sum_over_ranks(dist, rank + 1) == world * (world + 1) // 2
     if rank == 0:
         total = ctx.lincomb(gathered, [1] * world)
         full_dl = [prng.scalar(0x5EEE, i) for i in range(n_total)]

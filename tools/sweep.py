@@ -22,6 +22,9 @@ def main():
     ap.add_argument("--async-tail", type=int, nargs="+", default=[1])
     ap.add_argument("--sort-blocks", type=int, nargs="+", default=[-1])
     ap.add_argument("--quad-threshold", type=int, default=-1, help="experiment: VMSM_OPT_QUAD_THRESHOLD")
+    ap.add_argument("--precompute", type=int, nargs="+", default=[-1],
+                    help="-1: plain path; 0 / 8..16: tables of 2^(c*w)*P_i with this window (0 = by size)")
+    ap.add_argument("--pre-sets", type=int, nargs="+", default=[0], help="VMSM_OPT_PRE_SETS values to sweep")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -34,10 +37,16 @@ def main():
     for logn in args.logn:
         n = 1 << logn
         sets = [(ctx.fixed_base(seed=0x5EEE + 16 * k, n=n), ctx.synth_scalars(0x5EED + 16 * k, n)) for k in range(3)]
-        for c in args.windows:
+        for pre, c in [(p_, c_) for p_ in args.precompute for c_ in args.windows]:
+            if pre >= 0:
+                for pts, _ in sets:
+                    pts.precompute(pre)
+            ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 256 if pre >= 0 else 1 << 30)
             for sort in args.sort:
-                for radix, cap, at, sb in [(r, cp, a, b) for r in args.radix for cp in args.cap for a in args.async_tail
-                                           for b in args.sort_blocks]:
+                for radix, cap, at, sb, ps in [(r, cp, a, b, q) for r in args.radix for cp in args.cap
+                                               for a in args.async_tail for b in args.sort_blocks
+                                               for q in (args.pre_sets if pre >= 0 else [0])]:
+                    ctx.set_option(_lib.OPT_PRE_SETS, ps)
                     if sb >= 0:
                         ctx.set_option(_lib.OPT_SORT_BLOCKS, sb)
                     if cap:
@@ -55,7 +64,7 @@ def main():
                         ctx.msm_dev(*sets[s % 3], slot=s % 32)
                     ms = ctx.timer_stop() / args.steps
                     ph, calls = ctx.phase_times()
-                    rec = {"log2n": logn, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "Mpts_s": n / ms / 1e3,
+                    rec = {"log2n": logn, "precompute": pre, "pre_sets": ps, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "Mpts_s": n / ms / 1e3,
                            "imad_peak_tlps": peak, "phase_ms": {k: round(v / calls, 5) for k, v in ph.items()}}
                     print(json.dumps(rec), flush=True)
                     if out:

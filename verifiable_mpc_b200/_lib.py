@@ -17,6 +17,7 @@ OPT_QUAD_THRESHOLD, OPT_ASYNC_TAIL, OPT_CAP_FACTOR, OPT_SHARD_SEQ, OPT_ASYNC_SOR
 OPT_SORT_BLOCKS = 11
 OPT_FOLD_QUAD_MAX = 12
 OPT_BN_QUAD_ACC = 13
+OPT_PRE_SETS, OPT_PRE_MIN_TERMS = 14, 15
 FOLD_WITNESS, FOLD_FORM = 0, 1
 AXPY_ADD_SCALED, AXPY_SCALE_ADD, AXPY_SCALE = 0, 1, 2
 PHASES = ("digits", "scan", "scatter", "order", "handoff", "accumulate", "reduce", "final")
@@ -48,6 +49,7 @@ SIGNATURES = {
     "vmsm_launch_count": [_u64, _pu64],
     "vmsm_points_upload": [_u64, _i32, _p, _u64, _pu64],
     "vmsm_points_fixed_base": [_u64, _i32, _p, _u64, _u64, _pu64],
+    "vmsm_points_precompute": [_u64, _u64, _u32],
     "vmsm_points_download": [_u64, _u64, _u64, _u64, _p],
     "vmsm_points_text": [_u64, _u64, _u64, _u64, _p, _u64, _pu64],
     "vmsm_points_download_ptr": [_u64, _u64, _u64, _u64, ctypes.POINTER(_p)],

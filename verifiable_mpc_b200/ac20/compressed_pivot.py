@@ -213,6 +213,10 @@ def _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i):
 def _final_check(g_hat, k, Q, coeffs, gf, proof):
     Q = _resolve(Q)
     z_prime = proof["z_prime"]
+    # the proof is untrusted input: the reference asserts on a length mismatch inside L_prime(z_prime) (pivot.py:62-64)
+    assert len(z_prime) == len(coeffs) == len(g_hat), "Length of input vector and linear form do not match."
+    if not all(isinstance(zp, (int, gf)) for zp in z_prime):
+        raise NotImplementedError
     gamma = int(sum([gf(cf) * zp for cf, zp in zip(coeffs, z_prime)]) + 0)
     Q_check = pivot.vector_commitment(z_prime, gamma, g_hat, k)
     return Q_check == Q
@@ -412,7 +416,13 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
         Ld = ctx.upload_scalars([cf.value for cf in L.coeffs] + [0], order)
         t = gf(ctx.scalars_dot(Ld, 0, zd, 0, n)) + L.constant
         logger_cp.debug("Calculate A.")
-        ctx.msm_dev(g_hat.dev, zd, slot=0, poff=g_hat.off, soff=0, n=n + 1)  # h**rho * prod g_i**r_i
+        g_fixed = generators["g"]
+        if isinstance(g_fixed, DevicePointList) and getattr(g_fixed.dev, "precomputed", False) and len(g_fixed) >= n:
+            # fixed generators with a table (DevicePointList.precompute): A through it, h as the extra term
+            hd = pivot._device_single(group, generators["h"])
+            ctx.msm_dev_ext(g_fixed.dev, g_fixed.off, n, zd, 0, hd, 0, [rho], slot=0)
+        else:
+            ctx.msm_dev(g_hat.dev, zd, slot=0, poff=g_hat.off, soff=0, n=n + 1)  # h**rho * prod g_i**r_i
         A = group._make(ctx.result(0))
         proof["t"] = t
         proof["A"] = A
@@ -459,7 +469,10 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     r = pivot.random_residues(prng, order, n)
     rho = prng.randrange(order)
     logger_cp.debug("Calculate t.")
-    fast = FAST_INT_PATH and _all_in_field(L.coeffs, gf) and _all_in_field(x, gf) and L.constant == 0
+    # the residue paths reduce modulo gf.order while the round loop reduces modulo the group order: same thing only when
+    # the field IS the exponent field of the group (always so in the reference's drivers); otherwise the generic path
+    fast = (FAST_INT_PATH and gf.order == k.order and _all_in_field(L.coeffs, gf) and _all_in_field(x, gf)
+            and L.constant == 0)
     if fast and len(L.coeffs) == n:
         g_hat = _g_hat(g, h, group)
         if _use_device_scalars(g_hat, order, DEVICE_SCALAR_MIN_PROVER):
@@ -528,7 +541,7 @@ def protocol_5_verifier(generators, P, L, y, proof, gf):
     logger_cp.debug("Load from proof: t, A.")
     t, A = proof["t"], proof["A"]
     g_hat = _g_hat(g, h, group)
-    if (FAST_INT_PATH and _all_in_field(L.coeffs, gf) and len(L.coeffs) + 1 == len(g_hat)
+    if (FAST_INT_PATH and gf.order == k.order and _all_in_field(L.coeffs, gf) and len(L.coeffs) + 1 == len(g_hat)
             and _use_device_scalars(g_hat, order)):
         Ld = g_hat.dev.ctx.upload_scalars([cf.value for cf in L.coeffs] + [0], order)
         try:
@@ -542,7 +555,7 @@ def protocol_5_verifier(generators, P, L, y, proof, gf):
         return _protocol_4_verifier_dev(g_hat, k, Q, Ld, gf, proof, 0)
     c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf)
     Q = group.lincomb([A, P, k], [1, c0, int(c1 * (c0 * y + t))])
-    if FAST_INT_PATH and _all_in_field(L.coeffs, gf):
+    if FAST_INT_PATH and gf.order == k.order and _all_in_field(L.coeffs, gf):
         coeffs = [cf.value * c1 % order for cf in L.coeffs] + [0]
         return _protocol_4_verifier_fast(g_hat, k, Q, coeffs, gf, proof, 0)
     L_tilde = pivot.LinearForm(L.coeffs + [0]) * c1

@@ -124,7 +124,18 @@ struct MsmGeom {
     uint32_t c;   // window bits
     uint32_t W;   // windows, c*W >= scalar_bits + 1
     uint32_t NB;  // buckets per window = 2^(c-1), bucket b holds |digit| = b+1
+    // Bucket sets.  Plain MSM: S = W, window w owns bucket set w (its sum carries the weight 2^(c*w), applied by the
+    // Horner chain).  MSM over PRECOMPUTED bases (tables of 2^(c*w) * P_i, KPrecompute): the weight is already in the
+    // base, so windows may share buckets -- window w goes to set w % S with k = w / S recorded in the CSR entry
+    // (entry = term index | k << lg | sign << 31), S * NB buckets in all, no doublings anywhere.
+    uint32_t S;   // bucket sets, 1 <= S <= W
+    uint32_t lg;  // bit position of k in a CSR entry: 2^lg >= n (unused when S == W: k is always 0)
 };
+// position in idx where bucket set s starts: n * (number of windows in the sets before it)
+VMSM_HD uint32_t geom_set_start(const MsmGeom &g, uint32_t s) {
+    uint32_t q = g.W / g.S, r = g.W % g.S;
+    return g.n * (s * q + (s < r ? s : r));
+}
 
 struct sc256 {
     uint32_t v[9];  // v[8] = 0 sentinel so window extraction can read one limb past the top
@@ -198,13 +209,14 @@ struct KDigitsHist {
     MsmGeom g;
     VMSM_HD void operator()(uint32_t tid) const {
         sc256 s = ld_scalar(scalars, tid);
-        uint32_t carry = 0;
+        uint32_t carry = 0, set = 0;
         for (uint32_t w = 0; w < g.W; w++) {
             int32_t d = sc_digit(s, w, g.c, carry);
             if (d != 0) {
                 uint32_t a = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-                VMSM_ATOMIC_ADD(&counts[w * g.NB + (a - 1)], 1u);
+                VMSM_ATOMIC_ADD(&counts[set * g.NB + (a - 1)], 1u);
             }
+            if (++set == g.S) set = 0;
         }
     }
 };
@@ -217,14 +229,15 @@ struct KScatter {
     MsmGeom g;
     VMSM_HD void operator()(uint32_t tid) const {
         sc256 s = ld_scalar(scalars, tid);
-        uint32_t carry = 0;
+        uint32_t carry = 0, set = 0, k = 0;
         for (uint32_t w = 0; w < g.W; w++) {
             int32_t d = sc_digit(s, w, g.c, carry);
             if (d != 0) {
                 uint32_t a = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-                uint32_t pos = VMSM_ATOMIC_ADD(&cursor[w * g.NB + (a - 1)], 1u);
-                idx[pos] = tid | (d < 0 ? 0x80000000u : 0u);
+                uint32_t pos = VMSM_ATOMIC_ADD(&cursor[set * g.NB + (a - 1)], 1u);
+                idx[pos] = tid | (k << g.lg) | (d < 0 ? 0x80000000u : 0u);
             }
+            if (++set == g.S) set = 0, k++;
         }
     }
 };
@@ -249,22 +262,41 @@ struct OverflowCtl {
 // Measured dead ends (profiles/r01/accumulate_variants.md): forcing 5 or 6 blocks/SM with __launch_bounds__ (96 / 80
 // registers, +1.5 % / +8 % time), and prefetch.global.L2/.L1 of the next base one addition ahead (+4 %): at 100
 // registers and 16 warps/SM the gather latency is already covered by the other warps' additions.
-struct KAccumulate {
-    enum { kBlock = 128 };
+// Where the base of a CSR entry lives.  Plain MSM: bases[i] / extra[i - n_main].  Precomputed bases (PRE): level
+// w = set + k * S of the table, i.e. the point 2^(c*w) * P_i, at bases[w * stride + i] (`bases` already points at the
+// first term of the MSM inside level 0); the few extra terms (h, k of a Pedersen commitment) have their own table.
+struct BaseRef {
     const ge_niels *bases;
-    const uint32_t *offsets;  // W x NB exclusive prefix (absolute position in idx)
-    const uint32_t *counts;   // W x NB
+    const ge_niels *extra;    // may be null
+    uint32_t n_main;
+    uint32_t stride, extra_stride;  // points per table level (PRE only)
+    uint32_t lg, S, log2NB;         // CSR entry layout / bucket id -> set (PRE only)
+    template <bool PRE>
+    VMSM_HD const ge_niels *ptr(uint32_t e, uint32_t bucket) const {
+        if (!PRE) {
+            uint32_t i = e & 0x7fffffffu;
+            return i < n_main ? bases + i : extra + (i - n_main);
+        }
+        uint32_t i = e & ((1u << lg) - 1u);
+        uint32_t w = (bucket >> log2NB) + ((e & 0x7fffffffu) >> lg) * S;
+        return i < n_main ? bases + (size_t)w * stride + i : extra + (size_t)w * extra_stride + (i - n_main);
+    }
+};
+
+template <bool PRE>
+struct KAccumulateT {
+    enum { kBlock = 128 };
+    BaseRef br;
+    const uint32_t *offsets;  // sets x NB exclusive prefix (absolute position in idx)
+    const uint32_t *counts;   // sets x NB
     const uint32_t *idx;
     const uint32_t *order;    // may be null
-    ge_ext *buckets;          // W x NB
+    ge_ext *buckets;          // sets x NB
     uint32_t nbuckets;
     uint32_t cap;             // entries summed by the bucket's own thread
     OverflowCtl *ctl;
     OverflowTask *tasks;
     LongBucket *longs;
-    const ge_niels *extra;    // bases n_main, n_main+1, ... (e.g. the h / k of a Pedersen commitment); may be null
-    uint32_t n_main;
-    VMSM_HD const ge_niels *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
     VMSM_HD void operator()(uint32_t tid) const {
         uint32_t b = order ? order[tid] : tid;
         uint32_t pos = offsets[b], cnt = counts[b];
@@ -288,11 +320,11 @@ struct KAccumulate {
         if (cnt) {
             uint32_t e = idx[pos];
             uint32_t en = cnt > 1 ? idx[pos + 1] : 0u;
-            acc = ge_from_niels(ld_niels(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);  // first base: 1M instead of 7M
+            acc = ge_from_niels(ld_niels(br.template ptr<PRE>(e, b)), (e >> 31) != 0);  // first base: 1M instead of 7M
             e = en;
             for (uint32_t k = 1; k < cnt; k++) {
                 en = (k + 1 < cnt) ? idx[pos + k + 1] : 0u;  // index prefetch: one load ahead of the gather
-                ge_niels q = ld_niels(base_ptr(e & 0x7fffffffu));
+                ge_niels q = ld_niels(br.template ptr<PRE>(e, b));
                 acc = ge_madd(acc, q, (e >> 31) != 0);
                 e = en;
             }
@@ -300,20 +332,20 @@ struct KAccumulate {
         st_ext(buckets + b, acc);
     }
 };
+typedef KAccumulateT<false> KAccumulate;
+typedef KAccumulateT<true> KAccumulatePre;
 
 // One warp per overflow task (grid-stride over the device-side task count): lanes stride over the segment, then a
 // shuffle tree adds the 32 lane sums.
-struct KOverflow {
+template <bool PRE>
+struct KOverflowT {
     enum { kBlock = 128 };
-    const ge_niels *bases;
+    BaseRef br;
     const uint32_t *idx;
     const OverflowCtl *ctl;
     const OverflowTask *tasks;
     ge_ext *partials;
     uint32_t nwarps;
-    const ge_niels *extra;
-    uint32_t n_main;
-    VMSM_HD const ge_niels *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
     VMSM_HD void operator()(uint32_t tid) const {
         const uint32_t ntasks = ctl->ntasks;
 #if defined(__CUDA_ARCH__)
@@ -323,7 +355,7 @@ struct KOverflow {
             ge_ext acc = ge_identity();
             for (uint32_t k = lane; k < tk.count; k += 32) {
                 uint32_t e = idx[tk.first + k];
-                acc = ge_madd(acc, ld_niels(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+                acc = ge_madd(acc, ld_niels(br.template ptr<PRE>(e, tk.bucket)), (e >> 31) != 0);
             }
 #pragma unroll 1
             for (int d = 16; d >= 1; d >>= 1) {
@@ -346,13 +378,15 @@ struct KOverflow {
             ge_ext acc = ge_identity();
             for (uint32_t k = 0; k < tk.count; k++) {
                 uint32_t e = idx[tk.first + k];
-                acc = ge_madd(acc, ld_niels(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+                acc = ge_madd(acc, ld_niels(br.template ptr<PRE>(e, tk.bucket)), (e >> 31) != 0);
             }
             st_ext(partials + t, acc);
         }
 #endif
     }
 };
+typedef KOverflowT<false> KOverflow;
+typedef KOverflowT<true> KOverflowPre;
 
 // One thread per long bucket (grid-stride): bucket += its task partials.
 struct KCombine {
@@ -619,6 +653,29 @@ struct KNormalize {
         ge_aff a = ge_ext_to_aff(ld_ext(in + tid));
         st_aff(aff + tid, a);
         st_niels(niels + tid, ge_aff_to_niels(a));
+    }
+};
+
+// Base tables for FIXED generators.  The generators of a Pedersen vector commitment are created once
+// (circuit_sat_r1cs.py:47-93) and then used for every commitment of every proof (circuit_sat_cb.py:103,
+// compressed_pivot.py:110), so the doublings a windowed MSM spends on the weights 2^(c*w) can be paid once per
+// generator instead of once per MSM: table[w][i] = 2^(c*w) * P_i in niels form, w < W.  One thread per point walks
+// the levels (c doublings + one inversion each).  With the table all W windows of all points are just n*W independent
+// (digit, base) pairs: they may share buckets, the bucket tree shrinks accordingly and the Horner chain disappears.
+struct KPrecompute {
+    enum { kBlock = 128 };
+    const ge_aff *aff;   // n points
+    ge_niels *table;     // W x stride
+    uint32_t stride, c, W;
+    VMSM_HD void operator()(uint32_t tid) const {
+        ge_aff a = ld_aff(aff + tid);
+        st_niels(table + tid, ge_aff_to_niels(a));
+        for (uint32_t w = 1; w < W; w++) {
+            ge_ext p = ge_aff_to_ext(a);
+            for (uint32_t k = 0; k < c; k++) p = ge_dbl(p);
+            a = ge_ext_to_aff(p);
+            st_niels(table + (size_t)w * stride + tid, ge_aff_to_niels(a));
+        }
     }
 };
 

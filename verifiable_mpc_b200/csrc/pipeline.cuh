@@ -34,6 +34,15 @@ struct MsmOptions {
     uint32_t cap_factor = 8;   // a bucket's own thread sums at most max(64, cap_factor * n / NB) entries (kernels.cuh)
     uint32_t w_quad_acc = 1;       // BN256 accumulate with four lanes per bucket: 0 never, 1 by size, 2 always
     uint32_t quad_threshold = 16384;  // tree levels with at most this many output nodes run quad-cooperative; 0 = never
+    uint32_t pre_sets = 0;     // MSMs over precomputed bases: number of bucket sets the windows share; 0 = auto
+};
+
+// Precomputed bases of an MSM call (KPrecompute): level w of `table` holds 2^(c*w) * P_i at table[w * stride + i].
+// The MSM's `bases` argument then points at its first term inside level 0.
+struct PreTable {
+    uint32_t stride, c, W;
+    const ge_niels *extra_table;  // table of the extra terms (same c, W), or null when the call has none
+    uint32_t extra_stride;
 };
 
 struct Workspace {
@@ -93,20 +102,34 @@ inline uint32_t choose_window(uint64_t n, uint32_t scalar_bits, bool avoid_skew 
     return best_c ? best_c : 8;
 }
 
-inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits) {
+inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits, uint32_t sets = 0) {
     MsmGeom g;
     g.n = n;
     g.c = c;
     g.W = (scalar_bits + 1 + c - 1) / c;
     g.NB = 1u << (c - 1);
+    g.S = sets && sets < g.W ? sets : g.W;
+    g.lg = 0;
+    while ((1ull << g.lg) < n) g.lg++;
     return g;
+}
+
+// Bucket sets of an MSM over precomputed bases: as few as keep the accumulate kernel (one thread per bucket) wide
+// enough -- every set costs a bucket tree of 2.3 * NB full additions, every window sharing a set lengthens its
+// buckets' chains.  Aim at ~32 entries per bucket (what the plain path has at 2^20 terms, c = 16).
+inline uint32_t choose_sets(uint64_t n, uint32_t c, uint32_t W) {
+    uint64_t per_bucket_one_set = (n * W) >> (c - 1);
+    uint32_t s = 1;
+    while (s * 2 <= W && per_bucket_one_set / (s * 2) >= 32) s *= 2;
+    if (s * 2 > W) s = W;  // e.g. W = 20: 16 would leave four sets with two windows each
+    return s;
 }
 
 template <class BE>
 int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_bytes = sizeof(ge_ext),
               uint32_t cap_floor = 64, uint32_t seg_floor = 256, int ways = kTailWaysEd) {
-    size_t nb = (size_t)g.W * g.NB, ni = (size_t)g.W * g.n, nn = (size_t)g.W * ((g.NB + R - 1) / R);
-    if (nn < g.W) nn = g.W;
+    size_t nb = (size_t)g.S * g.NB, ni = (size_t)g.W * g.n, nn = (size_t)g.S * ((g.NB + R - 1) / R);
+    if (nn < g.S) nn = g.S;
     if (ways > ws.ways) {  // more MSM tails in flight than before: (re)allocate the per-way buffers
         ws.cap_buckets = ws.cap_nodes = ws.cap_tasks = 0;
         ws.ways = ways;
@@ -189,18 +212,23 @@ void ws_release(BE &be, Workspace &ws) {
 template <class BE>
 int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, const ge_niels *bases,
             const uint32_t *scalars, uint32_t n, ge_ext *out_ext, ge_aff *out_aff, uint32_t seq = 0,
-            const ge_niels *extra = nullptr, uint32_t n_extra = 0) {
+            const ge_niels *extra = nullptr, uint32_t n_extra = 0, const PreTable *pre = nullptr) {
     // terms 0 .. n-n_extra-1 use `bases`, the last n_extra terms use `extra` (scalars are contiguous)
     const uint32_t n_main = n - n_extra;
-    uint32_t c = opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits);
-    MsmGeom g = make_geom(n, c, scalar_bits);
+    // precomputed bases fix the window (the table was built for it); the windows then share `S` bucket sets
+    uint32_t c = pre ? pre->c : opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits);
+    MsmGeom g = make_geom(n, c, scalar_bits, pre ? (opt.pre_sets ? opt.pre_sets : choose_sets(n, c, (scalar_bits + c) / c)) : 0);
+    if (pre && (pre->W != g.W || (n_extra && !pre->extra_table))) return -2;
     uint32_t R = 1u << opt.reduce_log2r;
     // small MSMs are bound by their tails (~0.45 ms of dependent doublings against a ~0.1 ms head): more of them in flight
     const int ways = n < (1u << 18) ? (int)kTailWays : (int)kTailWaysEd;
     if (ws_ensure(be, ws, g, R, sizeof(ge_ext), 64, 256, ways)) return -1;
-    uint32_t nbuckets = g.W * g.NB;
+    uint32_t nbuckets = g.S * g.NB;
     const int par = (int)(seq & 1);
     uint32_t *counts = ws.counts_[par], *offsets = ws.offsets_[par], *cursor = ws.cursor_[par], *idx = ws.idx_[par];
+    uint32_t log2NB = g.c - 1;
+    BaseRef br = {bases, extra, n_main, pre ? pre->stride : 0u, pre ? pre->extra_stride : 0u, g.lg, g.S, log2NB};
+    if (pre) br.extra = pre->extra_table;
 
     // counting sort of (window, |digit|) -> CSR lists, on the sort stream (double-buffered by parity)
     be.sort_begin(par);
@@ -229,20 +257,32 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.head_wait_tail(tw);
     void *const buckets = ws.buckets_[tw];
     {
-        uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
+        const uint32_t wins_per_set = (g.W + g.S - 1) / g.S;
+        uint32_t cap = opt.cap_factor * (uint32_t)(((uint64_t)n * wins_per_set) >> (g.c - 1));
         if (cap < 64) cap = 64;
         be.zero(ws.ctl_[tw], sizeof(OverflowCtl));
-        KAccumulate k5 = {bases, offsets, counts, idx, order, (ge_ext *)buckets, nbuckets, cap, ws.ctl_[tw], ws.tasks_[tw],
-                          ws.longs_[tw], extra, n_main};
-        be.launch(k5, nbuckets);
+        if (pre) {
+            KAccumulatePre k5 = {br, offsets, counts, idx, order, (ge_ext *)buckets, nbuckets, cap, ws.ctl_[tw],
+                                 ws.tasks_[tw], ws.longs_[tw]};
+            be.launch(k5, nbuckets);
+        } else {
+            KAccumulate k5 = {br, offsets, counts, idx, order, (ge_ext *)buckets, nbuckets, cap, ws.ctl_[tw], ws.tasks_[tw],
+                              ws.longs_[tw]};
+            be.launch(k5, nbuckets);
+        }
         be.phase_mark(PH_ACCUMULATE);
         // everything after the accumulate kernel belongs to this MSM's tail: long-bucket overflow tasks, combine, bucket
         // tree, Horner -- on the CUDA backend on side stream `tw`, so the next MSM's accumulate kernel follows at once
         be.tail_begin(tw);
-        if (n > cap) {  // otherwise no bucket can be long
+        if ((uint64_t)n * wins_per_set > cap) {  // otherwise no bucket can be long
             const uint32_t ow = be.overflow_warps();
-            KOverflow ko = {bases, idx, ws.ctl_[tw], ws.tasks_[tw], (ge_ext *)ws.partials_[tw], ow, extra, n_main};
-            be.launch(ko, ow * 32);
+            if (pre) {
+                KOverflowPre ko = {br, idx, ws.ctl_[tw], ws.tasks_[tw], (ge_ext *)ws.partials_[tw], ow};
+                be.launch(ko, ow * 32);
+            } else {
+                KOverflow ko = {br, idx, ws.ctl_[tw], ws.tasks_[tw], (ge_ext *)ws.partials_[tw], ow};
+                be.launch(ko, ow * 32);
+            }
             be.acc_done(par);  // the CSR lists of this parity are free again (the overflow tasks were their last reader)
             const uint32_t ct = be.combine_threads();
             KCombine kc = {ws.ctl_[tw], ws.longs_[tw], (const ge_ext *)ws.partials_[tw], (ge_ext *)buckets, ct};
@@ -257,7 +297,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     int pp = 0;
     do {
         uint32_t cnt_out = (cnt + R - 1) / R;
-        uint32_t nodes = g.W * cnt_out;
+        uint32_t nodes = g.S * cnt_out;
         if (nodes <= opt.quad_threshold) {
             KReduceQ k6 = {inS, inT, (ge_ext *)ws.nodeS[tw][pp], (ge_ext *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s, nodes};
             be.launch(k6, (4 * nodes + 31) & ~31u);
@@ -273,11 +313,13 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
     {
+        // one root per bucket set; over precomputed bases the sets carry no weight: zero doublings between them
+        const uint32_t dbl = pre ? 0u : g.c;
         if (opt.quad_threshold) {
-            KFinalQ k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
+            KFinalQ k7 = {inS, inT, out_ext, out_aff, g.S, dbl};
             be.launch(k7, 32);
         } else {
-            KFinal k7 = {inS, inT, out_ext, out_aff, g.W, g.c};
+            KFinal k7 = {inS, inT, out_ext, out_aff, g.S, dbl};
             be.launch(k7, 1);
         }
     }

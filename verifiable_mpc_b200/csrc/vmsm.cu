@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(SCAN_TILE) vmsm_scan_offsets(const uint32_t *_
     uint32_t cnt = i < g.NB ? cw[i] : 0u;
     uint32_t excl = block_scan_1024(cnt, warp_sums, &total);
     if (i < g.NB) {
-        uint32_t off = w * g.n + prefix + excl;
+        uint32_t off = geom_set_start(g, w) + prefix + excl;
         offsets[(size_t)w * g.NB + i] = off;
         cursor[(size_t)w * g.NB + i] = off;
     }
@@ -241,6 +241,10 @@ struct PointSet {
     ge_niels *niels;  // Ed25519: (y+x, y-x, 2dxy)
     void *w_wire;     // BN256: plain canonical affine (wire form), waff<F>[n]; identity = all zero
     void *w_base;     // BN256: Montgomery affine, waff<F>[n]
+    // optional table of 2^(pre_c * w) * P_i, w < pre_W, pre_n points per level (vmsm_points_precompute)
+    void *pre = nullptr;
+    uint32_t pre_c = 0, pre_W = 0;
+    uint64_t pre_n = 0;
 };
 
 inline size_t wire_bytes(int32_t curve) { return curve == VMSM_CURVE_BN256_G2 ? 128 : 64; }
@@ -266,6 +270,7 @@ inline void dot_stage_sizes(uint64_t n, uint32_t *T, uint32_t *T2) {
 }
 
 struct Ctx {
+    std::recursive_mutex mu;  // serialises the entry points that use this context (GET_CTX)
     int device = 0;
     cudaStream_t stream = nullptr;  // main stream: everything except MSM tails
     cudaStream_t tails[kTailWays] = {};  // side streams: upper bucket-tree levels + Horner of the previous MSMs
@@ -326,6 +331,7 @@ struct Ctx {
     uint32_t shard_seq = 0;  // != 0 while a sharded MSM is being issued
     uint32_t shard_next = 0;  // VMSM_OPT_SHARD_SEQ: applies to the next MSM call of any flavour, then clears
     MsmOptions opt;
+    uint64_t pre_min_terms = 256;  // MSMs shorter than this ignore a precomputed table (VMSM_OPT_PRE_MIN_TERMS)
     bool phase_timing = false;
     bool check_points = true;
     Workspace ws;
@@ -395,8 +401,7 @@ struct CudaBE {
         note(cudaStreamWaitEvent(c->stream, c->ev_sorted[par], 0));
         cur = c->stream;
     }
-    void acc_done(int par) {
-        if (!c->async_sort) return;
+    void acc_done(int par) {  // recorded whatever the sort mode: vmsm_fold / vmsm_points_free order themselves on it
         note(cudaEventRecord(c->ev_acc_done[par], cur));  // on the stream of the last reader of the CSR lists
         c->acc_pending[par] = true;
     }
@@ -458,7 +463,7 @@ struct CudaBE {
     }
     void scan_offsets(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g) {
         uint32_t tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
-        vmsm_scan_offsets<<<g.W * tiles, SCAN_TILE, 0, cur>>>(counts, offsets, cursor, g, tiles);
+        vmsm_scan_offsets<<<g.S * tiles, SCAN_TILE, 0, cur>>>(counts, offsets, cursor, g, tiles);  // one row per bucket set
         c->launches++;
         note(cudaGetLastError());
     }
@@ -490,6 +495,18 @@ struct CudaBE {
     }
     void phase_end() {}
 };
+
+// The last readers of an MSM's bases (and CSR lists) are its accumulate kernel on the main stream and, for long
+// buckets, its overflow kernel on a tail stream; `ev_acc_done` is recorded right after whichever comes last.  Anything
+// that rewrites bases in place (vmsm_fold) or hands their memory to the pool (vmsm_points_free) goes through here.
+cudaError_t wait_bases_released(Ctx *c, bool host_side) {
+    for (int k = 0; k < 2; k++)
+        if (c->acc_pending[k]) {
+            cudaError_t e = host_side ? cudaEventSynchronize(c->ev_acc_done[k]) : cudaStreamWaitEvent(c->stream, c->ev_acc_done[k], 0);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
+}
 
 // make the main stream wait for every MSM tail issued so far (tails are ordered on the side stream)
 cudaError_t join_tail(Ctx *c) {
@@ -591,7 +608,7 @@ int32_t ensure_tmp(Ctx *c, size_t n_pts) {
 }
 
 int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t n, uint32_t slot,
-                const ge_niels *extra = nullptr, uint32_t n_extra = 0) {
+                const ge_niels *extra = nullptr, uint32_t n_extra = 0, const PreTable *pre = nullptr) {
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "n = %llu exceeds 2^26 terms per MSM call", (unsigned long long)n);
     CudaBE be(c);
     c->cur_slot = slot;
@@ -602,11 +619,61 @@ int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t
         c->shard_next = 0;
     }
     int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff_host + slot,
-                     c->msm_seq++, extra, n_extra);
+                     c->msm_seq++, extra, n_extra, pre);
     c->shard_seq = 0;
+    if (rc == -2) return fail(VMSM_ERR_INVALID, "precomputed table does not match the MSM geometry");
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
     return VMSM_OK;
+}
+
+// table of 2^(cb * w) * P_i for one point vector (vmsm_points_precompute; built lazily for the extra terms of an MSM)
+int32_t precompute_ps(Ctx *c, PointSet &ps, uint32_t cb) {
+    if (ps.curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "precomputed tables exist for the Ed25519 path only");
+    if (ps.pre && ps.pre_c == cb) return VMSM_OK;
+    if (ps.n == 0) return VMSM_OK;
+    CU(wait_bases_released(c, true));
+    if (ps.pre) pool_free(ps.pre);
+    ps.pre = nullptr;
+    ps.pre_c = ps.pre_W = 0;
+    const uint32_t W = (253 + cb) / cb;
+    ge_niels *tbl = nullptr;
+    cudaError_t e = pool_alloc(&tbl, (size_t)W * ps.n * sizeof(ge_niels));
+    if (e != cudaSuccess)
+        return fail(VMSM_ERR_NOMEM, "table of %u levels x %llu points: %s", W, (unsigned long long)ps.n, cudaGetErrorString(e));
+    CudaBE be(c);
+    KPrecompute k = {ps.aff, tbl, (uint32_t)ps.n, cb, W};
+    be.launch(k, (uint32_t)ps.n);
+    if (be.err != cudaSuccess) {
+        pool_free(tbl);
+        return fail(VMSM_ERR_CUDA, "precompute: %s", cudaGetErrorString(be.err));
+    }
+    ps.pre = tbl;
+    ps.pre_c = cb;
+    ps.pre_W = W;
+    ps.pre_n = ps.n;
+    return VMSM_OK;
+}
+
+// Ed25519 MSM over terms [off, off + n_total - n_extra) of `ps` plus n_extra terms of `eps`: through the precomputed
+// tables when both vectors have one for the same window (vmsm_points_precompute), else the plain windowed path.
+int32_t run_msm_ps(Ctx *c, const PointSet &ps, uint64_t off, const uint32_t *scalars, uint64_t n_total, uint32_t slot,
+                   PointSet *eps = nullptr, uint64_t eoff = 0, uint32_t n_extra = 0) {
+    bool pre_ok = ps.pre && n_total >= c->pre_min_terms;
+    if (pre_ok && n_extra && !(eps->pre && eps->pre_c == ps.pre_c)) {
+        // the blinding bases (h, k: one-element vectors cached by the caller) get their table on first use
+        if (eps->n <= 64 && eps != &ps) {
+            int32_t rc = precompute_ps(c, *eps, ps.pre_c);
+            if (rc) return rc;
+        } else {
+            pre_ok = false;
+        }
+    }
+    if (!pre_ok)
+        return run_msm(c, ps.niels + off, scalars, n_total, slot, eps ? eps->niels + eoff : nullptr, n_extra);
+    PreTable pt = {(uint32_t)ps.pre_n, ps.pre_c, ps.pre_W, n_extra ? (const ge_niels *)eps->pre + eoff : nullptr,
+                   n_extra ? (uint32_t)eps->pre_n : 0u};
+    return run_msm(c, (const ge_niels *)ps.pre + off, scalars, n_total, slot, nullptr, n_extra, &pt);
 }
 
 
@@ -728,9 +795,13 @@ int32_t fetch_slot(Ctx *c, uint32_t slot, uint8_t *out) {
 
 }  // namespace
 
+// Entry points on one context are serialised by a per-context lock: host threads may share a context (the prover
+// hashes its first pre-image on a worker thread; Python finalizers free handles from whatever thread the collector
+// runs on) and ctypes drops the GIL around every call.
 #define GET_CTX(h)                                                        \
     Ctx *c = get_ctx(h);                                                  \
     if (!c) return fail(VMSM_ERR_INVALID, "invalid context handle");      \
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);                \
     tl_ctx = c;                                                           \
     CU(cudaSetDevice(c->device))
 
@@ -830,7 +901,16 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
 }
 
 int32_t vmsm_ctx_destroy(uint64_t ctx) {
-    GET_CTX(ctx);
+    Ctx *c = get_ctx(ctx);
+    if (!c) return fail(VMSM_ERR_INVALID, "invalid context handle");
+    {  // unpublish first (no new call can find the handle), then let a call still inside the context drain
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_ctxs.erase(c);
+    }
+    c->mu.lock();
+    c->mu.unlock();
+    tl_ctx = c;
+    CU(cudaSetDevice(c->device));
     cudaStreamSynchronize(c->copy);
     cudaStreamSynchronize(c->sort);
     for (int w = 0; w < kTailWays; w++) cudaStreamSynchronize(c->tails[w]);
@@ -853,7 +933,8 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     }
     cudaStreamDestroy(c->copy);
     for (auto &kv : c->points)
-        cudaFree(kv.second.aff), cudaFree(kv.second.niels), cudaFree(kv.second.w_wire), cudaFree(kv.second.w_base);
+        cudaFree(kv.second.aff), cudaFree(kv.second.niels), cudaFree(kv.second.w_wire), cudaFree(kv.second.w_base),
+            cudaFree(kv.second.pre);
     for (auto &kv : c->scalars) cudaFree(kv.second.data);
     for (auto &kv : c->pool) cudaFree(kv.second);
     CudaBE be(c);
@@ -870,10 +951,6 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     cudaEventDestroy(c->ev_sort_in);
     for (int k = 0; k < 2; k++) cudaEventDestroy(c->ev_sorted[k]), cudaEventDestroy(c->ev_acc_done[k]);
     cudaStreamDestroy(c->stream);
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        g_ctxs.erase(c);
-    }
     delete c;
     return VMSM_OK;
 }
@@ -911,6 +988,14 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             return VMSM_OK;
         case VMSM_OPT_ASYNC_SORT:
             c->async_sort = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_PRE_SETS:
+            if (value < 0 || value > 32) return fail(VMSM_ERR_INVALID, "bucket sets out of range");
+            c->opt.pre_sets = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_PRE_MIN_TERMS:
+            if (value < 0) return fail(VMSM_ERR_INVALID, "negative term count");
+            c->pre_min_terms = (uint64_t)value;
             return VMSM_OK;
         case VMSM_OPT_BN_QUAD_ACC:
             if (value < 0 || value > 2) return fail(VMSM_ERR_INVALID, "BN quad accumulate mode out of range");
@@ -1077,6 +1162,15 @@ int32_t vmsm_points_fixed_base(uint64_t ctx, int32_t curve, const uint8_t *scala
     return VMSM_OK;
 }
 
+int32_t vmsm_points_precompute(uint64_t ctx, uint64_t pts, uint32_t window_bits) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    if (window_bits != 0 && (window_bits < 8 || window_bits > 16))
+        return fail(VMSM_ERR_INVALID, "table window must be 0 (auto) or in [8, 16]");
+    return precompute_ps(c, it->second, window_bits ? window_bits : (it->second.n >= (1u << 13) ? 16u : 13u));
+}
+
 int32_t vmsm_points_download(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint8_t *affine_out) {
     GET_CTX(ctx);
     auto it = c->points.find(pts);
@@ -1214,7 +1308,9 @@ int32_t vmsm_points_free(uint64_t ctx, uint64_t pts) {
     auto it = c->points.find(pts);
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
     CU(cudaStreamSynchronize(c->stream));
+    CU(wait_bases_released(c, true));  // overflow kernels of MSMs still in flight read the bases on tail streams
     pool_free(it->second.aff), pool_free(it->second.niels), pool_free(it->second.w_wire), pool_free(it->second.w_base);
+    pool_free(it->second.pre);
     c->points.erase(it);
     return VMSM_OK;
 }
@@ -1301,7 +1397,7 @@ int32_t vmsm_msm(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uin
     if (n) CU(cudaMemcpyAsync(c->stage_scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev_sort_in, c->stream));
     c->scalars_ready = c->ev_sort_in;
-    if (it->second.curve == VMSM_CURVE_ED25519) rc = run_msm(c, it->second.niels + off, c->stage_scalars, n, kSlots - 1);
+    if (it->second.curve == VMSM_CURVE_ED25519) rc = run_msm_ps(c, it->second, off, c->stage_scalars, n, kSlots - 1);
     else rc = w_run_msm_any(c, it->second, off, c->stage_scalars, n, kSlots - 1);
     if (rc) return rc;
     return fetch_slot(c, kSlots - 1, out_affine);  // the final kernel wrote the point into mapped pinned memory
@@ -1325,8 +1421,7 @@ int32_t vmsm_msm_ext(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, uint6
     c->scalars_ready = c->ev_sort_in;
     if (it->second.curve != ie->second.curve) return fail(VMSM_ERR_INVALID, "point vectors are on different curves");
     if (it->second.curve == VMSM_CURVE_ED25519)
-        rc = run_msm(c, it->second.niels + off, c->stage_scalars, tot, kSlots - 1, ie->second.niels + extra_off,
-                     (uint32_t)n_extra);
+        rc = run_msm_ps(c, it->second, off, c->stage_scalars, tot, kSlots - 1, &ie->second, extra_off, (uint32_t)n_extra);
     else
         rc = w_run_msm_any(c, it->second, off, c->stage_scalars, tot, kSlots - 1, &ie->second, extra_off, (uint32_t)n_extra);
     if (rc) return rc;
@@ -1466,7 +1561,7 @@ int32_t vmsm_msm_dev_shard(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n
     if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
     if (it->second.curve != VMSM_CURVE_ED25519) return fail(VMSM_ERR_UNSUPPORTED, "sharded MSM: Ed25519 only");
     c->shard_next = seq;
-    return run_msm(c, it->second.niels + poff, is->second.data + soff * 8, n, slot);
+    return run_msm_ps(c, it->second, poff, is->second.data + soff * 8, n, slot);
 }
 
 int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, const uint8_t *scalars_le32,
@@ -1492,7 +1587,7 @@ int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, con
     CU(cudaEventRecord(c->ev_copied[b], c->copy));
     if (c->async_sort) c->scalars_ready = c->ev_copied[b];  // only the sort stream reads the scalars
     else CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-    int32_t rc = it->second.curve == VMSM_CURVE_ED25519 ? run_msm(c, it->second.niels + off, c->astage[b], n, slot)
+    int32_t rc = it->second.curve == VMSM_CURVE_ED25519 ? run_msm_ps(c, it->second, off, c->astage[b], n, slot)
                                                         : w_run_msm_any(c, it->second, off, c->astage[b], n, slot);
     if (rc) return rc;
     // the scalars are read by the counting sort only: the staging buffer is free again once that is done
@@ -1514,7 +1609,7 @@ int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint
     // the sort stream reads the scalars in place: order it after a fold kernel that may have just written them
     if (c->sc_dirty && c->async_sort && !c->scalars_ready) c->scalars_ready = c->ev_sc_written;
     if (it->second.curve != VMSM_CURVE_ED25519) return w_run_msm_any(c, it->second, poff, is->second.data + soff * 8, n, slot);
-    return run_msm(c, it->second.niels + poff, is->second.data + soff * 8, n, slot);
+    return run_msm_ps(c, it->second, poff, is->second.data + soff * 8, n, slot);
 }
 
 // ---- device-resident scalar vectors modulo the Ed25519 group order (witness / linear-form halving)
@@ -1668,7 +1763,7 @@ int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, 
     CU(cudaEventRecord(c->ev_copied[b], c->copy));
     if (c->async_sort) c->scalars_ready = c->ev_copied[b];
     else CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-    int32_t rc = run_msm(c, it->second.niels + poff, c->astage[b], tot, slot, ie->second.niels + extra_off, (uint32_t)n_extra);
+    int32_t rc = run_msm_ps(c, it->second, poff, c->astage[b], tot, slot, &ie->second, extra_off, (uint32_t)n_extra);
     if (rc) return rc;
     CU(cudaEventRecord(c->ev_consumed[b], c->async_sort ? c->sort : c->stream));
     c->astage_used[b] = true;
@@ -1704,6 +1799,13 @@ int32_t vmsm_fold(uint64_t ctx, uint64_t pts, uint64_t half, const uint8_t *c_le
     if (rc) return rc;
     uint32_t cs[8];
     memcpy(cs, c_le32, 32);
+    CU(wait_bases_released(c, false));  // the fold rewrites niels in place: order it after every reader in flight
+    if (it->second.pre) {  // a table describes the generators it was built from, not the folded ones
+        CU(wait_bases_released(c, true));
+        pool_free(it->second.pre);
+        it->second.pre = nullptr;
+        it->second.pre_c = it->second.pre_W = 0;
+    }
     CudaBE be(c);
     fold_run(be, it->second.aff, it->second.niels, c->tmp_ext, (uint32_t)half, cs, c->fold_quad_max);
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "fold: %s", cudaGetErrorString(be.err));

@@ -100,6 +100,7 @@ class DevicePoints:
 
     def __init__(self, ctx, handle, n, curve):
         self.ctx, self.handle, self.n, self.curve = ctx, handle, n, curve
+        self.precomputed = False
 
     def __len__(self):
         return self.n
@@ -123,6 +124,13 @@ class DevicePoints:
         nbytes = n * WIRE_BYTES[self.curve]
         return (ctypes.c_char * nbytes).from_address(ptr.value) if nbytes else b""
 
+    def precompute(self, window_bits=0):
+        """Build the table of ``2^(c*w) * P_i`` for a vector of FIXED generators (see ``vmsm_points_precompute``):
+        later MSMs on this vector run without doublings.  Dropped again by ``fold``."""
+        check(self.ctx.lib.vmsm_points_precompute(self.ctx.h, self.handle, window_bits))
+        self.precomputed = True
+        return self
+
     def text_bytes(self, off=0, n=None):
         """``b"[x0, y0, 1], [x1, y1, 1], ..."`` formatted on the device (the inside of repr(list of points))."""
         n = self.n - off if n is None else n
@@ -139,6 +147,7 @@ class DevicePoints:
         cb = (int(c) % ED_L).to_bytes(32, "little")
         check(self.ctx.lib.vmsm_fold(self.ctx.h, self.handle, half, cb))
         self.n = half
+        self.precomputed = False
         return self
 
     def free(self):

@@ -339,6 +339,13 @@ class DevicePointList:
             raise IndexError(i)
         return self.group._make(self.dev.tolist(self.off + i, 1)[0])
 
+    def precompute(self, window_bits=0):
+        """Fixed generators: build the table of ``2^(c*w) * g_i`` once (``vmsm_points_precompute``); every later
+        ``pivot.vector_commitment`` on this list -- the z commitment and the announcement A of each proof
+        (circuit_sat_cb.py:103, compressed_pivot.py:110) -- then runs without doublings."""
+        self.dev.precompute(window_bits)
+        return self
+
     def affine_list(self):
         return unpack_points(self.dev.download(self.off, self.n))
 

@@ -1,8 +1,8 @@
 """Host-side helpers for the index-range split of one MSM over the GPUs of a box.
 
 One process per GPU.  The process group (any ``torch.distributed``-like object with ``broadcast_object_list``,
-``all_reduce`` and ``barrier``; gloo is enough) carries only the 64-byte CUDA-IPC handle of the owner's mailbox, the
-barrier and scalar reductions of timings -- never point or scalar data.
+``barrier``; gloo is enough) carries only the 64-byte CUDA-IPC handle of the owner's mailbox and the barrier -- never
+point or scalar data.  (The timing reductions of bench.py live in tools/dist_util.py: this package imports no torch.)
 """
 
 
@@ -21,19 +21,3 @@ def setup_mailbox(ctx, dist, rank, world):
         ctx.mailbox_open_ipc(obj[0], rank, world)
     dist.barrier()
     return obj[0]
-
-
-def max_over_ranks(dist, value):
-    import torch
-
-    t = torch.tensor([float(value)], dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
-def sum_over_ranks(dist, value):
-    import torch
-
-    t = torch.tensor([int(value)], dtype=torch.int64)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return int(t.item())
