@@ -63,6 +63,14 @@ extern "C" {
 #define VMSM_OPT_PRE_SETS 14 /* MSMs over precomputed bases (vmsm_points_precompute): bucket sets shared by the windows;
                                0 (default) = chosen from the term count */
 #define VMSM_OPT_PRE_MIN_TERMS 15 /* MSM calls with fewer terms ignore a precomputed table (default 256) */
+#define VMSM_OPT_SEG_LEN 16 /* entries summed by one thread of the balanced (segmented) accumulate kernel; 0 (default) =
+                              sized so that the launch is a whole number of waves of resident threads, at most 32 */
+#define VMSM_OPT_SEG_MODE 17 /* accumulate kernel: 0 = one thread per bucket, 2 = equal segments of the sorted entries,
+                               1 (default) = by geometry (segments when the windows of a table-based MSM share one
+                               bucket set, below 2^19 terms) */
+#define VMSM_OPT_HOST_NORMALIZE 18 /* 1 (default): Ed25519 results leave the device in extended coordinates and the
+                                     fetching call inverts Z on the CPU (~15 us) instead of a lone GPU thread (0.19 ms at
+                                     the end of every MSM); 0 = normalise on the device.  Same canonical output. */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */
@@ -188,6 +196,12 @@ int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint
 int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
                          uint64_t extra_pts, uint64_t extra_off, uint64_t n_extra, const uint8_t *extra_scalars_le32,
                          uint32_t slot);
+/* The same commitment with the scalar of its ONE extra term computed on the device as the inner product
+ * <dot_a[dot_aoff ..], dot_b[dot_boff ..]> of dot_n residues mod l: the cross term L_R(z_L) of
+ * compressed_pivot.py:41-42 never visits the host (two host round trips less per folding round).  Ed25519. */
+int32_t vmsm_msm_dev_ext_dot(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
+                             uint64_t extra_pts, uint64_t extra_off, uint64_t dot_a, uint64_t dot_aoff, uint64_t dot_b,
+                             uint64_t dot_boff, uint64_t dot_n, uint32_t slot);
 int32_t vmsm_result_affine(uint64_t ctx, uint32_t slot, uint8_t *out_affine);      /* synchronises */
 int32_t vmsm_result_extended(uint64_t ctx, uint32_t slot, uint8_t *out_extended);  /* synchronises */
 

@@ -162,6 +162,11 @@ class FakeContext:
             self._slots = {}
         self._slots[slot] = E.msm_naive(sc, bases)
 
+    def msm_dev_ext_dot(self, points, poff, n, scalars, soff, extra, extra_off, dot_a, dot_aoff, dot_b, dot_boff, dot_n,
+                        slot=0):
+        s = self.scalars_dot(dot_a, dot_aoff, dot_b, dot_boff, dot_n)
+        self.msm_dev_ext(points, poff, n, scalars, soff, extra, extra_off, [s], slot=slot)
+
     def msm_dev(self, points, scalars, slot=0, poff=0, soff=0, n=None):
         FakeContext.calls += 1
         if n is None:

@@ -34,6 +34,23 @@ struct HostBE {
             }
         }
     }
+    void scan_offsets_flat(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g,
+                           uint32_t *row_totals, uint32_t *seg_bucket, uint32_t *total, uint32_t L) {
+        uint32_t run = 0;
+        for (uint32_t w = 0; w < g.S; w++) {
+            uint32_t start = run;
+            for (uint32_t i = 0; i < g.NB; i++) {
+                uint32_t b = w * g.NB + i, cnt = counts[b];
+                offsets[b] = cursor[b] = run;
+                for (uint32_t k = (run + L - 1) / L; (uint64_t)k * L < (uint64_t)run + cnt; k++) seg_bucket[k] = b;
+                run += cnt;
+            }
+            row_totals[w] = run - start;
+        }
+        *total = run;
+    }
+    uint32_t resident_threads(bool) { return resident; }
+    uint32_t resident = 48;  // small on purpose: several waves and straddling buckets even in tiny test cases
     bool order_buckets(const uint32_t *counts, uint32_t *order, uint32_t nb, uint32_t n) {
         if (n == 0) return false;
         std::iota(order, order + nb, 0u);
@@ -55,7 +72,15 @@ struct HostBE {
     void phase_end() {}
 };
 
+static uint32_t g_seg_mode = 1, g_seg_len = 0;
+
 extern "C" {
+
+// accumulate-kernel selection for the following hostemu_msm* calls (MsmOptions::seg_mode / seg_len)
+void hostemu_set_seg(uint32_t mode, uint32_t len) {
+    g_seg_mode = mode;
+    g_seg_len = len;
+}
 
 void hostemu_fe_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out) {
     HostBE be;
@@ -84,6 +109,7 @@ uint32_t hostemu_msm(const uint8_t *affine, const uint8_t *scalars, uint32_t n, 
     opt.window_bits = window_bits;
     opt.sort_buckets = sort != 0;
     opt.reduce_log2r = log2r;
+    opt.seg_mode = g_seg_mode, opt.seg_len = g_seg_len;
     ge_ext oe;
     ge_aff oa;
     msm_run(be, ws, opt, 253, niels.data(), sc.data(), n, &oe, &oa);
@@ -112,6 +138,7 @@ uint32_t hostemu_msm_ext(const uint8_t *affine, uint32_t n_main, const uint8_t *
     Workspace ws;
     MsmOptions opt;
     opt.window_bits = window_bits;
+    opt.seg_mode = g_seg_mode, opt.seg_len = g_seg_len;
     ge_ext oe;
     ge_aff oa;
     msm_run(be, ws, opt, 253, niels.data(), sc.data(), n, &oe, &oa, 0, nielsx.data(), n_extra);
@@ -140,6 +167,7 @@ int hostemu_msm_pre(const uint8_t *affine, uint32_t n_pts, uint32_t off, uint32_
     Workspace ws;
     MsmOptions opt;
     opt.pre_sets = sets;
+    opt.seg_mode = g_seg_mode, opt.seg_len = g_seg_len;
     PreTable pt = {n_pts, table_bits, W, n_extra ? tblx.data() : nullptr, n_extra};
     ge_ext oe;
     ge_aff oa;

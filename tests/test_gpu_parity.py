@@ -529,11 +529,16 @@ def test_msm_precomputed_small_matches_oracle(ctx, known_points):
         for cb in (8, 11, 13, 16):
             dev = ctx.upload_points(pts[:n]).precompute(cb)
             W = (253 + cb) // cb
-            for sets in sorted({0, 1, 2, 3, W - 1, W}):
-                ctx.set_option(_lib.OPT_PRE_SETS, sets)
-                assert ctx.msm(dev, scs) == want, (cb, sets)
-                assert ctx.msm(dev, scs[:17]) == E.msm_naive(scs[:17], pts[:17]), (cb, sets)
+            for mode, seg_len in ((1, 0), (0, 0), (2, 3), (2, 64)):  # by geometry / per bucket / segments
+                ctx.set_option(_lib.OPT_SEG_MODE, mode)
+                ctx.set_option(_lib.OPT_SEG_LEN, seg_len)
+                for sets in sorted({0, 1, 2, 3, W - 1, W}):
+                    ctx.set_option(_lib.OPT_PRE_SETS, sets)
+                    assert ctx.msm(dev, scs) == want, (cb, sets, mode, seg_len)
+                    assert ctx.msm(dev, scs[:17]) == E.msm_naive(scs[:17], pts[:17]), (cb, sets, mode, seg_len)
             ctx.set_option(_lib.OPT_PRE_SETS, 0)
+            ctx.set_option(_lib.OPT_SEG_MODE, 1)
+            ctx.set_option(_lib.OPT_SEG_LEN, 0)
             # sub-range + extra terms: the one-element vector gets its table on first use
             extra = ctx.upload_points([pts[200], E.affine_neg(pts[201])])
             sc2 = scs[10:30] + [prng.scalar(9, 0), prng.scalar(9, 1)]
@@ -557,6 +562,8 @@ def test_msm_precomputed_small_matches_oracle(ctx, known_points):
     finally:
         ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 256)
         ctx.set_option(_lib.OPT_PRE_SETS, 0)
+        ctx.set_option(_lib.OPT_SEG_MODE, 1)
+        ctx.set_option(_lib.OPT_SEG_LEN, 0)
 
 
 @pytest.mark.parametrize("logn", [10, 12, 16, 18, 20])
@@ -573,12 +580,15 @@ def test_msm_precomputed_large_known_dlog(ctx, logn):
     assert plain == E.scalar_mul(E.B, _dlog_sum(0x5EED, 0x5EEE, n))
     dev.precompute()
     try:
-        for sets in ((0, 1, 4) if logn <= 16 else (0, 8)):
-            ctx.set_option(_lib.OPT_PRE_SETS, sets)
-            for j in range(3):
-                ctx.msm_dev(dev, sc, slot=2 + j)
-            assert [ctx.result(2 + j) for j in range(3)] == [plain] * 3, sets
+        for mode in (1, 0, 2):  # accumulate kernel by geometry / one thread per bucket / equal segments
+            ctx.set_option(_lib.OPT_SEG_MODE, mode)
+            for sets in ((0, 1, 4) if logn <= 16 else (0, 8)):
+                ctx.set_option(_lib.OPT_PRE_SETS, sets)
+                for j in range(3):
+                    ctx.msm_dev(dev, sc, slot=2 + j)
+                assert [ctx.result(2 + j) for j in range(3)] == [plain] * 3, (mode, sets)
         ctx.set_option(_lib.OPT_PRE_SETS, 0)
+        ctx.set_option(_lib.OPT_SEG_MODE, 1)
         m = min(n, 1 << 14)
         rnd = random.Random(logn)
         bits = [rnd.randrange(2) for _ in range(m)]
@@ -586,9 +596,53 @@ def test_msm_precomputed_large_known_dlog(ctx, logn):
         assert ctx.msm(dev, bits) == E.msm_known_dlog(bits, dl)
         # sub-range starting in the middle of the vector
         off = n // 2 + 3
-        sub = [prng.scalar(0x77, i) for i in range(1000)]
-        assert ctx.msm(dev, sub, off=off) == E.msm_known_dlog(sub, [prng.scalar(0x5EEE, off + i) for i in range(1000)])
+        sub = [prng.scalar(0x77, i) for i in range(min(1000, n - off))]
+        assert ctx.msm(dev, sub, off=off) == E.msm_known_dlog(sub, [prng.scalar(0x5EEE, off + i) for i in range(len(sub))])
+        # the plain path through the segmented kernel as well (boolean scalars: a bucket spanning thousands of segments)
+        ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 1 << 30)
+        ctx.set_option(_lib.OPT_SEG_MODE, 2)
+        ctx.msm_dev(dev, sc, slot=7)
+        assert ctx.result(7) == plain
+        assert ctx.msm(dev, bits) == E.msm_known_dlog(bits, dl)
     finally:
         ctx.set_option(_lib.OPT_PRE_SETS, 0)
+        ctx.set_option(_lib.OPT_SEG_MODE, 1)
+        ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 256)
         dev.free()
         sc.free()
+
+
+def test_fused_cross_term_commitment_and_host_normalisation(ctx, known_points):
+    """vmsm_msm_dev_ext_dot: the scalar of the extra term is an inner product computed on the device (the cross terms
+    of compressed_pivot.py:41-42), checked against the oracle; and VMSM_OPT_HOST_NORMALIZE on / off give the same
+    canonical point (the CPU or a GPU thread inverts Z)."""
+    from verifiable_mpc_b200 import _lib
+
+    dl, pts = known_points
+    n = 64
+    dev = ctx.upload_points(pts[:2 * n])
+    kd = ctx.upload_points([pts[250]])
+    z = [prng.scalar(0xA1, i) for i in range(2 * n)]
+    Lc = [prng.scalar(0xA2, i) for i in range(2 * n)]
+    z[3], Lc[5], z[n + 1] = 0, E.L - 1, 1
+    zd, Ld = ctx.upload_scalars(z), ctx.upload_scalars(Lc)
+    s_a = sum(a * b for a, b in zip(Lc[n:], z[:n])) % E.L
+    s_b = sum(a * b for a, b in zip(Lc[:n], z[n:])) % E.L
+    want_a = E.msm_known_dlog(z[:n] + [s_a], dl[n:2 * n] + [dl[250]])
+    want_b = E.msm_known_dlog(z[n:] + [s_b], dl[:n] + [dl[250]])
+    try:
+        for host_norm in (1, 0):
+            ctx.set_option(_lib.OPT_HOST_NORMALIZE, host_norm)
+            for rep in range(3):  # both staging parities, back to back
+                ctx.msm_dev_ext_dot(dev, n, n, zd, 0, kd, 0, Ld, n, zd, 0, n, slot=0)
+                ctx.msm_dev_ext_dot(dev, 0, n, zd, n, kd, 0, Ld, 0, zd, n, n, slot=1)
+                assert ctx.result(0) == want_a and ctx.result(1) == want_b, (host_norm, rep)
+            assert ctx.msm(dev, z) == E.msm_known_dlog(z, dl[:2 * n])
+            assert ctx.lincomb(pts[:3], [5, E.L - 1, 0]) == E.msm_naive([5, E.L - 1, 0], pts[:3])
+            assert ctx.msm(dev, [0] * 8) == E.IDENTITY
+    finally:
+        ctx.set_option(_lib.OPT_HOST_NORMALIZE, 1)
+    with pytest.raises(Exception):
+        ctx.msm_dev_ext_dot(dev, 0, n, zd, n, kd, 0, Ld, 0, zd, n + 1, n, slot=1)  # inner product range out of bounds
+    for d in (dev, kd, zd, Ld):
+        d.free()

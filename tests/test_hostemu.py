@@ -59,6 +59,14 @@ def test_msm_known_dlog(hostemu, known_points, n):
         for r in ([1, 3, 4] if n <= 17 else [3]):
             for sort in (0, 1):
                 assert run_msm(hostemu, pts, scs, c, sort, r) == exp, (n, c, r, sort)
+    # the segmented accumulate kernel forced on the plain path (several segment lengths: straddling and long buckets)
+    try:
+        for seg_len in (0, 1, 3, 8, 50):
+            hostemu.hostemu_set_seg(2, seg_len)
+            for c in ([0, 3, 8, 16] if n <= 64 else [0, 7]):
+                assert run_msm(hostemu, pts, scs, c, 1, 3) == exp, (n, c, seg_len)
+    finally:
+        hostemu.hostemu_set_seg(1, 0)
 
 
 def test_msm_matches_reference_algorithm(hostemu, known_points):
@@ -84,6 +92,12 @@ def test_msm_skewed_scalars_long_buckets(hostemu):
     for scs in ([rnd.randrange(2) for _ in range(n)], [7] * n, [rnd.randrange(1, 4) * (1 << 240) for _ in range(n)]):
         for c in (0, 4, 13):
             assert run_msm(hostemu, pts, scs, c) == E.msm_known_dlog(scs, dl), c
+        try:  # the same through the segmented kernel: one bucket spanning hundreds of segments (KSegLongFix)
+            for seg_len in (0, 2):
+                hostemu.hostemu_set_seg(2, seg_len)
+                assert run_msm(hostemu, pts, scs, 4) == E.msm_known_dlog(scs, dl), seg_len
+        finally:
+            hostemu.hostemu_set_seg(1, 0)
 
 
 def test_msm_ext_pedersen_form(hostemu, known_points):
@@ -286,8 +300,13 @@ def test_msm_over_precomputed_bases(hostemu, known_points, table_bits):
     scs = [prng.scalar(0x5EED, i) for i in range(n)]
     scs[:6] = [0, 1, E.L - 1, 2**252, 2**(table_bits - 1), 2**table_bits - 1]
     want = E.msm_known_dlog(scs, dl[:n])
-    for sets in sorted({0, 1, 2, 3, 5, W - 1, W}):
-        assert run_msm_pre(hostemu, pts[:n], 0, n, [], scs, table_bits, sets) == want, sets
+    try:
+        for mode, seg_len in ((1, 0), (0, 0), (2, 5), (2, 64)):  # by geometry / one thread per bucket / segments
+            hostemu.hostemu_set_seg(mode, seg_len)
+            for sets in sorted({0, 1, 2, 3, 5, W - 1, W}):
+                assert run_msm_pre(hostemu, pts[:n], 0, n, [], scs, table_bits, sets) == want, (mode, seg_len, sets)
+    finally:
+        hostemu.hostemu_set_seg(1, 0)
     # sub-range of a longer vector + two extra terms (the h / k of a commitment)
     extra = [pts[200], E.affine_neg(pts[201])]
     sc2 = scs[:20] + [prng.scalar(9, 0), prng.scalar(9, 1)]
@@ -309,5 +328,10 @@ def test_msm_over_precomputed_bases_long_buckets(hostemu):
     rnd = random.Random(4)
     for sc in ([rnd.randrange(2) for _ in range(n)], [7] * n, [rnd.randrange(1, 4) << 240 for _ in range(n)]):
         want = E.scalar_mul(E.B, sum(s * (i % 30 + 1) for i, s in enumerate(sc)) % E.L)
-        for sets in (1, 2):
-            assert run_msm_pre(hostemu, pts, 0, n, [], sc, 8, sets) == want
+        try:
+            for mode, seg_len in ((1, 0), (0, 0), (2, 2)):  # seg_len 2: buckets spanning > 32 segments (long fix-up)
+                hostemu.hostemu_set_seg(mode, seg_len)
+                for sets in (1, 2):
+                    assert run_msm_pre(hostemu, pts, 0, n, [], sc, 8, sets) == want, (mode, seg_len, sets)
+        finally:
+            hostemu.hostemu_set_seg(1, 0)

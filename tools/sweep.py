@@ -6,6 +6,7 @@ import argparse
 import json
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -21,10 +22,12 @@ def main():
     ap.add_argument("--cap", type=int, nargs="+", default=[0])
     ap.add_argument("--async-tail", type=int, nargs="+", default=[1])
     ap.add_argument("--sort-blocks", type=int, nargs="+", default=[-1])
+    ap.add_argument("--async-sort", type=int, default=1, help="0: counting sort on the main stream (serial phase times)")
     ap.add_argument("--quad-threshold", type=int, default=-1, help="experiment: VMSM_OPT_QUAD_THRESHOLD")
     ap.add_argument("--precompute", type=int, nargs="+", default=[-1],
                     help="-1: plain path; 0 / 8..16: tables of 2^(c*w)*P_i with this window (0 = by size)")
     ap.add_argument("--pre-sets", type=int, nargs="+", default=[0], help="VMSM_OPT_PRE_SETS values to sweep")
+    ap.add_argument("--seg-len", type=int, nargs="+", default=[0], help="VMSM_OPT_SEG_LEN values to sweep (0 = whole waves)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -32,6 +35,7 @@ def main():
     ctx.set_option(_lib.OPT_PHASE_TIMING, 1)
     if args.quad_threshold >= 0:
         ctx.set_option(_lib.OPT_QUAD_THRESHOLD, args.quad_threshold)
+    ctx.set_option(_lib.OPT_ASYNC_SORT, args.async_sort)
     peak = ctx.imad_peak()
     out = open(args.out, "a") if args.out else None
     for logn in args.logn:
@@ -43,10 +47,11 @@ def main():
                     pts.precompute(pre)
             ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 256 if pre >= 0 else 1 << 30)
             for sort in args.sort:
-                for radix, cap, at, sb, ps in [(r, cp, a, b, q) for r in args.radix for cp in args.cap
-                                               for a in args.async_tail for b in args.sort_blocks
-                                               for q in (args.pre_sets if pre >= 0 else [0])]:
+                for radix, cap, at, sb, ps, sl in [(r, cp, a, b, q, z) for r in args.radix for cp in args.cap
+                                                   for a in args.async_tail for b in args.sort_blocks
+                                                   for q in (args.pre_sets if pre >= 0 else [0]) for z in args.seg_len]:
                     ctx.set_option(_lib.OPT_PRE_SETS, ps)
+                    ctx.set_option(_lib.OPT_SEG_LEN, sl)
                     if sb >= 0:
                         ctx.set_option(_lib.OPT_SORT_BLOCKS, sb)
                     if cap:
@@ -60,11 +65,13 @@ def main():
                     ctx.sync()
                     ctx.phase_times()
                     ctx.timer_start()
+                    h0 = time.perf_counter()
                     for s in range(args.steps):
                         ctx.msm_dev(*sets[s % 3], slot=s % 32)
+                    host_ms = 1e3 * (time.perf_counter() - h0) / args.steps  # host time to ISSUE one MSM (no sync)
                     ms = ctx.timer_stop() / args.steps
                     ph, calls = ctx.phase_times()
-                    rec = {"log2n": logn, "precompute": pre, "pre_sets": ps, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "Mpts_s": n / ms / 1e3,
+                    rec = {"log2n": logn, "precompute": pre, "pre_sets": ps, "seg_len": sl, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "host_issue_ms": round(host_ms, 4), "Mpts_s": n / ms / 1e3,
                            "imad_peak_tlps": peak, "phase_ms": {k: round(v / calls, 5) for k, v in ph.items()}}
                     print(json.dumps(rec), flush=True)
                     if out:

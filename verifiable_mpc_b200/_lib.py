@@ -17,7 +17,7 @@ OPT_QUAD_THRESHOLD, OPT_ASYNC_TAIL, OPT_CAP_FACTOR, OPT_SHARD_SEQ, OPT_ASYNC_SOR
 OPT_SORT_BLOCKS = 11
 OPT_FOLD_QUAD_MAX = 12
 OPT_BN_QUAD_ACC = 13
-OPT_PRE_SETS, OPT_PRE_MIN_TERMS = 14, 15
+OPT_PRE_SETS, OPT_PRE_MIN_TERMS, OPT_SEG_LEN, OPT_SEG_MODE, OPT_HOST_NORMALIZE = 14, 15, 16, 17, 18
 FOLD_WITNESS, FOLD_FORM = 0, 1
 AXPY_ADD_SCALED, AXPY_SCALE_ADD, AXPY_SCALE = 0, 1, 2
 PHASES = ("digits", "scan", "scatter", "order", "handoff", "accumulate", "reduce", "final")
@@ -71,6 +71,7 @@ SIGNATURES = {
     "vmsm_msm_async": [_u64, _u64, _u64, _u64, _p, _u32],
     "vmsm_msm_dev": [_u64, _u64, _u64, _u64, _u64, _u64, _u32],
     "vmsm_msm_dev_ext": [_u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _p, _u32],
+    "vmsm_msm_dev_ext_dot": [_u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u32],
     "vmsm_scalars_fold": [_u64, _u64, _u64, _p, _i32],
     "vmsm_scalars_axpy": [_u64, _u64, _u64, _u64, _u64, _u64, _p, _i32],
     "vmsm_scalars_dot": [_u64, _u64, _u64, _u64, _u64, _u64, _p],

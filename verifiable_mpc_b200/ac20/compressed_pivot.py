@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 from random import SystemRandom
 
 from . import pivot
-from .. import _lib
+from .. import _lib, hostpack
 from ..engine import ED_L
 from ..fingroups import DevicePointList
 
@@ -46,6 +46,14 @@ FAST_INT_PATH = True
 
 def _all_in_field(values, gf):
     return set(map(type, values)) <= {gf}
+
+
+def _pack_field(values, gf, order):
+    """n x 32 bytes of the residues of a list of gf elements (hostpack: one C loop when the helper module is built)."""
+    raw = hostpack.pack_residues(values, gf, order, False)
+    if raw is None:  # a look-alike element class: through .value in Python
+        raw = pivot.pack_scalars([v.value for v in values], order)
+    return raw
 
 
 def _field_text(ints, q, signed=True):
@@ -230,6 +238,7 @@ def _final_check(g_hat, k, Q, coeffs, gf, proof):
 DEVICE_SCALAR_PATH = True
 DEVICE_SCALAR_MIN = 256          # verifier (no commitments per round: the integer loop is as fast below this)
 DEVICE_SCALAR_MIN_PROVER = 2     # prover: A_i and B_i are issued as an asynchronous pair only on the device path
+FUSED_CROSS_TERMS = True         # cross terms feed their commitments on the device (vmsm_msm_dev_ext_dot)
 
 
 class _DevForm:
@@ -242,12 +251,30 @@ class _DevForm:
     def repr_bytes(self):
         return b"[" + self.sc.text_bytes(0, self.n, self.signed) + b"], " + self.constant.encode("ascii")
 
+    def feed_repr(self, h):
+        if hasattr(self.sc, "text_view"):  # hashed in place from the pinned buffer
+            h.update(b"[")
+            h.update(self.sc.text_view(0, self.n, self.signed))
+            h.update(b"], " + self.constant.encode("ascii"))
+        else:
+            h.update(self.repr_bytes())
+
     def transcript_scalars(self):
         view = self.sc.wire_view(0, self.n) if hasattr(self.sc, "wire_view") else self.sc.download(0, self.n)
         return self.n, view, int(self.constant)
 
     def __repr__(self):
         return self.repr_bytes().decode("ascii")
+
+
+TRACE = None  # tools/profile_ac20.py sets a list: (label, perf_counter()) marks of the device-resident prover
+
+
+def _mark(label):
+    if TRACE is not None:
+        import time
+
+        TRACE.append((label, time.perf_counter()))
 
 
 def _use_device_scalars(g_hat, q, min_n=None):
@@ -274,24 +301,36 @@ def _protocol_4_prover_dev(g_hat, k, Q, Ld, zd, gf, proof, round_i):
     signed = bool(gf.is_signed)
     kd = pivot._device_single(group, k)
     min_n = DEVICE_SCALAR_MIN_PROVER
+    fused = FUSED_CROSS_TERMS and hasattr(ctx, "msm_dev_ext_dot")
     try:
         n = len(g_hat)
         while n > min_n:
             half = n // 2
             logger_cp.debug("Calculate A_i, B_i.")
-            s_a = ctx.scalars_dot(Ld, half, zd, 0, half)  # L_tilde([0]*half + z_L)
-            s_b = ctx.scalars_dot(Ld, 0, zd, half, half)  # L_tilde(z_R + [0]*half)
-            ctx.msm_dev_ext(g_hat.dev, g_hat.off + half, half, zd, 0, kd, 0, [s_a], slot=0)
-            ctx.msm_dev_ext(g_hat.dev, g_hat.off, half, zd, half, kd, 0, [s_b], slot=1)
+            _mark("round:start")
+            if fused:
+                # the cross terms L_tilde([0]*half + z_L), L_tilde(z_R + [0]*half) stay on the device: each is the
+                # scalar of the k-term of its commitment (no host round trip between the inner product and the MSM)
+                ctx.msm_dev_ext_dot(g_hat.dev, g_hat.off + half, half, zd, 0, kd, 0, Ld, half, zd, 0, half, slot=0)
+                ctx.msm_dev_ext_dot(g_hat.dev, g_hat.off, half, zd, half, kd, 0, Ld, 0, zd, half, half, slot=1)
+            else:
+                s_a = ctx.scalars_dot(Ld, half, zd, 0, half)  # L_tilde([0]*half + z_L)
+                s_b = ctx.scalars_dot(Ld, 0, zd, half, half)  # L_tilde(z_R + [0]*half)
+                _mark("round:dots")
+                ctx.msm_dev_ext(g_hat.dev, g_hat.off + half, half, zd, 0, kd, 0, [s_a], slot=0)
+                ctx.msm_dev_ext(g_hat.dev, g_hat.off, half, zd, half, kd, 0, [s_b], slot=1)
             A, B = group._make(ctx.result(0)), group._make(ctx.result(1))
+            _mark("round:A,B")
             proof["A" + str(round_i)] = A
             proof["B" + str(round_i)] = B
             Q = _resolve(Q)
             c = _fold_challenge(A, B, g_hat, k, Q, _DevForm(Ld, n, signed), q)
+            _mark("round:challenge")
             g_hat = _fold_generators(g_hat, c)
             Q = _q_prime(group, A, Q, B, c)
             Ld.fold(half, c, _lib.FOLD_FORM)
             zd.fold(half, c, _lib.FOLD_WITNESS)
+            _mark("round:folds issued")
             n = half
             if n <= 2:
                 proof["z_prime"] = [gf(v) for v in zd.tolist(0, n)]
@@ -410,10 +449,15 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
     n = len(x)
     ctx = g_hat.dev.ctx
     proof = {}
-    zd = ctx.upload_scalars(r + [rho], order)
+    _mark("p5:start")
+    if isinstance(r, list):
+        zd = ctx.upload_scalars(r + [rho], order)
+    else:  # packed draws (pivot.random_residues_packed)
+        zd = ctx.upload_scalars(r.tobytes() + (rho % order).to_bytes(32, "little"), order)
     Ld = xd = None
     try:
-        Ld = ctx.upload_scalars([cf.value for cf in L.coeffs] + [0], order)
+        Ld = ctx.upload_scalars(_pack_field(L.coeffs, gf, order) + bytes(32), order)
+        _mark("p5:uploads")
         t = gf(ctx.scalars_dot(Ld, 0, zd, 0, n)) + L.constant
         logger_cp.debug("Calculate A.")
         g_fixed = generators["g"]
@@ -424,6 +468,7 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
         else:
             ctx.msm_dev(g_hat.dev, zd, slot=0, poff=g_hat.off, soff=0, n=n + 1)  # h**rho * prod g_i**r_i
         A = group._make(ctx.result(0))
+        _mark("p5:t,A")
         proof["t"] = t
         proof["A"] = A
         # the first pre-image (text of the generators and of L: device calls + SHA-256, no GIL) is hashed on a worker
@@ -432,11 +477,12 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
         if n >= FIRST_HASH_THREAD_MIN:  # below that, starting a thread costs more than the overlap returns
             with _WORKER() as pool:
                 pending = pool.submit(_first_prefix, t, A, generators, P, L, y, order, gf, L_text)
-                x_raw = pivot.pack_scalars([v.value for v in x] + [pivot._int(gamma) % order], order)
+                x_raw = _pack_field(x, gf, order) + pivot.pack_scalars([pivot._int(gamma)], order)
                 state = pending.result()
         else:
             state = _first_prefix(t, A, generators, P, L, y, order, gf, L_text)
-            x_raw = pivot.pack_scalars([v.value for v in x] + [pivot._int(gamma) % order], order)
+            x_raw = _pack_field(x, gf, order) + pivot.pack_scalars([pivot._int(gamma)], order)
+        _mark("p5:first hash + pack x")
         xd = ctx.upload_scalars(x_raw, order)
         c0, c1 = _first_finish(state, order)
         zd.axpy(c0, xd, _lib.AXPY_ADD_SCALED)
@@ -445,6 +491,7 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
         l_z = ctx.scalars_dot(Ld, 0, zd, 0, n)
         Ld.axpy(c1, None, _lib.AXPY_SCALE)
         assert l_z * c1 % order == ctx.scalars_dot(Ld, 0, zd, 0, n + 1)  # L(z) * c1 == L_tilde(z_hat)
+        _mark("p5:z, Q, L_tilde")
     except BaseException:
         zd.free()
         if Ld is not None:
@@ -466,9 +513,6 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     assert bin(n + 1).count("1") == 1, \
         "This implementation requires n+1 to be power of 2 (else, use padding with zeros)."
     order = gf.order
-    r = pivot.random_residues(prng, order, n)
-    rho = prng.randrange(order)
-    logger_cp.debug("Calculate t.")
     # the residue paths reduce modulo gf.order while the round loop reduces modulo the group order: same thing only when
     # the field IS the exponent field of the group (always so in the reference's drivers); otherwise the generic path
     fast = (FAST_INT_PATH and gf.order == k.order and _all_in_field(L.coeffs, gf) and _all_in_field(x, gf)
@@ -476,8 +520,17 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     if fast and len(L.coeffs) == n:
         g_hat = _g_hat(g, h, group)
         if _use_device_scalars(g_hat, order, DEVICE_SCALAR_MIN_PROVER):
+            # the announcement randomness only ever lives on the device here: drawn (same draws, same generator state
+            # as the reference's n randrange calls, compressed_pivot.py:105-106) straight into packed bytes
+            r = pivot.random_residues_packed(prng, order, n)
+            if r is None:
+                r = pivot.random_residues(prng, order, n)
+            rho = prng.randrange(order)
             return _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho)
         del g_hat
+    r = pivot.random_residues(prng, order, n)
+    rho = prng.randrange(order)
+    logger_cp.debug("Calculate t.")
     t = gf(_dot([cf.value for cf in L.coeffs], r, order)) + L.constant if fast else L(r)
     logger_cp.debug("Calculate A.")
     A = pivot.vector_commitment(r, rho, g, h)
@@ -543,7 +596,7 @@ def protocol_5_verifier(generators, P, L, y, proof, gf):
     g_hat = _g_hat(g, h, group)
     if (FAST_INT_PATH and gf.order == k.order and _all_in_field(L.coeffs, gf) and len(L.coeffs) + 1 == len(g_hat)
             and _use_device_scalars(g_hat, order)):
-        Ld = g_hat.dev.ctx.upload_scalars([cf.value for cf in L.coeffs] + [0], order)
+        Ld = g_hat.dev.ctx.upload_scalars(_pack_field(L.coeffs, gf, order) + bytes(32), order)
         try:
             c0, c1 = _first_challenges(t, A, generators, P, L, y, order, gf,
                                        L_text=_DevForm(Ld, len(L.coeffs), bool(gf.is_signed), L.constant))

@@ -17,6 +17,7 @@ from .. import fingroups
 from ..engine import pack_scalars
 from ..fingroups import DevicePointList, EllipticCurvePoint as EllipticCurveElement
 
+from .. import hostpack
 from .forms import field_types as _field_types, secure_types as _secure_types
 from .forms import AffineForm, LinearForm, SecureObject  # noqa: F401  (the reference exports them from pivot)
 
@@ -44,6 +45,45 @@ def random_residues(rng, order, n):
             append(v)
         return out
     return [rng.randrange(order) for _ in range(n)]
+
+
+def random_residues_packed(rng, order, n):
+    """The draws of ``random_residues(rng, order, n)`` as n x 32 little-endian bytes (what the device wants), leaving
+    the generator in the same state, without creating n Python ints; None when ``rng`` is not a stdlib generator.
+
+    ``Random.randrange(order)`` is ``getrandbits(bits)`` repeated until the value is below ``order``, and
+    ``getrandbits(bits)`` consumes ceil(bits / 32) words of the Mersenne twister, least significant first, the last
+    one shifted down to the remaining bits.  One ``getrandbits`` of many words therefore yields the same words in
+    the same order; numpy applies the shift and the rejection test to all candidates of a batch at once."""
+    import random as _random
+
+    import numpy as np
+
+    bits = order.bit_length()
+    if type(rng) not in (_random.Random, _random.SystemRandom) or order <= 1 or bits > 256 or n == 0:
+        return None
+    words = (bits + 31) // 32
+    shift = 32 * words - bits
+    limbs = [(order >> (32 * k)) & 0xFFFFFFFF for k in range(words)]
+    need, chunks = n, []
+    while need:
+        # `need` more accepted values take at least `need` more candidates: drawing exactly that many never consumes
+        # a word the sequential rejection loop would not have consumed, so the generator ends in the same state
+        m = need
+        raw = rng.getrandbits(32 * words * m).to_bytes(4 * words * m, "little")
+        cand = np.frombuffer(raw, dtype="<u4").reshape(m, words)
+        if shift:
+            cand = cand.copy()
+            cand[:, -1] >>= shift
+        below = np.zeros(m, dtype=bool)
+        for k in range(words):  # lexicographic candidate < order, least significant limb first
+            below = (cand[:, k] < limbs[k]) | ((cand[:, k] == limbs[k]) & below)
+        idx = np.flatnonzero(below)
+        chunks.append(cand[idx])
+        need -= len(idx)
+    out = np.zeros((n, 8), dtype="<u4")
+    out[:, :words] = np.concatenate(chunks) if len(chunks) > 1 else chunks[0]
+    return out.view(np.uint8).reshape(n, 32)
 
 
 def _int(value):
@@ -133,8 +173,11 @@ def transcript_challenge(label, items, order):
 def _feed_repr(h, item):
     """h.update(repr(item).encode()) without building the large strings: device-resident generator lists offer
     ``repr_bytes()`` (decimal text produced on the GPU); dicts (the ``generators`` argument) are walked."""
+    feed = getattr(item, "feed_repr", None)
     rb = getattr(item, "repr_bytes", None)
-    if rb is not None:
+    if feed is not None:
+        feed(h)
+    elif rb is not None:
         h.update(rb())
     elif type(item) is dict:
         h.update(b"{")
@@ -216,9 +259,15 @@ def vector_commitment(x, gamma, g, h):
     assert len(g) >= len(x), "Not enough generators."
     group = type(h)
     dev = as_device_list(g, group)
-    scalars = [_int(v) for v in x] + [_int(gamma)]
+    order = group.order
+    # ints and elements of the exponent field in one C pass (hostpack); anything else through the reference's _int
+    cls = hostpack.field_class_for(x, order) if isinstance(x, (list, tuple)) else False
+    raw = hostpack.pack_residues(x, cls, order) if cls is not False else None
+    if raw is None:
+        raw = pack_scalars([_int(v) for v in x], order)
+    raw += pack_scalars([_int(gamma)], order)
     hd = _device_single(group, h)
-    xy = dev.dev.ctx.msm_ext(dev.dev, dev.off, len(x), hd, 0, 1, pack_scalars(scalars, group.order))
+    xy = dev.dev.ctx.msm_ext(dev.dev, dev.off, len(x), hd, 0, 1, raw)
     return group._make(xy)
 
 

@@ -407,6 +407,150 @@ struct KCombine {
     }
 };
 
+// ---------------------------------------------------------------------------------------------- segmented accumulate
+// Balanced bucket accumulation.  One thread per BUCKET (KAccumulateT above) runs as fast as the machine allows only when
+// there are many more buckets than resident threads and their populations are alike: a 2^17-term slice of a sharded
+// MSM, or windows sharing bucket sets over precomputed bases, have neither (measured: 2^20 terms over ONE bucket set,
+// 32768 buckets of 512 entries, 2.36 ms against 1.13 ms for 16 sets).  Here the sorted CSR array is cut into equal
+// SEGMENTS of L entries instead, one thread each, whatever buckets they fall into:
+//   * a bucket that lies inside one segment is summed and stored by that thread;
+//   * a bucket that straddles segments leaves one partial sum per segment -- a thread has at most two such partials,
+//     for the run that reaches it from the previous segment ("head") and the run that leaves it ("tail");
+//   * KSegFixup (one thread per bucket) adds the partials of a straddling bucket, writes the identity into empty
+//     buckets and hands buckets spanning more than `long_span` segments to KSegLongFix (one warp per bucket).
+// Every thread does the same number of mixed additions, so the launch is sized in whole waves of resident threads
+// (seg_plan) and skewed scalars (boolean witnesses: one bucket holding half the MSM) need no separate path.
+// seg_bucket[t] = the bucket holding entry t * L (written by the scan that produces the CSR offsets).
+template <bool PRE>
+struct KAccumulateSegT {
+    // 48 KB of (unused) dynamic shared memory per block: at most FOUR blocks per SM.  At 96 registers a fifth block
+    // would fit, which measured no faster alone (profiles/r01/accumulate_variants.md) and leaves no registers for the
+    // thin counting-sort blocks of the next MSM that run underneath this kernel (2^20 terms: 1.55 instead of 1.45 ms).
+    enum { kBlock = 128, kDynSmem = 48 * 1024 };
+    BaseRef br;
+    const uint32_t *offsets;     // per bucket, positions in the CONTIGUOUS idx array
+    const uint32_t *counts;
+    const uint32_t *idx;
+    const uint32_t *seg_bucket;  // per segment
+    const uint32_t *total;       // device word: number of CSR entries E
+    ge_ext *buckets;
+    ge_ext *partials;            // [2t] head, [2t + 1] tail of segment t
+    uint32_t L;
+    VMSM_HD void flush(uint32_t tid, uint32_t b, const ge_ext &acc, bool cont, bool more) const {
+        if (cont) st_ext(partials + 2 * (size_t)tid, acc);
+        else if (more) st_ext(partials + 2 * (size_t)tid + 1, acc);
+        else st_ext(buckets + b, acc);
+    }
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint32_t E = *total;
+        const uint32_t pos0 = tid * L;
+        if (pos0 >= E) return;
+        const uint32_t pos1 = E - pos0 < L ? E : pos0 + L;
+        uint32_t b = seg_bucket[tid];
+        uint32_t off = offsets[b];
+        uint32_t bend = off + counts[b];
+        bool cont = off < pos0;  // the first run started in an earlier segment
+        ge_ext acc = ge_identity();
+        uint32_t e = idx[pos0];
+        for (uint32_t pos = pos0; pos < pos1; pos++) {
+            uint32_t en = pos + 1 < pos1 ? idx[pos + 1] : 0u;  // index prefetch: one load ahead of the gather
+            if (pos == bend) {  // the run of bucket b is complete: next non-empty bucket (rare, divergent, cheap)
+                flush(tid, b, acc, cont, false);
+                cont = false;
+                uint32_t c;
+                do {
+                    b++;
+                    c = counts[b];
+                } while (c == 0);
+                bend += c;  // offsets are contiguous: bucket b starts where its predecessor ended
+                acc = ge_identity();
+            }
+            // the mixed addition stays outside every divergent branch (a run's first base is added to the identity:
+            // 7M instead of 1M once per run, in exchange for a warp that never executes two variants of the step)
+            acc = ge_madd(acc, ld_niels(br.template ptr<PRE>(e, b)), (e >> 31) != 0);
+            e = en;
+        }
+        flush(tid, b, acc, cont, bend > pos1);
+    }
+};
+typedef KAccumulateSegT<false> KAccumulateSeg;
+typedef KAccumulateSegT<true> KAccumulateSegPre;
+
+struct KSegFixup {
+    enum { kBlock = 128 };
+    const uint32_t *offsets;
+    const uint32_t *counts;
+    const ge_ext *partials;
+    ge_ext *buckets;
+    uint32_t L, long_span;
+    OverflowCtl *ctl;   // nlong
+    LongBucket *longs;  // {bucket, first segment, segments after the first}
+    VMSM_HD void operator()(uint32_t b) const {
+        const uint32_t cnt = counts[b];
+        if (!cnt) {
+            st_ext(buckets + b, ge_identity());
+            return;
+        }
+        const uint32_t off = offsets[b];
+        const uint32_t t0 = off / L, t1 = (off + cnt - 1) / L;
+        if (t0 == t1) return;  // summed and stored by its segment's thread
+        if (t1 - t0 > long_span) {
+            uint32_t lpos = VMSM_ATOMIC_ADD(&ctl->nlong, 1u);
+            LongBucket lb = {b, t0, t1 - t0};
+            longs[lpos] = lb;
+            return;
+        }
+        ge_ext acc = ld_ext(partials + 2 * (size_t)t0 + 1);
+        for (uint32_t t = t0 + 1; t <= t1; t++) acc = ge_add(acc, ld_ext(partials + 2 * (size_t)t));
+        st_ext(buckets + b, acc);
+    }
+};
+
+// One warp per long bucket (grid-stride over the device-side count): lanes stride over its partials, shuffle tree.
+struct KSegLongFix {
+    enum { kBlock = 128 };
+    const OverflowCtl *ctl;
+    const LongBucket *longs;
+    const ge_ext *partials;
+    ge_ext *buckets;
+    uint32_t nwarps;
+    VMSM_HD const ge_ext *part(const LongBucket &lb, uint32_t k) const {
+        return k == 0 ? partials + 2 * (size_t)lb.task_base + 1 : partials + 2 * ((size_t)lb.task_base + k);
+    }
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint32_t nlong = ctl->nlong;
+#if defined(__CUDA_ARCH__)
+        const uint32_t lane = tid & 31;
+        for (uint32_t l = tid >> 5; l < nlong; l += nwarps) {
+            LongBucket lb = longs[l];
+            ge_ext acc = ge_identity();
+            for (uint32_t k = lane; k <= lb.ntask; k += 32) acc = ge_add(acc, ld_ext(part(lb, k)));
+#pragma unroll 1
+            for (int d = 16; d >= 1; d >>= 1) {
+                ge_ext o;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    o.X.v[i] = __shfl_down_sync(0xffffffffu, acc.X.v[i], d);
+                    o.Y.v[i] = __shfl_down_sync(0xffffffffu, acc.Y.v[i], d);
+                    o.Z.v[i] = __shfl_down_sync(0xffffffffu, acc.Z.v[i], d);
+                    o.T.v[i] = __shfl_down_sync(0xffffffffu, acc.T.v[i], d);
+                }
+                acc = ge_add(acc, o);
+            }
+            if (lane == 0) st_ext(buckets + lb.bucket, acc);
+        }
+#else
+        if (tid & 31) return;
+        for (uint32_t l = tid >> 5; l < nlong; l += nwarps) {
+            LongBucket lb = longs[l];
+            ge_ext acc = ge_identity();
+            for (uint32_t k = 0; k <= lb.ntask; k++) acc = ge_add(acc, ld_ext(part(lb, k)));
+            st_ext(buckets + lb.bucket, acc);
+        }
+#endif
+    }
+};
+
 // Radix-R merge of bucket-tree nodes.  A node covering buckets [lo, lo + s) carries
 //   S = sum B_k            T = sum (k - lo) B_k
 // Leaves are the buckets themselves (s = 1, T = 0, inT == null).  Merging children i = 0..m-1 of size s:
@@ -450,6 +594,9 @@ struct KFinal {
     ge_ext *out_ext;
     ge_aff *out_aff;
     uint32_t W, c;
+    // when set: the extended result goes to host-mapped memory and the HOST normalises it (one inversion is ~265
+    // dependent field multiplications: 0.19 ms for a lone GPU thread, ~15 us for a CPU core)
+    ge_ext *out_host_ext;
     VMSM_HD void operator()(uint32_t) const {
         ge_ext acc = ge_identity();
         for (int32_t w = (int32_t)W - 1; w >= 0; w--) {
@@ -458,6 +605,10 @@ struct KFinal {
             acc = ge_add(acc, ge_add(ld_ext(S + w), ld_ext(T + w)));
         }
         st_ext(out_ext, acc);
+        if (out_host_ext) {
+            st_ext(out_host_ext, acc);
+            return;
+        }
         st_aff(out_aff, ge_ext_to_aff(acc));
     }
 };
@@ -513,6 +664,7 @@ struct KFinalQ {
     ge_ext *out_ext;
     ge_aff *out_aff;
     uint32_t W, c;
+    ge_ext *out_host_ext;  // see KFinal
     VMSM_HD void operator()(uint32_t tid) const {
 #if defined(__CUDA_ARCH__)
         const int q = tid & 3;
@@ -522,13 +674,20 @@ struct KFinalQ {
                 for (uint32_t k = 0; k < c; k++) acc = quad_dbl(q, acc);
             acc = quad_add(q, acc, quad_add(q, quad_load(S + w, q), quad_load(T + w, q)));
         }
+        if (out_host_ext) {
+            if (tid < 4) {
+                quad_store(out_ext, q, acc);
+                quad_store(out_host_ext, q, acc);
+            }
+            return;
+        }
         fe zi = fe_inv(quad_get(acc, 2));
         fe aff = fe_canon(fe_mul(acc, zi));  // lane 0: x, lane 1: y
         if (tid < 4) quad_store(out_ext, q, acc);
         if (tid < 2) st_fe(q == 0 ? &out_aff->x : &out_aff->y, aff);
 #else
         if (tid) return;
-        KFinal k = {S, T, out_ext, out_aff, W, c};
+        KFinal k = {S, T, out_ext, out_aff, W, c, out_host_ext};
         k(0);
 #endif
     }

@@ -35,6 +35,8 @@ struct MsmOptions {
     uint32_t w_quad_acc = 1;       // BN256 accumulate with four lanes per bucket: 0 never, 1 by size, 2 always
     uint32_t quad_threshold = 16384;  // tree levels with at most this many output nodes run quad-cooperative; 0 = never
     uint32_t pre_sets = 0;     // MSMs over precomputed bases: number of bucket sets the windows share; 0 = auto
+    uint32_t seg_len = 0;      // entries per thread of the balanced accumulate kernel; 0 = whole waves (seg_plan)
+    uint32_t seg_mode = 1;     // accumulate kernel: 0 one thread per bucket, 1 by geometry (default), 2 segments
 };
 
 // Precomputed bases of an MSM call (KPrecompute): level w of `table` holds 2^(c*w) * P_i at table[w * stride + i].
@@ -66,6 +68,11 @@ struct Workspace {
     OverflowTask *tasks_[kTailWays] = {};
     LongBucket *longs_[kTailWays] = {};
     void *partials_[kTailWays] = {};
+    // segmented accumulate (Ed25519): per-segment start bucket, entry total and row totals ride with the CSR parity;
+    // the two partial sums per segment belong to the MSM's tail way (read by the fix-up kernels on its side stream)
+    uint32_t *seg_bucket_[2] = {nullptr, nullptr}, *seg_total_[2] = {nullptr, nullptr}, *row_totals_[2] = {nullptr, nullptr};
+    void *seg_partials_[kTailWays] = {};
+    size_t cap_seg = 0, cap_seg_part = 0;  // segments
     size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0, cap_tasks = 0;  // element counts
     int ways = 0;  // tail ways that have buckets / node buffers (grows to the largest count requested)
     size_t elem_bytes = 0;  // size of one accumulator point the point buffers were allocated for
@@ -114,15 +121,45 @@ inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits, uint32_t 
     return g;
 }
 
-// Bucket sets of an MSM over precomputed bases: as few as keep the accumulate kernel (one thread per bucket) wide
-// enough -- every set costs a bucket tree of 2.3 * NB full additions, every window sharing a set lengthens its
-// buckets' chains.  Aim at ~32 entries per bucket (what the plain path has at 2^20 terms, c = 16).
-inline uint32_t choose_sets(uint64_t n, uint32_t c, uint32_t W) {
-    uint64_t per_bucket_one_set = (n * W) >> (c - 1);
-    uint32_t s = 1;
-    while (s * 2 <= W && per_bucket_one_set / (s * 2) >= 32) s *= 2;
-    if (s * 2 > W) s = W;  // e.g. W = 20: 16 would leave four sets with two windows each
-    return s;
+// Segment plan of the balanced accumulate kernel: whole waves of `resident` threads, at most 32 entries per thread.
+struct SegPlan {
+    uint32_t L, T;  // entries per segment, segments (threads) launched
+};
+inline SegPlan seg_plan(uint64_t max_entries, uint32_t resident, uint32_t forced_L = 0) {
+    SegPlan p;
+    if (max_entries == 0) max_entries = 1;
+    uint64_t waves = (max_entries + 32ull * resident - 1) / (32ull * resident);
+    uint64_t L = (max_entries + waves * resident - 1) / (waves * resident);
+    if (L < 8) L = 8;  // tiny MSMs: a few threads with a handful of entries each
+    if (forced_L) L = forced_L;
+    p.L = (uint32_t)L;
+    p.T = (uint32_t)((max_entries + L - 1) / L);
+    return p;
+}
+
+template <class BE>
+int ws_ensure_seg(BE &be, Workspace &ws, size_t segs) {
+    if (segs > ws.cap_seg) {
+        ws.cap_seg = 0;
+        for (int k = 0; k < 2; k++) {
+            be.free(ws.seg_bucket_[k]), be.free(ws.seg_total_[k]), be.free(ws.row_totals_[k]);
+            ws.seg_bucket_[k] = (uint32_t *)be.alloc(segs * 4);
+            ws.seg_total_[k] = (uint32_t *)be.alloc(16);
+            ws.row_totals_[k] = (uint32_t *)be.alloc(256 * 4);  // one per bucket set: at most 127 (c = 2)
+            if (!ws.seg_bucket_[k] || !ws.seg_total_[k] || !ws.row_totals_[k]) return -1;
+        }
+        ws.cap_seg = segs;
+    }
+    if (segs > ws.cap_seg_part) {  // after ws_ensure: ws.ways is final
+        ws.cap_seg_part = 0;
+        for (int k = 0; k < ws.ways; k++) {
+            be.free(ws.seg_partials_[k]);
+            ws.seg_partials_[k] = be.alloc(2 * segs * sizeof(ge_ext));
+            if (!ws.seg_partials_[k]) return -1;
+        }
+        ws.cap_seg_part = segs;
+    }
+    return 0;
 }
 
 template <class BE>
@@ -131,7 +168,7 @@ int ws_ensure(BE &be, Workspace &ws, const MsmGeom &g, uint32_t R, size_t elem_b
     size_t nb = (size_t)g.S * g.NB, ni = (size_t)g.W * g.n, nn = (size_t)g.S * ((g.NB + R - 1) / R);
     if (nn < g.S) nn = g.S;
     if (ways > ws.ways) {  // more MSM tails in flight than before: (re)allocate the per-way buffers
-        ws.cap_buckets = ws.cap_nodes = ws.cap_tasks = 0;
+        ws.cap_buckets = ws.cap_nodes = ws.cap_tasks = ws.cap_seg_part = 0;
         ws.ways = ways;
     }
     if (elem_bytes > ws.elem_bytes) {  // a wider accumulator type than before: regrow the point buffers
@@ -205,6 +242,8 @@ void ws_release(BE &be, Workspace &ws) {
         be.free(ws.ctl_[k]), be.free(ws.tasks_[k]), be.free(ws.longs_[k]), be.free(ws.partials_[k]);
     for (int par = 0; par < kTailWays; par++)
         for (int k = 0; k < 2; k++) be.free(ws.nodeS[par][k]), be.free(ws.nodeT[par][k]);
+    for (int k = 0; k < 2; k++) be.free(ws.seg_bucket_[k]), be.free(ws.seg_total_[k]), be.free(ws.row_totals_[k]);
+    for (int k = 0; k < kTailWays; k++) be.free(ws.seg_partials_[k]);
     ws = Workspace();
 }
 
@@ -212,12 +251,19 @@ void ws_release(BE &be, Workspace &ws) {
 template <class BE>
 int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, const ge_niels *bases,
             const uint32_t *scalars, uint32_t n, ge_ext *out_ext, ge_aff *out_aff, uint32_t seq = 0,
-            const ge_niels *extra = nullptr, uint32_t n_extra = 0, const PreTable *pre = nullptr) {
+            const ge_niels *extra = nullptr, uint32_t n_extra = 0, const PreTable *pre = nullptr,
+            ge_ext *out_host_ext = nullptr) {
     // terms 0 .. n-n_extra-1 use `bases`, the last n_extra terms use `extra` (scalars are contiguous)
     const uint32_t n_main = n - n_extra;
     // precomputed bases fix the window (the table was built for it); the windows then share `S` bucket sets
     uint32_t c = pre ? pre->c : opt.window_bits ? opt.window_bits : choose_window(n, scalar_bits);
-    MsmGeom g = make_geom(n, c, scalar_bits, pre ? (opt.pre_sets ? opt.pre_sets : choose_sets(n, c, (scalar_bits + c) / c)) : 0);
+    // Two accumulate kernels (measured, profiles/r02/accumulate_segmented.md): one thread per BUCKET when there are many
+    // more buckets than resident threads (the plain path: W bucket sets; large MSMs over tables: 8 sets), equal
+    // SEGMENTS of the CSR array when the windows of a table-based MSM share one bucket set (few, long buckets).
+    const uint32_t W_c = (scalar_bits + c) / c;
+    const bool seg = opt.seg_mode == 2 || (opt.seg_mode == 1 && pre && n < (1u << 19));
+    const uint32_t sets = !pre ? 0u : opt.pre_sets ? opt.pre_sets : seg ? 1u : (W_c < 8 ? W_c : 8u);
+    MsmGeom g = make_geom(n, c, scalar_bits, sets);
     if (pre && (pre->W != g.W || (n_extra && !pre->extra_table))) return -2;
     uint32_t R = 1u << opt.reduce_log2r;
     // small MSMs are bound by their tails (~0.45 ms of dependent doublings against a ~0.1 ms head): more of them in flight
@@ -229,6 +275,14 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     uint32_t log2NB = g.c - 1;
     BaseRef br = {bases, extra, n_main, pre ? pre->stride : 0u, pre ? pre->extra_stride : 0u, g.lg, g.S, log2NB};
     if (pre) br.extra = pre->extra_table;
+    // balanced accumulate: the CSR array (at most n * W entries) in equal segments, whole waves of resident threads
+    SegPlan sp = {0, 0};
+    uint32_t *seg_bucket = nullptr, *seg_total = nullptr;
+    if (seg) {
+        sp = seg_plan((uint64_t)n * g.W, be.resident_threads(pre != nullptr), opt.seg_len);
+        if (ws_ensure_seg(be, ws, sp.T)) return -1;
+        seg_bucket = ws.seg_bucket_[par], seg_total = ws.seg_total_[par];
+    }
 
     // counting sort of (window, |digit|) -> CSR lists, on the sort stream (double-buffered by parity)
     be.sort_begin(par);
@@ -239,15 +293,16 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         be.launch_sort(k1, n);
     }
     be.phase_mark(PH_DIGITS);
-    be.scan_offsets(counts, offsets, cursor, g);
+    if (seg) be.scan_offsets_flat(counts, offsets, cursor, g, ws.row_totals_[par], seg_bucket, seg_total, sp.L);
+    else be.scan_offsets(counts, offsets, cursor, g);
     be.phase_mark(PH_SCAN);
     if (n) {
         KScatter k3 = {scalars, cursor, idx, g};
         be.launch_sort(k3, n);
     }
     be.phase_mark(PH_SCATTER);
-    const uint32_t *order = nullptr;
-    if (opt.sort_buckets && be.order_buckets(counts, ws.order_[par], nbuckets, n)) order = ws.order_[par];
+    const uint32_t *order = nullptr;  // per-bucket kernel: buckets by decreasing population (segments are equal anyway)
+    if (!seg && opt.sort_buckets && be.order_buckets(counts, ws.order_[par], nbuckets, n)) order = ws.order_[par];
     be.phase_mark(PH_ORDER);
     be.sort_end(par);
     be.phase_mark(PH_HANDOFF);
@@ -256,11 +311,33 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     const int tw = (int)(seq % (uint32_t)ways);
     be.head_wait_tail(tw);
     void *const buckets = ws.buckets_[tw];
-    {
-        const uint32_t wins_per_set = (g.W + g.S - 1) / g.S;
+    const uint32_t wins_per_set = (g.W + g.S - 1) / g.S;
+    be.zero(ws.ctl_[tw], sizeof(OverflowCtl));
+    if (seg) {
+        ge_ext *partials = (ge_ext *)ws.seg_partials_[tw];
+        if (pre) {
+            KAccumulateSegPre k5 = {br, offsets, counts, idx, seg_bucket, seg_total, (ge_ext *)buckets, partials, sp.L};
+            be.launch(k5, sp.T);
+        } else {
+            KAccumulateSeg k5 = {br, offsets, counts, idx, seg_bucket, seg_total, (ge_ext *)buckets, partials, sp.L};
+            be.launch(k5, sp.T);
+        }
+        be.phase_mark(PH_ACCUMULATE);
+        // everything after the accumulate kernel belongs to this MSM's tail: partial sums of straddling buckets, bucket
+        // tree, Horner -- on the CUDA backend on side stream `tw`, so the next MSM's accumulate kernel follows at once
+        be.tail_begin(tw);
+        const uint32_t long_span = 32;
+        KSegFixup kf = {offsets, counts, partials, (ge_ext *)buckets, sp.L, long_span, ws.ctl_[tw], ws.longs_[tw]};
+        be.launch(kf, nbuckets);
+        be.acc_done(par);  // the CSR lists of this parity are free again (the fix-up was their last reader)
+        if ((uint64_t)n * wins_per_set > (uint64_t)sp.L * long_span) {  // otherwise no bucket can span that many segments
+            const uint32_t ow = be.overflow_warps();
+            KSegLongFix kl = {ws.ctl_[tw], ws.longs_[tw], partials, (ge_ext *)buckets, ow};
+            be.launch(kl, ow * 32);
+        }
+    } else {
         uint32_t cap = opt.cap_factor * (uint32_t)(((uint64_t)n * wins_per_set) >> (g.c - 1));
         if (cap < 64) cap = 64;
-        be.zero(ws.ctl_[tw], sizeof(OverflowCtl));
         if (pre) {
             KAccumulatePre k5 = {br, offsets, counts, idx, order, (ge_ext *)buckets, nbuckets, cap, ws.ctl_[tw],
                                  ws.tasks_[tw], ws.longs_[tw]};
@@ -316,10 +393,10 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         // one root per bucket set; over precomputed bases the sets carry no weight: zero doublings between them
         const uint32_t dbl = pre ? 0u : g.c;
         if (opt.quad_threshold) {
-            KFinalQ k7 = {inS, inT, out_ext, out_aff, g.S, dbl};
+            KFinalQ k7 = {inS, inT, out_ext, out_aff, g.S, dbl, out_host_ext};
             be.launch(k7, 32);
         } else {
-            KFinal k7 = {inS, inT, out_ext, out_aff, g.S, dbl};
+            KFinal k7 = {inS, inT, out_ext, out_aff, g.S, dbl, out_host_ext};
             be.launch(k7, 1);
         }
     }

@@ -42,6 +42,16 @@ struct min_blocks {
     static constexpr int value = get<F>(nullptr);
 };
 
+// dynamic shared memory a kernel asks for WITHOUT using it: an occupancy limiter (kDynSmem in the functor)
+template <class F>
+struct dyn_smem {
+    template <class G>
+    static constexpr int get(decltype(G::kDynSmem) *) { return G::kDynSmem; }
+    template <class G>
+    static constexpr int get(...) { return 0; }
+    static constexpr int value = get<F>(nullptr);
+};
+
 template <class F>
 __global__ void __launch_bounds__(F::kBlock, min_blocks<F>::value) vmsm_kernel(const F f, uint32_t n) {
     uint32_t tid = blockIdx.x * (uint32_t)F::kBlock + threadIdx.x;
@@ -108,6 +118,56 @@ __global__ void __launch_bounds__(SCAN_TILE) vmsm_scan_offsets(const uint32_t *_
         uint32_t off = geom_set_start(g, w) + prefix + excl;
         offsets[(size_t)w * g.NB + i] = off;
         cursor[(size_t)w * g.NB + i] = off;
+    }
+}
+
+// Contiguous variant for the segmented accumulate kernel (Ed25519 path): the rows (bucket sets) follow each other
+// without gaps, so the CSR array is one run of E = sum(counts) entries; the scan also records, for every segment of L
+// entries, the bucket that holds its first entry, and E itself.
+__global__ void __launch_bounds__(1024) vmsm_row_totals(const uint32_t *__restrict__ counts, uint32_t NB,
+                                                        uint32_t *__restrict__ row_totals) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total;
+    const uint32_t *cw = counts + (size_t)blockIdx.x * NB;
+    uint32_t s = 0;
+    for (uint32_t i = threadIdx.x; i < NB; i += 1024) s += cw[i];
+    block_scan_1024(s, warp_sums, &total);
+    if (threadIdx.x == 0) row_totals[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_TILE) vmsm_scan_offsets_flat(const uint32_t *__restrict__ counts,
+                                                                    uint32_t *__restrict__ offsets,
+                                                                    uint32_t *__restrict__ cursor, MsmGeom g,
+                                                                    uint32_t tiles_per_row,
+                                                                    const uint32_t *__restrict__ row_totals,
+                                                                    uint32_t *__restrict__ seg_bucket,
+                                                                    uint32_t *__restrict__ total_out, uint32_t L) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total;
+    const uint32_t w = blockIdx.x / tiles_per_row, tile = blockIdx.x - w * tiles_per_row, t = threadIdx.x;
+    const uint32_t *cw = counts + (size_t)w * g.NB;
+    uint32_t row_base = 0;
+    for (uint32_t r = 0; r < w; r++) row_base += row_totals[r];
+    if (blockIdx.x == 0 && t == 0) {
+        uint32_t e = 0;
+        for (uint32_t r = 0; r < g.S; r++) e += row_totals[r];
+        *total_out = e;
+    }
+    uint32_t before = 0;
+    for (uint32_t i = t; i < tile * SCAN_TILE; i += SCAN_TILE) before += cw[i];
+    block_scan_1024(before, warp_sums, &total);
+    uint32_t prefix = total;
+    __syncthreads();
+    uint32_t i = tile * SCAN_TILE + t;
+    uint32_t cnt = i < g.NB ? cw[i] : 0u;
+    uint32_t excl = block_scan_1024(cnt, warp_sums, &total);
+    if (i < g.NB) {
+        uint32_t off = row_base + prefix + excl;
+        uint32_t b = w * g.NB + i;
+        offsets[b] = off;
+        cursor[b] = off;
+        // segments whose first entry lies in this bucket (usually none or one; a skewed bucket owns many)
+        for (uint32_t k = (off + L - 1) / L; (uint64_t)k * L < (uint64_t)off + cnt; k++) seg_bucket[k] = b;
     }
 }
 
@@ -290,7 +350,7 @@ struct Ctx {
     cudaStream_t copy = nullptr;
     uint32_t *astage[2] = {nullptr, nullptr};
     size_t astage_cap[2] = {0, 0};
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_dot[2] = {nullptr, nullptr};
     bool astage_used[2] = {false, false};
     // vmsm_lincomb_async: a ring of private staging sets (64 points + 64 scalars + error word each)
     ge_aff *la_aff = nullptr;
@@ -312,6 +372,11 @@ struct Ctx {
     cudaEvent_t ev_slot[64] = {nullptr};
     uint32_t cur_slot = 0;
     ge_aff *res_aff_host = nullptr;  // pinned + mapped, kSlots entries: written by the final kernel itself
+    // host-side normalisation (default): the final kernel stores the EXTENDED result here and fetch_slot inverts Z on
+    // the CPU -- the device inversion is a 0.19 ms dependent chain at the end of every MSM, a CPU core needs ~15 us
+    ge_ext *res_xyz_host = nullptr;  // pinned + mapped, kSlots entries
+    bool host_norm = true;
+    bool slot_host_norm[64] = {false};
     // BN256 results: Jacobian on the device, plain affine in mapped pinned memory; which curve a slot last held
     uint8_t *res_w_dev = nullptr;   // kSlots x 192 B
     uint8_t *res_w_host = nullptr;  // kSlots x 128 B, mapped
@@ -331,6 +396,7 @@ struct Ctx {
     uint32_t shard_seq = 0;  // != 0 while a sharded MSM is being issued
     uint32_t shard_next = 0;  // VMSM_OPT_SHARD_SEQ: applies to the next MSM call of any flavour, then clears
     MsmOptions opt;
+    uint32_t seg_resident[2] = {0, 0};  // resident threads of the segmented accumulate kernels (plain / tables), cached
     uint64_t pre_min_terms = 256;  // MSMs shorter than this ignore a precomputed table (VMSM_OPT_PRE_MIN_TERMS)
     bool phase_timing = false;
     bool check_points = true;
@@ -448,7 +514,7 @@ struct CudaBE {
     void launch(const F &f, uint32_t n) {
         if (!n) return;
         uint32_t grid = (n + F::kBlock - 1) / F::kBlock;
-        vmsm_kernel<F><<<grid, F::kBlock, 0, cur>>>(f, n);
+        vmsm_kernel<F><<<grid, F::kBlock, dyn_smem<F>::value, cur>>>(f, n);
         c->launches++;
         note(cudaGetLastError());
     }
@@ -466,6 +532,27 @@ struct CudaBE {
         vmsm_scan_offsets<<<g.S * tiles, SCAN_TILE, 0, cur>>>(counts, offsets, cursor, g, tiles);  // one row per bucket set
         c->launches++;
         note(cudaGetLastError());
+    }
+    void scan_offsets_flat(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, const MsmGeom &g,
+                           uint32_t *row_totals, uint32_t *seg_bucket, uint32_t *total, uint32_t L) {
+        uint32_t tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
+        vmsm_row_totals<<<g.S, 1024, 0, cur>>>(counts, g.NB, row_totals);
+        vmsm_scan_offsets_flat<<<g.S * tiles, SCAN_TILE, 0, cur>>>(counts, offsets, cursor, g, tiles, row_totals, seg_bucket,
+                                                                   total, L);
+        c->launches += 2;
+        note(cudaGetLastError());
+    }
+    // threads of the segmented accumulate kernel one wave holds: SMs x resident blocks x block size
+    uint32_t resident_threads(bool pre) {
+        uint32_t &r = c->seg_resident[pre ? 1 : 0];
+        if (!r) {
+            int blocks = 0, sms = 0;
+            if (pre) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, vmsm_kernel<KAccumulateSegPre>, KAccumulateSegPre::kBlock, KAccumulateSegPre::kDynSmem);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, vmsm_kernel<KAccumulateSeg>, KAccumulateSeg::kBlock, KAccumulateSeg::kDynSmem);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+            r = (uint32_t)(blocks > 0 ? blocks : 4) * (uint32_t)(sms > 0 ? sms : 148) * KAccumulateSeg::kBlock;
+        }
+        return r;
     }
     bool order_buckets(const uint32_t *counts, uint32_t *order, uint32_t nb, uint32_t n) {
         if (nb < 8192 || n == 0) return false;  // too few buckets for ordering to matter
@@ -618,8 +705,11 @@ int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t
         c->shard_seq = c->shard_next;
         c->shard_next = 0;
     }
+    // a sharded MSM is finished by the owner's gather kernel on the device; everything else is normalised by the host
+    const bool hn = c->host_norm && !c->shard_seq;
+    c->slot_host_norm[slot] = hn;
     int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff_host + slot,
-                     c->msm_seq++, extra, n_extra, pre);
+                     c->msm_seq++, extra, n_extra, pre, hn ? c->res_xyz_host + slot : nullptr);
     c->shard_seq = 0;
     if (rc == -2) return fail(VMSM_ERR_INVALID, "precomputed table does not match the MSM geometry");
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
@@ -788,8 +878,16 @@ int32_t fetch_slot(Ctx *c, uint32_t slot, uint8_t *out) {
         if (st == 2) return fail(VMSM_ERR_POINT, "invalid point in the input of the asynchronous call for slot %u", slot);
         return fail(VMSM_ERR_TIMEOUT, "a multi-GPU partial for slot %u did not arrive", slot);
     }
-    if (c->slot_curve[slot] == VMSM_CURVE_ED25519) memcpy(out, c->res_aff_host + slot, sizeof(ge_aff));
-    else memcpy(out, c->res_w_host + 128 * slot, wire_bytes(c->slot_curve[slot]));
+    if (c->slot_curve[slot] == VMSM_CURVE_ED25519) {
+        if (c->slot_host_norm[slot]) {
+            ge_aff a = ge_ext_to_aff(c->res_xyz_host[slot]);  // portable host path of fe25519.cuh: one inversion on the CPU
+            memcpy(out, &a, sizeof(ge_aff));
+        } else {
+            memcpy(out, c->res_aff_host + slot, sizeof(ge_aff));
+        }
+    } else {
+        memcpy(out, c->res_w_host + 128 * slot, wire_bytes(c->slot_curve[slot]));
+    }
     return VMSM_OK;
 }
 
@@ -858,7 +956,7 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     CU(cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
     for (int w = 0; w < kTailWays; w++) CU(cudaEventCreateWithFlags(&c->ev_tail[w], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_sc_written, cudaEventDisableTiming));
-    CU(cudaMalloc(&c->dot_scratch, (kDotT1 + kDotT2 + 1) * 32));
+    CU(cudaMalloc(&c->dot_scratch, (kDotT1 + kDotT2 + 3) * 32));  // partial sums, the result, two results kept on the device
     CU(cudaMalloc(&c->la_aff, kLaRing * 64 * sizeof(ge_aff)));
     CU(cudaMalloc(&c->la_niels, kLaRing * 64 * sizeof(ge_niels)));
     CU(cudaMalloc(&c->la_scalars, kLaRing * 64 * 32));
@@ -873,6 +971,7 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     CU(cudaMalloc(&c->small_niels, 64 * sizeof(ge_niels)));
     CU(cudaHostAlloc(&c->pin, 4096, cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->res_aff_host, kSlots * sizeof(ge_aff), cudaHostAllocMapped));
+    CU(cudaHostAlloc(&c->res_xyz_host, kSlots * sizeof(ge_ext), cudaHostAllocMapped));
     CU(cudaHostAlloc(&c->res_status_host, kSlots * sizeof(uint32_t), cudaHostAllocMapped));
     CU(cudaMalloc(&c->res_w_dev, kSlots * 192));
     CU(cudaHostAlloc(&c->res_w_host, kSlots * 128, cudaHostAllocMapped));
@@ -883,6 +982,7 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     for (int k = 0; k < 2; k++) {
         CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_dot[k], cudaEventDisableTiming));
     }
     for (uint32_t k = 0; k < kSlots; k++) CU(cudaEventCreateWithFlags(&c->ev_slot[k], cudaEventDisableTiming));
     CU(cudaEventCreate(&c->t0));
@@ -915,9 +1015,11 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     cudaStreamSynchronize(c->sort);
     for (int w = 0; w < kTailWays; w++) cudaStreamSynchronize(c->tails[w]);
     cudaStreamSynchronize(c->stream);
-    for (int k = 0; k < 2; k++) cudaFree(c->astage[k]), cudaEventDestroy(c->ev_copied[k]), cudaEventDestroy(c->ev_consumed[k]);
+    for (int k = 0; k < 2; k++)
+        cudaFree(c->astage[k]), cudaEventDestroy(c->ev_copied[k]), cudaEventDestroy(c->ev_consumed[k]), cudaEventDestroy(c->ev_dot[k]);
     for (uint32_t k = 0; k < kSlots; k++) cudaEventDestroy(c->ev_slot[k]);
     cudaFreeHost(c->res_aff_host);
+    cudaFreeHost(c->res_xyz_host);
     cudaFreeHost(c->res_status_host);
     cudaEventDestroy(c->ev_sc_written);
     cudaFree(c->dot_scratch);
@@ -992,6 +1094,17 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
         case VMSM_OPT_PRE_SETS:
             if (value < 0 || value > 32) return fail(VMSM_ERR_INVALID, "bucket sets out of range");
             c->opt.pre_sets = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_HOST_NORMALIZE:
+            c->host_norm = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_SEG_MODE:
+            if (value < 0 || value > 2) return fail(VMSM_ERR_INVALID, "segment mode out of range");
+            c->opt.seg_mode = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_SEG_LEN:
+            if (value < 0 || value > 4096) return fail(VMSM_ERR_INVALID, "segment length out of range");
+            c->opt.seg_len = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_PRE_MIN_TERMS:
             if (value < 0) return fail(VMSM_ERR_INVALID, "negative term count");
@@ -1677,6 +1790,20 @@ int32_t vmsm_scalars_axpy(uint64_t ctx, uint64_t dst, uint64_t doff, uint64_t sr
     return VMSM_OK;
 }
 
+// <a, b> mod l into the 32 bytes at `dst` (device), on the main stream: three latency-bound stages (T threads multiply
+// and pre-sum n/T terms, T2 threads sum T/T2 of those, one thread finishes) with serial chains of comparable length
+static void launch_dot(Ctx *c, CudaBE &be, const uint32_t *a, const uint32_t *b, uint64_t n, uint32_t *dst) {
+    uint32_t T, T2;
+    dot_stage_sizes(n, &T, &T2);
+    uint32_t *p1 = c->dot_scratch, *p2 = p1 + kDotT1 * 8;
+    KScalarDotPartial k1 = {a, b, (uint32_t)n, T, p1};
+    be.launch(k1, T);
+    KScalarSum k2 = {p1, T, T2, p2, 0};
+    be.launch(k2, T2);
+    KScalarSum k3 = {p2, T2, 1, dst, 1};
+    be.launch(k3, 1);
+}
+
 int32_t vmsm_scalars_dot(uint64_t ctx, uint64_t a, uint64_t aoff, uint64_t b, uint64_t boff, uint64_t n,
                          uint8_t *out_le32) {
     GET_CTX(ctx);
@@ -1689,17 +1816,8 @@ int32_t vmsm_scalars_dot(uint64_t ctx, uint64_t a, uint64_t aoff, uint64_t b, ui
     memset(out_le32, 0, 32);
     if (!n) return VMSM_OK;
     CudaBE be(c);
-    // three latency-bound stages (T threads multiply and pre-sum n/T terms, T2 threads sum T/T2 of those, one thread
-    // finishes): keep the three serial chains of comparable length
-    uint32_t T, T2;
-    dot_stage_sizes(n, &T, &T2);
-    uint32_t *p1 = c->dot_scratch, *p2 = p1 + kDotT1 * 8, *p3 = p2 + kDotT2 * 8;
-    KScalarDotPartial k1 = {ia->second.data + aoff * 8, ib->second.data + boff * 8, (uint32_t)n, T, p1};
-    be.launch(k1, T);
-    KScalarSum k2 = {p1, T, T2, p2, 0};
-    be.launch(k2, T2);
-    KScalarSum k3 = {p2, T2, 1, p3, 1};
-    be.launch(k3, 1);
+    uint32_t *p3 = c->dot_scratch + (kDotT1 + kDotT2) * 8;
+    launch_dot(c, be, ia->second.data + aoff * 8, ib->second.data + boff * 8, n, p3);
     be.note(cudaMemcpyAsync(c->pin, p3, 32, cudaMemcpyDeviceToHost, c->stream));
     be.note(cudaStreamSynchronize(c->stream));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "scalars_dot: %s", cudaGetErrorString(be.err));
@@ -1764,6 +1882,61 @@ int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, 
     if (c->async_sort) c->scalars_ready = c->ev_copied[b];
     else CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
     int32_t rc = run_msm_ps(c, it->second, poff, c->astage[b], tot, slot, &ie->second, extra_off, (uint32_t)n_extra);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_consumed[b], c->async_sort ? c->sort : c->stream));
+    c->astage_used[b] = true;
+    return VMSM_OK;
+}
+
+// One commitment of a folding round without a host round trip (compressed_pivot.py:41-42: A_i = g_R^{z_L} k^{L_R(z_L)}):
+// sum_{i<n} s[soff+i] P[poff+i]  +  <a[aoff..], b[boff..]> * E[extra_off], the inner product computed on the device and
+// handed to the MSM as the scalar of its extra term.
+int32_t vmsm_msm_dev_ext_dot(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
+                             uint64_t extra_pts, uint64_t extra_off, uint64_t dot_a, uint64_t dot_aoff, uint64_t dot_b,
+                             uint64_t dot_boff, uint64_t dot_n, uint32_t slot) {
+    GET_CTX(ctx);
+    auto it = c->points.find(pts);
+    auto ie = c->points.find(extra_pts);
+    if (it == c->points.end() || ie == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
+    auto is = c->scalars.find(sc), ia = c->scalars.find(dot_a), ib = c->scalars.find(dot_b);
+    if (is == c->scalars.end() || ia == c->scalars.end() || ib == c->scalars.end())
+        return fail(VMSM_ERR_INVALID, "invalid scalars handle");
+    if (it->second.curve != VMSM_CURVE_ED25519 || ie->second.curve != VMSM_CURVE_ED25519)
+        return fail(VMSM_ERR_UNSUPPORTED, "msm_dev_ext_dot: Ed25519 only");
+    if (poff > it->second.n || n > it->second.n - poff) return fail(VMSM_ERR_INVALID, "Not enough generators.");
+    if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+    if (extra_off >= ie->second.n) return fail(VMSM_ERR_INVALID, "extra range out of bounds");
+    if (dot_aoff > ia->second.n || dot_n > ia->second.n - dot_aoff || dot_boff > ib->second.n || dot_n > ib->second.n - dot_boff)
+        return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
+    if (dot_n == 0 || dot_n > (1ull << 28)) return fail(VMSM_ERR_INVALID, "inner product length out of range");
+    if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
+    const uint64_t tot = n + 1;
+    const int b = (int)(c->async_seq++ & 1);
+    if (tot > c->astage_cap[b]) {
+        if (c->astage[b]) cudaFree(c->astage[b]);  // synchronises the device
+        c->astage[b] = nullptr;
+        c->astage_cap[b] = 0;
+        CU(cudaMalloc(&c->astage[b], tot * 32));
+        c->astage_cap[b] = tot;
+        c->astage_used[b] = false;
+    }
+    // the inner product on the main stream (after the kernels that last wrote the vectors), into this parity's result word
+    CudaBE be(c);
+    uint32_t *dres = c->dot_scratch + (kDotT1 + kDotT2 + 1 + (uint32_t)b) * 8;
+    launch_dot(c, be, ia->second.data + dot_aoff * 8, ib->second.data + dot_boff * 8, dot_n, dres);
+    if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm_dev_ext_dot: %s", cudaGetErrorString(be.err));
+    CU(cudaEventRecord(c->ev_dot[b], c->stream));
+    // staging on the copy stream: after the inner product, after the kernel that last wrote the device scalars, and
+    // after the MSM that last read this staging buffer
+    CU(cudaStreamWaitEvent(c->copy, c->ev_dot[b], 0));
+    if (c->sc_dirty) CU(cudaStreamWaitEvent(c->copy, c->ev_sc_written, 0));
+    if (c->astage_used[b]) CU(cudaStreamWaitEvent(c->copy, c->ev_consumed[b], 0));
+    if (n) CU(cudaMemcpyAsync(c->astage[b], is->second.data + soff * 8, n * 32, cudaMemcpyDeviceToDevice, c->copy));
+    CU(cudaMemcpyAsync(c->astage[b] + n * 8, dres, 32, cudaMemcpyDeviceToDevice, c->copy));
+    CU(cudaEventRecord(c->ev_copied[b], c->copy));
+    if (c->async_sort) c->scalars_ready = c->ev_copied[b];
+    else CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    int32_t rc = run_msm_ps(c, it->second, poff, c->astage[b], tot, slot, &ie->second, extra_off, 1);
     if (rc) return rc;
     CU(cudaEventRecord(c->ev_consumed[b], c->async_sort ? c->sort : c->stream));
     c->astage_used[b] = true;
@@ -1866,9 +2039,11 @@ int32_t vmsm_lincomb(uint64_t ctx, int32_t curve, const uint8_t *affine, const u
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->pin + 64, c->err_word, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));
-    if (n && *reinterpret_cast<uint32_t *>(c->pin + 64)) return fail(VMSM_ERR_POINT, "invalid point in lincomb input");
-    memcpy(out_affine, c->res_aff_host + (kSlots - 1), sizeof(ge_aff));
+    if (n && *reinterpret_cast<uint32_t *>(c->pin + 64)) {
+        CU(cudaEventSynchronize(c->ev_slot[kSlots - 1]));
+        return fail(VMSM_ERR_POINT, "invalid point in lincomb input");
+    }
+    return fetch_slot(c, kSlots - 1, out_affine);
     return VMSM_OK;
 }
 

@@ -138,6 +138,14 @@ class DevicePoints:
         check(self.ctx.lib.vmsm_points_text_ptr(self.ctx.h, self.handle, off, n, ctypes.byref(ptr), ctypes.byref(ln)))
         return ctypes.string_at(ptr, ln.value) if ln.value else b""
 
+    def text_view(self, off=0, n=None):
+        """As ``text_bytes`` without the copy: a ctypes char array over the context's pinned buffer, valid until the
+        next ``*_view`` / ``text_*`` call on this context (hashlib reads it in place)."""
+        n = self.n - off if n is None else n
+        ptr, ln = ctypes.c_void_p(), ctypes.c_uint64()
+        check(self.ctx.lib.vmsm_points_text_ptr(self.ctx.h, self.handle, off, n, ctypes.byref(ptr), ctypes.byref(ln)))
+        return (ctypes.c_char * ln.value).from_address(ptr.value) if ln.value else b""
+
     def text(self, off=0, n=None):
         return self.text_bytes(off, n).decode("ascii")
 
@@ -203,6 +211,14 @@ class DeviceScalars:
         check(self.ctx.lib.vmsm_scalars_text_ptr(self.ctx.h, self.handle, off, n, 1 if signed else 0,
                                                  ctypes.byref(ptr), ctypes.byref(ln)))
         return ctypes.string_at(ptr, ln.value) if ln.value else b""
+
+    def text_view(self, off=0, n=None, signed=True):
+        """As ``text_bytes`` without the copy (see ``DevicePoints.text_view``)."""
+        n = self.n - off if n is None else n
+        ptr, ln = ctypes.c_void_p(), ctypes.c_uint64()
+        check(self.ctx.lib.vmsm_scalars_text_ptr(self.ctx.h, self.handle, off, n, 1 if signed else 0,
+                                                 ctypes.byref(ptr), ctypes.byref(ln)))
+        return (ctypes.c_char * ln.value).from_address(ptr.value) if ln.value else b""
 
     def free(self):
         if self.handle and self.ctx.h:
@@ -370,6 +386,13 @@ class Context:
         raw = pack_scalars(extra_scalars, ORDERS[points.curve])
         check(self.lib.vmsm_msm_dev_ext(self.h, points.handle, poff, n, scalars.handle, soff, extra.handle, extra_off,
                                         len(extra_scalars), raw, slot))
+
+    def msm_dev_ext_dot(self, points, poff, n, scalars, soff, extra, extra_off, dot_a, dot_aoff, dot_b, dot_boff, dot_n,
+                        slot=0):
+        """As ``msm_dev_ext`` with ONE extra term whose scalar is ``<dot_a[dot_aoff:], dot_b[dot_boff:]>`` (dot_n
+        residues), computed on the device and never fetched: a folding round's cross term (compressed_pivot.py:41-42)."""
+        check(self.lib.vmsm_msm_dev_ext_dot(self.h, points.handle, poff, n, scalars.handle, soff, extra.handle, extra_off,
+                                            dot_a.handle, dot_aoff, dot_b.handle, dot_boff, dot_n, slot))
 
     def scalars_dot(self, a, aoff, b, boff, n):
         """sum_i a[aoff+i] * b[boff+i] modulo the Ed25519 group order, computed on the device."""

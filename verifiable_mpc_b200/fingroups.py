@@ -371,6 +371,16 @@ class DevicePointList:
             return b"[" + self.dev.text_bytes(self.off, self.n) + b"]"
         return repr(self).encode("utf-8")
 
+    def feed_repr(self, h):
+        """h.update(repr(self).encode()) with the text hashed IN PLACE from the context's pinned buffer: no Python
+        bytes object of the ~160 bytes per point is ever built (two 10 MB copies per round at N = 2^16 otherwise)."""
+        if hasattr(self.dev, "text_view"):
+            h.update(b"[")
+            h.update(self.dev.text_view(self.off, self.n))
+            h.update(b"]")
+        else:
+            h.update(self.repr_bytes())
+
     def wire_bytes(self):
         """Canonical 64-byte encodings x || y of the whole view (binary transcript mode); a zero-copy view of the
         context's pinned buffer when the engine offers one."""

@@ -1,0 +1,41 @@
+"""Packing of the host-side vectors the reference's API hands over (lists of ints / field elements) into n x 32
+little-endian residues.  Uses the C loop of ``_hostpack`` (csrc/_hostpack.c, built in-tree by
+``__graft_entry__.build()``) when it is there, the same conversion in Python otherwise -- marshalling only, no group
+or field arithmetic happens here."""
+try:
+    from . import _hostpack as _c
+except ImportError:  # not built: pure Python, same results
+    _c = None
+
+
+def pack_residues(seq, cls, order, allow_int=True):
+    """``seq``: exact ints (unless ``allow_int`` is False) and / or instances of exactly ``cls`` (a prime-field element
+    class with modulus ``order`` and the residue in ``.value``; None: ints only).  -> bytes, or None when an element
+    is of another type."""
+    if _c is not None:
+        return _c.pack_residues(seq, cls, order, allow_int)
+    out = []
+    for item in seq:
+        t = type(item)
+        if allow_int and t is int:
+            v = item
+        elif cls is not None and t is cls:
+            v = item.value
+            if not isinstance(v, int):
+                return None
+        else:
+            return None
+        if not 0 <= v < order:
+            v %= order
+        out.append(v.to_bytes(32, "little"))
+    return b"".join(out)
+
+
+def field_class_for(seq, order):
+    """The field-element class to expect in ``seq``: the type of its first non-int element when that is a prime-field
+    class with this modulus, else None (ints only)."""
+    for item in seq:
+        if type(item) is not int:
+            t = type(item)
+            return t if getattr(t, "modulus", None) == order and hasattr(item, "value") else False
+    return None
