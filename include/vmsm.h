@@ -71,6 +71,9 @@ extern "C" {
 #define VMSM_OPT_HOST_NORMALIZE 18 /* 1 (default): Ed25519 results leave the device in extended coordinates and the
                                      fetching call inverts Z on the CPU (~15 us) instead of a lone GPU thread (0.19 ms at
                                      the end of every MSM); 0 = normalise on the device.  Same canonical output. */
+#define VMSM_OPT_DUAL_HEAD 19 /* 1 (default): consecutive Ed25519 MSMs run their accumulate kernels on two alternating
+                                streams (one launch below ~2^18 terms is one or two waves that end together: the next
+                                MSM's kernel fills the ramp-down); 0 = all accumulate kernels on the context's stream */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
 
 /* phases reported by vmsm_phase_times */

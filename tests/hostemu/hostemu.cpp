@@ -59,6 +59,8 @@ struct HostBE {
     }
     uint32_t overflow_warps() { return 3; }
     uint32_t combine_threads() { return 5; }
+    void use_head(uint32_t) {}
+    void head_done(uint32_t) {}
     void sort_begin(int) {}
     void sort_end(int) {}
     void acc_done(int) {}

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--cap", type=int, nargs="+", default=[0])
     ap.add_argument("--async-tail", type=int, nargs="+", default=[1])
     ap.add_argument("--sort-blocks", type=int, nargs="+", default=[-1])
+    ap.add_argument("--dual-head", type=int, default=1, help="VMSM_OPT_DUAL_HEAD")
     ap.add_argument("--async-sort", type=int, default=1, help="0: counting sort on the main stream (serial phase times)")
     ap.add_argument("--quad-threshold", type=int, default=-1, help="experiment: VMSM_OPT_QUAD_THRESHOLD")
     ap.add_argument("--precompute", type=int, nargs="+", default=[-1],
@@ -36,6 +37,7 @@ def main():
     if args.quad_threshold >= 0:
         ctx.set_option(_lib.OPT_QUAD_THRESHOLD, args.quad_threshold)
     ctx.set_option(_lib.OPT_ASYNC_SORT, args.async_sort)
+    ctx.set_option(_lib.OPT_DUAL_HEAD, args.dual_head)
     peak = ctx.imad_peak()
     out = open(args.out, "a") if args.out else None
     for logn in args.logn:

@@ -285,6 +285,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     }
 
     // counting sort of (window, |digit|) -> CSR lists, on the sort stream (double-buffered by parity)
+    be.use_head(seq);
     be.sort_begin(par);
     be.phase_begin();
     be.zero(counts, (size_t)nbuckets * 4);
@@ -404,6 +405,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     be.after_final(out_ext, out_aff);  // multi-GPU: push this partial to the owner's mailbox / gather on the owner
     be.result_ready();
     be.tail_end(tw);
+    be.head_done(seq);  // everything this MSM put on its head stream (the tail too when side streams are off)
     be.phase_end();
     return 0;
 }

@@ -335,6 +335,13 @@ struct Ctx {
     cudaStream_t stream = nullptr;  // main stream: everything except MSM tails
     cudaStream_t tails[kTailWays] = {};  // side streams: upper bucket-tree levels + Horner of the previous MSMs
     cudaStream_t sort = nullptr;    // side stream: counting sort (digits, scan, scatter, order) of the NEXT MSM
+    // two HEAD streams taken in turn by consecutive MSMs for their accumulate kernel, so the ramp-down of one overlaps
+    // the ramp-up of the next (below ~2^18 terms a launch is one or two waves of threads that finish together); all
+    // other work of the context stays ordered on `stream`
+    cudaStream_t heads[2] = {nullptr, nullptr};
+    cudaEvent_t ev_issue = nullptr, ev_head_done[2] = {nullptr, nullptr};
+    bool head_pending[2] = {false, false};
+    bool dual_head = true;
     cudaEvent_t ev_sorted[2] = {nullptr, nullptr}, ev_acc_done[2] = {nullptr, nullptr}, ev_sort_in = nullptr;
     bool acc_pending[2] = {false, false};
     bool async_sort = true;
@@ -439,13 +446,27 @@ struct CudaBE {
     Ctx *c;
     cudaError_t err = cudaSuccess;
     cudaStream_t cur = nullptr;  // stream the next launch goes to (main unless inside a tail)
-    explicit CudaBE(Ctx *ctx) : c(ctx), cur(ctx->stream) {}
+    cudaStream_t head = nullptr;  // stream of this MSM's accumulate kernel: one of c->heads, or the main stream
+    explicit CudaBE(Ctx *ctx) : c(ctx), cur(ctx->stream), head(ctx->stream) {}
+    // consecutive MSMs alternate between the two head streams; each starts after everything issued on the main stream
+    void use_head(uint32_t seq) {
+        if (!c->dual_head) return;
+        const int h = (int)(seq & 1);
+        head = c->heads[h];
+        note(cudaEventRecord(c->ev_issue, c->stream));
+        note(cudaStreamWaitEvent(head, c->ev_issue, 0));
+        c->head_pending[h] = true;
+        cur = head;
+    }
+    void head_done(uint32_t seq) {
+        if (c->dual_head) note(cudaEventRecord(c->ev_head_done[seq & 1], head));
+    }
     uint32_t overflow_warps() { return 148u * 8u * 4u; }  // 8 blocks of 4 warps per SM, grid-stride over the tasks
     uint32_t combine_threads() { return 148u * 128u; }
     // the node buffers of parity `par` may still be read by the tail of the MSM two calls ago
     bool thin_sort = false;
     void head_wait_tail(int par) {
-        if (c->tail_pending[par]) note(cudaStreamWaitEvent(c->stream, c->ev_tail[par], 0));
+        if (c->tail_pending[par]) note(cudaStreamWaitEvent(head, c->ev_tail[par], 0));
     }
     // counting sort on its own stream: ordered after whatever produced the scalars on the main stream (H2D, synth)
     // and after the accumulate kernel that last read this parity's CSR lists
@@ -464,8 +485,8 @@ struct CudaBE {
     void sort_end(int par) {
         if (!c->async_sort) return;
         note(cudaEventRecord(c->ev_sorted[par], c->sort));
-        note(cudaStreamWaitEvent(c->stream, c->ev_sorted[par], 0));
-        cur = c->stream;
+        note(cudaStreamWaitEvent(head, c->ev_sorted[par], 0));
+        cur = head;
     }
     void acc_done(int par) {  // recorded whatever the sort mode: vmsm_fold / vmsm_points_free order themselves on it
         note(cudaEventRecord(c->ev_acc_done[par], cur));  // on the stream of the last reader of the CSR lists
@@ -484,7 +505,7 @@ struct CudaBE {
     void result_ready() { note(cudaEventRecord(c->ev_slot[c->cur_slot], cur)); }
     void tail_begin(int way) {
         if (!c->async_tail) return;
-        note(cudaEventRecord(c->ev_head, c->stream));
+        note(cudaEventRecord(c->ev_head, head));
         note(cudaStreamWaitEvent(c->tails[way], c->ev_head, 0));
         cur = c->tails[way];
     }
@@ -492,7 +513,7 @@ struct CudaBE {
         if (!c->async_tail) return;
         note(cudaEventRecord(c->ev_tail[way], c->tails[way]));
         c->tail_pending[way] = true;
-        cur = c->stream;
+        cur = head;
     }
     void note(cudaError_t e) {
         if (err == cudaSuccess && e != cudaSuccess) err = e;
@@ -597,6 +618,11 @@ cudaError_t wait_bases_released(Ctx *c, bool host_side) {
 
 // make the main stream wait for every MSM tail issued so far (tails are ordered on the side stream)
 cudaError_t join_tail(Ctx *c) {
+    for (int h = 0; h < 2; h++)
+        if (c->head_pending[h]) {
+            cudaError_t e = cudaStreamWaitEvent(c->stream, c->ev_head_done[h], 0);
+            if (e != cudaSuccess) return e;
+        }
     for (int w = 0; w < kTailWays; w++)
         if (c->tail_pending[w]) {
             cudaError_t e = cudaStreamWaitEvent(c->stream, c->ev_tail[w], 0);
@@ -938,6 +964,11 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     // one block of the sort kernels per SM: measured best at 2^14 .. 2^22 (profiles/r01/sweep_sort_blocks.jsonl)
     c->sort_blocks = (uint32_t)prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int h = 0; h < 2; h++) {
+        CU(cudaStreamCreateWithFlags(&c->heads[h], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_head_done[h], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_issue, cudaEventDisableTiming));
     {
         int lo = 0, hi = 0;  // hi = numerically smallest = greatest priority
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1014,6 +1045,7 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     cudaStreamSynchronize(c->copy);
     cudaStreamSynchronize(c->sort);
     for (int w = 0; w < kTailWays; w++) cudaStreamSynchronize(c->tails[w]);
+    for (int h = 0; h < 2; h++) cudaStreamSynchronize(c->heads[h]);
     cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 2; k++)
         cudaFree(c->astage[k]), cudaEventDestroy(c->ev_copied[k]), cudaEventDestroy(c->ev_consumed[k]), cudaEventDestroy(c->ev_dot[k]);
@@ -1052,6 +1084,8 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     cudaStreamDestroy(c->sort);
     cudaEventDestroy(c->ev_sort_in);
     for (int k = 0; k < 2; k++) cudaEventDestroy(c->ev_sorted[k]), cudaEventDestroy(c->ev_acc_done[k]);
+    for (int h = 0; h < 2; h++) cudaStreamDestroy(c->heads[h]), cudaEventDestroy(c->ev_head_done[h]);
+    cudaEventDestroy(c->ev_issue);
     cudaStreamDestroy(c->stream);
     delete c;
     return VMSM_OK;
@@ -1094,6 +1128,11 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
         case VMSM_OPT_PRE_SETS:
             if (value < 0 || value > 32) return fail(VMSM_ERR_INVALID, "bucket sets out of range");
             c->opt.pre_sets = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_DUAL_HEAD:
+            CU(join_tail(c));
+            CU(cudaStreamSynchronize(c->stream));
+            c->dual_head = value != 0;
             return VMSM_OK;
         case VMSM_OPT_HOST_NORMALIZE:
             c->host_norm = value != 0;
@@ -2062,6 +2101,8 @@ int32_t vmsm_lincomb_async(uint64_t ctx, int32_t curve, const uint8_t *affine, c
     // the staging set may still be read by the sort of the call that used it kLaRing calls ago (its points are read
     // by that call's accumulate kernel, which precedes this copy on the main stream anyway)
     if (c->la_used[r]) be.note(cudaStreamWaitEvent(c->stream, c->ev_la_sorted[r], 0));
+    // ... and its points by that call's accumulate kernel, which runs on a head stream
+    if (c->la_used[r]) be.note(wait_bases_released(c, false));
     be.zero(err, 4);
     if (n) {
         be.note(cudaMemcpyAsync(aff, affine, n * sizeof(ge_aff), cudaMemcpyHostToDevice, c->stream));
