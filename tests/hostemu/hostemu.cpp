@@ -317,6 +317,48 @@ static uint32_t bn_msm(const uint8_t *wire, const uint8_t *scalars, uint32_t n, 
     memcpy(out_wire, &ow, sizeof(ow));
     return err;
 }
+// MSM over key tables (KPrecomputeW, window `table_bits`): main terms [off, off + n_main) of n_pts points + n_extra
+// extra terms with their own table; host-side normalisation of the Jacobian result as vmsm.cu's fetch_slot does it
+template <class F>
+static int bn_msm_pre(const uint8_t *wire, uint32_t n_pts, uint32_t off, uint32_t n_main, const uint8_t *wire_extra,
+                      uint32_t n_extra, const uint8_t *scalars, uint32_t table_bits, uint8_t *out_wire) {
+    HostBE be;
+    uint32_t err = 0;
+    const uint32_t W = (256 + table_bits) / table_bits;
+    std::vector<waff<F>> w(n_pts ? n_pts : 1), base(n_pts ? n_pts : 1), wx(n_extra ? n_extra : 1), basex(n_extra ? n_extra : 1);
+    memcpy(w.data(), wire, (size_t)n_pts * sizeof(waff<F>));
+    memcpy(wx.data(), wire_extra, (size_t)n_extra * sizeof(waff<F>));
+    KUploadW<F> ku = {w.data(), base.data(), &err, 1u};
+    be.launch(ku, n_pts);
+    KUploadW<F> kx = {wx.data(), basex.data(), &err, 1u};
+    be.launch(kx, n_extra);
+    std::vector<waff<F>> tbl((size_t)W * (n_pts ? n_pts : 1)), tblx((size_t)W * (n_extra ? n_extra : 1));
+    KPrecomputeW<F> kp = {base.data(), tbl.data(), n_pts, table_bits, W};
+    be.launch(kp, n_pts);
+    KPrecomputeW<F> kpx = {basex.data(), tblx.data(), n_extra, table_bits, W};
+    be.launch(kpx, n_extra);
+    uint32_t n = n_main + n_extra;
+    std::vector<uint32_t> sc((size_t)(n ? n : 1) * 8 + 8);
+    memcpy(sc.data(), scalars, (size_t)n * 32);
+    Workspace ws;
+    MsmOptions opt;
+    PreTable pt = {n_pts, table_bits, W, nullptr, n_extra};
+    wjac<F> oj, hj;
+    waff<F> ow;
+    int rc = msm_run_w<HostBE, F>(be, ws, opt, tbl.data() + off, sc.data(), n, &oj, &ow, nullptr, n_extra, 0, &pt,
+                                  n_extra ? tblx.data() : nullptr, &hj);
+    ws_release(be, ws);
+    ow = wa_to_wire(wj_to_aff(hj));
+    memcpy(out_wire, &ow, sizeof(ow));
+    return rc ? rc : (int)err;
+}
+extern "C" int hostemu_bn_msm_pre(int g2, const uint8_t *wire, uint32_t n_pts, uint32_t off, uint32_t n_main,
+                                  const uint8_t *wire_extra, uint32_t n_extra, const uint8_t *scalars, uint32_t table_bits,
+                                  uint8_t *out_wire) {
+    return g2 ? bn_msm_pre<Fp2BN>(wire, n_pts, off, n_main, wire_extra, n_extra, scalars, table_bits, out_wire)
+              : bn_msm_pre<FpBN>(wire, n_pts, off, n_main, wire_extra, n_extra, scalars, table_bits, out_wire);
+}
+
 extern "C" uint32_t hostemu_bn_msm(int g2, const uint8_t *wire, const uint8_t *scalars, uint32_t n, uint32_t window_bits,
                         uint8_t *out_wire) {
     return g2 ? bn_msm<Fp2BN>(wire, scalars, n, window_bits, out_wire) : bn_msm<FpBN>(wire, scalars, n, window_bits, out_wire);

@@ -145,6 +145,15 @@ def check_big_compute_proof(k, g1_group, g2_group, via_dict=False):
         proof = twin.compute_proof(qap, c, hp, prepared, None)
         for key, val in gold["proof_nozk"].items():
             assert proof[key].affine() == dec(val), key
+        # key tables (PreparedEvalKey.precompute): the same proofs without a single doubling in the eight sums
+        if hasattr(prepared.bases["h*g1"], "precompute"):
+            prepared.precompute()
+            proof = twin.compute_proof(qap, c, hp, prepared, dl)
+            for key, val in gold["proof"].items():
+                assert proof[key].affine() == dec(val), ("tables", key)
+            proof = twin.compute_proof(qap, c, hp, prepared, None)
+            for key, val in gold["proof_nozk"].items():
+                assert proof[key].affine() == dec(val), ("tables", key)
         if via_dict:  # the reference's calling convention: a dict of group elements, uploaded per call
             evalkey = {}
             for name, template, delta_terms in twin._MID_SUMS:

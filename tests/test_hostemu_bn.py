@@ -78,3 +78,35 @@ def test_group_fixed_base_and_msm(hostemu, g2):
     assert msm(pts[:9], sc)[1] == B.msm_naive(F, sc, pts[:9])
     # validation
     assert msm([(pts[0][0], pts[1][1])], [1])[0] & 2
+
+
+@pytest.mark.parametrize("g2", [0, 1])
+def test_msm_over_key_tables(hostemu, g2):
+    """KPrecomputeW tables (2^(c*w) * P_i): no doublings in the MSM, every window its own bucket set; sub-range of the
+    vector, extra terms with their own table, the exceptional cases (repeated / negated / identity bases), and the
+    host-side normalisation of the Jacobian result."""
+    lib = hostemu
+    F, G = (B.FP2, B.G2) if g2 else (B.FP, B.G1)
+    sz, n = (128 if g2 else 64), 24
+    dl = [prng.scalar_bn(0x710 + g2, i) for i in range(n)]
+    pts = [B.scalar_mul(F, G, d) for d in dl]
+
+    def msm_pre(points, off, n_main, extra, scalars, c):
+        o = ctypes.create_string_buffer(sz)
+        rc = lib.hostemu_bn_msm_pre(g2, b"".join(B.point_to_bytes(F, p) for p in points), len(points), off, n_main,
+                                    b"".join(B.point_to_bytes(F, p) for p in extra), len(extra),
+                                    b"".join(B.fp_to_bytes(s % B.N) for s in scalars), c, o)
+        assert rc == 0
+        return B.point_from_bytes(F, o.raw)
+
+    sc = [prng.scalar_bn(0x810, i) for i in range(n)]
+    sc[:4] = [0, 1, B.N - 1, 2**255]
+    for c in (8, 13):
+        assert msm_pre(pts, 0, n, [], sc, c) == B.msm_known_dlog(F, sc, dl), c
+    extra = [pts[3], B.affine_neg(F, pts[5])]
+    sc2 = sc[:10] + [7, 9]
+    assert msm_pre(pts, 4, 10, extra, sc2, 13) == B.msm_known_dlog(F, sc2, dl[4:14] + [dl[3], B.N - dl[5]])
+    pp = [pts[0]] * 4 + [B.affine_neg(F, pts[0])] * 2 + [None] + [pts[1]]
+    s3 = [5, 5, 7, 1, 3, 9, 1234, B.N - 1]
+    assert msm_pre(pp, 0, len(pp), [], s3, 8) == B.msm_naive(F, s3, pp)
+    assert msm_pre(pp, 0, len(pp), [], [1, 1, 1, 1, 2, 2, 0, 0], 8) is None

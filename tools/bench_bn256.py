@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--windows", type=int, nargs="+", default=[0])
     ap.add_argument("--radix", type=int, default=-1, help="experiment: VMSM_OPT_REDUCE_RADIX (log2 of the tree radix)")
     ap.add_argument("--quad-acc", type=int, default=-1, help="experiment: VMSM_OPT_BN_QUAD_ACC")
+    ap.add_argument("--curves", type=int, nargs="+", default=[1, 2], help="1 = G1, 2 = G2")
+    ap.add_argument("--no-proof", action="store_true", help="skip the compute_proof part")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     from verifiable_mpc_b200 import Context, _lib, fingroups
@@ -41,7 +43,7 @@ def main():
 
     for logn in args.log2n:
         n = 1 << logn
-        for curve, name in ((1, "G1"), (2, "G2")):
+        for curve, name in [(cv, "G%d" % cv) for cv in args.curves]:
             sets = [(ctx.fixed_base(seed=0x5EEE + 16 * k, n=n, curve=curve), ctx.synth_scalars(0x5EED + 16 * k, n, curve=curve))
                     for k in range(3)]
             for c in args.windows:
@@ -62,6 +64,9 @@ def main():
                 p.free()
                 s.free()
 
+    if args.no_proof:
+        ctx.close()
+        return
     # compute_proof twin on a synthetic QAP of 2^14 mid wires
     g1 = fingroups.EllipticCurve("BN256", "jacobian")
     g2 = fingroups.EllipticCurve("BN256_twist", "jacobian")
@@ -96,14 +101,39 @@ def main():
             self.bases["h*g1"] = ctx.fixed_base(seed=99, n=m, curve=1)
 
     prepared = Prepared()
-    twin.compute_proof(Q, c, H(), prepared, D)
-    best = 1e9
-    for _ in range(3):
-        t0 = time.perf_counter()
-        proof = twin.compute_proof(Q, c, H(), prepared, D)
-        best = min(best, time.perf_counter() - t0)
-    emit({"bench": "pynocchio_compute_proof", "mid": m, "len_h": m, "prove_s": best,
-          "note": "8 MSMs (6 G1 + 1 G2 over mid wires, 1 G1 over h), bases resident, scalars packed on the host per call"})
+    for tables in (False, True):
+        if tables:
+            t0 = time.perf_counter()
+            prepared.precompute()
+            ctx.sync()
+            t_tab = time.perf_counter() - t0
+        ref = twin.compute_proof(Q, c, H(), prepared, D)
+        best = 1e9
+        for _ in range(5):
+            t0 = time.perf_counter()
+            proof = twin.compute_proof(Q, c, H(), prepared, D)
+            best = min(best, time.perf_counter() - t0)
+        if tables:
+            assert all(proof[k] == first[k] for k in first), "tables changed the proof"
+        first = proof
+        emit({"bench": "pynocchio_compute_proof", "mid": m, "len_h": m, "prove_s": best, "key_tables": tables,
+              "table_build_s": t_tab if tables else None,
+              "note": "8 MSMs (6 G1 + 1 G2 over mid wires, 1 G1 over h), bases resident, scalars packed on the host per call"})
+    # device-timed MSMs over the tables
+    for curve, name in ((1, "G1"), (2, "G2")):
+        sets = [(ctx.fixed_base(seed=0x5EEE + 16 * k, n=m, curve=curve).precompute(), ctx.synth_scalars(0x5EED + 16 * k, m, curve=curve))
+                for k in range(3)]
+        for w in range(3):
+            ctx.msm_dev(*sets[w % 3], slot=0)
+        ctx.sync()
+        ctx.phase_times()
+        ctx.timer_start()
+        for s in range(args.steps):
+            ctx.msm_dev(*sets[s % 3], slot=s % 32)
+        ms = ctx.timer_stop() / args.steps
+        ph, calls = ctx.phase_times()
+        emit({"bench": "bn256_msm_key_tables", "group": name, "log2n": max(args.log2n), "ms": ms, "Mpts_s": m / ms / 1e3,
+              "phase_ms": {k: round(v / max(calls, 1), 4) for k, v in ph.items()}})
     ctx.close()
 
 

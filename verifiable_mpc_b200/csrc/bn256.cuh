@@ -40,7 +40,7 @@ VMSM_HD wjac<F> wa_to_jac(const waff<F> &a) {
 
 // 2P, dbl-2009-l (a = 0): 2M + 5S.  Z = 0 stays Z = 0.
 template <class F>
-VMSM_HD_NOINLINE wjac<F> wj_dbl(const wjac<F> &p) {
+VMSM_HD wjac<F> wj_dbl(const wjac<F> &p) {
     typedef typename F::T T;
     T A = F::sqr(p.X), B = F::sqr(p.Y), C = F::sqr(B);
     T t = F::sqr(F::add(p.X, B));
@@ -57,7 +57,7 @@ VMSM_HD_NOINLINE wjac<F> wj_dbl(const wjac<F> &p) {
 
 // P + (neg ? -Q : Q) with Q affine, madd-2007-bl: 7M + 4S
 template <class F>
-VMSM_HD_NOINLINE wjac<F> wj_madd(const wjac<F> &p, const waff<F> &q, bool neg) {
+VMSM_HD wjac<F> wj_madd(const wjac<F> &p, const waff<F> &q, bool neg) {
     typedef typename F::T T;
     if (wa_is_identity(q)) return p;
     T qy = neg ? F::neg(q.y) : q.y;
@@ -88,7 +88,7 @@ VMSM_HD_NOINLINE wjac<F> wj_madd(const wjac<F> &p, const waff<F> &q, bool neg) {
 
 // P + Q, both Jacobian, add-2007-bl: 11M + 5S
 template <class F>
-VMSM_HD_NOINLINE wjac<F> wj_add(const wjac<F> &p, const wjac<F> &q) {
+VMSM_HD wjac<F> wj_add(const wjac<F> &p, const wjac<F> &q) {
     typedef typename F::T T;
     if (F::is_zero(p.Z)) return q;
     if (F::is_zero(q.Z)) return p;

@@ -11,9 +11,13 @@
 
 namespace vmsm {
 
-// Code-size control.  The base-field multiplication is inlined, but the Fp2 multiplication / squaring, the field
-// inversion and the point operations of bn256.cuh are real functions on the device: a fully inlined G2 point addition
-// contains 48 Montgomery multiplications and ptxas needs tens of minutes for such kernels.
+// Code-size control.  On the device every Montgomery multiplication in Fp / Fp2 is a CALL to one real function that
+// takes and returns its operands BY VALUE -- the device ABI keeps 32 / 64-byte aggregates in registers, so a call
+// costs a dozen moves, no local memory -- and the point operations of bn256.cuh are inlined around those calls.
+// Round 1 did the opposite (multiplication inlined, point operations as functions taking references): a mixed
+// addition was 12 000 SASS instructions that missed the instruction cache on every pass (ncu: stall_no_instruction
+// 1.2 warps per issue) and every point crossed a call boundary through local memory (350 B of LDL/STL per addition
+// in G1, 2 KB in G2).  The field inversion stays a function of its own.
 #if defined(__CUDACC__)
 #define VMSM_HD_NOINLINE static __host__ __device__ __noinline__
 #else
@@ -237,11 +241,17 @@ VMSM_HD fbn fbn_redc(uint32_t *t) {
 #endif
 }
 
-VMSM_HD fbn fbn_mul(const fbn &a, const fbn &b) {
+VMSM_HD fbn fbn_mul_inl(const fbn &a, const fbn &b) {
     uint32_t t[16];
     mp_mul8(a.v, b.v, t);
     return fbn_redc(t);
 }
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ fbn fbn_mul_fn(fbn a, fbn b) { return fbn_mul_inl(a, b); }
+VMSM_HD fbn fbn_mul(const fbn &a, const fbn &b) { return fbn_mul_fn(a, b); }
+#else
+VMSM_HD fbn fbn_mul(const fbn &a, const fbn &b) { return fbn_mul_inl(a, b); }
+#endif
 VMSM_HD fbn fbn_sqr(const fbn &a) { return fbn_mul(a, a); }
 
 // plain integer (< p) <-> Montgomery form
@@ -291,19 +301,28 @@ VMSM_HD f2bn f2bn_select(bool c, const f2bn &a, const f2bn &b) {
     f2bn r = {fbn_select(c, a.c0, b.c0), fbn_select(c, a.c1, b.c1)};
     return r;
 }
-// Karatsuba: 3 base-field multiplications (a real function on the device, see VMSM_HD_NOINLINE)
-VMSM_HD_NOINLINE f2bn f2bn_mul(const f2bn &a, const f2bn &b) {
+// Karatsuba: 3 base-field multiplications
+VMSM_HD f2bn f2bn_mul_inl(const f2bn &a, const f2bn &b) {
     fbn t0 = fbn_mul(a.c0, b.c0), t1 = fbn_mul(a.c1, b.c1);
     fbn t2 = fbn_mul(fbn_add(a.c0, a.c1), fbn_add(b.c0, b.c1));
     f2bn r = {fbn_sub(t0, t1), fbn_sub(fbn_sub(t2, t0), t1)};
     return r;
 }
 // (a0 + a1 i)^2 = (a0+a1)(a0-a1) + 2 a0 a1 i : 2 multiplications
-VMSM_HD_NOINLINE f2bn f2bn_sqr(const f2bn &a) {
+VMSM_HD f2bn f2bn_sqr_inl(const f2bn &a) {
     fbn m = fbn_mul(a.c0, a.c1);
     f2bn r = {fbn_mul(fbn_add(a.c0, a.c1), fbn_sub(a.c0, a.c1)), fbn_dbl(m)};
     return r;
 }
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ f2bn f2bn_mul_fn(f2bn a, f2bn b) { return f2bn_mul_inl(a, b); }
+static __device__ __noinline__ f2bn f2bn_sqr_fn(f2bn a) { return f2bn_sqr_inl(a); }
+VMSM_HD f2bn f2bn_mul(const f2bn &a, const f2bn &b) { return f2bn_mul_fn(a, b); }
+VMSM_HD f2bn f2bn_sqr(const f2bn &a) { return f2bn_sqr_fn(a); }
+#else
+VMSM_HD f2bn f2bn_mul(const f2bn &a, const f2bn &b) { return f2bn_mul_inl(a, b); }
+VMSM_HD f2bn f2bn_sqr(const f2bn &a) { return f2bn_sqr_inl(a); }
+#endif
 VMSM_HD f2bn f2bn_inv(const f2bn &a) {
     fbn d = fbn_inv(fbn_add(fbn_sqr(a.c0), fbn_sqr(a.c1)));
     f2bn r = {fbn_mul(a.c0, d), fbn_neg(fbn_mul(a.c1, d))};

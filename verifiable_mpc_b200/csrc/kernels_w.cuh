@@ -56,20 +56,32 @@ VMSM_HD sc256 synth_scalar_bn(uint64_t seed, uint64_t i) {
     return s;
 }
 
+// Where a base lives: plain (stride == 0) bases[i] / extra[i - n_main]; over tables of 2^(c*w) * P_i (stride != 0, see
+// KPrecomputeW) level w = bucket >> log2NB, i.e. the window that owns the bucket set.
+template <class F>
+struct BaseRefW {
+    const waff<F> *bases;
+    const waff<F> *extra;
+    uint32_t n_main;
+    uint32_t stride, extra_stride, log2NB;
+    VMSM_HD const waff<F> *ptr(uint32_t i, uint32_t bucket) const {
+        if (!stride) return i < n_main ? bases + i : extra + (i - n_main);
+        const size_t w = bucket >> log2NB;
+        return i < n_main ? bases + w * stride + i : extra + w * extra_stride + (i - n_main);
+    }
+};
+
 template <class F>
 struct KAccumulateW {
     enum { kBlock = 128 };
-    const waff<F> *bases;
+    BaseRefW<F> br;
     const uint32_t *offsets, *counts, *idx, *order;
     wjac<F> *buckets;
     uint32_t nbuckets, cap;
     OverflowCtl *ctl;
     OverflowTask *tasks;
     LongBucket *longs;
-    const waff<F> *extra;
-    uint32_t n_main;
     uint32_t seg_min;  // shortest overflow segment (a multiple of 32)
-    VMSM_HD const waff<F> *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
     VMSM_HD void operator()(uint32_t tid) const {
         uint32_t b = order ? order[tid] : tid;
         uint32_t pos = offsets[b], cnt = counts[b];
@@ -92,7 +104,7 @@ struct KAccumulateW {
         wjac<F> acc = wj_identity<F>();
         for (uint32_t k = 0; k < cnt; k++) {
             uint32_t e = idx[pos + k];
-            acc = wj_madd(acc, ld_obj(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+            acc = wj_madd(acc, ld_obj(br.ptr(e & 0x7fffffffu, b)), (e >> 31) != 0);
         }
         st_obj(buckets + b, acc);
     }
@@ -101,15 +113,12 @@ struct KAccumulateW {
 template <class F>
 struct KOverflowW {
     enum { kBlock = 128 };
-    const waff<F> *bases;
+    BaseRefW<F> br;
     const uint32_t *idx;
     const OverflowCtl *ctl;
     const OverflowTask *tasks;
     wjac<F> *partials;
     uint32_t nwarps;
-    const waff<F> *extra;
-    uint32_t n_main;
-    VMSM_HD const waff<F> *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
     VMSM_HD void operator()(uint32_t tid) const {
         const uint32_t ntasks = ctl->ntasks;
 #if defined(__CUDA_ARCH__)
@@ -119,7 +128,7 @@ struct KOverflowW {
             wjac<F> acc = wj_identity<F>();
             for (uint32_t k = lane; k < tk.count; k += 32) {
                 uint32_t e = idx[tk.first + k];
-                acc = wj_madd(acc, ld_obj(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+                acc = wj_madd(acc, ld_obj(br.ptr(e & 0x7fffffffu, tk.bucket)), (e >> 31) != 0);
             }
 #pragma unroll 1
             for (int d = 16; d >= 1; d >>= 1) {
@@ -139,7 +148,7 @@ struct KOverflowW {
             wjac<F> acc = wj_identity<F>();
             for (uint32_t k = 0; k < tk.count; k++) {
                 uint32_t e = idx[tk.first + k];
-                acc = wj_madd(acc, ld_obj(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+                acc = wj_madd(acc, ld_obj(br.ptr(e & 0x7fffffffu, tk.bucket)), (e >> 31) != 0);
             }
             st_obj(partials + t, acc);
         }
@@ -208,6 +217,7 @@ struct KFinalW {
     wjac<F> *out_jac;
     waff<F> *out_wire;
     uint32_t W, c;
+    wjac<F> *out_host_jac;  // when set: Jacobian result into host-mapped memory, the host normalises (see KFinal)
     VMSM_HD void operator()(uint32_t tid) const {
         if (tid) return;
         wjac<F> acc = wj_identity<F>();
@@ -217,6 +227,10 @@ struct KFinalW {
             acc = wj_add(acc, wj_add(ld_obj(S + w), ld_obj(T + w)));
         }
         st_obj(out_jac, acc);
+        if (out_host_jac) {
+            st_obj(out_host_jac, acc);
+            return;
+        }
         st_obj(out_wire, wa_to_wire(wj_to_aff(acc)));
     }
 };
@@ -340,17 +354,14 @@ static __device__ __noinline__ wjac<F> wq_madd(int q, const wjac<F> &p, const wa
 template <class F>
 struct KAccumulateWQ {
     enum { kBlock = 128 };
-    const waff<F> *bases;
+    BaseRefW<F> br;
     const uint32_t *offsets, *counts, *idx, *order;
     wjac<F> *buckets;
     uint32_t nbuckets, cap;
     OverflowCtl *ctl;
     OverflowTask *tasks;
     LongBucket *longs;
-    const waff<F> *extra;
-    uint32_t n_main;
     uint32_t seg_min;
-    VMSM_HD const waff<F> *base_ptr(uint32_t i) const { return i < n_main ? bases + i : extra + (i - n_main); }
     VMSM_HD void operator()(uint32_t tid) const {
 #if defined(__CUDA_ARCH__)
         const int q = tid & 3;
@@ -378,12 +389,12 @@ struct KAccumulateWQ {
         wjac<F> acc = wj_identity<F>();
         for (uint32_t k = 0; k < cnt; k++) {
             uint32_t e = idx[pos + k];
-            acc = wq_madd<F>(q, acc, ld_obj(base_ptr(e & 0x7fffffffu)), (e >> 31) != 0);
+            acc = wq_madd<F>(q, acc, ld_obj(br.ptr(e & 0x7fffffffu, b)), (e >> 31) != 0);
         }
         if (q == 0) st_obj(buckets + b, acc);
 #else
         if (tid & 3) return;
-        KAccumulateW<F> k = {bases, offsets, counts, idx, order, buckets, nbuckets, cap, ctl, tasks, longs, extra, n_main, seg_min};
+        KAccumulateW<F> k = {br, offsets, counts, idx, order, buckets, nbuckets, cap, ctl, tasks, longs, seg_min};
         k(tid >> 2);
 #endif
     }
@@ -435,6 +446,7 @@ struct KFinalWQ {
     wjac<F> *out_jac;
     waff<F> *out_wire;
     uint32_t W, c;
+    wjac<F> *out_host_jac;
     VMSM_HD void operator()(uint32_t tid) const {
 #if defined(__CUDA_ARCH__)
         const int q = tid & 3;
@@ -446,12 +458,34 @@ struct KFinalWQ {
         }
         if (tid == 0) {
             st_obj(out_jac, acc);
-            st_obj(out_wire, wa_to_wire(wj_to_aff(acc)));
+            if (out_host_jac) st_obj(out_host_jac, acc);
+            else st_obj(out_wire, wa_to_wire(wj_to_aff(acc)));
         }
 #else
-        KFinalW<F> k = {S, T, out_jac, out_wire, W, c};
+        KFinalW<F> k = {S, T, out_jac, out_wire, W, c, out_host_jac};
         k(tid);
 #endif
+    }
+};
+
+// Tables for a FIXED key (the evaluation key of pynocchio.py:101-167 is made once per circuit and used by every
+// compute_proof): table[w][i] = 2^(c*w) * P_i in Montgomery affine form, w < W.  One thread per point, c doublings and
+// one inversion per level.  An MSM over the tables needs no doubling at all: every window's bucket set carries weight 1.
+template <class F>
+struct KPrecomputeW {
+    enum { kBlock = 128 };
+    const waff<F> *base;  // n points
+    waff<F> *table;       // W x stride
+    uint32_t stride, c, W;
+    VMSM_HD void operator()(uint32_t tid) const {
+        waff<F> a = ld_obj(base + tid);
+        st_obj(table + tid, a);
+        for (uint32_t w = 1; w < W; w++) {
+            wjac<F> p = wa_to_jac(a);
+            for (uint32_t k = 0; k < c; k++) p = wj_dbl(p);
+            a = wj_to_aff(p);
+            st_obj(table + (size_t)w * stride + tid, a);
+        }
     }
 };
 

@@ -415,7 +415,8 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
 template <class BE, class F>
 int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases, const uint32_t *scalars, uint32_t n,
               wjac<F> *out_jac, waff<F> *out_wire, const waff<F> *extra = nullptr, uint32_t n_extra = 0,
-              uint32_t seq = 0) {
+              uint32_t seq = 0, const PreTable *pre = nullptr, const waff<F> *extra_table = nullptr,
+              wjac<F> *out_host_jac = nullptr) {
     const uint32_t scalar_bits = 256, n_main = n - n_extra;
     // Jacobian costs in field multiplications (mixed addition 7M+4S, addition 11M+5S); the long-bucket path makes any
     // window safe, so skewed top windows are allowed here (these MSMs are small and latency matters more)
@@ -425,7 +426,10 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     // short bucket chains and a bucket tree of exactly six full radix-4 levels (4096 = 4^6); measured fastest or tied at 2^10, 2^12,
     // 2^14 and 2^16 on G1 and G2 (profiles/r01/bn256_msm_v5_windows.jsonl), 35 % faster than the work-minimising c = 11
     if (!opt.window_bits && n >= 512 && n <= (1u << 16)) c = 13;
+    if (pre) c = pre->c;  // tables fix the window; every window keeps its own bucket set (weight 1: no Horner chain)
     MsmGeom g = make_geom(n, c, scalar_bits);
+    if (pre && (pre->W != g.W || (n_extra && !extra_table))) return -2;
+    BaseRefW<F> br = {bases, pre ? extra_table : extra, n_main, pre ? pre->stride : 0u, pre ? pre->extra_stride : 0u, g.c - 1};
     uint32_t R = 1u << opt.reduce_log2r_w;
     // long-bucket granularity for this curve: additions are 3-9x dearer than on Ed25519 and the MSMs are small, so a
     // bucket's own thread takes at most max(16, ...) entries and overflow segments may be as short as one warp pass
@@ -465,12 +469,12 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         // four lanes per bucket where measured faster (2^15: -8 %, 2^16: -14 %; slower at <= 2^14, where the tails set
         // the pace, and from 2^17, where the kernel is throughput-bound): profiles/r01/bn256_msm_v5_windows.md
         if (opt.w_quad_acc == 2 || (opt.w_quad_acc == 1 && n > (1u << 14) && n <= (1u << 16))) {
-            KAccumulateWQ<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl_[tw],
-                                   ws.tasks_[tw], ws.longs_[tw], extra, n_main, kSegFloor};
+            KAccumulateWQ<F> k5 = {br, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl_[tw],
+                                   ws.tasks_[tw], ws.longs_[tw], kSegFloor};
             be.launch(k5, 4 * nbuckets);
         } else {
-            KAccumulateW<F> k5 = {bases, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl_[tw],
-                                  ws.tasks_[tw], ws.longs_[tw], extra, n_main, kSegFloor};
+            KAccumulateW<F> k5 = {br, offsets, counts, idx, order, (wjac<F> *)buckets, nbuckets, cap, ws.ctl_[tw],
+                                  ws.tasks_[tw], ws.longs_[tw], kSegFloor};
             be.launch(k5, nbuckets);
         }
         be.phase_mark(PH_ACCUMULATE);
@@ -479,7 +483,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         be.tail_begin(tw);
         if (n > cap) {
             const uint32_t ow = be.overflow_warps();
-            KOverflowW<F> ko = {bases, idx, ws.ctl_[tw], ws.tasks_[tw], (wjac<F> *)ws.partials_[tw], ow, extra, n_main};
+            KOverflowW<F> ko = {br, idx, ws.ctl_[tw], ws.tasks_[tw], (wjac<F> *)ws.partials_[tw], ow};
             be.launch(ko, ow * 32);
             be.acc_done(par);
             const uint32_t ct = be.combine_threads();
@@ -504,7 +508,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         log2s += opt.reduce_log2r_w;
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
-    KFinalWQ<F> k7 = {inS, inT, out_jac, out_wire, g.W, g.c};
+    KFinalWQ<F> k7 = {inS, inT, out_jac, out_wire, g.W, pre ? 0u : g.c, out_host_jac};
     be.launch(k7, 32);
     be.phase_mark(PH_FINAL);
     be.result_ready();

@@ -387,6 +387,7 @@ struct Ctx {
     // BN256 results: Jacobian on the device, plain affine in mapped pinned memory; which curve a slot last held
     uint8_t *res_w_dev = nullptr;   // kSlots x 192 B
     uint8_t *res_w_host = nullptr;  // kSlots x 128 B, mapped
+    uint8_t *res_wj_host = nullptr;  // kSlots x 192 B, mapped: Jacobian results for host-side normalisation
     int32_t slot_curve[64] = {0};
     void *fbw_table[2] = {nullptr, nullptr};  // fixed-base tables for G1 / G2 (520 entries), built on first use
     void *small_w_wire = nullptr, *small_w_base = nullptr;  // lincomb scratch, 64 x 128 B each
@@ -875,23 +876,73 @@ int32_t w_fixed_base(Ctx *c, int32_t curve, const uint8_t *scalars, uint64_t see
 }
 
 template <class F>
+int32_t w_precompute_ps(Ctx *c, PointSet &ps, uint32_t cb) {
+    if (ps.pre && ps.pre_c == cb) return VMSM_OK;
+    if (ps.n == 0) return VMSM_OK;
+    CU(wait_bases_released(c, true));
+    if (ps.pre) pool_free(ps.pre);
+    ps.pre = nullptr;
+    ps.pre_c = ps.pre_W = 0;
+    const uint32_t W = (256 + cb) / cb;
+    waff<F> *tbl = nullptr;
+    cudaError_t e = pool_alloc(&tbl, (size_t)W * ps.n * sizeof(waff<F>));
+    if (e != cudaSuccess)
+        return fail(VMSM_ERR_NOMEM, "table of %u levels x %llu points: %s", W, (unsigned long long)ps.n, cudaGetErrorString(e));
+    CudaBE be(c);
+    KPrecomputeW<F> k = {(const waff<F> *)ps.w_base, tbl, (uint32_t)ps.n, cb, W};
+    be.launch(k, (uint32_t)ps.n);
+    if (be.err != cudaSuccess) {
+        pool_free(tbl);
+        return fail(VMSM_ERR_CUDA, "precompute: %s", cudaGetErrorString(be.err));
+    }
+    ps.pre = tbl;
+    ps.pre_c = cb;
+    ps.pre_W = W;
+    ps.pre_n = ps.n;
+    return VMSM_OK;
+}
+
+template <class F>
 int32_t w_run_msm(Ctx *c, const PointSet &ps, uint64_t off, const uint32_t *scalars, uint64_t n_total, uint32_t slot,
-                  const PointSet *extra, uint64_t extra_off, uint32_t n_extra) {
+                  PointSet *extra, uint64_t extra_off, uint32_t n_extra) {
     if (n_total > (1ull << 24)) return fail(VMSM_ERR_UNSUPPORTED, "BN256 MSMs are limited to 2^24 terms");
+    // through the key tables (vmsm_points_precompute) when the vector has one; a few extra terms get theirs on first use
+    bool pre_ok = ps.pre && n_total >= c->pre_min_terms && !c->opt.window_bits;
+    if (pre_ok && n_extra && !(extra->pre && extra->pre_c == ps.pre_c)) {
+        if (extra->n <= 64 && extra != &ps) {
+            int32_t rcp = w_precompute_ps<F>(c, *extra, ps.pre_c);
+            if (rcp) return rcp;
+        } else {
+            pre_ok = false;
+        }
+    }
     CudaBE be(c);
     c->cur_slot = slot;
     c->slot_curve[slot] = ps.curve;
+    c->slot_host_norm[slot] = c->host_norm;
     MsmOptions opt = c->opt;
-    int rc = msm_run_w<CudaBE, F>(be, c->ws, opt, (const waff<F> *)ps.w_base + off, scalars, (uint32_t)n_total,
+    wjac<F> *host_jac = c->host_norm ? (wjac<F> *)(c->res_wj_host + 192 * slot) : nullptr;
+    int rc;
+    if (pre_ok) {
+        PreTable pt = {(uint32_t)ps.pre_n, ps.pre_c, ps.pre_W, nullptr, n_extra ? (uint32_t)extra->pre_n : 0u};
+        rc = msm_run_w<CudaBE, F>(be, c->ws, opt, (const waff<F> *)ps.pre + off, scalars, (uint32_t)n_total,
+                                  (wjac<F> *)(c->res_w_dev + 192 * slot), (waff<F> *)(c->res_w_host + 128 * slot), nullptr,
+                                  n_extra, c->msm_seq++, &pt, n_extra ? (const waff<F> *)extra->pre + extra_off : nullptr,
+                                  host_jac);
+    } else {
+        rc = msm_run_w<CudaBE, F>(be, c->ws, opt, (const waff<F> *)ps.w_base + off, scalars, (uint32_t)n_total,
                                   (wjac<F> *)(c->res_w_dev + 192 * slot), (waff<F> *)(c->res_w_host + 128 * slot),
-                                  extra ? (const waff<F> *)extra->w_base + extra_off : nullptr, n_extra, c->msm_seq++);
+                                  extra ? (const waff<F> *)extra->w_base + extra_off : nullptr, n_extra, c->msm_seq++,
+                                  nullptr, nullptr, host_jac);
+    }
+    if (rc == -2) return fail(VMSM_ERR_INVALID, "precomputed table does not match the MSM geometry");
     if (rc) return fail(VMSM_ERR_NOMEM, "workspace allocation failed: %s", cudaGetErrorString(be.err));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(be.err));
     return VMSM_OK;
 }
 
 int32_t w_run_msm_any(Ctx *c, const PointSet &ps, uint64_t off, const uint32_t *scalars, uint64_t n_total, uint32_t slot,
-                      const PointSet *extra = nullptr, uint64_t extra_off = 0, uint32_t n_extra = 0) {
+                      PointSet *extra = nullptr, uint64_t extra_off = 0, uint32_t n_extra = 0) {
     if (ps.curve == VMSM_CURVE_BN256_G1) return w_run_msm<FpBN>(c, ps, off, scalars, n_total, slot, extra, extra_off, n_extra);
     return w_run_msm<Fp2BN>(c, ps, off, scalars, n_total, slot, extra, extra_off, n_extra);
 }
@@ -910,6 +961,14 @@ int32_t fetch_slot(Ctx *c, uint32_t slot, uint8_t *out) {
             memcpy(out, &a, sizeof(ge_aff));
         } else {
             memcpy(out, c->res_aff_host + slot, sizeof(ge_aff));
+        }
+    } else if (c->slot_host_norm[slot]) {  // Jacobian from the device, one inversion in Fp / Fp2 on the CPU
+        if (c->slot_curve[slot] == VMSM_CURVE_BN256_G1) {
+            waff<FpBN> w = wa_to_wire(wj_to_aff(*(const wjac<FpBN> *)(c->res_wj_host + 192 * slot)));
+            memcpy(out, &w, sizeof(w));
+        } else {
+            waff<Fp2BN> w = wa_to_wire(wj_to_aff(*(const wjac<Fp2BN> *)(c->res_wj_host + 192 * slot)));
+            memcpy(out, &w, sizeof(w));
         }
     } else {
         memcpy(out, c->res_w_host + 128 * slot, wire_bytes(c->slot_curve[slot]));
@@ -1003,6 +1062,7 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
     CU(cudaHostAlloc(&c->pin, 4096, cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->res_aff_host, kSlots * sizeof(ge_aff), cudaHostAllocMapped));
     CU(cudaHostAlloc(&c->res_xyz_host, kSlots * sizeof(ge_ext), cudaHostAllocMapped));
+    CU(cudaHostAlloc(&c->res_wj_host, kSlots * 192, cudaHostAllocMapped));
     CU(cudaHostAlloc(&c->res_status_host, kSlots * sizeof(uint32_t), cudaHostAllocMapped));
     CU(cudaMalloc(&c->res_w_dev, kSlots * 192));
     CU(cudaHostAlloc(&c->res_w_host, kSlots * 128, cudaHostAllocMapped));
@@ -1052,6 +1112,7 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (uint32_t k = 0; k < kSlots; k++) cudaEventDestroy(c->ev_slot[k]);
     cudaFreeHost(c->res_aff_host);
     cudaFreeHost(c->res_xyz_host);
+    cudaFreeHost(c->res_wj_host);
     cudaFreeHost(c->res_status_host);
     cudaEventDestroy(c->ev_sc_written);
     cudaFree(c->dot_scratch);
@@ -1320,6 +1381,8 @@ int32_t vmsm_points_precompute(uint64_t ctx, uint64_t pts, uint32_t window_bits)
     if (it == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
     if (window_bits != 0 && (window_bits < 8 || window_bits > 16))
         return fail(VMSM_ERR_INVALID, "table window must be 0 (auto) or in [8, 16]");
+    if (it->second.curve == VMSM_CURVE_BN256_G1) return w_precompute_ps<FpBN>(c, it->second, window_bits ? window_bits : 13u);
+    if (it->second.curve == VMSM_CURVE_BN256_G2) return w_precompute_ps<Fp2BN>(c, it->second, window_bits ? window_bits : 13u);
     return precompute_ps(c, it->second, window_bits ? window_bits : (it->second.n >= (1u << 13) ? 16u : 13u));
 }
 

@@ -7,7 +7,7 @@ shifts.  Here every one of the eight proof elements is ONE device MSM (libvmsm.s
 arithmetic) with the zero-knowledge terms riding along as extra terms of the same MSM.  Same signature, same proof
 keys; key generation and the pairing-based ``verify`` stay the reference's (north_star: "pairing verify unchanged").
 """
-from .. import _lib
+from .. import _lib, hostpack
 from ..engine import BN_N, pack_scalars
 
 # (proof key, evalkey key template for mid index i, delta terms [(delta attribute, evalkey key)])
@@ -33,6 +33,14 @@ def apply_to_list(op, inputs):
 
 def point_add(a, b):
     return a @ b
+
+
+def _pack(values):
+    """Witness / quotient coefficients (ints or elements of GF(n)) -> packed residues mod n; one C loop when the
+    hostpack helper is built, ``int(v) % n`` per element otherwise (what the reference's ``int(c[i]) * P`` sees)."""
+    cls = hostpack.field_class_for(values, BN_N)
+    raw = hostpack.pack_residues(values, cls, BN_N) if cls is not False else None
+    return raw if raw is not None else pack_scalars([int(v) for v in values], BN_N)
 
 
 def _msm(points, scalars):
@@ -66,6 +74,14 @@ class PreparedEvalKey:
         produced by ``generate_evalkey``-style fixed-base batches without a round trip through host objects."""
         self = cls.__new__(cls)
         self.indices_mid, self.h_len, self.groups, self.bases = list(indices_mid), h_len, dict(groups), dict(bases)
+        return self
+
+    def precompute(self, window_bits=0):
+        """Key tables (``vmsm_points_precompute``: 2^(13 w) * P for every key entry, 20 levels): the evaluation key is
+        fixed per circuit, so the ~250 doublings of each of the eight sums are paid once per key instead of once per
+        proof.  Costs 20 x the key's size in HBM (2^14 mid wires: 7 x 21 MB + 42 MB for the G2 sum)."""
+        for dev in self.bases.values():
+            dev.precompute(window_bits)
         return self
 
     def _put(self, name, pts):
@@ -151,7 +167,7 @@ def compute_proof(qap, c, h, evalkey, deltas=None):
     mid = prepared.indices_mid if prepared else list(qap.indices_mid)
     if prepared:
         assert len(h) <= prepared.h_len, "Not enough generators."
-    c_mid_raw = pack_scalars([int(c[i]) for i in mid], BN_N)
+    c_mid_raw = _pack([c[i] for i in mid])
 
     jobs, keep, proof = [], [], {}  # jobs: (name, group, device points, owned?)
 
@@ -176,7 +192,7 @@ def compute_proof(qap, c, h, evalkey, deltas=None):
                 group = type(pts[0])
                 issue(name, group, group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id), True, raw)
         # the coefficients of h are packed while the device works on the seven sums already issued
-        raw_h = pack_scalars([int(h.coeffs[i]) for i in range(0, len(h))], BN_N)
+        raw_h = _pack(h.coeffs[:len(h)] if isinstance(h.coeffs, list) else [h.coeffs[i] for i in range(0, len(h))])
         if prepared:
             issue("h*g1", prepared.groups["h*g1"], prepared.bases["h*g1"], False, raw_h)
         else:
