@@ -376,6 +376,7 @@ def run_gpu(args, rank, world, dist):
     # the next MSM's counting sort / the previous MSM's tail with the accumulate kernel), CUDA events around each phase
     ctx.set_option(_lib.OPT_ASYNC_SORT, 0)
     ctx.set_option(_lib.OPT_ASYNC_TAIL, 0)
+    ctx.set_option(_lib.OPT_DUAL_HEAD, 0)
     for w in range(2):
         issue("dev", w % NSETS, 0)
     ctx.sync()
@@ -388,6 +389,7 @@ def run_gpu(args, rank, world, dist):
     serial_phases, serial_calls = ctx.phase_times()
     ctx.set_option(_lib.OPT_ASYNC_SORT, 1)
     ctx.set_option(_lib.OPT_ASYNC_TAIL, 1)
+    ctx.set_option(_lib.OPT_DUAL_HEAD, 1)
     barrier()
 
     # correctness of what was just timed: the last MSM's input set, against the known-dlog identity
@@ -479,7 +481,7 @@ def run_gpu(args, rank, world, dist):
         "e2e": {"value": total_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": R * n * 32 * world,
                 "d2h_bytes_per_step": R * 64 * world, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "Context.msm_async(points, pinned_scalars, slot) + Context.result(slot), pipelined %d deep" % E2E_DEPTH},
-        "roofline": {"bound": "imad", "kernel": "vmsm_kernel<KAccumulate>", "achieved": achieved, "peak": peak_tlps,
+        "roofline": {"bound": "imad", "kernel": "vmsm_kernel<KAccumulateT<false>> (one thread per bucket, plain bases)", "achieved": achieved, "peak": peak_tlps,
                      "unit": "T limb-products/s", "frac": (achieved / peak_tlps) if achieved else None,
                      "traffic": _ncu_traffic_bytes() if args.log2n == 20 else None, "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/)",
                      "algorithmic_gather_bytes_per_launch": n * W_c * 96,
