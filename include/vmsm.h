@@ -75,6 +75,14 @@ extern "C" {
                                 streams (one launch below ~2^18 terms is one or two waves that end together: the next
                                 MSM's kernel fills the ramp-down); 0 = all accumulate kernels on the context's stream */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
+#define VMSM_OPT_BLOCK_SORT 20 /* 1: counting sort of the digits with per-block shared-memory counters (digits recoded
+                                 once into 16-bit codes, no global atomics) for Ed25519 MSMs of at least
+                                 VMSM_OPT_BLOCK_SORT_MIN terms and windows c <= 16; 0 (default) = two passes with global
+                                 atomics, which measured faster on B200 (profiles/r02/block_sort_experiment.md) */
+#define VMSM_OPT_BLOCK_SORT_MIN 21 /* smallest MSM that takes the block-privatised sort (default 2^15 terms) */
+#define VMSM_OPT_ACC_CARVEOUT 22 /* experiment: preferred shared-memory carveout (percent, -1 = driver default, which is
+                                   what the library uses) of the accumulate kernels; the blocks of VMSM_OPT_BLOCK_SORT
+                                   need 128 KB of shared memory on the SMs those kernels occupy */
 
 /* phases reported by vmsm_phase_times */
 #define VMSM_PHASE_DIGITS 0

@@ -13,6 +13,8 @@
 
 using namespace vmsm;
 
+static uint32_t g_bs_chunks = 0;  // hostemu_set_block_sort
+
 struct HostBE {
     void *alloc(size_t bytes) { return aligned_alloc(64, (bytes + 63) / 64 * 64 + 64); }
     void free(void *p) { ::free(p); }
@@ -49,6 +51,58 @@ struct HostBE {
         }
         *total = run;
     }
+    // block-privatised counting sort, restated as loops (CUDA: vmsm_bsort_* in vmsm.cu): KRecode is the shared kernel
+    // body; per (set, chunk) histograms, exclusive prefix over the chunks, per-block cursors
+    uint32_t bs_chunks = g_bs_chunks;  // 0 = atomic two-pass sort (default)
+    std::vector<uint16_t> bs_dig;
+    std::vector<uint32_t> bs_hist;
+    uint32_t bsort_chunks(const MsmGeom &g) { return g.c <= 16 && g.n ? bs_chunks : 0; }
+    int bsort_ensure(const MsmGeom &g, uint32_t C, int) {
+        bs_dig.assign((size_t)g.W * ((g.n + 7u) & ~7u), 0xabcd);
+        bs_hist.assign((size_t)g.S * C * g.NB, 0);
+        return 0;
+    }
+    template <class F>
+    void bsort_each(const MsmGeom &g, uint32_t C, F f) {
+        const uint32_t stride = (g.n + 7u) & ~7u, per = (((g.n + C - 1) / C) + 7u) & ~7u;
+        for (uint32_t s = 0; s < g.S; s++)
+            for (uint32_t ch = 0; ch < C; ch++) {
+                const uint32_t lo = ch * per;
+                if (lo >= g.n) continue;
+                const uint32_t hi = g.n - lo < per ? g.n : lo + per;
+                for (uint32_t w = s, k = 0; w < g.W; w += g.S, k++)
+                    for (uint32_t i = lo; i < hi; i++) {
+                        uint32_t code = bs_dig[(size_t)w * stride + i];
+                        if (code != 0xffffu) f(s, ch, k, i, code);
+                    }
+            }
+    }
+    void bsort_hist(const uint32_t *scalars, const MsmGeom &g, uint32_t C, int, uint32_t *counts) {
+        KRecode k0 = {scalars, bs_dig.data(), (g.n + 7u) & ~7u, g};
+        launch(k0, g.n);
+        bsort_each(g, C, [&](uint32_t s, uint32_t ch, uint32_t, uint32_t, uint32_t code) {
+            bs_hist[((size_t)s * C + ch) * g.NB + (code & 0x7fffu)]++;
+        });
+        for (uint32_t s = 0; s < g.S; s++)
+            for (uint32_t b = 0; b < g.NB; b++) {
+                uint32_t run = 0;
+                for (uint32_t ch = 0; ch < C; ch++) {
+                    uint32_t &v = bs_hist[((size_t)s * C + ch) * g.NB + b], t = v;
+                    v = run;
+                    run += t;
+                }
+                counts[(size_t)s * g.NB + b] = run;
+            }
+    }
+    void bsort_scatter(const MsmGeom &g, uint32_t C, int, const uint32_t *offsets, uint32_t *idx) {
+        for (uint32_t s = 0; s < g.S; s++)
+            for (uint32_t ch = 0; ch < C; ch++)
+                for (uint32_t b = 0; b < g.NB; b++) bs_hist[((size_t)s * C + ch) * g.NB + b] += offsets[(size_t)s * g.NB + b];
+        bsort_each(g, C, [&](uint32_t s, uint32_t ch, uint32_t k, uint32_t i, uint32_t code) {
+            uint32_t pos = bs_hist[((size_t)s * C + ch) * g.NB + (code & 0x7fffu)]++;
+            idx[pos] = i | (k << g.lg) | ((code & 0x8000u) << 16);
+        });
+    }
     uint32_t resident_threads(bool) { return resident; }
     uint32_t resident = 48;  // small on purpose: several waves and straddling buckets even in tiny test cases
     bool order_buckets(const uint32_t *counts, uint32_t *order, uint32_t nb, uint32_t n) {
@@ -79,6 +133,9 @@ static uint32_t g_seg_mode = 1, g_seg_len = 0;
 extern "C" {
 
 // accumulate-kernel selection for the following hostemu_msm* calls (MsmOptions::seg_mode / seg_len)
+// counting-sort selection: 0 = two passes with atomics, C > 0 = block-privatised with C scalar chunks per bucket set
+void hostemu_set_block_sort(uint32_t chunks) { g_bs_chunks = chunks; }
+
 void hostemu_set_seg(uint32_t mode, uint32_t len) {
     g_seg_mode = mode;
     g_seg_len = len;

@@ -646,3 +646,51 @@ def test_fused_cross_term_commitment_and_host_normalisation(ctx, known_points):
         ctx.msm_dev_ext_dot(dev, 0, n, zd, n, kd, 0, Ld, 0, zd, n + 1, n, slot=1)  # inner product range out of bounds
     for d in (dev, kd, zd, Ld):
         d.free()
+
+
+@pytest.mark.parametrize("n", [1, 13, 1000, (1 << 12) - 5, 1 << 14])
+def test_block_privatised_sort(ctx, n):
+    """VMSM_OPT_BLOCK_SORT: digits recoded once into 16-bit codes, per-block shared-memory counters (vmsm_bsort_*).  With
+    the size threshold lowered every geometry goes through it: plain windows (own bucket set each), forced windows up to
+    c = 16 (128 KB of counters per block), tables with shared bucket sets, skewed scalars, ragged lengths, and MSMs issued
+    back to back (256-thread blocks under the previous accumulate kernel, 1024-thread blocks alone).  Same results as
+    the atomic two-pass sort and as the known-dlog identity."""
+    from verifiable_mpc_b200 import _lib
+
+    dev = ctx.fixed_base(seed=0x5EEE, n=n)
+    dl = [prng.scalar(0x5EEE, i) for i in range(n)]
+    rnd = random.Random(n)
+    cases = [[prng.scalar(0xB50, i) for i in range(n)], [rnd.randrange(2) for _ in range(n)],
+             [rnd.randrange(1, 4) << 240 for _ in range(n)]]
+    cases[0][:3] = [0, E.L - 1, 1 << 15][:min(3, n)]
+    want = [E.msm_known_dlog(sc, dl) for sc in cases]
+    ups = [ctx.upload_scalars(sc) for sc in cases]
+    try:
+        ctx.set_option(_lib.OPT_BLOCK_SORT_MIN, 1)
+        for bs in (1, 0):
+            ctx.set_option(_lib.OPT_BLOCK_SORT, bs)
+            for c in (0, 5, 12, 16):
+                ctx.set_option(_lib.OPT_WINDOW_BITS, c)
+                for j in range(9):  # back to back: the later ones sort underneath their predecessors
+                    ctx.msm_dev(dev, ups[j % 3], slot=j)
+                for j in range(9):
+                    assert ctx.result(j) == want[j % 3], (bs, c, j)
+        ctx.set_option(_lib.OPT_WINDOW_BITS, 0)
+        ctx.set_option(_lib.OPT_BLOCK_SORT, 1)
+        ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 1)
+        dev.precompute(16)
+        for sets in (0, 1, 8):
+            ctx.set_option(_lib.OPT_PRE_SETS, sets)
+            for j in range(6):
+                ctx.msm_dev(dev, ups[j % 3], slot=j)
+            for j in range(6):
+                assert ctx.result(j) == want[j % 3], (sets, j)
+    finally:
+        ctx.set_option(_lib.OPT_WINDOW_BITS, 0)
+        ctx.set_option(_lib.OPT_PRE_SETS, 0)
+        ctx.set_option(_lib.OPT_PRE_MIN_TERMS, 256)
+        ctx.set_option(_lib.OPT_BLOCK_SORT_MIN, 1 << 15)
+        ctx.set_option(_lib.OPT_BLOCK_SORT, 0)
+        dev.free()
+        for u in ups:
+            u.free()

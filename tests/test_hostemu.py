@@ -319,6 +319,35 @@ def test_msm_over_precomputed_bases(hostemu, known_points, table_bits):
     assert run_msm_pre(hostemu, pts[:3], 0, 0, [], [], table_bits, 0) == E.IDENTITY
 
 
+def test_block_privatised_sort_gives_the_same_sums(hostemu, known_points):
+    """The block-privatised counting sort (digits recoded once into 16-bit codes, per-(set, chunk) histograms, chunk
+    prefix, per-block cursors: vmsm_bsort_* on the device, restated as loops in the emulation around the shared KRecode
+    body) feeds the same accumulate kernels: plain path, shared bucket sets over tables, segments, skewed scalars."""
+    dl, pts = known_points
+    n = 203  # not a multiple of 8: ragged last vector of codes, ragged last chunk
+    scs = [prng.scalar(0xB5, i) for i in range(n)]
+    scs[:7] = [0, 1, E.L - 1, 2**252, 2**15, 2**15 + 1, 2**16 - 1]
+    want = E.msm_known_dlog(scs, dl[:n])
+    try:
+        for chunks in (1, 3, 8, 300):  # 300 > n / 8: most chunks are empty
+            hostemu.hostemu_set_block_sort(chunks)
+            for c in (0, 4, 11, 16):
+                assert run_msm(hostemu, pts[:n], scs, c, 1, 3) == want, (chunks, c)
+            for mode, seg_len in ((1, 0), (0, 0), (2, 5)):
+                hostemu.hostemu_set_seg(mode, seg_len)
+                for sets in (0, 1, 3):
+                    assert run_msm_pre(hostemu, pts[:n], 0, n, [], scs, 8, sets) == want, (chunks, mode, seg_len, sets)
+            hostemu.hostemu_set_seg(1, 0)
+        rnd = random.Random(5)
+        bits = [rnd.randrange(2) for _ in range(n)]
+        hostemu.hostemu_set_block_sort(4)
+        assert run_msm(hostemu, pts[:n], bits, 13) == E.msm_known_dlog(bits, dl[:n])
+        assert run_msm_pre(hostemu, pts[:n], 0, n, [], bits, 8, 1) == E.msm_known_dlog(bits, dl[:n])
+    finally:
+        hostemu.hostemu_set_seg(1, 0)
+        hostemu.hostemu_set_block_sort(0)
+
+
 def test_msm_over_precomputed_bases_long_buckets(hostemu):
     """Boolean / constant scalars over shared bucket sets: every window's entries pile into a few buckets (overflow
     tasks across windows)."""

@@ -242,6 +242,31 @@ struct KScatter {
     }
 };
 
+// Block-privatised counting sort (CUDA backend: vmsm_bsort_* in vmsm.cu; restated in a loop by the host emulation).
+// The two-pass sort above spends 2 x W global atomics per scalar, which is what bounds it (L2 atomic throughput, 6 % of
+// the HBM roofline) and what it steals from the accumulate kernel it runs under.  Here the digits are recoded ONCE into
+// a window-major array of 16-bit codes; a block then owns (bucket set, chunk of the scalars), keeps the 2^(c-1)
+// counters of its set in shared memory, and both the histogram and the scatter pass use shared-memory atomics only.
+// code = (|d| - 1) | (d < 0) << 15, 0xffff for a zero digit (|d| - 1 = 32767 with the sign set would be d = -2^15,
+// outside the digit range [-(2^(c-1) - 1), 2^(c-1)] for every c <= 16).
+struct KRecode {
+    enum { kBlock = 256 };
+    const uint32_t *scalars;
+    uint16_t *dig;    // W rows of `stride` codes
+    uint32_t stride;  // >= n, multiple of 8 (rows stay 16-byte aligned)
+    MsmGeom g;
+    VMSM_HD void operator()(uint32_t tid) const {
+        sc256 s = ld_scalar(scalars, tid);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < g.W; w++) {
+            int32_t d = sc_digit(s, w, g.c, carry);
+            uint32_t code = 0xffffu;
+            if (d != 0) code = d < 0 ? ((uint32_t)(-d) - 1u) | 0x8000u : (uint32_t)d - 1u;
+            dig[(size_t)w * stride + tid] = (uint16_t)code;
+        }
+    }
+};
+
 // Long buckets.  A thread of KAccumulate sums at most `cap` entries of its bucket; what is left of a longer bucket is
 // cut into at most 64 segments ("overflow tasks", each a multiple of 32 entries, >= 256) that KOverflow sums with one
 // warp per task, and KCombine folds the task partials back into the bucket.  This bounds the serial chain of any

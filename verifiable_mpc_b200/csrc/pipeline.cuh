@@ -37,6 +37,11 @@ struct MsmOptions {
     uint32_t pre_sets = 0;     // MSMs over precomputed bases: number of bucket sets the windows share; 0 = auto
     uint32_t seg_len = 0;      // entries per thread of the balanced accumulate kernel; 0 = whole waves (seg_plan)
     uint32_t seg_mode = 1;     // accumulate kernel: 0 one thread per bucket, 1 by geometry (default), 2 segments
+    // counting sort: 0 (default) two passes with global atomics, 1 block-privatised (shared-memory counters) where the
+    // backend supports the geometry.  Measured NOT faster on B200 (profiles/r02/block_sort_experiment.md): shared-memory
+    // atomics on random counters run at ~1-2 per clock per SM, and the largest carveout the sort blocks need slows the
+    // accumulate kernel by 14 %; kept as a tested option and as the evidence for the atomic sort
+    uint32_t block_sort = 0;
 };
 
 // Precomputed bases of an MSM call (KPrecompute): level w of `table` holds 2^(c*w) * P_i at table[w * stride + i].
@@ -284,20 +289,30 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
         seg_bucket = ws.seg_bucket_[par], seg_total = ws.seg_total_[par];
     }
 
-    // counting sort of (window, |digit|) -> CSR lists, on the sort stream (double-buffered by parity)
+    // counting sort of (window, |digit|) -> CSR lists, on the sort stream (double-buffered by parity): block-privatised
+    // (digits recoded once, shared-memory counters, kernels.cuh: KRecode) where the backend offers it for this geometry,
+    // else two passes over the scalars with global atomics
+    const uint32_t bs_chunks = opt.block_sort ? be.bsort_chunks(g) : 0u;
+    if (bs_chunks && be.bsort_ensure(g, bs_chunks, par)) return -1;
     be.use_head(seq);
     be.sort_begin(par);
     be.phase_begin();
-    be.zero(counts, (size_t)nbuckets * 4);
-    if (n) {
-        KDigitsHist k1 = {scalars, counts, g};
-        be.launch_sort(k1, n);
+    if (bs_chunks) {
+        be.bsort_hist(scalars, g, bs_chunks, par, counts);
+    } else {
+        be.zero(counts, (size_t)nbuckets * 4);
+        if (n) {
+            KDigitsHist k1 = {scalars, counts, g};
+            be.launch_sort(k1, n);
+        }
     }
     be.phase_mark(PH_DIGITS);
     if (seg) be.scan_offsets_flat(counts, offsets, cursor, g, ws.row_totals_[par], seg_bucket, seg_total, sp.L);
     else be.scan_offsets(counts, offsets, cursor, g);
     be.phase_mark(PH_SCAN);
-    if (n) {
+    if (bs_chunks) {
+        be.bsort_scatter(g, bs_chunks, par, offsets, idx);
+    } else if (n) {
         KScatter k3 = {scalars, cursor, idx, g};
         be.launch_sort(k3, n);
     }

@@ -171,6 +171,84 @@ __global__ void __launch_bounds__(SCAN_TILE) vmsm_scan_offsets_flat(const uint32
     }
 }
 
+// ---- block-privatised counting sort (kernels.cuh: KRecode).  Block (set s, chunk ch) owns the codes of the windows
+// of bucket set s for scalars [ch * per, (ch + 1) * per) and the NB counters of the set in shared memory:
+//   vmsm_bsort_hist     per-block histogram -> blockhist[s][ch][b]
+//   vmsm_bsort_colscan  blockhist[s][.][b] -> exclusive prefix over the chunks, counts[s][b] = bucket population
+//   (vmsm_scan_offsets / _flat: counts -> CSR offsets, as for the atomic sort)
+//   vmsm_bsort_scatter  cursor[b] = offsets[s][b] + blockhist[s][ch][b] in shared memory; entries written to idx
+// No global atomics; the codes (2 B per digit, window-major) are read with 16-byte loads.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 8 : 1)
+    vmsm_bsort_hist(const uint16_t *__restrict__ dig, uint32_t stride, MsmGeom g, uint32_t C, uint32_t per,
+                    uint32_t *__restrict__ blockhist) {
+    extern __shared__ uint32_t bs_smem[];
+    const uint32_t s = blockIdx.x / C, ch = blockIdx.x - s * C;
+    for (uint32_t i = threadIdx.x; i < g.NB; i += BLOCK) bs_smem[i] = 0;
+    __syncthreads();
+    const uint32_t lo = ch * per, hi = g.n - lo < per ? g.n : lo + per;
+    if (lo < g.n) {
+        const uint32_t vecs = (hi - lo + 7) >> 3, nw = (g.W - s + g.S - 1) / g.S;
+        for (uint32_t t = threadIdx.x; t < nw * vecs; t += BLOCK) {
+            const uint32_t wi = t / vecs, v = t - wi * vecs, i = lo + 8 * v;
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(dig + (size_t)(s + wi * g.S) * stride + i));
+            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t code = (wd[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                if (code != 0xffffu && i + j < hi) atomicAdd(&bs_smem[code & 0x7fffu], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t *out = blockhist + (size_t)blockIdx.x * g.NB;
+    for (uint32_t i = threadIdx.x; i < g.NB; i += BLOCK) out[i] = bs_smem[i];
+}
+
+__global__ void __launch_bounds__(256) vmsm_bsort_colscan(uint32_t *__restrict__ blockhist, uint32_t C, uint32_t NB,
+                                                          uint32_t nbuckets, uint32_t *__restrict__ counts) {
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= nbuckets) return;
+    const uint32_t s = t / NB, b = t - s * NB;
+    uint32_t *p = blockhist + (size_t)s * C * NB + b;
+    uint32_t run = 0;
+    for (uint32_t ch = 0; ch < C; ch++, p += NB) {
+        const uint32_t v = *p;
+        *p = run;
+        run += v;
+    }
+    counts[t] = run;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 8 : 1)
+    vmsm_bsort_scatter(const uint16_t *__restrict__ dig, uint32_t stride, MsmGeom g, uint32_t C, uint32_t per,
+                       const uint32_t *__restrict__ blockhist, const uint32_t *__restrict__ offsets,
+                       uint32_t *__restrict__ idx) {
+    extern __shared__ uint32_t bs_smem[];
+    const uint32_t s = blockIdx.x / C, ch = blockIdx.x - s * C;
+    const uint32_t lo = ch * per, hi = g.n - lo < per ? g.n : lo + per;
+    if (lo >= g.n) return;
+    const uint32_t *bh = blockhist + (size_t)blockIdx.x * g.NB, *off = offsets + (size_t)s * g.NB;
+    for (uint32_t i = threadIdx.x; i < g.NB; i += BLOCK) bs_smem[i] = off[i] + bh[i];
+    __syncthreads();
+    const uint32_t vecs = (hi - lo + 7) >> 3, nw = (g.W - s + g.S - 1) / g.S;
+    for (uint32_t t = threadIdx.x; t < nw * vecs; t += BLOCK) {
+        const uint32_t wi = t / vecs, v = t - wi * vecs, i = lo + 8 * v;
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(dig + (size_t)(s + wi * g.S) * stride + i));
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t kbits = wi << g.lg;  // windows sharing a bucket set: which of them (MsmGeom)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t code = (wd[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            if (code != 0xffffu && i + j < hi) {
+                const uint32_t pos = atomicAdd(&bs_smem[code & 0x7fffu], 1u);
+                idx[pos] = (i + j) | kbits | ((code & 0x8000u) << 16);
+            }
+        }
+    }
+}
+
 // Exclusive prefix sums of n 32-bit lengths into 64-bit offsets (transcript text compaction): per-block sums,
 // one block scanning the block sums, then a per-block scan with the block's base.  Returns the total in totals[nblk].
 __global__ void __launch_bounds__(1024) vmsm_lens_block_sums(const uint32_t *__restrict__ lens, uint32_t n,
@@ -404,6 +482,13 @@ struct Ctx {
     uint32_t shard_seq = 0;  // != 0 while a sharded MSM is being issued
     uint32_t shard_next = 0;  // VMSM_OPT_SHARD_SEQ: applies to the next MSM call of any flavour, then clears
     MsmOptions opt;
+    // block-privatised counting sort: digit codes (W x stride x 2 B) and per-block histograms (S x C x NB x 4 B),
+    // double-buffered by MSM parity like the CSR lists
+    uint16_t *bs_dig[2] = {nullptr, nullptr};
+    uint32_t *bs_hist[2] = {nullptr, nullptr};
+    size_t bs_dig_cap[2] = {0, 0}, bs_hist_cap[2] = {0, 0};
+    uint32_t bs_min_terms = 1u << 15;  // smaller MSMs are latency-bound: three short kernels beat five
+    bool bs_attr_set = false;
     uint32_t seg_resident[2] = {0, 0};  // resident threads of the segmented accumulate kernels (plain / tables), cached
     uint64_t pre_min_terms = 256;  // MSMs shorter than this ignore a precomputed table (VMSM_OPT_PRE_MIN_TERMS)
     bool phase_timing = false;
@@ -562,6 +647,61 @@ struct CudaBE {
         vmsm_scan_offsets_flat<<<g.S * tiles, SCAN_TILE, 0, cur>>>(counts, offsets, cursor, g, tiles, row_totals, seg_bucket,
                                                                    total, L);
         c->launches += 2;
+        note(cudaGetLastError());
+    }
+    // ---- block-privatised counting sort (vmsm_bsort_*): number of scalar chunks, or 0 = not for this geometry
+    uint32_t bsort_chunks(const MsmGeom &g) {
+        if (g.n < c->bs_min_terms || g.c > 16 || g.NB * 4u > 160u * 1024u || g.S > 148u) return 0;
+        uint32_t C = 148u / g.S;  // about one block per SM
+        return C ? C : 1u;
+    }
+    static uint32_t bsort_stride(const MsmGeom &g) { return (g.n + 7u) & ~7u; }
+    static uint32_t bsort_per(const MsmGeom &g, uint32_t C) { return (((g.n + C - 1) / C) + 7u) & ~7u; }
+    int bsort_ensure(const MsmGeom &g, uint32_t C, int par) {
+        if (!c->bs_attr_set) {
+            const int big = 160 * 1024;
+            note(cudaFuncSetAttribute(vmsm_bsort_hist<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            note(cudaFuncSetAttribute(vmsm_bsort_hist<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            note(cudaFuncSetAttribute(vmsm_bsort_scatter<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            note(cudaFuncSetAttribute(vmsm_bsort_scatter<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            c->bs_attr_set = true;
+        }
+        const size_t need_dig = (size_t)g.W * bsort_stride(g) * 2, need_hist = (size_t)g.S * C * g.NB * 4;
+        if (need_dig > c->bs_dig_cap[par]) {
+            if (c->bs_dig[par]) cudaFree(c->bs_dig[par]);
+            c->bs_dig_cap[par] = 0;
+            c->bs_dig[par] = (uint16_t *)alloc(need_dig);
+            if (!c->bs_dig[par]) return -1;
+            c->bs_dig_cap[par] = need_dig;
+        }
+        if (need_hist > c->bs_hist_cap[par]) {
+            if (c->bs_hist[par]) cudaFree(c->bs_hist[par]);
+            c->bs_hist_cap[par] = 0;
+            c->bs_hist[par] = (uint32_t *)alloc(need_hist);
+            if (!c->bs_hist[par]) return -1;
+            c->bs_hist_cap[par] = need_hist;
+        }
+        return 0;
+    }
+    void bsort_hist(const uint32_t *scalars, const MsmGeom &g, uint32_t C, int par, uint32_t *counts) {
+        const uint32_t stride = bsort_stride(g), per = bsort_per(g, C), nb = g.S * g.NB;
+        KRecode k0 = {scalars, c->bs_dig[par], stride, g};
+        launch_sort(k0, g.n);
+        // underneath an accumulate kernel: 256 threads at <= 32 registers, what four resident accumulate blocks leave
+        // free on an SM; alone: 1024 threads per block
+        if (thin_sort) vmsm_bsort_hist<256><<<g.S * C, 256, g.NB * 4, cur>>>(c->bs_dig[par], stride, g, C, per, c->bs_hist[par]);
+        else vmsm_bsort_hist<1024><<<g.S * C, 1024, g.NB * 4, cur>>>(c->bs_dig[par], stride, g, C, per, c->bs_hist[par]);
+        vmsm_bsort_colscan<<<(nb + 255) / 256, 256, 0, cur>>>(c->bs_hist[par], C, g.NB, nb, counts);
+        c->launches += 2;
+        note(cudaGetLastError());
+    }
+    void bsort_scatter(const MsmGeom &g, uint32_t C, int par, const uint32_t *offsets, uint32_t *idx) {
+        const uint32_t stride = bsort_stride(g), per = bsort_per(g, C);
+        if (thin_sort)
+            vmsm_bsort_scatter<256><<<g.S * C, 256, g.NB * 4, cur>>>(c->bs_dig[par], stride, g, C, per, c->bs_hist[par], offsets, idx);
+        else
+            vmsm_bsort_scatter<1024><<<g.S * C, 1024, g.NB * 4, cur>>>(c->bs_dig[par], stride, g, C, per, c->bs_hist[par], offsets, idx);
+        c->launches++;
         note(cudaGetLastError());
     }
     // threads of the segmented accumulate kernel one wave holds: SMs x resident blocks x block size
@@ -1134,6 +1274,7 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (auto &kv : c->pool) cudaFree(kv.second);
     CudaBE be(c);
     ws_release(be, c->ws);
+    for (int k = 0; k < 2; k++) cudaFree(c->bs_dig[k]), cudaFree(c->bs_hist[k]);
     cudaFree(c->order_bins), cudaFree(c->err_word), cudaFree(c->fb_table), cudaFree(c->res_ext), cudaFree(c->res_aff);
     cudaFree(c->stage_scalars), cudaFree(c->tmp_ext), cudaFree(c->small_aff), cudaFree(c->small_niels);
     cudaFreeHost(c->pin);
@@ -1226,6 +1367,22 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             if (value < 0 || value > (1 << 24)) return fail(VMSM_ERR_INVALID, "quad threshold out of range");
             c->opt.quad_threshold = (uint32_t)value;
             return VMSM_OK;
+        case VMSM_OPT_BLOCK_SORT:
+            c->opt.block_sort = value != 0;
+            return VMSM_OK;
+        case VMSM_OPT_BLOCK_SORT_MIN:
+            if (value < 0 || value > (1ll << 26)) return fail(VMSM_ERR_INVALID, "block sort threshold out of range");
+            c->bs_min_terms = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_ACC_CARVEOUT: {
+            if (value < -1 || value > 100) return fail(VMSM_ERR_INVALID, "carveout must be -1 (driver default) or a percentage");
+            const int pct = (int)value;
+            CU(cudaFuncSetAttribute(vmsm_kernel<KAccumulate>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            CU(cudaFuncSetAttribute(vmsm_kernel<KAccumulatePre>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            CU(cudaFuncSetAttribute(vmsm_kernel<KAccumulateSeg>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            CU(cudaFuncSetAttribute(vmsm_kernel<KAccumulateSegPre>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            return VMSM_OK;
+        }
     }
     return fail(VMSM_ERR_INVALID, "unknown option %d", key);
 }
