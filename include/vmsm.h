@@ -75,6 +75,9 @@ extern "C" {
                                 streams (one launch below ~2^18 terms is one or two waves that end together: the next
                                 MSM's kernel fills the ramp-down); 0 = all accumulate kernels on the context's stream */
 #define VMSM_OPT_QUAD_THRESHOLD 6 /* bucket-tree levels with <= this many nodes use 4 lanes per node (0 = never) */
+#define VMSM_OPT_BN_PRE_SETS 23 /* BN256 MSMs over key tables: bucket sets shared by the windows (0 = default: 2 with the
+                                  balanced accumulate kernel, one per window with VMSM_OPT_SEG_MODE 0) */
+#define VMSM_OPT_BN_SEG_LEN 24 /* BN256: entries per thread of the balanced accumulate kernel (0 = whole waves, >= 8) */
 #define VMSM_OPT_BLOCK_SORT 20 /* 1: counting sort of the digits with per-block shared-memory counters (digits recoded
                                  once into 16-bit codes, no global atomics) for Ed25519 MSMs of at least
                                  VMSM_OPT_BLOCK_SORT_MIN terms and windows c <= 16; 0 (default) = two passes with global
@@ -162,7 +165,9 @@ int32_t vmsm_scalars_download_ptr(uint64_t ctx, uint64_t sc, uint64_t off, uint6
  *   VMSM_FOLD_FORM     L'_j = c * L_j + L_{half+j}      compressed_pivot.py:68-73 (L_prime), :189-193 (verifier)
  * vmsm_scalars_dot: sum_i a[aoff+i] * b[boff+i] mod l -- L_tilde([0]*half + z_L), L_tilde(z_R + [0]*half), :41-42.
  * vmsm_scalars_text_ptr: "v0, v1, ..." as MPyC prints field elements (is_signed: representatives in (-l/2, l/2]),
- *   the coefficient text of L_tilde in the Fiat-Shamir pre-image, :51-54; *text as for vmsm_points_text_ptr.
+ *   the coefficient text of L_tilde in the Fiat-Shamir pre-image, :51-54; *text points into a second page-locked
+ *   buffer of the context (valid until the next vmsm_scalars_text_ptr call), so the text of the generators and of the
+ *   form of one round can both be fetched while that round's commitments A_i, B_i are still being computed.
  * vmsm_scalars_axpy, the same element-wise operations on two vectors (ranges must not overlap):
  *   VMSM_AXPY_ADD_SCALED  dst_j = dst_j + c * src_j      z = r + c0 * x, phi = rho + c0 * gamma   :134-135
  *   VMSM_AXPY_SCALE_ADD   dst_j = c * dst_j + src_j

@@ -104,6 +104,8 @@ struct HostBE {
         });
     }
     uint32_t resident_threads(bool) { return resident; }
+    template <class F>
+    uint32_t resident_threads_w() { return resident; }
     uint32_t resident = 48;  // small on purpose: several waves and straddling buckets even in tiny test cases
     bool order_buckets(const uint32_t *counts, uint32_t *order, uint32_t nb, uint32_t n) {
         if (n == 0) return false;
@@ -128,13 +130,15 @@ struct HostBE {
     void phase_end() {}
 };
 
-static uint32_t g_seg_mode = 1, g_seg_len = 0;
+static uint32_t g_seg_mode = 1, g_seg_len = 0, g_bn_sets = 0;
 
 extern "C" {
 
 // accumulate-kernel selection for the following hostemu_msm* calls (MsmOptions::seg_mode / seg_len)
 // counting-sort selection: 0 = two passes with atomics, C > 0 = block-privatised with C scalar chunks per bucket set
 void hostemu_set_block_sort(uint32_t chunks) { g_bs_chunks = chunks; }
+
+void hostemu_set_bn_sets(uint32_t sets) { g_bn_sets = sets; }  // MsmOptions::pre_sets_w
 
 void hostemu_set_seg(uint32_t mode, uint32_t len) {
     g_seg_mode = mode;
@@ -399,6 +403,7 @@ static int bn_msm_pre(const uint8_t *wire, uint32_t n_pts, uint32_t off, uint32_
     memcpy(sc.data(), scalars, (size_t)n * 32);
     Workspace ws;
     MsmOptions opt;
+    opt.seg_mode = g_seg_mode, opt.seg_len_w = g_seg_len, opt.pre_sets_w = g_bn_sets;
     PreTable pt = {n_pts, table_bits, W, nullptr, n_extra};
     wjac<F> oj, hj;
     waff<F> ow;

@@ -110,3 +110,38 @@ def test_msm_over_key_tables(hostemu, g2):
     s3 = [5, 5, 7, 1, 3, 9, 1234, B.N - 1]
     assert msm_pre(pp, 0, len(pp), [], s3, 8) == B.msm_naive(F, s3, pp)
     assert msm_pre(pp, 0, len(pp), [], [1, 1, 1, 1, 2, 2, 0, 0], 8) is None
+
+
+@pytest.mark.parametrize("g2", [0, 1])
+def test_msm_over_key_tables_shared_sets_and_segments(hostemu, g2):
+    """Windows sharing S bucket sets over the key tables (CSR entries carry which window: BaseRefW) summed by one thread
+    per bucket (+ long-bucket tasks) or by equal segments (KAccumulateSegW / KSegFixupW / KSegLongFixW): every
+    combination gives the known-dlog result, also for skewed scalars whose entries pile into one bucket."""
+    import random
+
+    lib = hostemu
+    F, G = (B.FP2, B.G2) if g2 else (B.FP, B.G1)
+    sz, n = (128 if g2 else 64), 40 if g2 else 300
+    base = [B.scalar_mul(F, G, k + 1) for k in range(10)]
+    pts = [base[i % 10] for i in range(n)]
+    dl = [i % 10 + 1 for i in range(n)]
+
+    def msm_pre(scalars, c):
+        o = ctypes.create_string_buffer(sz)
+        rc = lib.hostemu_bn_msm_pre(g2, b"".join(B.point_to_bytes(F, p) for p in pts), n, 0, n, b"", 0,
+                                    b"".join(B.fp_to_bytes(s % B.N) for s in scalars), c, o)
+        assert rc == 0
+        return B.point_from_bytes(F, o.raw)
+
+    rnd = random.Random(11 + g2)
+    cases = [[prng.scalar_bn(0x820, i) for i in range(n)], [rnd.randrange(2) for _ in range(n)], [7] * n]
+    try:
+        for mode, seg_len in ((1, 0), (0, 0), (2, 3)):  # n >= 256 on G1: segments by default; 40 terms on G2: forced
+            hostemu.hostemu_set_seg(mode, seg_len)
+            for sets in ((0, 1, 3) if g2 else (0, 1, 2, 5, 32)):
+                hostemu.hostemu_set_bn_sets(sets)
+                for sc in cases[:2] if g2 else cases:
+                    assert msm_pre(sc, 8) == B.msm_known_dlog(F, sc, dl), (mode, seg_len, sets)
+    finally:
+        hostemu.hostemu_set_seg(1, 0)
+        hostemu.hostemu_set_bn_sets(0)

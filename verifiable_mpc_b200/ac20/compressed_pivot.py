@@ -243,18 +243,26 @@ FUSED_CROSS_TERMS = True         # cross terms feed their commitments on the dev
 
 class _DevForm:
     """The form whose coefficients live on the device, for the Fiat-Shamir pre-image ("[coeffs], constant")."""
-    __slots__ = ("sc", "n", "signed", "constant")
+    __slots__ = ("sc", "n", "signed", "constant", "view")
 
     def __init__(self, sc, n, signed, constant="0"):
-        self.sc, self.n, self.signed, self.constant = sc, n, signed, str(constant)
+        self.sc, self.n, self.signed, self.constant, self.view = sc, n, signed, str(constant), None
+
+    def prefetch_repr(self):
+        """Coefficient text fetched ahead of the hash (see DevicePointList.prefetch_repr); this object describes one
+        state of the vector and is discarded with it."""
+        if hasattr(self.sc, "text_view"):
+            self.view = self.sc.text_view(0, self.n, self.signed)
+        return self
 
     def repr_bytes(self):
         return b"[" + self.sc.text_bytes(0, self.n, self.signed) + b"], " + self.constant.encode("ascii")
 
     def feed_repr(self, h):
         if hasattr(self.sc, "text_view"):  # hashed in place from the pinned buffer
+            view, self.view = self.view, None
             h.update(b"[")
-            h.update(self.sc.text_view(0, self.n, self.signed))
+            h.update(view if view is not None else self.sc.text_view(0, self.n, self.signed))
             h.update(b"], " + self.constant.encode("ascii"))
         else:
             h.update(self.repr_bytes())
@@ -266,6 +274,8 @@ class _DevForm:
     def __repr__(self):
         return self.repr_bytes().decode("ascii")
 
+
+PREFETCH_TEXT = True  # device prover: fetch the round's transcript text underneath the A_i, B_i commitments
 
 TRACE = None  # tools/profile_ac20.py sets a list: (label, perf_counter()) marks of the device-resident prover
 
@@ -319,12 +329,19 @@ def _protocol_4_prover_dev(g_hat, k, Q, Ld, zd, gf, proof, round_i):
                 _mark("round:dots")
                 ctx.msm_dev_ext(g_hat.dev, g_hat.off + half, half, zd, 0, kd, 0, [s_a], slot=0)
                 ctx.msm_dev_ext(g_hat.dev, g_hat.off, half, zd, half, kd, 0, [s_b], slot=1)
+            # the O(n) text of this round's pre-image (generators, coefficients of L_tilde) does not depend on A_i, B_i:
+            # it is produced and copied to the host while the two commitments are being computed
+            form = _DevForm(Ld, n, signed)
+            if PREFETCH_TEXT and pivot.TRANSCRIPT != "binary":
+                g_hat.prefetch_repr()
+                form.prefetch_repr()
+                _mark("round:text")
             A, B = group._make(ctx.result(0)), group._make(ctx.result(1))
             _mark("round:A,B")
             proof["A" + str(round_i)] = A
             proof["B" + str(round_i)] = B
             Q = _resolve(Q)
-            c = _fold_challenge(A, B, g_hat, k, Q, _DevForm(Ld, n, signed), q)
+            c = _fold_challenge(A, B, g_hat, k, Q, form, q)
             _mark("round:challenge")
             g_hat = _fold_generators(g_hat, c)
             Q = _q_prime(group, A, Q, B, c)

@@ -56,17 +56,23 @@ VMSM_HD sc256 synth_scalar_bn(uint64_t seed, uint64_t i) {
     return s;
 }
 
-// Where a base lives: plain (stride == 0) bases[i] / extra[i - n_main]; over tables of 2^(c*w) * P_i (stride != 0, see
-// KPrecomputeW) level w = bucket >> log2NB, i.e. the window that owns the bucket set.
+// Where the base of a CSR entry e lives: plain (stride == 0) bases[i] / extra[i - n_main] with i = e & 0x7fffffff; over
+// tables of 2^(c*w) * P_i (stride != 0, see KPrecomputeW) level w = set + k * S of the table, where set = bucket >>
+// log2NB and k (which of the windows sharing that bucket set, MsmGeom) sits above bit lg of the entry.
 template <class F>
 struct BaseRefW {
     const waff<F> *bases;
     const waff<F> *extra;
     uint32_t n_main;
     uint32_t stride, extra_stride, log2NB;
-    VMSM_HD const waff<F> *ptr(uint32_t i, uint32_t bucket) const {
-        if (!stride) return i < n_main ? bases + i : extra + (i - n_main);
-        const size_t w = bucket >> log2NB;
+    uint32_t lg, S;
+    VMSM_HD const waff<F> *ptr(uint32_t e, uint32_t bucket) const {
+        if (!stride) {
+            const uint32_t i = e & 0x7fffffffu;
+            return i < n_main ? bases + i : extra + (i - n_main);
+        }
+        const uint32_t i = e & ((1u << lg) - 1u);
+        const size_t w = (bucket >> log2NB) + (size_t)((e & 0x7fffffffu) >> lg) * S;
         return i < n_main ? bases + w * stride + i : extra + w * extra_stride + (i - n_main);
     }
 };
@@ -104,7 +110,7 @@ struct KAccumulateW {
         wjac<F> acc = wj_identity<F>();
         for (uint32_t k = 0; k < cnt; k++) {
             uint32_t e = idx[pos + k];
-            acc = wj_madd(acc, ld_obj(br.ptr(e & 0x7fffffffu, b)), (e >> 31) != 0);
+            acc = wj_madd(acc, ld_obj(br.ptr(e, b)), (e >> 31) != 0);
         }
         st_obj(buckets + b, acc);
     }
@@ -128,7 +134,7 @@ struct KOverflowW {
             wjac<F> acc = wj_identity<F>();
             for (uint32_t k = lane; k < tk.count; k += 32) {
                 uint32_t e = idx[tk.first + k];
-                acc = wj_madd(acc, ld_obj(br.ptr(e & 0x7fffffffu, tk.bucket)), (e >> 31) != 0);
+                acc = wj_madd(acc, ld_obj(br.ptr(e, tk.bucket)), (e >> 31) != 0);
             }
 #pragma unroll 1
             for (int d = 16; d >= 1; d >>= 1) {
@@ -148,7 +154,7 @@ struct KOverflowW {
             wjac<F> acc = wj_identity<F>();
             for (uint32_t k = 0; k < tk.count; k++) {
                 uint32_t e = idx[tk.first + k];
-                acc = wj_madd(acc, ld_obj(br.ptr(e & 0x7fffffffu, tk.bucket)), (e >> 31) != 0);
+                acc = wj_madd(acc, ld_obj(br.ptr(e, tk.bucket)), (e >> 31) != 0);
             }
             st_obj(partials + t, acc);
         }
@@ -172,6 +178,125 @@ struct KCombineW {
             for (uint32_t k = 0; k < lb.ntask; k++) acc = wj_add(acc, ld_obj(partials + lb.task_base + k));
             st_obj(buckets + lb.bucket, acc);
         }
+    }
+};
+
+// Balanced (segmented) accumulation over key tables whose windows share bucket sets: the Weierstrass twin of
+// KAccumulateSegT / KSegFixup / KSegLongFix in kernels.cuh (equal segments of the sorted CSR array, one thread each; a
+// bucket that straddles segments leaves partial sums that the fix-up kernels add).  A 2^14-term MSM with c = 13 has 20
+// windows x 4096 buckets of FOUR entries each: one thread per bucket is a launch of short chains plus a bucket tree as
+// dear as the accumulation itself; over S shared sets the tree shrinks by W / S and the segments keep every resident
+// thread equally busy whatever the bucket populations are.
+template <class F>
+struct KAccumulateSegW {
+    enum { kBlock = 128 };
+    BaseRefW<F> br;
+    const uint32_t *offsets, *counts, *idx, *seg_bucket, *total;
+    wjac<F> *buckets, *partials;  // partials: [2t] head, [2t + 1] tail of segment t
+    uint32_t L;
+    VMSM_HD void flush(uint32_t tid, uint32_t b, const wjac<F> &acc, bool cont, bool more) const {
+        if (cont) st_obj(partials + 2 * (size_t)tid, acc);
+        else if (more) st_obj(partials + 2 * (size_t)tid + 1, acc);
+        else st_obj(buckets + b, acc);
+    }
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint32_t E = *total;
+        const uint32_t pos0 = tid * L;
+        if (pos0 >= E) return;
+        const uint32_t pos1 = E - pos0 < L ? E : pos0 + L;
+        uint32_t b = seg_bucket[tid];
+        const uint32_t off = offsets[b];
+        uint32_t bend = off + counts[b];
+        bool cont = off < pos0;
+        wjac<F> acc = wj_identity<F>();
+        for (uint32_t pos = pos0; pos < pos1; pos++) {
+            if (pos == bend) {
+                flush(tid, b, acc, cont, false);
+                cont = false;
+                uint32_t c;
+                do {
+                    b++;
+                    c = counts[b];
+                } while (c == 0);
+                bend += c;
+                acc = wj_identity<F>();
+            }
+            const uint32_t e = idx[pos];
+            acc = wj_madd(acc, ld_obj(br.ptr(e, b)), (e >> 31) != 0);
+        }
+        flush(tid, b, acc, cont, bend > pos1);
+    }
+};
+
+template <class F>
+struct KSegFixupW {
+    enum { kBlock = 128 };
+    const uint32_t *offsets, *counts;
+    const wjac<F> *partials;
+    wjac<F> *buckets;
+    uint32_t L, long_span;
+    OverflowCtl *ctl;
+    LongBucket *longs;  // {bucket, first segment, segments after the first}
+    VMSM_HD void operator()(uint32_t b) const {
+        const uint32_t cnt = counts[b];
+        if (!cnt) {
+            st_obj(buckets + b, wj_identity<F>());
+            return;
+        }
+        const uint32_t off = offsets[b];
+        const uint32_t t0 = off / L, t1 = (off + cnt - 1) / L;
+        if (t0 == t1) return;
+        if (t1 - t0 > long_span) {
+            uint32_t lpos = VMSM_ATOMIC_ADD(&ctl->nlong, 1u);
+            LongBucket lb = {b, t0, t1 - t0};
+            longs[lpos] = lb;
+            return;
+        }
+        wjac<F> acc = ld_obj(partials + 2 * (size_t)t0 + 1);
+        for (uint32_t t = t0 + 1; t <= t1; t++) acc = wj_add(acc, ld_obj(partials + 2 * (size_t)t));
+        st_obj(buckets + b, acc);
+    }
+};
+
+template <class F>
+struct KSegLongFixW {
+    enum { kBlock = 128 };
+    const OverflowCtl *ctl;
+    const LongBucket *longs;
+    const wjac<F> *partials;
+    wjac<F> *buckets;
+    uint32_t nwarps;
+    VMSM_HD const wjac<F> *part(const LongBucket &lb, uint32_t k) const {
+        return k == 0 ? partials + 2 * (size_t)lb.task_base + 1 : partials + 2 * ((size_t)lb.task_base + k);
+    }
+    VMSM_HD void operator()(uint32_t tid) const {
+        const uint32_t nlong = ctl->nlong;
+#if defined(__CUDA_ARCH__)
+        const uint32_t lane = tid & 31;
+        for (uint32_t l = tid >> 5; l < nlong; l += nwarps) {
+            LongBucket lb = longs[l];
+            wjac<F> acc = wj_identity<F>();
+            for (uint32_t k = lane; k <= lb.ntask; k += 32) acc = wj_add(acc, ld_obj(part(lb, k)));
+#pragma unroll 1
+            for (int d = 16; d >= 1; d >>= 1) {
+                wjac<F> o;
+                uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+                const uint32_t *aw = reinterpret_cast<const uint32_t *>(&acc);
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(wjac<F>) / 4); i++) ow[i] = __shfl_down_sync(0xffffffffu, aw[i], d);
+                acc = wj_add(acc, o);
+            }
+            if (lane == 0) st_obj(buckets + lb.bucket, acc);
+        }
+#else
+        if (tid & 31) return;
+        for (uint32_t l = tid >> 5; l < nlong; l += nwarps) {
+            LongBucket lb = longs[l];
+            wjac<F> acc = wj_identity<F>();
+            for (uint32_t k = 0; k <= lb.ntask; k++) acc = wj_add(acc, ld_obj(part(lb, k)));
+            st_obj(buckets + lb.bucket, acc);
+        }
+#endif
     }
 };
 
@@ -389,7 +514,7 @@ struct KAccumulateWQ {
         wjac<F> acc = wj_identity<F>();
         for (uint32_t k = 0; k < cnt; k++) {
             uint32_t e = idx[pos + k];
-            acc = wq_madd<F>(q, acc, ld_obj(br.ptr(e & 0x7fffffffu, b)), (e >> 31) != 0);
+            acc = wq_madd<F>(q, acc, ld_obj(br.ptr(e, b)), (e >> 31) != 0);
         }
         if (q == 0) st_obj(buckets + b, acc);
 #else

@@ -37,6 +37,8 @@ struct MsmOptions {
     uint32_t pre_sets = 0;     // MSMs over precomputed bases: number of bucket sets the windows share; 0 = auto
     uint32_t seg_len = 0;      // entries per thread of the balanced accumulate kernel; 0 = whole waves (seg_plan)
     uint32_t seg_mode = 1;     // accumulate kernel: 0 one thread per bucket, 1 by geometry (default), 2 segments
+    uint32_t pre_sets_w = 0;   // BN256 MSMs over key tables: bucket sets shared by the windows; 0 = auto
+    uint32_t seg_len_w = 0;    // BN256: entries per thread of the balanced accumulate kernel; 0 = auto
     // counting sort: 0 (default) two passes with global atomics, 1 block-privatised (shared-memory counters) where the
     // backend supports the geometry.  Measured NOT faster on B200 (profiles/r02/block_sort_experiment.md): shared-memory
     // atomics on random counters run at ~1-2 per clock per SM, and the largest carveout the sort blocks need slows the
@@ -77,7 +79,7 @@ struct Workspace {
     // the two partial sums per segment belong to the MSM's tail way (read by the fix-up kernels on its side stream)
     uint32_t *seg_bucket_[2] = {nullptr, nullptr}, *seg_total_[2] = {nullptr, nullptr}, *row_totals_[2] = {nullptr, nullptr};
     void *seg_partials_[kTailWays] = {};
-    size_t cap_seg = 0, cap_seg_part = 0;  // segments
+    size_t cap_seg = 0, cap_seg_part = 0;  // segments; bytes of one way's partial sums
     size_t cap_buckets = 0, cap_idx = 0, cap_nodes = 0, cap_tasks = 0;  // element counts
     int ways = 0;  // tail ways that have buckets / node buffers (grows to the largest count requested)
     size_t elem_bytes = 0;  // size of one accumulator point the point buffers were allocated for
@@ -130,12 +132,12 @@ inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits, uint32_t 
 struct SegPlan {
     uint32_t L, T;  // entries per segment, segments (threads) launched
 };
-inline SegPlan seg_plan(uint64_t max_entries, uint32_t resident, uint32_t forced_L = 0) {
+inline SegPlan seg_plan(uint64_t max_entries, uint32_t resident, uint32_t forced_L = 0, uint32_t min_L = 8) {
     SegPlan p;
     if (max_entries == 0) max_entries = 1;
     uint64_t waves = (max_entries + 32ull * resident - 1) / (32ull * resident);
     uint64_t L = (max_entries + waves * resident - 1) / (waves * resident);
-    if (L < 8) L = 8;  // tiny MSMs: a few threads with a handful of entries each
+    if (L < min_L) L = min_L;  // small MSMs: fewer threads with a handful of entries each
     if (forced_L) L = forced_L;
     p.L = (uint32_t)L;
     p.T = (uint32_t)((max_entries + L - 1) / L);
@@ -143,7 +145,7 @@ inline SegPlan seg_plan(uint64_t max_entries, uint32_t resident, uint32_t forced
 }
 
 template <class BE>
-int ws_ensure_seg(BE &be, Workspace &ws, size_t segs) {
+int ws_ensure_seg(BE &be, Workspace &ws, size_t segs, size_t elem_bytes = sizeof(ge_ext)) {
     if (segs > ws.cap_seg) {
         ws.cap_seg = 0;
         for (int k = 0; k < 2; k++) {
@@ -155,14 +157,14 @@ int ws_ensure_seg(BE &be, Workspace &ws, size_t segs) {
         }
         ws.cap_seg = segs;
     }
-    if (segs > ws.cap_seg_part) {  // after ws_ensure: ws.ways is final
+    if (2 * segs * elem_bytes > ws.cap_seg_part) {  // after ws_ensure: ws.ways is final; capacity in bytes
         ws.cap_seg_part = 0;
         for (int k = 0; k < ws.ways; k++) {
             be.free(ws.seg_partials_[k]);
-            ws.seg_partials_[k] = be.alloc(2 * segs * sizeof(ge_ext));
+            ws.seg_partials_[k] = be.alloc(2 * segs * elem_bytes);
             if (!ws.seg_partials_[k]) return -1;
         }
-        ws.cap_seg_part = segs;
+        ws.cap_seg_part = 2 * segs * elem_bytes;
     }
     return 0;
 }
@@ -441,18 +443,37 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     // short bucket chains and a bucket tree of exactly six full radix-4 levels (4096 = 4^6); measured fastest or tied at 2^10, 2^12,
     // 2^14 and 2^16 on G1 and G2 (profiles/r01/bn256_msm_v5_windows.jsonl), 35 % faster than the work-minimising c = 11
     if (!opt.window_bits && n >= 512 && n <= (1u << 16)) c = 13;
-    if (pre) c = pre->c;  // tables fix the window; every window keeps its own bucket set (weight 1: no Horner chain)
-    MsmGeom g = make_geom(n, c, scalar_bits);
+    if (pre) c = pre->c;  // tables fix the window
+    // Over key tables the bucket sets carry no weight (no Horner chain), so the W windows may share S < W sets: the
+    // bucket tree, which costs as much as the accumulation at these sizes (2.3 full additions per bucket against n * W
+    // / (W * NB) = 4 mixed additions per bucket at 2^14 terms), shrinks by W / S.  Fewer, fuller buckets are then summed
+    // by equal SEGMENTS of the sorted entries (KAccumulateSegW), as on the Ed25519 path.
+    const uint32_t W_c = (scalar_bits + c) / c;
+    const bool seg = pre && n >= 256 && (opt.seg_mode == 2 || opt.seg_mode == 1);
+    const uint32_t sets = !pre ? 0u : opt.pre_sets_w ? opt.pre_sets_w : seg ? 2u : W_c;
+    MsmGeom g = make_geom(n, c, scalar_bits, sets);
     if (pre && (pre->W != g.W || (n_extra && !extra_table))) return -2;
-    BaseRefW<F> br = {bases, pre ? extra_table : extra, n_main, pre ? pre->stride : 0u, pre ? pre->extra_stride : 0u, g.c - 1};
+    BaseRefW<F> br = {bases, pre ? extra_table : extra, n_main, pre ? pre->stride : 0u, pre ? pre->extra_stride : 0u, g.c - 1,
+                      g.lg, g.S};
     uint32_t R = 1u << opt.reduce_log2r_w;
     // long-bucket granularity for this curve: additions are 3-9x dearer than on Ed25519 and the MSMs are small, so a
     // bucket's own thread takes at most max(16, ...) entries and overflow segments may be as short as one warp pass
     const uint32_t kCapFloor = 16, kSegFloor = 32;
     if (ws_ensure(be, ws, g, R, sizeof(wjac<F>), kCapFloor, kSegFloor, kTailWaysBN)) return -1;
-    uint32_t nbuckets = g.W * g.NB;
+    uint32_t nbuckets = g.S * g.NB;
+    const uint32_t wins_per_set = (g.W + g.S - 1) / g.S;
     const int par = (int)(seq & 1);
     uint32_t *counts = ws.counts_[par], *offsets = ws.offsets_[par], *cursor = ws.cursor_[par], *idx = ws.idx_[par];
+    SegPlan sp = {0, 0};
+    uint32_t *seg_bucket = nullptr, *seg_total = nullptr;
+    if (seg) {
+        // at least 12 entries per thread: at 2^14 terms that is half a wave of threads, which measured faster than a
+        // full wave of 8-entry segments (fewer partial sums to fix up; several MSMs are in flight anyway) and than 16
+        // (profiles/r02/bn256_shared_sets_segments.md)
+        sp = seg_plan((uint64_t)n * g.W, be.template resident_threads_w<F>(), opt.seg_len_w, 12);
+        if (ws_ensure_seg(be, ws, sp.T, sizeof(wjac<F>))) return -1;
+        seg_bucket = ws.seg_bucket_[par], seg_total = ws.seg_total_[par];
+    }
     be.sort_begin(par);
     be.phase_begin();
     be.zero(counts, (size_t)nbuckets * 4);
@@ -461,7 +482,8 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         be.launch_sort(k1, n);
     }
     be.phase_mark(PH_DIGITS);
-    be.scan_offsets(counts, offsets, cursor, g);
+    if (seg) be.scan_offsets_flat(counts, offsets, cursor, g, ws.row_totals_[par], seg_bucket, seg_total, sp.L);
+    else be.scan_offsets(counts, offsets, cursor, g);
     be.phase_mark(PH_SCAN);
     if (n) {
         KScatter k3 = {scalars, cursor, idx, g};
@@ -469,7 +491,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     }
     be.phase_mark(PH_SCATTER);
     const uint32_t *order = nullptr;
-    if (opt.sort_buckets && be.order_buckets(counts, ws.order_[par], nbuckets, n)) order = ws.order_[par];
+    if (!seg && opt.sort_buckets && be.order_buckets(counts, ws.order_[par], nbuckets, n)) order = ws.order_[par];
     be.phase_mark(PH_ORDER);
     be.sort_end(par);
     be.phase_mark(PH_HANDOFF);
@@ -477,10 +499,25 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     const int tw = (int)(seq % kTailWaysBN);
     be.head_wait_tail(tw);
     void *const buckets = ws.buckets_[tw];
-    {
-        uint32_t cap = opt.cap_factor * (n >> (g.c - 1));
+    be.zero(ws.ctl_[tw], sizeof(OverflowCtl));
+    if (seg) {
+        wjac<F> *partials = (wjac<F> *)ws.seg_partials_[tw];
+        KAccumulateSegW<F> k5 = {br, offsets, counts, idx, seg_bucket, seg_total, (wjac<F> *)buckets, partials, sp.L};
+        be.launch(k5, sp.T);
+        be.phase_mark(PH_ACCUMULATE);
+        be.tail_begin(tw);
+        const uint32_t long_span = 32;
+        KSegFixupW<F> kf = {offsets, counts, partials, (wjac<F> *)buckets, sp.L, long_span, ws.ctl_[tw], ws.longs_[tw]};
+        be.launch(kf, nbuckets);
+        be.acc_done(par);
+        if ((uint64_t)n * wins_per_set > (uint64_t)sp.L * long_span) {
+            const uint32_t ow = be.overflow_warps();
+            KSegLongFixW<F> kl = {ws.ctl_[tw], ws.longs_[tw], partials, (wjac<F> *)buckets, ow};
+            be.launch(kl, ow * 32);
+        }
+    } else {
+        uint32_t cap = opt.cap_factor * (uint32_t)(((uint64_t)n * wins_per_set) >> (g.c - 1));
         if (cap < kCapFloor) cap = kCapFloor;
-        be.zero(ws.ctl_[tw], sizeof(OverflowCtl));
         // four lanes per bucket where measured faster (2^15: -8 %, 2^16: -14 %; slower at <= 2^14, where the tails set
         // the pace, and from 2^17, where the kernel is throughput-bound): profiles/r01/bn256_msm_v5_windows.md
         if (opt.w_quad_acc == 2 || (opt.w_quad_acc == 1 && n > (1u << 14) && n <= (1u << 16))) {
@@ -496,7 +533,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         // overflow tasks, combine, bucket tree, Horner and inversion on side stream `tw`, underneath the heads of the
         // following MSMs (the eight MSMs of a Pinocchio proof are independent)
         be.tail_begin(tw);
-        if (n > cap) {
+        if ((uint64_t)n * wins_per_set > cap) {
             const uint32_t ow = be.overflow_warps();
             KOverflowW<F> ko = {br, idx, ws.ctl_[tw], ws.tasks_[tw], (wjac<F> *)ws.partials_[tw], ow};
             be.launch(ko, ow * 32);
@@ -515,7 +552,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         uint32_t cnt_out = (cnt + R - 1) / R;
         // four lanes per node: these MSMs are small, the tree is latency-bound at every level
         KReduceWQ<F> k6 = {inS, inT, (wjac<F> *)ws.nodeS[tw][pp], (wjac<F> *)ws.nodeT[tw][pp], cnt, cnt_out, R, log2s};
-        be.launch(k6, 4 * g.W * cnt_out);
+        be.launch(k6, 4 * g.S * cnt_out);
         inS = (const wjac<F> *)ws.nodeS[tw][pp];
         inT = (const wjac<F> *)ws.nodeT[tw][pp];
         pp ^= 1;
@@ -523,7 +560,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
         log2s += opt.reduce_log2r_w;
     } while (cnt > 1);
     be.phase_mark(PH_REDUCE);
-    KFinalWQ<F> k7 = {inS, inT, out_jac, out_wire, g.W, pre ? 0u : g.c, out_host_jac};
+    KFinalWQ<F> k7 = {inS, inT, out_jac, out_wire, g.S, pre ? 0u : g.c, out_host_jac};
     be.launch(k7, 32);
     be.phase_mark(PH_FINAL);
     be.result_ready();

@@ -471,6 +471,7 @@ struct Ctx {
     void *small_w_wire = nullptr, *small_w_base = nullptr;  // lincomb scratch, 64 x 128 B each
     // transcript text scratch (vmsm_points_text): grow-only device buffers and a pinned host buffer
     uint8_t *txt_slots = nullptr, *txt_text = nullptr, *txt_host = nullptr;
+    uint8_t *txt_host_sc = nullptr;  // scalar text has its own pinned buffer: a point view and a scalar view coexist
     uint32_t *txt_lens = nullptr;
     uint64_t *txt_offsets = nullptr, *txt_sums = nullptr;
     size_t txt_cap = 0;
@@ -489,6 +490,7 @@ struct Ctx {
     size_t bs_dig_cap[2] = {0, 0}, bs_hist_cap[2] = {0, 0};
     uint32_t bs_min_terms = 1u << 15;  // smaller MSMs are latency-bound: three short kernels beat five
     bool bs_attr_set = false;
+    uint32_t seg_resident_w[2] = {0, 0};  // same for the BN256 kernels (G1 / G2)
     uint32_t seg_resident[2] = {0, 0};  // resident threads of the segmented accumulate kernels (plain / tables), cached
     uint64_t pre_min_terms = 256;  // MSMs shorter than this ignore a precomputed table (VMSM_OPT_PRE_MIN_TERMS)
     bool phase_timing = false;
@@ -713,6 +715,17 @@ struct CudaBE {
             else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, vmsm_kernel<KAccumulateSeg>, KAccumulateSeg::kBlock, KAccumulateSeg::kDynSmem);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
             r = (uint32_t)(blocks > 0 ? blocks : 4) * (uint32_t)(sms > 0 ? sms : 148) * KAccumulateSeg::kBlock;
+        }
+        return r;
+    }
+    template <class F>
+    uint32_t resident_threads_w() {
+        uint32_t &r = c->seg_resident_w[sizeof(typename F::T) > 32 ? 1 : 0];
+        if (!r) {
+            int blocks = 0, sms = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, vmsm_kernel<KAccumulateSegW<F>>, KAccumulateSegW<F>::kBlock, 0);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+            r = (uint32_t)(blocks > 0 ? blocks : 2) * (uint32_t)(sms > 0 ? sms : 148) * KAccumulateSegW<F>::kBlock;
         }
         return r;
     }
@@ -1260,6 +1273,7 @@ int32_t vmsm_ctx_destroy(uint64_t ctx) {
     for (uint32_t k = 0; k < kLaRing; k++) cudaEventDestroy(c->ev_la_sorted[k]);
     cudaFree(c->txt_slots), cudaFree(c->txt_text), cudaFree(c->txt_lens), cudaFree(c->txt_offsets), cudaFree(c->txt_sums);
     if (c->txt_host) cudaFreeHost(c->txt_host);
+    if (c->txt_host_sc) cudaFreeHost(c->txt_host_sc);
     cudaFree(c->res_w_dev), cudaFreeHost(c->res_w_host), cudaFree(c->fbw_table[0]), cudaFree(c->fbw_table[1]);
     cudaFree(c->small_w_wire), cudaFree(c->small_w_base);
     if (c->mailbox) {
@@ -1366,6 +1380,14 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
         case VMSM_OPT_QUAD_THRESHOLD:
             if (value < 0 || value > (1 << 24)) return fail(VMSM_ERR_INVALID, "quad threshold out of range");
             c->opt.quad_threshold = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_BN_PRE_SETS:
+            if (value < 0 || value > 64) return fail(VMSM_ERR_INVALID, "bucket sets out of range");
+            c->opt.pre_sets_w = (uint32_t)value;
+            return VMSM_OK;
+        case VMSM_OPT_BN_SEG_LEN:
+            if (value < 0 || value > 4096) return fail(VMSM_ERR_INVALID, "segment length out of range");
+            c->opt.seg_len_w = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_BLOCK_SORT:
             c->opt.block_sort = value != 0;
@@ -1564,7 +1586,8 @@ static int32_t text_ensure(Ctx *c, uint64_t n) {
     if (n <= c->txt_cap) return VMSM_OK;
     cudaFree(c->txt_slots), cudaFree(c->txt_text), cudaFree(c->txt_lens), cudaFree(c->txt_offsets), cudaFree(c->txt_sums);
     if (c->txt_host) cudaFreeHost(c->txt_host);
-    c->txt_slots = c->txt_text = c->txt_host = nullptr;
+    if (c->txt_host_sc) cudaFreeHost(c->txt_host_sc);
+    c->txt_slots = c->txt_text = c->txt_host = c->txt_host_sc = nullptr;
     c->txt_lens = nullptr;
     c->txt_offsets = c->txt_sums = nullptr;
     c->txt_cap = 0;
@@ -1575,12 +1598,14 @@ static int32_t text_ensure(Ctx *c, uint64_t n) {
     CU(cudaMalloc(&c->txt_offsets, cap * 8));
     CU(cudaMalloc(&c->txt_sums, (cap / 1024 + 2) * 8));
     CU(cudaHostAlloc(&c->txt_host, cap * VMSM_TEXT_SLOT, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->txt_host_sc, cap * VMSM_SCALAR_TEXT_SLOT, cudaHostAllocDefault));
     c->txt_cap = cap;
     return VMSM_OK;
 }
 
 // slots + lens (already launched on the main stream) -> ", "-joined text in c->txt_host; *len = its length
-static int32_t text_finish(Ctx *c, CudaBE &be, uint64_t n, uint32_t slot_bytes, uint64_t *len) {
+static int32_t text_finish(Ctx *c, CudaBE &be, uint64_t n, uint32_t slot_bytes, uint64_t *len, uint8_t *host = nullptr) {
+    if (!host) host = c->txt_host;
     uint32_t nblk = (uint32_t)((n + 1023) / 1024);
     vmsm_lens_block_sums<<<nblk, 1024, 0, c->stream>>>(c->txt_lens, (uint32_t)n, c->txt_sums);
     vmsm_lens_scan_sums<<<1, 32, 0, c->stream>>>(c->txt_sums, nblk);
@@ -1592,7 +1617,7 @@ static int32_t text_finish(Ctx *c, CudaBE &be, uint64_t n, uint32_t slot_bytes, 
     be.note(cudaStreamSynchronize(c->stream));
     if (be.err != cudaSuccess) return fail(VMSM_ERR_CUDA, "text: %s", cudaGetErrorString(be.err));
     uint64_t total = *reinterpret_cast<uint64_t *>(c->pin);
-    CU(cudaMemcpyAsync(c->txt_host, c->txt_text, total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(host, c->txt_text, total, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *len = total;
     return VMSM_OK;
@@ -2096,12 +2121,12 @@ int32_t vmsm_scalars_text_ptr(uint64_t ctx, uint64_t sc, uint64_t off, uint64_t 
     if (n > (1ull << 26)) return fail(VMSM_ERR_UNSUPPORTED, "too many scalars");
     int32_t rc = text_ensure(c, n ? n : 1);
     if (rc) return rc;
-    *text = c->txt_host;
+    *text = c->txt_host_sc;
     if (!n) return VMSM_OK;
     CudaBE be(c);
     KScalarText kt = {it->second.data + off * 8, c->txt_slots, c->txt_lens, (uint32_t)n, is_signed};
     be.launch(kt, (uint32_t)n);
-    return text_finish(c, be, n, VMSM_SCALAR_TEXT_SLOT, len);
+    return text_finish(c, be, n, VMSM_SCALAR_TEXT_SLOT, len, c->txt_host_sc);
 }
 
 int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,

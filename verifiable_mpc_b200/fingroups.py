@@ -371,12 +371,23 @@ class DevicePointList:
             return b"[" + self.dev.text_bytes(self.off, self.n) + b"]"
         return repr(self).encode("utf-8")
 
+    def prefetch_repr(self):
+        """Produce the text of the current view now (device kernels + copy into the context's pinned buffer) and keep
+        the view for the next ``feed_repr``.  The prover calls this while the commitments that precede the generators in
+        the round's pre-image are still being computed; the view is dropped by anything that changes the vector."""
+        if hasattr(self.dev, "text_view"):
+            self._text = ((self.dev.handle, self.off, self.n), self.dev.text_view(self.off, self.n))
+
     def feed_repr(self, h):
         """h.update(repr(self).encode()) with the text hashed IN PLACE from the context's pinned buffer: no Python
         bytes object of the ~160 bytes per point is ever built (two 10 MB copies per round at N = 2^16 otherwise)."""
         if hasattr(self.dev, "text_view"):
+            key, view = getattr(self, "_text", None) or (None, None)
+            self._text = None  # single use: the pinned buffer belongs to the next text call
+            if key != (self.dev.handle, self.off, self.n):
+                view = self.dev.text_view(self.off, self.n)
             h.update(b"[")
-            h.update(self.dev.text_view(self.off, self.n))
+            h.update(view)
             h.update(b"]")
         else:
             h.update(self.repr_bytes())
