@@ -208,7 +208,9 @@ int32_t vmsm_msm_async(uint64_t ctx, uint64_t pts, uint64_t off, uint64_t n, con
 int32_t vmsm_msm_dev(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
                      uint32_t slot);
 /* As vmsm_msm_dev with n_extra more terms whose scalars come from the host (the k^{L(z)} factor of the cross terms):
- * A_i = g_R^{z_L} * k^{L_R(z_L)} with z resident in HBM -- verifiable_mpc/ac20/compressed_pivot.py:41-42.  Ed25519. */
+ * A_i = g_R^{z_L} * k^{L_R(z_L)} with z resident in HBM -- verifiable_mpc/ac20/compressed_pivot.py:41-42; on the BN256
+ * groups the seven mid-wire sums of pynocchio.py:248-262 share ONE device-resident witness and append their own
+ * zero-knowledge delta terms this way.  Both vectors on the same curve; at most 64 extra terms. */
 int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, uint64_t sc, uint64_t soff,
                          uint64_t extra_pts, uint64_t extra_off, uint64_t n_extra, const uint8_t *extra_scalars_le32,
                          uint32_t slot);

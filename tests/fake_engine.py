@@ -51,8 +51,8 @@ def _unpack_scalars(raw):
 class FakeScalars:
     """Device-resident scalar vector modulo the Ed25519 group order, on Python ints."""
 
-    def __init__(self, ctx, vals):
-        self.ctx, self.vals, self.handle = ctx, [int(v) % E.L for v in vals], 1
+    def __init__(self, ctx, vals, order=E.L):
+        self.ctx, self.vals, self.handle = ctx, [int(v) % order for v in vals], 1
 
     @property
     def n(self):
@@ -146,8 +146,8 @@ class FakeContext:
         return E.msm_naive(sc, points.pts[off:off + len(sc)])
 
     def upload_scalars(self, scalars, order=E.L):
-        assert order == E.L
-        return FakeScalars(self, _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else scalars)
+        assert order in (E.L, BN.N)
+        return FakeScalars(self, _unpack_scalars(scalars) if isinstance(scalars, (bytes, bytearray)) else scalars, order)
 
     def scalars_dot(self, a, aoff, b, boff, n):
         assert aoff + n <= a.n and boff + n <= b.n
@@ -156,11 +156,14 @@ class FakeContext:
     def msm_dev_ext(self, points, poff, n, scalars, soff, extra, extra_off, extra_scalars, slot=0):
         FakeContext.calls += 1
         assert poff + n <= points.n and soff + n <= scalars.n
-        sc = scalars.vals[soff:soff + n] + [int(s) % E.L for s in extra_scalars]
+        assert extra_off + len(extra_scalars) <= extra.n and len(extra_scalars) <= 64
+        curve = getattr(points, "curve", 0)
+        assert getattr(extra, "curve", 0) == curve
+        sc = scalars.vals[soff:soff + n] + [int(s) % (BN.N if curve else E.L) for s in extra_scalars]
         bases = points.pts[poff:poff + n] + extra.pts[extra_off:extra_off + len(extra_scalars)]
         if not hasattr(self, "_slots"):
             self._slots = {}
-        self._slots[slot] = E.msm_naive(sc, bases)
+        self._slots[slot] = BN.msm_naive(BN.FP2 if curve == 2 else BN.FP, sc, bases) if curve else E.msm_naive(sc, bases)
 
     def msm_dev_ext_dot(self, points, poff, n, scalars, soff, extra, extra_off, dot_a, dot_aoff, dot_b, dot_boff, dot_n,
                         slot=0):
@@ -173,7 +176,9 @@ class FakeContext:
             n = min(points.n - poff, scalars.n - soff)
         if not hasattr(self, "_slots"):
             self._slots = {}
-        self._slots[slot] = E.msm_naive(scalars.vals[soff:soff + n], points.pts[poff:poff + n])
+        curve = getattr(points, "curve", 0)
+        sc, bases = scalars.vals[soff:soff + n], points.pts[poff:poff + n]
+        self._slots[slot] = BN.msm_naive(BN.FP2 if curve == 2 else BN.FP, sc, bases) if curve else E.msm_naive(sc, bases)
 
     def msm_async(self, points, ptr, off, n, slot):
         import ctypes

@@ -124,6 +124,11 @@ def main():
                   "table_build_s": t_tab if tables else None,
                   "note": "8 MSMs (6 G1 + 1 G2 over mid wires, 1 G1 over h), bases resident, scalars packed on the host per call"})
         if args.profile:
+            twin.TRACE = []
+            twin.compute_proof(Q, c, H(), prepared, D)
+            t0 = twin.TRACE[0][1]
+            print("compute_proof timeline (ms):", [(lab, round(1e3 * (t - t0), 3)) for lab, t in twin.TRACE])
+            twin.TRACE = None
             import cProfile
             import io
             import pstats

@@ -29,7 +29,8 @@ def main():
                     help="-1: plain path; 0 / 8..16: tables of 2^(c*w)*P_i with this window (0 = by size)")
     ap.add_argument("--pre-sets", type=int, nargs="+", default=[0], help="VMSM_OPT_PRE_SETS values to sweep")
     ap.add_argument("--seg-len", type=int, nargs="+", default=[0], help="VMSM_OPT_SEG_LEN values to sweep (0 = whole waves)")
-    ap.add_argument("--block-sort", type=int, nargs="+", default=[1], help="VMSM_OPT_BLOCK_SORT values to sweep")
+    ap.add_argument("--seg-mode", type=int, nargs="+", default=[1], help="VMSM_OPT_SEG_MODE values to sweep")
+    ap.add_argument("--block-sort", type=int, nargs="+", default=[0], help="VMSM_OPT_BLOCK_SORT values to sweep")
     ap.add_argument("--block-sort-min", type=int, default=-1, help="VMSM_OPT_BLOCK_SORT_MIN")
     ap.add_argument("--acc-carveout", type=int, default=-2, help="VMSM_OPT_ACC_CARVEOUT (-1 = driver default)")
     ap.add_argument("--steps", type=int, default=10)
@@ -60,6 +61,8 @@ def main():
                                                        for a in args.async_tail for b in args.sort_blocks
                                                        for q in (args.pre_sets if pre >= 0 else [0]) for z in args.seg_len
                                                        for y in args.block_sort]:
+                  for sm in args.seg_mode:
+                    ctx.set_option(_lib.OPT_SEG_MODE, sm)
                     ctx.set_option(_lib.OPT_BLOCK_SORT, bs)
                     ctx.set_option(_lib.OPT_PRE_SETS, ps)
                     ctx.set_option(_lib.OPT_SEG_LEN, sl)
@@ -82,7 +85,7 @@ def main():
                     host_ms = 1e3 * (time.perf_counter() - h0) / args.steps  # host time to ISSUE one MSM (no sync)
                     ms = ctx.timer_stop() / args.steps
                     ph, calls = ctx.phase_times()
-                    rec = {"log2n": logn, "block_sort": bs, "acc_carveout": args.acc_carveout, "precompute": pre, "pre_sets": ps, "seg_len": sl, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "host_issue_ms": round(host_ms, 4), "Mpts_s": n / ms / 1e3,
+                    rec = {"log2n": logn, "seg_mode": sm, "block_sort": bs, "acc_carveout": args.acc_carveout, "precompute": pre, "pre_sets": ps, "seg_len": sl, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "host_issue_ms": round(host_ms, 4), "Mpts_s": n / ms / 1e3,
                            "imad_peak_tlps": peak, "phase_ms": {k: round(v / calls, 5) for k, v in ph.items()}}
                     print(json.dumps(rec), flush=True)
                     if out:

@@ -261,8 +261,7 @@ def vector_commitment(x, gamma, g, h):
     dev = as_device_list(g, group)
     order = group.order
     # ints and elements of the exponent field in one C pass (hostpack); anything else through the reference's _int
-    cls = hostpack.field_class_for(x, order) if isinstance(x, (list, tuple)) else False
-    raw = hostpack.pack_residues(x, cls, order) if cls is not False else None
+    raw = hostpack.pack_auto(x, order) if isinstance(x, (list, tuple)) else None
     if raw is None:
         raw = pack_scalars([_int(v) for v in x], order)
     raw += pack_scalars([_int(gamma)], order)

@@ -21,6 +21,8 @@ static int lt_le32(const unsigned char *a, const unsigned char *b) { /* a < b, 3
  * Every element must be an exact int or an instance of exactly `cls` (a prime-field element class whose modulus is
  * `order`, carrying its residue in `.value`); anything else -> None (the caller takes its generic path); with
  * allow_int false, ints are "anything else" too (the transcript text of a plain int differs from a field element's).
+ * cls = True: the class is taken from the first non-int element (hostpack.field_class_for's rule, without a separate
+ * Python pass over the list).
  * Values outside
  * [0, order) -- negative ints, unreduced products, compressed_pivot.py:66,134 -- are reduced with Python's %. */
 static PyObject *pack_residues(PyObject *self, PyObject *args) {
@@ -53,6 +55,19 @@ static PyObject *pack_residues(PyObject *self, PyObject *args) {
         int owned = 0;
         if (allow_int && PyLong_CheckExact(item)) {
             v = item;
+        } else if (cls == Py_True) {
+            /* auto: the first non-int element fixes the class -- a prime-field class with this modulus and a .value */
+            PyObject *t = (PyObject *)Py_TYPE(item);
+            PyObject *m = PyObject_GetAttrString(t, "modulus");
+            int same = m ? PyObject_RichCompareBool(m, order, Py_EQ) : 0;
+            Py_XDECREF(m);
+            if (same <= 0 || !PyObject_HasAttr(item, str_value)) {
+                PyErr_Clear();
+                goto unsupported;
+            }
+            cls = t;
+            i--, buf -= 32; /* again, now as an instance of cls */
+            continue;
         } else if (cls != Py_None && (PyObject *)Py_TYPE(item) == cls) {
             v = PyObject_GetAttr(item, str_value);
             owned = 1;

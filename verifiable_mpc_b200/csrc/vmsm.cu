@@ -2138,13 +2138,13 @@ int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, 
     if (it == c->points.end() || ie == c->points.end()) return fail(VMSM_ERR_INVALID, "invalid points handle");
     auto is = c->scalars.find(sc);
     if (is == c->scalars.end()) return fail(VMSM_ERR_INVALID, "invalid scalars handle");
-    if (it->second.curve != VMSM_CURVE_ED25519 || ie->second.curve != VMSM_CURVE_ED25519)
-        return fail(VMSM_ERR_UNSUPPORTED, "msm_dev_ext: Ed25519 only");
+    if (it->second.curve != ie->second.curve) return fail(VMSM_ERR_INVALID, "msm_dev_ext: the two point vectors are on different curves");
     if (poff > it->second.n || n > it->second.n - poff) return fail(VMSM_ERR_INVALID, "Not enough generators.");
     if (soff > is->second.n || n > is->second.n - soff) return fail(VMSM_ERR_INVALID, "scalar range out of bounds");
     if (extra_off > ie->second.n || n_extra > ie->second.n - extra_off)
         return fail(VMSM_ERR_INVALID, "extra range out of bounds");
     if (n_extra && !extra_scalars_le32) return fail(VMSM_ERR_INVALID, "null argument");
+    if (n_extra > 64) return fail(VMSM_ERR_INVALID, "at most 64 extra terms");
     if (slot >= kSlots - 1) return fail(VMSM_ERR_INVALID, "slot must be < %u", kSlots - 1);
     const uint64_t tot = n + n_extra;
     const int b = (int)(c->async_seq++ & 1);
@@ -2165,7 +2165,13 @@ int32_t vmsm_msm_dev_ext(uint64_t ctx, uint64_t pts, uint64_t poff, uint64_t n, 
     CU(cudaEventRecord(c->ev_copied[b], c->copy));
     if (c->async_sort) c->scalars_ready = c->ev_copied[b];
     else CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-    int32_t rc = run_msm_ps(c, it->second, poff, c->astage[b], tot, slot, &ie->second, extra_off, (uint32_t)n_extra);
+    // extra terms that simply continue the main range of the same vector (the delta terms a Pinocchio key keeps right
+    // after its mid-wire elements, pynocchio.py:248-262) make one plain range, which also keeps the vector's table usable
+    const bool contiguous = extra_pts == pts && extra_off == poff + n;
+    PointSet *eps = contiguous ? nullptr : &ie->second;
+    const uint32_t nx = contiguous ? 0u : (uint32_t)n_extra;
+    int32_t rc = it->second.curve == VMSM_CURVE_ED25519 ? run_msm_ps(c, it->second, poff, c->astage[b], tot, slot, eps, extra_off, nx)
+                                                        : w_run_msm_any(c, it->second, poff, c->astage[b], tot, slot, eps, extra_off, nx);
     if (rc) return rc;
     CU(cudaEventRecord(c->ev_consumed[b], c->async_sort ? c->sort : c->stream));
     c->astage_used[b] = true;

@@ -31,6 +31,15 @@ def pack_residues(seq, cls, order, allow_int=True):
     return b"".join(out)
 
 
+def pack_auto(seq, order):
+    """``pack_residues`` with the element class taken from the first non-int element (``field_class_for``'s rule) in
+    the same pass: ints and / or elements of ONE prime-field class with this modulus -> bytes, anything else -> None."""
+    if _c is not None:
+        return _c.pack_residues(seq, True, order, True)
+    cls = field_class_for(seq, order)
+    return None if cls is False else pack_residues(seq, cls, order)
+
+
 def field_class_for(seq, order):
     """The field-element class to expect in ``seq``: the type of its first non-int element when that is a prime-field
     class with this modulus, else None (ints only)."""

@@ -38,8 +38,7 @@ def point_add(a, b):
 def _pack(values):
     """Witness / quotient coefficients (ints or elements of GF(n)) -> packed residues mod n; one C loop when the
     hostpack helper is built, ``int(v) % n`` per element otherwise (what the reference's ``int(c[i]) * P`` sees)."""
-    cls = hostpack.field_class_for(values, BN_N)
-    raw = hostpack.pack_residues(values, cls, BN_N) if cls is not False else None
+    raw = hostpack.pack_auto(values, BN_N)
     return raw if raw is not None else pack_scalars([int(v) for v in values], BN_N)
 
 
@@ -154,6 +153,18 @@ def generate_evalkey(td, qap, gen):
     return {k: out[k] for k in order_keys}
 
 
+RESIDENT_WITNESS = True  # prepared keys: one upload of the witness shared by the seven mid-wire sums
+
+TRACE = None  # tools/bench_bn256.py --trace sets a list: (label, perf_counter()) marks inside compute_proof
+
+
+def _mark(label):
+    if TRACE is not None:
+        import time
+
+        TRACE.append((label, time.perf_counter()))
+
+
 def compute_proof(qap, c, h, evalkey, deltas=None):
     """Pinocchio proof elements for witness ``c`` and quotient polynomial ``h`` (reference :228-273).
 
@@ -167,9 +178,27 @@ def compute_proof(qap, c, h, evalkey, deltas=None):
     mid = prepared.indices_mid if prepared else list(qap.indices_mid)
     if prepared:
         assert len(h) <= prepared.h_len, "Not enough generators."
+    _mark("start")
     c_mid_raw = _pack([c[i] for i in mid])
+    _mark("packed witness")
 
     jobs, keep, proof = [], [], {}  # jobs: (name, group, device points, owned?)
+    witness = {}  # context id -> the packed witness as a device-resident scalar vector (prepared keys)
+
+    def issue_resident(name, group, dev, extra_scalars):
+        """Mid-wire sum over a prepared key: the witness is uploaded ONCE and read in place by all seven sums; a sum's
+        zero-knowledge terms continue the key vector and bring their scalars along (vmsm_msm_dev_ext).  No per-sum
+        staging of 32 bytes x |mid| from pageable host memory, which made every issue wait for the sum two before it."""
+        ctx = group._ctx()
+        sc = witness.get(id(ctx))
+        if sc is None:
+            sc = witness[id(ctx)] = ctx.upload_scalars(c_mid_raw, BN_N)
+        jobs.append((name, group, dev, False))
+        slot = len(jobs) - 1
+        if extra_scalars:
+            ctx.msm_dev_ext(dev, 0, len(mid), sc, 0, dev, len(mid), extra_scalars, slot=slot)
+        else:
+            ctx.msm_dev(dev, sc, slot=slot, poff=0, soff=0, n=len(mid))
 
     def issue(name, group, dev, owned, raw):
         buf = ctypes.create_string_buffer(raw, len(raw)) if raw else ctypes.create_string_buffer(1)
@@ -180,10 +209,11 @@ def compute_proof(qap, c, h, evalkey, deltas=None):
     try:
         # the G2 sum first: its tail is the longest and then overlaps the other seven
         for name, template, delta_terms in sorted(_MID_SUMS, key=lambda t: not t[0].endswith("g2")):
-            raw = c_mid_raw
-            if deltas is not None:
-                raw = raw + pack_scalars([int(getattr(deltas, attr)) for attr, _ in delta_terms], BN_N)
-            if prepared:
+            extra = [int(getattr(deltas, attr)) for attr, _ in delta_terms] if deltas is not None else []
+            raw = c_mid_raw + pack_scalars(extra, BN_N) if extra else c_mid_raw
+            if prepared and RESIDENT_WITNESS and mid:
+                issue_resident(name, prepared.groups[name], prepared.bases[name], extra)
+            elif prepared:
                 issue(name, prepared.groups[name], prepared.bases[name], False, raw)
             else:
                 pts = [evalkey[template.format(i=i)] for i in mid]
@@ -191,19 +221,25 @@ def compute_proof(qap, c, h, evalkey, deltas=None):
                     pts += [evalkey[k] for _, k in delta_terms]
                 group = type(pts[0])
                 issue(name, group, group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id), True, raw)
+        _mark("issued mid sums")
         # the coefficients of h are packed while the device works on the seven sums already issued
         raw_h = _pack(h.coeffs[:len(h)] if isinstance(h.coeffs, list) else [h.coeffs[i] for i in range(0, len(h))])
+        _mark("packed h")
         if prepared:
             issue("h*g1", prepared.groups["h*g1"], prepared.bases["h*g1"], False, raw_h)
         else:
             pts = [evalkey["s^" + str(i) + "*g1"] for i in range(0, len(h))]
             group = type(pts[0])
             issue("h*g1", group, group._ctx().upload_points([p.affine() for p in pts], curve=group.curve_id), True, raw_h)
+        _mark("issued h sum")
         for slot, (name, group, dev, owned) in enumerate(jobs):
             proof[name] = group._make(group._ctx().result(slot, curve=group.curve_id))
+            _mark("result " + name)
     finally:
         for name, group, dev, owned in jobs:
             if owned:
                 dev.free()
+        for sc in witness.values():
+            sc.free()
     # same key order as the reference's dict
     return {name: proof[name] for name in [t[0] for t in _MID_SUMS] + ["h*g1"]}
