@@ -10,8 +10,9 @@ bases resident in HBM (a batch, so that the driver's K = 20 steps time ~0.7 s in
 split of (N * 2^log2n)-term MSMs, every rank computes the partial sum of its slice, rank 0 adds the N partials
 ("weak" scaling: per-GPU work fixed).  Prints ONE JSON line on rank 0.  Beside the headline the same line carries the
 rest of BASELINE.json's metric: `sweep` (2^16, 2^18 points/s and roofline fraction), `fixed_generators` (the same sizes
-over precomputed generator tables), `ac20` (compressed-pivot prove / verify latency at N = 2^16 with a CPU figure) and
-`strong` (one fixed 2^20-term MSM split over the N GPUs).
+over precomputed generator tables), `ac20` (compressed-pivot prove / verify latency at N = 2^16 with a CPU figure),
+`bn256` (the BN256 G1 / G2 prover-key MSMs and the compute_proof twin for a 2^14-constraint QAP) and `strong` (one fixed
+2^20-term MSM split over the N GPUs).
 """
 import argparse
 import json
@@ -284,6 +285,70 @@ def ac20_block(ctx):
                                        "look-alike in the build container (tests/golden/make_ac20_big_golden.py 16)"}}
 
 
+# BN256 work model: Montgomery multiplication 136 limb products; Jacobian mixed addition 7M+4S, addition
+# 11M+5S, doubling 2M+5S; G2 (Karatsuba Fp2) x 3
+BN_M = 136
+BN_MADD, BN_ADD, BN_DBL = 11 * BN_M, 16 * BN_M, 7 * BN_M
+
+
+def lp_msm_bn(n, c, g2=False):
+    W = -(-257 // c)
+    lp = n * W * BN_MADD + W * 2 * (1 << (c - 1)) * BN_ADD + (W - 1) * c * BN_DBL + W * BN_ADD
+    return 3 * lp if g2 else lp
+
+
+def bn256_block(ctx, peak_tlps, logn=14):
+    """BASELINE.json config 4: the prover-key multi-exponentiations of a 2^14-constraint QAP.  Device-timed G1 / G2 MSMs
+    over the key tables (and the plain path beside them), and the wall time of the compute_proof twin (reference
+    signature: witness and quotient coefficients as host lists in, proof dict out) on a synthetic prepared key."""
+    from tools import bench_bn256
+    from verifiable_mpc_b200 import _lib, fingroups
+    from verifiable_mpc_b200.trinocchio import pynocchio as twin
+
+    n = 1 << logn
+    out = {"log2n": logn, "msm": []}
+    for curve, name in ((1, "G1"), (2, "G2")):
+        pairs = [(ctx.fixed_base(seed=SEED_BASES + 0x7000 + 16 * k, n=n, curve=curve),
+                  ctx.synth_scalars(SEED_SCALARS + 0x7000 + 16 * k, n, curve=curve)) for k in range(NSETS)]
+        count = 96
+        ms_plain = time_msms(ctx, pairs, count)
+        plain_last = ctx.result((count - 1) % 48, curve=curve)
+        for pts, _ in pairs:
+            pts.precompute()
+        ctx.sync()
+        ms = time_msms(ctx, pairs, count)
+        ok = bool(ctx.result((count - 1) % 48, curve=curve) == plain_last)
+        lp_min = min(lp_msm_bn(n, c, curve == 2) for c in range(4, 17))
+        out["msm"].append({"group": name, "ms_per_msm_key_tables": ms, "ms_per_msm_plain": ms_plain, "msms_timed": count,
+                           "points_per_s": n / (ms * 1e-3), "equals_plain_path_result": ok,
+                           "frac_on_survey_work_model": lp_min / (ms * 1e-3) / (peak_tlps * 1e12),
+                           "frac_on_work_of_the_executed_window": lp_msm_bn(n, 13, curve == 2) / (ms * 1e-3) / (peak_tlps * 1e12),
+                           "lp_survey_model": lp_min, "lp_executed_window_c13": lp_msm_bn(n, 13, curve == 2)})
+        for pts, sc in pairs:
+            pts.free()
+            sc.free()
+    old = fingroups.BN256Point.context
+    try:
+        Q, c, H, D, prepared = bench_bn256.synthetic_proof_case(ctx, n)
+        prepared.precompute()
+        ctx.sync()
+        twin.compute_proof(Q, c, H(), prepared, D)
+        best = 1e9
+        for _ in range(5):
+            t0 = time.perf_counter()
+            twin.compute_proof(Q, c, H(), prepared, D)
+            best = min(best, time.perf_counter() - t0)
+        out["compute_proof_ms"] = 1e3 * best
+        out["compute_proof"] = ("trinocchio.pynocchio.compute_proof twin, |mid| = len(h) = 2^%d, prepared key with tables, witness "
+                                "and h as host lists of ints (packed and uploaded inside the timed call), 8 MSMs (6 G1 + 1 G2 "
+                                "over the mid wires, 1 G1 over h) with the zero-knowledge delta terms; best of 5" % logn)
+        for dev in prepared.bases.values():
+            dev.free()
+    finally:
+        fingroups.BN256Point.context = old
+    return out
+
+
 def run_gpu(args, rank, world, dist):
     from tools import dist_util
     from verifiable_mpc_b200 import Context, _lib, shard, synth
@@ -442,10 +507,11 @@ def run_gpu(args, rank, world, dist):
     strong = strong_block(ctx, dist, rank, world, issue_seq=seq_counter, bases_full=bases if args.log2n == STRONG_LOG2N else None,
                           scal_full=scal if args.log2n == STRONG_LOG2N else None, recycle=recycle_slots, barrier=barrier)
 
-    sweep = fixed = ac20 = None
+    sweep = fixed = ac20 = bn256 = None
     if world == 1 and args.extras:
         sweep, fixed = sweep_block(ctx, peak_tlps)
         ac20 = ac20_block(ctx)
+        bn256 = bn256_block(ctx, peak_tlps)
 
     if rank != 0:
         return
@@ -506,6 +572,7 @@ def run_gpu(args, rank, world, dist):
         line["sweep"] = sweep
         line["fixed_generators"] = fixed
         line["ac20"] = ac20
+        line["bn256"] = bn256
     if args.cpu_baseline:
         cores = os.cpu_count() or 1
         rate, dt = cpu_reference_rate(args.cpu_points, cores)

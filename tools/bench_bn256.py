@@ -13,6 +13,45 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def synthetic_proof_case(ctx, m, seed=7):
+    """A synthetic compute_proof input below the QAP front end: |mid| = len(h) = m, every base vector of the evaluation
+    key generated on the device (r_i * G) instead of uploaded.  Returns (qap, witness, h class, deltas, prepared key)."""
+    from verifiable_mpc_b200 import fingroups
+    from verifiable_mpc_b200.engine import BN_N
+    from verifiable_mpc_b200.trinocchio import pynocchio as twin
+
+    g1 = fingroups.EllipticCurve("BN256", "jacobian")
+    g2 = fingroups.EllipticCurve("BN256_twist", "jacobian")
+    fingroups.BN256Point.context = ctx
+    rng = random.Random(seed)
+
+    class Q:
+        indices_mid = range(3, 3 + m)
+
+    class H:
+        coeffs = [rng.randrange(BN_N) for _ in range(m)]
+
+        def __len__(self):
+            return len(self.coeffs)
+
+    class D:
+        v, w, y = (rng.randrange(BN_N) for _ in range(3))
+
+    c = [rng.randrange(BN_N) for _ in range(m + 3)]
+
+    class Prepared(twin.PreparedEvalKey):
+        def __init__(self):
+            self.indices_mid, self.h_len, self.groups, self.bases = list(Q.indices_mid), m, {}, {}
+            for k, (name, _, deltas) in enumerate(twin._MID_SUMS):
+                group = g2 if name.endswith("g2") else g1
+                self.groups[name] = group
+                self.bases[name] = ctx.fixed_base(seed=100 + k, n=m + len(deltas), curve=group.curve_id)
+            self.groups["h*g1"] = g1
+            self.bases["h*g1"] = ctx.fixed_base(seed=99, n=m, curve=1)
+
+    return Q, c, H, D, Prepared()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2n", type=int, nargs="+", default=[10, 12, 14])
@@ -71,39 +110,8 @@ def main():
                 s.free()
 
     if not args.no_proof:
-        # compute_proof twin on a synthetic QAP of 2^14 mid wires
-        g1 = fingroups.EllipticCurve("BN256", "jacobian")
-        g2 = fingroups.EllipticCurve("BN256_twist", "jacobian")
-        fingroups.BN256Point.context = ctx
         m = 1 << max(args.log2n)
-        rng = random.Random(7)
-
-        class Q:
-            indices_mid = range(3, 3 + m)
-
-        class H:
-            coeffs = [rng.randrange(BN_N) for _ in range(m)]
-
-            def __len__(self):
-                return len(self.coeffs)
-
-        class D:
-            v, w, y = (rng.randrange(BN_N) for _ in range(3))
-
-        c = [rng.randrange(BN_N) for _ in range(m + 3)]
-
-        class Prepared(twin.PreparedEvalKey):
-            """Synthetic key: every base vector is generated on the device (r_i * G) instead of uploaded."""
-
-            def __init__(self):
-                self.indices_mid, self.h_len, self.groups, self.bases = list(Q.indices_mid), m, {}, {}
-                for k, (name, _, deltas) in enumerate(twin._MID_SUMS):
-                    group = g2 if name.endswith("g2") else g1
-                    self.groups[name] = group
-                    self.bases[name] = ctx.fixed_base(seed=100 + k, n=m + len(deltas), curve=group.curve_id)
-                self.groups["h*g1"] = g1
-                self.bases["h*g1"] = ctx.fixed_base(seed=99, n=m, curve=1)
-
+        Q, c, H, D, prepared = synthetic_proof_case(ctx, m)
         prepared = Prepared()
         for tables in (False, True):
             if tables:
