@@ -371,6 +371,7 @@ static uint32_t bn_msm(const uint8_t *wire, const uint8_t *scalars, uint32_t n, 
     Workspace ws;
     MsmOptions opt;
     opt.window_bits = window_bits;
+    opt.seg_mode = g_seg_mode, opt.seg_len_w = g_seg_len;
     wjac<F> oj;
     waff<F> ow;
     msm_run_w<HostBE, F>(be, ws, opt, base.data(), sc.data(), n, &oj, &ow);

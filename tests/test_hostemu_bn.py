@@ -145,3 +145,28 @@ def test_msm_over_key_tables_shared_sets_and_segments(hostemu, g2):
     finally:
         hostemu.hostemu_set_seg(1, 0)
         hostemu.hostemu_set_bn_sets(0)
+
+
+@pytest.mark.parametrize("g2", [0, 1])
+def test_plain_path_with_forced_segments(hostemu, g2):
+    """VMSM_OPT_SEG_MODE 2 on the plain path (own bucket set per window, Horner chain kept): same sums."""
+    lib = hostemu
+    lib.hostemu_bn_msm.restype = ctypes.c_uint32
+    F, G = (B.FP2, B.G2) if g2 else (B.FP, B.G1)
+    sz, n = (128 if g2 else 64), 300
+    base = [B.scalar_mul(F, G, k + 1) for k in range(8)]
+    pts = [base[i % 8] for i in range(n)]
+    dl = [i % 8 + 1 for i in range(n)]
+    sc = [prng.scalar_bn(0x840, i) for i in range(n)]
+    sc[:3] = [0, B.N - 1, 1]
+    try:
+        for seg_len in (0, 5):
+            hostemu.hostemu_set_seg(2, seg_len)
+            for c in ((0, 9) if not g2 else (9,)):
+                o = ctypes.create_string_buffer(sz)
+                err = lib.hostemu_bn_msm(g2, b"".join(B.point_to_bytes(F, p) for p in pts),
+                                         b"".join(B.fp_to_bytes(s) for s in sc), n, c, o)
+                assert err == 0
+                assert B.point_from_bytes(F, o.raw) == B.msm_known_dlog(F, sc, dl), (seg_len, c)
+    finally:
+        hostemu.hostemu_set_seg(1, 0)

@@ -66,6 +66,8 @@ def main():
     ap.add_argument("--bn-sets", type=int, nargs="+", default=[0], help="VMSM_OPT_BN_PRE_SETS values for the table MSMs")
     ap.add_argument("--bn-seg-len", type=int, nargs="+", default=[0], help="VMSM_OPT_BN_SEG_LEN values for the table MSMs")
     ap.add_argument("--seg-mode", type=int, nargs="+", default=[1], help="VMSM_OPT_SEG_MODE values for the table MSMs")
+    ap.add_argument("--plain-seg-mode", type=int, nargs="+", default=[1], help="VMSM_OPT_SEG_MODE values for the plain-path MSMs")
+    ap.add_argument("--plain-seg-len", type=int, nargs="+", default=[0], help="VMSM_OPT_BN_SEG_LEN values for the plain-path MSMs")
     ap.add_argument("--table-log2n", type=int, nargs="+", default=[], help="sizes of the table MSM sweep (default: max log2n)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -91,8 +93,10 @@ def main():
         for curve, name in [(cv, "G%d" % cv) for cv in args.curves]:
             sets = [(ctx.fixed_base(seed=0x5EEE + 16 * k, n=n, curve=curve), ctx.synth_scalars(0x5EED + 16 * k, n, curve=curve))
                     for k in range(3)]
-            for c in args.windows:
+            for c, psm, psl in [(c_, a, b) for c_ in args.windows for a in args.plain_seg_mode for b in args.plain_seg_len]:
                 ctx.set_option(_lib.OPT_WINDOW_BITS, c)
+                ctx.set_option(_lib.OPT_SEG_MODE, psm)
+                ctx.set_option(_lib.OPT_BN_SEG_LEN, psl)
                 for w in range(3):
                     ctx.msm_dev(*sets[w % 3], slot=0)
                 ctx.sync()
@@ -102,9 +106,12 @@ def main():
                     ctx.msm_dev(*sets[s % 3], slot=s % 32)
                 ms = ctx.timer_stop() / args.steps
                 ph, calls = ctx.phase_times()
-                emit({"bench": "bn256_msm", "group": name, "log2n": logn, "window": c, "ms": ms, "Mpts_s": n / ms / 1e3,
+                emit({"bench": "bn256_msm", "group": name, "log2n": logn, "window": c, "seg_mode": psm, "seg_len": psl,
+                      "ms": ms, "Mpts_s": n / ms / 1e3,
                       "phase_ms": {k: round(v / max(calls, 1), 4) for k, v in ph.items()}})
             ctx.set_option(_lib.OPT_WINDOW_BITS, 0)
+            ctx.set_option(_lib.OPT_SEG_MODE, 1)
+            ctx.set_option(_lib.OPT_BN_SEG_LEN, 0)
             for p, s in sets:
                 p.free()
                 s.free()

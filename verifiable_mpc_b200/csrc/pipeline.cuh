@@ -449,7 +449,8 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     // / (W * NB) = 4 mixed additions per bucket at 2^14 terms), shrinks by W / S.  Fewer, fuller buckets are then summed
     // by equal SEGMENTS of the sorted entries (KAccumulateSegW), as on the Ed25519 path.
     const uint32_t W_c = (scalar_bits + c) / c;
-    const bool seg = pre && n >= 256 && (opt.seg_mode == 2 || opt.seg_mode == 1);
+    // (the plain path takes the segments only when forced, VMSM_OPT_SEG_MODE 2: every window keeps its own bucket set there)
+    const bool seg = n >= 256 && (opt.seg_mode == 2 || (opt.seg_mode == 1 && pre));
     const uint32_t sets = !pre ? 0u : opt.pre_sets_w ? opt.pre_sets_w : seg ? 2u : W_c;
     MsmGeom g = make_geom(n, c, scalar_bits, sets);
     if (pre && (pre->W != g.W || (n_extra && !extra_table))) return -2;
