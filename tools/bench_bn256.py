@@ -119,7 +119,6 @@ def main():
     if not args.no_proof:
         m = 1 << max(args.log2n)
         Q, c, H, D, prepared = synthetic_proof_case(ctx, m)
-        prepared = Prepared()
         for tables in (False, True):
             if tables:
                 t0 = time.perf_counter()

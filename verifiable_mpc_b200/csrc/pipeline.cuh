@@ -132,11 +132,21 @@ inline MsmGeom make_geom(uint32_t n, uint32_t c, uint32_t scalar_bits, uint32_t 
 struct SegPlan {
     uint32_t L, T;  // entries per segment, segments (threads) launched
 };
-inline SegPlan seg_plan(uint64_t max_entries, uint32_t resident, uint32_t forced_L = 0, uint32_t min_L = 8) {
+// `fill_pct`: a launch that is a SINGLE wave is sized to this share of the resident threads instead of all of them.
+// Measured on the table-based Ed25519 path (profiles/r02/segment_length.md): 2^16 terms 0.157 -> 0.146 ms with 0.58 of a
+// wave, 2^17 terms 0.256 -> 0.234 ms with 0.69 -- fewer, longer segments leave fewer partial sums to fix up and leave
+// room on the SMs for the sort of the next MSM and the tails of the previous ones, which run at the same time.
+inline SegPlan seg_plan(uint64_t max_entries, uint32_t resident, uint32_t forced_L = 0, uint32_t min_L = 8,
+                        uint32_t fill_pct = 100) {
     SegPlan p;
     if (max_entries == 0) max_entries = 1;
     uint64_t waves = (max_entries + 32ull * resident - 1) / (32ull * resident);
     uint64_t L = (max_entries + waves * resident - 1) / (waves * resident);
+    if (waves == 1 && fill_pct < 100) {
+        uint64_t threads = (uint64_t)resident * fill_pct / 100;
+        if (threads == 0) threads = 1;
+        L = (max_entries + threads - 1) / threads;
+    }
     if (L < min_L) L = min_L;  // small MSMs: fewer threads with a handful of entries each
     if (forced_L) L = forced_L;
     p.L = (uint32_t)L;
@@ -286,7 +296,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     SegPlan sp = {0, 0};
     uint32_t *seg_bucket = nullptr, *seg_total = nullptr;
     if (seg) {
-        sp = seg_plan((uint64_t)n * g.W, be.resident_threads(pre != nullptr), opt.seg_len);
+        sp = seg_plan((uint64_t)n * g.W, be.resident_threads(pre != nullptr), opt.seg_len, 8, pre ? 65 : 100);
         if (ws_ensure_seg(be, ws, sp.T)) return -1;
         seg_bucket = ws.seg_bucket_[par], seg_total = ws.seg_total_[par];
     }
@@ -443,14 +453,19 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     // short bucket chains and a bucket tree of exactly six full radix-4 levels (4096 = 4^6); measured fastest or tied at 2^10, 2^12,
     // 2^14 and 2^16 on G1 and G2 (profiles/r01/bn256_msm_v5_windows.jsonl), 35 % faster than the work-minimising c = 11
     if (!opt.window_bits && n >= 512 && n <= (1u << 16)) c = 13;
+    // plain path from 2^11 terms: equal segments of the sorted entries instead of one thread per bucket, and then the
+    // chain length no longer depends on the window, so up to 2^14 terms the work-minimising c = 11 wins (1024 buckets
+    // per window: a bucket tree a quarter the size).  Measured, G1 / G2 ms per MSM (profiles/r02/bn256_shared_sets_segments.md):
+    // 2^12 0.252 -> 0.219 / 0.742 -> 0.615, 2^14 0.329 -> 0.279 / 0.825 -> 0.758, 2^16 (c = 13) 0.828 -> 0.502 / 2.63 -> 1.49
+    const bool seg_plain = !pre && n >= 2048 && opt.seg_mode == 1;
+    if (seg_plain && !opt.window_bits && n < (1u << 15)) c = 11;
     if (pre) c = pre->c;  // tables fix the window
     // Over key tables the bucket sets carry no weight (no Horner chain), so the W windows may share S < W sets: the
     // bucket tree, which costs as much as the accumulation at these sizes (2.3 full additions per bucket against n * W
     // / (W * NB) = 4 mixed additions per bucket at 2^14 terms), shrinks by W / S.  Fewer, fuller buckets are then summed
     // by equal SEGMENTS of the sorted entries (KAccumulateSegW), as on the Ed25519 path.
     const uint32_t W_c = (scalar_bits + c) / c;
-    // (the plain path takes the segments only when forced, VMSM_OPT_SEG_MODE 2: every window keeps its own bucket set there)
-    const bool seg = n >= 256 && (opt.seg_mode == 2 || (opt.seg_mode == 1 && pre));
+    const bool seg = (n >= 256 && (opt.seg_mode == 2 || (opt.seg_mode == 1 && pre))) || seg_plain;
     const uint32_t sets = !pre ? 0u : opt.pre_sets_w ? opt.pre_sets_w : seg ? 2u : W_c;
     MsmGeom g = make_geom(n, c, scalar_bits, sets);
     if (pre && (pre->W != g.W || (n_extra && !extra_table))) return -2;
