@@ -401,9 +401,14 @@ def run_gpu(args, rank, world, dist):
     def recycle_slots(i):
         """Result slots / mailbox entries are reused every 48 MSMs.  A single GPU needs nothing (an unread result is
         simply overwritten); with a mailbox a rank may not push MSM i into an entry the owner has not yet gathered
-        for MSM i - 48, so once per 48 MSMs the owner drains its pipeline and every rank waits for it."""
-        if dist is not None and i and i % 48 == 0:
-            ctx.sync()
+        for MSM i - 48.  Rolling flow control, no pipeline drain: every 24 MSMs the owner waits for its results of MSMs
+        i-32 .. i-25 (issued long ago; one per tail stream, so everything up to MSM i-25 has been gathered), then all
+        ranks meet at a host barrier while their GPUs keep working on the >= 24 MSMs still queued; the entries of
+        MSMs i-48 .. i-25 are then free for MSMs i .. i+23."""
+        if dist is not None and i >= 48 and i % 24 == 0:
+            if rank == 0:
+                for j in range(i - 32, i - 24):
+                    ctx.result(j % 48)
             dist.barrier()
 
     def combine(slot):

@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--block-sort", type=int, nargs="+", default=[0], help="VMSM_OPT_BLOCK_SORT values to sweep")
     ap.add_argument("--block-sort-min", type=int, default=-1, help="VMSM_OPT_BLOCK_SORT_MIN")
     ap.add_argument("--acc-carveout", type=int, default=-2, help="VMSM_OPT_ACC_CARVEOUT (-1 = driver default)")
+    ap.add_argument("--shard-self", type=int, default=0,
+                    help="1: every MSM is issued as the only shard of a 1-rank mailbox (push + gather kernels, device normalisation)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -46,6 +48,16 @@ def main():
         ctx.set_option(_lib.OPT_BLOCK_SORT_MIN, args.block_sort_min)
     if args.acc_carveout >= -1:
         ctx.set_option(_lib.OPT_ACC_CARVEOUT, args.acc_carveout)
+    if args.shard_self:
+        ctx.mailbox_create(1)
+    shard_seq = [0]
+
+    def issue(pts, sc, slot):
+        if args.shard_self:
+            shard_seq[0] += 1
+            ctx.set_option(_lib.OPT_SHARD_SEQ, shard_seq[0])
+        ctx.msm_dev(pts, sc, slot=slot)
+
     peak = ctx.imad_peak()
     out = open(args.out, "a") if args.out else None
     for logn in args.logn:
@@ -75,17 +87,19 @@ def main():
                     ctx.set_option(_lib.OPT_SORT_BUCKETS, sort)
                     ctx.set_option(_lib.OPT_REDUCE_RADIX, radix)
                     for w in range(3):
-                        ctx.msm_dev(*sets[w % 3], slot=0)
+                        issue(*sets[w % 3], slot=w)
                     ctx.sync()
                     ctx.phase_times()
                     ctx.timer_start()
                     h0 = time.perf_counter()
                     for s in range(args.steps):
-                        ctx.msm_dev(*sets[s % 3], slot=s % 32)
+                        if args.shard_self and s and s % 32 == 0:
+                            ctx.sync()  # a mailbox entry may not be pushed again before the owner has gathered it
+                        issue(*sets[s % 3], slot=s % 32)
                     host_ms = 1e3 * (time.perf_counter() - h0) / args.steps  # host time to ISSUE one MSM (no sync)
                     ms = ctx.timer_stop() / args.steps
                     ph, calls = ctx.phase_times()
-                    rec = {"log2n": logn, "seg_mode": sm, "block_sort": bs, "acc_carveout": args.acc_carveout, "precompute": pre, "pre_sets": ps, "seg_len": sl, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "host_issue_ms": round(host_ms, 4), "Mpts_s": n / ms / 1e3,
+                    rec = {"log2n": logn, "shard_self": args.shard_self, "seg_mode": sm, "block_sort": bs, "acc_carveout": args.acc_carveout, "precompute": pre, "pre_sets": ps, "seg_len": sl, "window": c, "sort": sort, "radix": radix, "cap": cap, "async_tail": at, "sort_blocks": sb, "ms": ms, "host_issue_ms": round(host_ms, 4), "Mpts_s": n / ms / 1e3,
                            "imad_peak_tlps": peak, "phase_ms": {k: round(v / calls, 5) for k, v in ph.items()}}
                     print(json.dumps(rec), flush=True)
                     if out:
