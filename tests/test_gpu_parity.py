@@ -483,7 +483,7 @@ def test_thin_counting_sort_grid(ctx, sort_blocks):
         for j in range(12):
             assert ctx.result(j) == want[j % 3], j
     finally:
-        ctx.set_option(_lib.OPT_SORT_BLOCKS, 148)
+        ctx.set_option(_lib.OPT_SORT_BLOCKS, -1)
 
 
 def test_pooled_allocations_are_recycled_safely(ctx, known_points):

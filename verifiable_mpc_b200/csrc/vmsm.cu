@@ -424,6 +424,8 @@ struct Ctx {
     bool acc_pending[2] = {false, false};
     bool async_sort = true;
     uint32_t sort_blocks = 0;
+    uint32_t sms = 148;
+    bool sort_blocks_auto = true;  // until VMSM_OPT_SORT_BLOCKS names a count
     uint32_t fold_quad_max = 1u << 13;  // measured crossover (profiles/r01/fold_kernel_quad.md)
     cudaEvent_t scalars_ready = nullptr;  // set by the entry point when the scalars of the next MSM are still in flight
     cudaEvent_t ev_head = nullptr, ev_tail[kTailWays] = {};
@@ -631,8 +633,12 @@ struct CudaBE {
     template <class F>
     void launch_sort(const F &f, uint32_t n) {
         uint32_t grid = (n + F::kBlock - 1) / F::kBlock;
-        if (!c->async_sort || !thin_sort || !c->sort_blocks || grid <= c->sort_blocks) return launch(f, n);
-        vmsm_kernel_strided<F><<<c->sort_blocks, F::kBlock, 0, cur>>>(f, n);
+        // thin grid: two blocks per SM, four below 2^18 terms (round 2, profiles/r02/sort_blocks_sweep.jsonl: with the
+        // accumulate kernels on two head streams and single-wave launches at 65 % of the resident threads, one block
+        // per SM -- the round-1 optimum -- is 1-5 % slower at every size from 2^16 to 2^20)
+        const uint32_t sb = c->sort_blocks_auto ? (n < (1u << 18) ? 4u : 2u) * c->sms : c->sort_blocks;
+        if (!c->async_sort || !thin_sort || !sb || grid <= sb) return launch(f, n);
+        vmsm_kernel_strided<F><<<sb, F::kBlock, 0, cur>>>(f, n);
         c->launches++;
         note(cudaGetLastError());
     }
@@ -1173,8 +1179,8 @@ int32_t vmsm_ctx_create(int32_t device, uint64_t *ctx) {
                     prop.major, prop.minor);
     Ctx *c = new Ctx();
     c->device = device;
-    // one block of the sort kernels per SM: measured best at 2^14 .. 2^22 (profiles/r01/sweep_sort_blocks.jsonl)
-    c->sort_blocks = (uint32_t)prop.multiProcessorCount;
+    c->sms = (uint32_t)prop.multiProcessorCount;
+    c->sort_blocks = 2 * c->sms;  // see CudaBE::launch_sort
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int h = 0; h < 2; h++) {
         CU(cudaStreamCreateWithFlags(&c->heads[h], cudaStreamNonBlocking));
@@ -1374,8 +1380,9 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             c->fold_quad_max = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_SORT_BLOCKS:
-            if (value < 0 || value > (1 << 20)) return fail(VMSM_ERR_INVALID, "sort blocks out of range");
-            c->sort_blocks = (uint32_t)value;
+            if (value < -1 || value > (1 << 20)) return fail(VMSM_ERR_INVALID, "sort blocks out of range");
+            c->sort_blocks_auto = value < 0;
+            if (value >= 0) c->sort_blocks = (uint32_t)value;
             return VMSM_OK;
         case VMSM_OPT_QUAD_THRESHOLD:
             if (value < 0 || value > (1 << 24)) return fail(VMSM_ERR_INVALID, "quad threshold out of range");
