@@ -15,7 +15,9 @@ $N --metrics $M -k regex:"KAccumulate" -c 4 --launch-skip 4 --csv --log-file gpu
 $N --metrics $M -k regex:"KDigitsHist|KScatter|vmsm_scan|vmsm_order|KReduce|KFinal|KOverflow|KCombine|KSegFix" -c 40 --launch-skip 60 --csv --log-file gpurun_out/ncu/ed_sort_tail_2p20.csv python tools/sweep.py --logn 20 --steps 6 > /dev/null 2>&1
 # 4. BN256 kernels at 2^14 (G1 then G2)
 for cv in 1 2; do
-  $N --metrics $M -k regex:"KAccumulateW|KReduceWQ|KFinalWQ|KOverflowW|KCombineW" -c 30 --launch-skip 30 --csv --log-file gpurun_out/ncu/bn_g${cv}_2p14.csv python tools/bench_bn256.py --log2n 14 --steps 4 --curves $cv --no-proof > /dev/null 2>&1
+  # plain path first (segments, c = 11, Horner chain), then the MSMs over key tables (two shared bucket sets): the last
+  # 40 matched launches belong to the table MSMs
+  $N --metrics $M -k regex:"KAccumulate|KSegFix|KSegLongFix|KReduceWQ|KFinalWQ|KOverflowW|KCombineW" -c 200 --csv --log-file gpurun_out/ncu/bn_g${cv}_2p14.csv python tools/bench_bn256.py --log2n 14 --steps 2 --curves $cv --no-proof > /dev/null 2>&1
 done
 # 5. transcript text kernels + fold kernels at N = 2^16
 $N --metrics $M -k regex:"KPointText|KTextCompact|KScalarText|KFold|KNormalize|vmsm_lens" -c 40 --csv --log-file gpurun_out/ncu/ac20_kernels_2p16.csv python tools/bench_ac20.py --log2n 16 --repeat 1 > /dev/null 2>&1
