@@ -599,7 +599,7 @@ def strong_block(ctx, dist, rank, world, issue_seq, bases_full, scal_full, recyc
     from verifiable_mpc_b200 import _lib, synth
 
     n_total = 1 << STRONG_LOG2N
-    count = 96
+    count = 480  # 0.1 s (8 GPUs) .. 0.66 s (1 GPU) per timed loop: the fill and drain of the pipeline (~1 ms) stay below 1 %
     own_full = bases_full is None
 
     def single_gpu_times():
