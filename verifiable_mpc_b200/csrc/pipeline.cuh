@@ -278,7 +278,10 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     // more buckets than resident threads (the plain path: W bucket sets; large MSMs over tables: 8 sets), equal
     // SEGMENTS of the CSR array when the windows of a table-based MSM share one bucket set (few, long buckets).
     const uint32_t W_c = (scalar_bits + c) / c;
-    const bool seg = opt.seg_mode == 2 || (opt.seg_mode == 1 && pre && n < (1u << 19));
+    // ... and on the plain path in the c = 11 regime (2^11 <= n < 49152: 24 x 1024 buckets of up to 48 entries, fewer
+    // buckets than resident threads): 2^13 terms 0.096 -> 0.090 ms, 2^15 0.138 -> 0.119 ms, and the accumulate phase of a
+    // lone MSM -- the cross-term commitments of a folding round -- 0.165 -> 0.102 ms (profiles/r02/segment_length.md)
+    const bool seg = opt.seg_mode == 2 || (opt.seg_mode == 1 && ((pre && n < (1u << 19)) || (!pre && n >= 2048 && n < 49152)));
     const uint32_t sets = !pre ? 0u : opt.pre_sets ? opt.pre_sets : seg ? 1u : (W_c < 8 ? W_c : 8u);
     MsmGeom g = make_geom(n, c, scalar_bits, sets);
     if (pre && (pre->W != g.W || (n_extra && !pre->extra_table))) return -2;
@@ -296,7 +299,7 @@ int msm_run(BE &be, Workspace &ws, const MsmOptions &opt, uint32_t scalar_bits, 
     SegPlan sp = {0, 0};
     uint32_t *seg_bucket = nullptr, *seg_total = nullptr;
     if (seg) {
-        sp = seg_plan((uint64_t)n * g.W, be.resident_threads(pre != nullptr), opt.seg_len, 8, pre ? 65 : 100);
+        sp = seg_plan((uint64_t)n * g.W, be.resident_threads(pre != nullptr), opt.seg_len, 8, 65);
         if (ws_ensure_seg(be, ws, sp.T)) return -1;
         seg_bucket = ws.seg_bucket_[par], seg_total = ws.seg_total_[par];
     }
