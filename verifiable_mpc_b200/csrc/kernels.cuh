@@ -263,6 +263,9 @@ struct KRecode {
             uint32_t code = 0xffffu;
             if (d != 0) code = d < 0 ? ((uint32_t)(-d) - 1u) | 0x8000u : (uint32_t)d - 1u;
             dig[(size_t)w * stride + tid] = (uint16_t)code;
+            // the last scalar's thread also fills the row's padding (the sort reads whole 16-byte vectors of codes)
+            if (tid + 1 == g.n)
+                for (uint32_t p = g.n; p < stride; p++) dig[(size_t)w * stride + p] = 0xffffu;
         }
     }
 };
