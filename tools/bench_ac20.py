@@ -116,6 +116,8 @@ def main():
     ap.add_argument("--transcript", default="reference", choices=["reference", "binary"],
                     help="binary: the opt-in canonical-bytes Fiat-Shamir transcript (not verifiable by the reference)")
     ap.add_argument("--precompute", action="store_true", help="fixed generators with a table (DevicePointList.precompute)")
+    ap.add_argument("--opt", type=int, nargs=2, action="append", default=[], metavar=("KEY", "VALUE"),
+                    help="experiment: vmsm_ctx_set_option(KEY, VALUE) before measuring (repeatable)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -129,9 +131,12 @@ def main():
     group.is_additive, group.is_multiplicative = False, True
     gf = GF(group.order)
     ctx = group._ctx()
+    for key, value in args.opt:
+        ctx.set_option(key, value)
     out = open(args.out, "a") if args.out else None
     for logn in args.log2n:
         best = measure(group, gf, logn, args.repeat, args.transcript, args.precompute)
+        best["options"] = args.opt
         print(json.dumps(best), flush=True)
         if out:
             out.write(json.dumps(best) + "\n")

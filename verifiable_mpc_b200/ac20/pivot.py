@@ -62,6 +62,10 @@ def random_residues_packed(rng, order, n):
     bits = order.bit_length()
     if type(rng) not in (_random.Random, _random.SystemRandom) or order <= 1 or bits > 256 or n == 0:
         return None
+    if type(rng) is _random.Random:  # the same stream from a C loop over the generator's own state (hostpack)
+        raw = hostpack.mt_randbelow_packed(rng, order, n)
+        if raw is not None:
+            return np.frombuffer(raw, dtype=np.uint8).reshape(n, 32)
     words = (bits + 31) // 32
     shift = 32 * words - bits
     limbs = [(order >> (32 * k)) & 0xFFFFFFFF for k in range(words)]

@@ -48,3 +48,20 @@ def field_class_for(seq, order):
             t = type(item)
             return t if getattr(t, "modulus", None) == order and hasattr(item, "value") else False
     return None
+
+
+def mt_randbelow_packed(rng, order, n):
+    """``[rng.randrange(order) for _ in range(n)]`` of a seeded ``random.Random`` as n x 32 little-endian bytes, leaving
+    ``rng`` in exactly the state the n calls would have left it (C loop over the generator's own Mersenne-twister state,
+    csrc/_hostpack.c); None when the helper is not built or ``rng`` is not a plain ``random.Random``."""
+    import random as _random
+    import struct
+
+    if _c is None or type(rng) is not _random.Random or not hasattr(_c, "mt_randbelow_packed") or order <= 1 or order >> 256:
+        return None
+    version, state, gauss = rng.getstate()
+    if version != 3 or len(state) != 625:
+        return None
+    out, key, pos = _c.mt_randbelow_packed(struct.pack("<624I", *state[:624]), state[624], order, n)
+    rng.setstate((version, struct.unpack("<624I", key) + (pos,), gauss))
+    return out
