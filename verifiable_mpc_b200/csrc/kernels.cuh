@@ -757,6 +757,7 @@ struct KGatherPartials {
     ge_ext *out_ext;
     ge_aff *out_aff;
     uint32_t *status;  // host-mapped: 0 ok, 1 timeout
+    ge_ext *out_host_ext;  // when set: extended sum into host-mapped memory, the host normalises (see KFinal)
     VMSM_HD void operator()(uint32_t tid) const {
         if (tid) return;
         ge_ext acc = ge_identity();
@@ -781,7 +782,8 @@ struct KGatherPartials {
             acc = ge_add(acc, ld_ext_plain(&box[r].pt));
         }
         st_ext(out_ext, acc);
-        st_aff(out_aff, ge_ext_to_aff(acc));
+        if (out_host_ext) st_ext(out_host_ext, acc);
+        else st_aff(out_aff, ge_ext_to_aff(acc));
         *status = 0u;
     }
 };

@@ -588,7 +588,8 @@ struct CudaBE {
         KPushPartial kp = {out_ext, box + c->mb_rank, c->shard_seq};
         launch(kp, 32);
         if (c->mb_owner) {
-            KGatherPartials kg = {box, c->mb_world, c->shard_seq, out_ext, out_aff, c->res_status_host + c->cur_slot};
+            KGatherPartials kg = {box, c->mb_world, c->shard_seq, out_ext, out_aff, c->res_status_host + c->cur_slot,
+                                  c->slot_host_norm[c->cur_slot] ? c->res_xyz_host + c->cur_slot : nullptr};
             launch(kg, 32);
         }
     }
@@ -891,8 +892,10 @@ int32_t run_msm(Ctx *c, const ge_niels *bases, const uint32_t *scalars, uint64_t
         c->shard_seq = c->shard_next;
         c->shard_next = 0;
     }
-    // a sharded MSM is finished by the owner's gather kernel on the device; everything else is normalised by the host
-    const bool hn = c->host_norm && !c->shard_seq;
+    // results leave the device in extended coordinates and the fetching call normalises on the CPU; a sharded MSM too:
+    // every rank's final kernel skips the inversion (only the extended partial is pushed), and the owner's gather kernel
+    // overwrites the owner's host slot with the extended sum (same stream, after its own final kernel)
+    const bool hn = c->host_norm;
     c->slot_host_norm[slot] = hn;
     int rc = msm_run(be, c->ws, c->opt, 253, bases, scalars, (uint32_t)n, c->res_ext + slot, c->res_aff_host + slot,
                      c->msm_seq++, extra, n_extra, pre, hn ? c->res_xyz_host + slot : nullptr);
