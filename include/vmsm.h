@@ -54,8 +54,8 @@ extern "C" {
 #define VMSM_OPT_SORT_BLOCKS 11 /* thread blocks of the digit-histogram and scatter kernels when they run on the sort
                                   stream (grid-stride); small = a thin slice of every SM for longer, so the sort
                                   shares the SMs with the accumulate kernel instead of displacing it (used only
-                                  while the previous MSM is still accumulating); -1 (default) = two blocks per SM, four
-                                  below 2^18 terms; 0 = always one thread per scalar */
+                                  while the previous MSM is still accumulating); -1 (default) = four blocks per SM below
+                                  2^18 terms, two up to 2^20, one from 2^21; 0 = always one thread per scalar */
 #define VMSM_OPT_FOLD_QUAD_MAX 12 /* generator folds of at most this many outputs use the 4-lanes-per-element kernel
                                     (latency-bound rounds); 0 = never */
 #define VMSM_OPT_BN_QUAD_ACC 13 /* BN256 accumulate kernel with four lanes per bucket: 0 never, 1 (default) for the sizes

@@ -634,10 +634,11 @@ struct CudaBE {
     template <class F>
     void launch_sort(const F &f, uint32_t n) {
         uint32_t grid = (n + F::kBlock - 1) / F::kBlock;
-        // thin grid: two blocks per SM, four below 2^18 terms (round 2, profiles/r02/sort_blocks_sweep.jsonl: with the
-        // accumulate kernels on two head streams and single-wave launches at 65 % of the resident threads, one block
-        // per SM -- the round-1 optimum -- is 1-5 % slower at every size from 2^16 to 2^20)
-        const uint32_t sb = c->sort_blocks_auto ? (n < (1u << 18) ? 4u : 2u) * c->sms : c->sort_blocks;
+        // thin grid: four blocks per SM below 2^18 terms, two up to 2^20, one from 2^21 (round 2,
+        // profiles/r02/sort_blocks_sweep.jsonl: with the accumulate kernels on two head streams and single-wave launches
+        // at 65 % of the resident threads, one block per SM -- the round-1 optimum at every size -- is 1-5 % slower from
+        // 2^16 to 2^20 and still 3-6 % faster at 2^21 / 2^22)
+        const uint32_t sb = c->sort_blocks_auto ? (n < (1u << 18) ? 4u : n < (1u << 21) ? 2u : 1u) * c->sms : c->sort_blocks;
         if (!c->async_sort || !thin_sort || !sb || grid <= sb) return launch(f, n);
         vmsm_kernel_strided<F><<<sb, F::kBlock, 0, cur>>>(f, n);
         c->launches++;
