@@ -686,6 +686,15 @@ def _ncu_traffic_bytes():
     import csv
     import glob
 
+    # newest first: the round-2 summaries (tools/ncu_summarize.py: one row per launch, dram_rd_MB / dram_wr_MB columns)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "ncu_ed_accumulate_plain_2p20.csv")), reverse=True):
+        try:
+            rows = [r for r in csv.DictReader(open(path)) if "KAccumulate" in (r.get("kernel") or "")]
+            tot = [1e6 * (float(r["dram_rd_MB"]) + float(r["dram_wr_MB"])) for r in rows if r.get("dram_rd_MB")]
+            if tot:
+                return sum(tot) / len(tot)
+        except Exception:
+            continue
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "ncu_full_KAccumulate.csv")), reverse=True):
         try:
             rows = list(csv.reader(open(path)))

@@ -45,9 +45,10 @@ def main(path):
             v /= 1e6
         d[SHORT[m]] = round(v, 3)
     cols = ["kernel", "grid", "block"] + [c for c in SHORT.values()]
-    print(",".join(cols))
+    w = csv.writer(sys.stdout, lineterminator="\n")  # grid / block contain commas: quoted
+    w.writerow(cols)
     for d in launches.values():
-        print(",".join(str(d.get(c, "")) for c in cols))
+        w.writerow([d.get(c, "") for c in cols])
 
 
 if __name__ == "__main__":
