@@ -454,7 +454,7 @@ int msm_run_w(BE &be, Workspace &ws, const MsmOptions &opt, const waff<F> *bases
     if (c > 16) c = 16;
     // 2^9 .. 2^16 terms are latency-bound on this curve (few, expensive additions per thread): c = 13 gives 20 x 4096
     // short bucket chains and a bucket tree of exactly six full radix-4 levels (4096 = 4^6); measured fastest or tied at 2^10, 2^12,
-    // 2^14 and 2^16 on G1 and G2 (profiles/r01/bn256_msm_v5_windows.jsonl), 35 % faster than the work-minimising c = 11
+    // 2^14 and 2^16 on G1 and G2 (profiles/r01/bn256_msm_v5_windows.md), 35 % faster than the work-minimising c = 11
     if (!opt.window_bits && n >= 512 && n <= (1u << 16)) c = 13;
     // plain path from 2^11 terms: equal segments of the sorted entries instead of one thread per bucket, and then the
     // chain length no longer depends on the window, so up to 2^14 terms the work-minimising c = 11 wins (1024 buckets

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(F::kBlock, min_blocks<F>::value) vmsm_kernel(c
 
 // grid-stride variant for the per-scalar kernels of the counting sort when they run underneath an accumulate kernel.
 // Deliberately plain: batching the scatter's atomics / prefetching the next scalar made the sort itself ~30 % faster
-// but slowed the accumulate kernel it shares the memory system with by more (profiles/r01/sweep_sort_blocks.jsonl).
+// but slowed the accumulate kernel it shares the memory system with by more (profiles/r01/accumulate_variants.md).
 template <class F>
 __global__ void __launch_bounds__(F::kBlock) vmsm_kernel_strided(const F f, uint32_t n) {
     const uint32_t stride = gridDim.x * (uint32_t)F::kBlock;
