@@ -393,10 +393,15 @@ def _protocol_4_verifier_dev(g_hat, k, Q, Ld, gf, proof, round_i):
     return _protocol_4_verifier_ints(g_hat, k, Q, coeffs, gf, proof, round_i)
 
 
-def _to_linear(L, y, n, gf):
+def _to_linear(L, y, n, gf, known=None):
     """pivot.affine_to_linear without evaluating L on n zeros one coefficient at a time: when every coefficient
-    lives in gf, L(0, ..., 0) is gf(0) + L.constant (what the reference's sum() produces)."""
-    if FAST_INT_PATH and _all_in_field(L.coeffs, gf):
+    lives in gf, L(0, ..., 0) is gf(0) + L.constant (what the reference's sum() produces).  `known`: a one-element list
+    that receives whether the coefficients were found to be gf elements (subtracting a constant keeps them so), which
+    saves the caller a second pass over them."""
+    in_field = FAST_INT_PATH and _all_in_field(L.coeffs, gf)
+    if known is not None:
+        known.append(bool(in_field))
+    if in_field:
         constant = gf(0) + L.constant
         return L - constant, y - constant
     return pivot.affine_to_linear(L, y, n)
@@ -473,9 +478,7 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
         zd = ctx.upload_scalars(r.tobytes() + (rho % order).to_bytes(32, "little"), order)
     Ld = xd = None
     try:
-        Ld = ctx.upload_scalars(_pack_field(L.coeffs, gf, order) + bytes(32), order)
-        _mark("p5:uploads")
-        t = gf(ctx.scalars_dot(Ld, 0, zd, 0, n)) + L.constant
+        # the announcement A only needs r: it is issued first and computed while the host packs the coefficients of L
         logger_cp.debug("Calculate A.")
         g_fixed = generators["g"]
         if isinstance(g_fixed, DevicePointList) and getattr(g_fixed.dev, "precomputed", False) and len(g_fixed) >= n:
@@ -484,6 +487,9 @@ def _protocol_5_prover_dev(generators, g_hat, P, L, y, x, gamma, gf, r, rho):
             ctx.msm_dev_ext(g_fixed.dev, g_fixed.off, n, zd, 0, hd, 0, [rho], slot=0)
         else:
             ctx.msm_dev(g_hat.dev, zd, slot=0, poff=g_hat.off, soff=0, n=n + 1)  # h**rho * prod g_i**r_i
+        Ld = ctx.upload_scalars(_pack_field(L.coeffs, gf, order) + bytes(32), order)
+        _mark("p5:uploads")
+        t = gf(ctx.scalars_dot(Ld, 0, zd, 0, n)) + L.constant
         A = group._make(ctx.result(0))
         _mark("p5:t,A")
         proof["t"] = t
@@ -526,13 +532,14 @@ def protocol_5_prover(generators, P, L, y, x, gamma, gf):
     group = type(h)
     proof = {}
     n = len(x)
-    L, y = _to_linear(L, y, n, gf)
+    coeffs_in_field = []
+    L, y = _to_linear(L, y, n, gf, coeffs_in_field)
     assert bin(n + 1).count("1") == 1, \
         "This implementation requires n+1 to be power of 2 (else, use padding with zeros)."
     order = gf.order
     # the residue paths reduce modulo gf.order while the round loop reduces modulo the group order: same thing only when
     # the field IS the exponent field of the group (always so in the reference's drivers); otherwise the generic path
-    fast = (FAST_INT_PATH and gf.order == k.order and _all_in_field(L.coeffs, gf) and _all_in_field(x, gf)
+    fast = (FAST_INT_PATH and gf.order == k.order and coeffs_in_field[0] and _all_in_field(x, gf)
             and L.constant == 0)
     if fast and len(L.coeffs) == n:
         g_hat = _g_hat(g, h, group)
