@@ -78,6 +78,7 @@ extern "C" {
 #define VMSM_OPT_BN_PRE_SETS 23 /* BN256 MSMs over key tables: bucket sets shared by the windows (0 = default: 2 with the
                                   balanced accumulate kernel, one per window with VMSM_OPT_SEG_MODE 0) */
 #define VMSM_OPT_BN_SEG_LEN 24 /* BN256: entries per thread of the balanced accumulate kernel (0 = whole waves, >= 8) */
+#define VMSM_OPT_BN_QUAD_FIX 25 /* BN256: 1 (default) = four lanes per bucket in the fix-up of buckets that straddle segments */
 #define VMSM_OPT_BLOCK_SORT 20 /* 1: counting sort of the digits with per-block shared-memory counters (digits recoded
                                  once into 16-bit codes, no global atomics) for Ed25519 MSMs of at least
                                  VMSM_OPT_BLOCK_SORT_MIN terms and windows c <= 16; 0 (default) = two passes with global

@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--bn-sets", type=int, nargs="+", default=[0], help="VMSM_OPT_BN_PRE_SETS values for the table MSMs")
     ap.add_argument("--bn-seg-len", type=int, nargs="+", default=[0], help="VMSM_OPT_BN_SEG_LEN values for the table MSMs")
     ap.add_argument("--seg-mode", type=int, nargs="+", default=[1], help="VMSM_OPT_SEG_MODE values for the table MSMs")
+    ap.add_argument("--quad-fix", type=int, default=-1, help="experiment: VMSM_OPT_BN_QUAD_FIX")
     ap.add_argument("--plain-seg-mode", type=int, nargs="+", default=[1], help="VMSM_OPT_SEG_MODE values for the plain-path MSMs")
     ap.add_argument("--plain-seg-len", type=int, nargs="+", default=[0], help="VMSM_OPT_BN_SEG_LEN values for the plain-path MSMs")
     ap.add_argument("--table-log2n", type=int, nargs="+", default=[], help="sizes of the table MSM sweep (default: max log2n)")
@@ -79,6 +80,8 @@ def main():
     ctx.set_option(_lib.OPT_PHASE_TIMING, 1)
     if args.quad_acc >= 0:
         ctx.set_option(_lib.OPT_BN_QUAD_ACC, args.quad_acc)
+    if args.quad_fix >= 0:
+        ctx.set_option(_lib.OPT_BN_QUAD_FIX, args.quad_fix)
     if args.radix >= 0:
         ctx.set_option(_lib.OPT_REDUCE_RADIX, args.radix)
     out = open(args.out, "a") if args.out else None

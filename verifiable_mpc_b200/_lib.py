@@ -20,7 +20,7 @@ OPT_BN_QUAD_ACC = 13
 OPT_PRE_SETS, OPT_PRE_MIN_TERMS, OPT_SEG_LEN, OPT_SEG_MODE, OPT_HOST_NORMALIZE = 14, 15, 16, 17, 18
 OPT_DUAL_HEAD = 19
 OPT_BLOCK_SORT, OPT_BLOCK_SORT_MIN, OPT_ACC_CARVEOUT = 20, 21, 22
-OPT_BN_PRE_SETS, OPT_BN_SEG_LEN = 23, 24
+OPT_BN_PRE_SETS, OPT_BN_SEG_LEN, OPT_BN_QUAD_FIX = 23, 24, 25
 FOLD_WITNESS, FOLD_FORM = 0, 1
 AXPY_ADD_SCALED, AXPY_SCALE_ADD, AXPY_SCALE = 0, 1, 2
 PHASES = ("digits", "scan", "scatter", "order", "handoff", "accumulate", "reduce", "final")

@@ -525,6 +525,49 @@ struct KAccumulateWQ {
     }
 };
 
+// Lane-cooperative twin of KSegFixupW: four lanes per bucket (launched with 4 * nbuckets threads).  A bucket of a
+// 2^14-term MSM over two shared sets holds ~40 entries in ~4 segments: three dependent full additions per bucket, the
+// longest chain between the accumulate kernel and the bucket tree.
+template <class F>
+struct KSegFixupWQ {
+    enum { kBlock = 128 };
+    const uint32_t *offsets, *counts;
+    const wjac<F> *partials;
+    wjac<F> *buckets;
+    uint32_t L, long_span;
+    OverflowCtl *ctl;
+    LongBucket *longs;
+    VMSM_HD void operator()(uint32_t tid) const {
+#if defined(__CUDA_ARCH__)
+        const int q = tid & 3;
+        const uint32_t b = tid >> 2;
+        const uint32_t cnt = counts[b];
+        if (!cnt) {
+            if (q == 0) st_obj(buckets + b, wj_identity<F>());
+            return;
+        }
+        const uint32_t off = offsets[b];
+        const uint32_t t0 = off / L, t1 = (off + cnt - 1) / L;
+        if (t0 == t1) return;
+        if (t1 - t0 > long_span) {
+            if (q == 0) {
+                uint32_t lpos = VMSM_ATOMIC_ADD(&ctl->nlong, 1u);
+                LongBucket lb = {b, t0, t1 - t0};
+                longs[lpos] = lb;
+            }
+            return;
+        }
+        wjac<F> acc = ld_obj(partials + 2 * (size_t)t0 + 1);
+        for (uint32_t t = t0 + 1; t <= t1; t++) acc = wq_add<F>(q, acc, ld_obj(partials + 2 * (size_t)t));
+        if (q == 0) st_obj(buckets + b, acc);
+#else
+        if (tid & 3) return;
+        KSegFixupW<F> k = {offsets, counts, partials, buckets, L, long_span, ctl, longs};
+        k(tid >> 2);
+#endif
+    }
+};
+
 // Lane-cooperative twin of KReduceW: four lanes per tree node (launched with 4 * nodes threads, a multiple of 4)
 template <class F>
 struct KReduceWQ {

@@ -1396,6 +1396,9 @@ int32_t vmsm_ctx_set_option(uint64_t ctx, int32_t key, int64_t value) {
             if (value < 0 || value > 64) return fail(VMSM_ERR_INVALID, "bucket sets out of range");
             c->opt.pre_sets_w = (uint32_t)value;
             return VMSM_OK;
+        case VMSM_OPT_BN_QUAD_FIX:
+            c->opt.w_quad_fix = value != 0;
+            return VMSM_OK;
         case VMSM_OPT_BN_SEG_LEN:
             if (value < 0 || value > 4096) return fail(VMSM_ERR_INVALID, "segment length out of range");
             c->opt.seg_len_w = (uint32_t)value;
